@@ -1,0 +1,676 @@
+// Implicit-GEMM 3-D convolution on Blackwell tensor cores (tcgen05.mma, accumulators in TMEM).
+//
+// Replaces the cuDNN calls behind nn.Conv3d on the RSPNet pretraining path
+// (reference call sites: models/resnet.py:21-27,130-136,170-175; models/c3d.py:21-50) and their
+// autograd (convolution_backward).  Activations are bf16 NDHWC, accumulation is fp32.
+//
+// One smem image serves all three GEMMs: a "panel" is R pixel rows x 128 B (64 bf16 channels of one
+// filter tap), 128-byte swizzled.
+//   fprop : D[pixel, cout] = sum_k  A[pixel, k] * Wp[cout, k]     A,B K-major    (k = tap*Cin + ci)
+//   dgrad : same kernel with the transposed gather (src = (dst + pad - tap)/stride) and Wd[ci, tap*Co+co]
+//   wgrad : D[k, cout]     = sum_pixel A[pixel, k] * dY[pixel, cout]   A,B MN-major, split over pixels,
+//           fp32 red.global.add into dWt[k, cout]
+// Producer warps gather rows with zero-filling cp.async (LDGSTS) that complete on an mbarrier; one elected
+// thread issues tcgen05.mma; the producer warps turn into the TMEM->register->global epilogue at the end.
+//
+// Two gather modes:
+//   GENERIC: Cs % 64 == 0, one K-block = one tap x 64 channels (one 128 B row segment)
+//   SMALLC : Cs == 4 (RGB padded), one K-block = S (kt,kh) rows x PXS w-pixels x 4 channels
+#include "common.cuh"
+#include "rspnet_b200.h"
+
+namespace rsp {
+
+constexpr int kProducerThreads = 128;
+constexpr int kThreads = 160;  // 4 producer/epilogue warps + 1 MMA warp
+
+struct GatherGeom {
+  const __nv_bfloat16* src;  // [N][Ts][Hs][Ws][Cs]
+  int N, Ts, Hs, Ws, Cs;
+  int Td, Hd, Wd;            // pixel grid that indexes GEMM rows
+  int kt, kh, kw;
+  int st, sh, sw;            // forward strides (for transposed: must be powers of two)
+  int pt, ph, pw;
+  int transposed;            // 0: src = d*s - p + k ; 1: src = (d + p - k)/s when divisible
+  int pxs;                   // SMALLC: w-pixels per (kt,kh) segment (4 or 8)
+  int numKb;                 // number of 64-wide K blocks
+  long long M;               // N*Td*Hd*Wd
+};
+
+struct ConvParams {
+  GatherGeom g;
+  const __nv_bfloat16* wgt;  // [Nout][numKb*64]
+  __nv_bfloat16* out;        // [M][Nout]
+  const float* bias;         // [Nout] or null
+  int Nout;
+};
+
+struct WgradParams {
+  GatherGeom g;
+  const __nv_bfloat16* dy;   // [M][Nout]
+  float* dwt;                // [numKb*64][Nout], accumulated with atomics
+  int Nout;
+  int pbPerSplit;            // 64-pixel blocks per z-slice
+};
+
+enum { MODE_GENERIC = 0, MODE_SMALLC = 1 };
+
+// ---------------------------------------------------------------------------------------------
+// row gather: where does (row pixel, K-block kb, 16B/8B chunk) come from?
+// ---------------------------------------------------------------------------------------------
+struct RowCoord {
+  int base;  // pixel index of (n,0,0,0) in src
+  int td, hd, wd;
+  int ok;    // row < M
+};
+
+__device__ __forceinline__ RowCoord decode_row(const GatherGeom& g, long long m) {
+  RowCoord r;
+  r.ok = m < g.M;
+  uint32_t mm = r.ok ? static_cast<uint32_t>(m) : 0u;  // host guarantees M < 2^31
+  uint32_t q = mm / static_cast<uint32_t>(g.Wd);
+  int wd = static_cast<int>(mm - q * g.Wd);
+  uint32_t q2 = q / static_cast<uint32_t>(g.Hd);
+  int hd = static_cast<int>(q - q2 * g.Hd);
+  uint32_t q3 = q2 / static_cast<uint32_t>(g.Td);
+  int td = static_cast<int>(q2 - q3 * g.Td);
+  int n = static_cast<int>(q3);
+  r.base = n * g.Ts * g.Hs * g.Ws;
+  r.td = td; r.hd = hd; r.wd = wd;
+  return r;
+}
+
+__device__ __forceinline__ bool map_coord(int d, int k, int s, int p, int transposed, int limit, int& out) {
+  if (!transposed) {
+    out = d * s - p + k;
+    return out >= 0 && out < limit;
+  }
+  int num = d + p - k;
+  if (num < 0 || (num & (s - 1))) return false;
+  out = num >> (31 - __clz(s));
+  return out < limit;
+}
+
+// GENERIC: one 16-byte chunk (8 channels) of a row for K-block kb.
+__device__ __forceinline__ const __nv_bfloat16* generic_src(const GatherGeom& g, const RowCoord& r, int a, int b,
+                                                           int c, int cc, int chunk, bool& valid) {
+  int ts, hs, ws;
+  bool v = r.ok;
+  v = map_coord(r.td, a, g.st, g.pt, g.transposed, g.Ts, ts) && v;
+  v = map_coord(r.hd, b, g.sh, g.ph, g.transposed, g.Hs, hs) && v;
+  v = map_coord(r.wd, c, g.sw, g.pw, g.transposed, g.Ws, ws) && v;
+  valid = v;
+  if (!v) return g.src;
+  size_t pix = static_cast<size_t>(r.base) + (static_cast<size_t>(ts) * g.Hs + hs) * g.Ws + ws;
+  return g.src + pix * g.Cs + cc * 64 + chunk * 8;
+}
+
+// SMALLC: one 8-byte chunk (one RGBx pixel) of a row for K-block kb. sub in [0,16).
+__device__ __forceinline__ const __nv_bfloat16* smallc_src(const GatherGeom& g, const RowCoord& r, int kb, int sub,
+                                                          bool& valid) {
+  int seg = sub / g.pxs, px = sub - seg * g.pxs;
+  int segs = 16 / g.pxs;
+  int rr = kb * segs + seg;
+  bool v = r.ok && rr < g.kt * g.kh && px < g.kw;
+  int a = rr / g.kh, b = rr - a * g.kh;
+  int ts = r.td * g.st - g.pt + a, hs = r.hd * g.sh - g.ph + b, ws = r.wd * g.sw - g.pw + px;
+  v = v && ts >= 0 && ts < g.Ts && hs >= 0 && hs < g.Hs && ws >= 0 && ws < g.Ws;
+  valid = v;
+  if (!v) return g.src;
+  size_t pix = static_cast<size_t>(r.base) + (static_cast<size_t>(ts) * g.Hs + hs) * g.Ws + ws;
+  return g.src + pix * 4;
+}
+
+// byte offset of logical (row, byte b) inside a 128B-swizzled panel whose base is 1024 B aligned
+__device__ __forceinline__ uint32_t swz(int row, int b) {
+  return static_cast<uint32_t>(row * 128 + ((((b >> 4) ^ (row & 7)) << 4) | (b & 15)));
+}
+
+// Gather ROWS rows of K-block kb into a panel. rows[] were decoded by the caller with the SAME thread mapping:
+//   GENERIC: chunk = t & 7,  row_i = (t >> 3) + 16*i, i < ROWS/16
+//   SMALLC : sub   = t & 15, row_i = (t >> 4) + 8*i,  i < ROWS/8
+template <int MODE, int ROWS>
+__device__ __forceinline__ void gather_panel(const GatherGeom& g, uint32_t panel, int kb, int t,
+                                             const RowCoord* rows) {
+  if (MODE == MODE_GENERIC) {
+    const int cchunks = g.Cs >> 6;
+    int tap = kb / cchunks, cc = kb - tap * cchunks;
+    bool kbok = kb < g.numKb;
+    int a = tap / (g.kh * g.kw);
+    int rem = tap - a * g.kh * g.kw;
+    int b = rem / g.kw, c = rem - b * g.kw;
+    const int chunk = t & 7;
+#pragma unroll
+    for (int i = 0; i < ROWS / 16; ++i) {
+      int row = (t >> 3) + 16 * i;
+      bool valid;
+      const __nv_bfloat16* s = generic_src(g, rows[i], a, b, c, cc, chunk, valid);
+      valid = valid && kbok;
+      cp_async16(panel + swz(row, chunk * 16), valid ? s : g.src, valid ? 16u : 0u);
+    }
+  } else {
+    const int sub = t & 15;
+    bool kbok = kb < g.numKb;
+#pragma unroll
+    for (int i = 0; i < ROWS / 8; ++i) {
+      int row = (t >> 4) + 8 * i;
+      bool valid;
+      const __nv_bfloat16* s = smallc_src(g, rows[i], kb, sub, valid);
+      valid = valid && kbok;
+      cp_async8(panel + swz(row, sub * 8), valid ? s : g.src, valid ? 8u : 0u);
+    }
+  }
+}
+
+// Plain rows: ROWS rows of 128 B taken from a row-major matrix (weights or dY).
+template <int ROWS>
+__device__ __forceinline__ void load_rows(uint32_t panel, const __nv_bfloat16* base, long long row0, long long nrows,
+                                          size_t ld, int t) {
+  const int chunk = t & 7;
+#pragma unroll
+  for (int i = 0; i < ROWS / 16; ++i) {
+    int row = (t >> 3) + 16 * i;
+    bool valid = (row0 + row) < nrows;
+    const __nv_bfloat16* s = base + (valid ? static_cast<size_t>(row0 + row) * ld + chunk * 8 : 0);
+    cp_async16(panel + swz(row, chunk * 16), s, valid ? 16u : 0u);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fprop / dgrad kernel:  out[M][Nout] = gather(src)[M][K] * wgt[Nout][K]^T (+ bias)
+// ---------------------------------------------------------------------------------------------
+template <int NT, int STAGES, int MODE>
+__global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int A_BYTES = 128 * 128;
+  constexpr int B_BYTES = NT * 128;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int ROWS_PER_THREAD = (MODE == MODE_GENERIC) ? 8 : 16;
+
+  // dynamic smem is only guaranteed 16 B aligned: round up to the 1024 B the 128B swizzle needs
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int t = threadIdx.x;
+  const int warp = t >> 5;
+  const long long m0 = static_cast<long long>(blockIdx.x) * 128;
+  const int n0 = blockIdx.y * NT;
+  const GatherGeom& g = p.g;
+  const int numKb = g.numKb;
+
+  if (t == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], kProducerThreads);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, NT);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ---------------- producers ----------------
+    RowCoord rows[ROWS_PER_THREAD];
+#pragma unroll
+    for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+      int row = (MODE == MODE_GENERIC) ? (t >> 3) + 16 * i : (t >> 4) + 8 * i;
+      rows[i] = decode_row(g, m0 + row);
+    }
+    const size_t ldw = static_cast<size_t>(numKb) * 64;
+    for (int kb = 0; kb < numKb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      const uint32_t a_panel = smem_u32(smem + s * STAGE_BYTES);
+      const uint32_t b_panel = a_panel + A_BYTES;
+      gather_panel<MODE, 128>(g, a_panel, kb, t, rows);
+      load_rows<NT>(b_panel, p.wgt + static_cast<size_t>(kb) * 64, n0, p.Nout, ldw, t);
+      cp_async_mbar_arrive(&full_bar[s]);
+      mbar_arrive(&full_bar[s]);
+    }
+    // ---------------- epilogue ----------------
+    mbar_wait(accum_bar, 0);
+    tc_fence_after_sync();
+    const long long row = m0 + warp * 32 + (t & 31);
+    const bool row_ok = row < g.M;
+    __nv_bfloat16* orow = p.out + static_cast<size_t>(row_ok ? row : 0) * p.Nout + n0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < NT; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            f[e] = __uint_as_float(v[j + e]);
+            if (p.bias) f[e] += __ldg(p.bias + n0 + c0 + j + e);
+          }
+          uint4 o;
+          o.x = pack_bf16x2(f[0], f[1]);
+          o.y = pack_bf16x2(f[2], f[3]);
+          o.z = pack_bf16x2(f[4], f[5]);
+          o.w = pack_bf16x2(f[6], f[7]);
+          *reinterpret_cast<uint4*>(orow + c0 + j) = o;
+        }
+      }
+    }
+  } else {
+    // ---------------- MMA issuer ----------------
+    constexpr uint32_t idesc = make_idesc_bf16(128, NT, 0, 0);
+    for (int kb = 0; kb < numKb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(&full_bar[s], ph);
+      fence_proxy_async_smem();
+      tc_fence_after_sync();
+      if ((t & 31) == 0) {
+        const uint32_t a_panel = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t b_panel = a_panel + A_BYTES;
+        const uint64_t adesc = make_smem_desc_sw128(a_panel, 16, 1024);
+        const uint64_t bdesc = make_smem_desc_sw128(b_panel, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // +32 B per K=16 step inside the 128 B swizzle row (descriptor address is in 16 B units)
+          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty_bar[s]);
+        if (kb == numKb - 1) umma_commit(accum_bar);
+      }
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, NT);
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad kernel: dwt[kb*64 + kk][cout] += sum_pixel gather(src)[pixel][kb*64+kk] * dy[pixel][cout]
+// grid: x = pairs of K blocks (M tile = 128 rows of the K axis), y = cout tile, z = pixel split
+// ---------------------------------------------------------------------------------------------
+template <int NT, int STAGES, int MODE>
+__global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int PANEL = 64 * 128;  // 64 pixel rows x 128 B
+  constexpr int NB = NT / 64;
+  constexpr int STAGE_BYTES = (2 + NB) * PANEL;
+  constexpr int ROWS_PER_THREAD = (MODE == MODE_GENERIC) ? 4 : 8;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int t = threadIdx.x;
+  const int warp = t >> 5;
+  const GatherGeom& g = p.g;
+  const int kb0 = blockIdx.x * 2;
+  const int n0 = blockIdx.y * NT;
+  const long long totalPb = (g.M + 63) / 64;
+  const long long pbBegin = static_cast<long long>(blockIdx.z) * p.pbPerSplit;
+  long long pbEnd = pbBegin + p.pbPerSplit;
+  if (pbEnd > totalPb) pbEnd = totalPb;
+  const int iters = pbEnd > pbBegin ? static_cast<int>(pbEnd - pbBegin) : 0;
+
+  if (t == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], kProducerThreads);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, NT);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (iters > 0) {
+    if (warp < 4) {
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        const long long prow0 = (pbBegin + it) * 64;
+        RowCoord rows[ROWS_PER_THREAD];
+#pragma unroll
+        for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+          int row = (MODE == MODE_GENERIC) ? (t >> 3) + 16 * i : (t >> 4) + 8 * i;
+          rows[i] = decode_row(g, prow0 + row);
+        }
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const uint32_t stage = smem_u32(smem + s * STAGE_BYTES);
+        gather_panel<MODE, 64>(g, stage, kb0, t, rows);
+        gather_panel<MODE, 64>(g, stage + PANEL, kb0 + 1, t, rows);
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+          load_rows<64>(stage + (2 + j) * PANEL, p.dy + n0 + j * 64, prow0, g.M, p.Nout, t);
+        cp_async_mbar_arrive(&full_bar[s]);
+        mbar_arrive(&full_bar[s]);
+      }
+      // epilogue: D row = K index inside the pair of K blocks, columns = cout
+      mbar_wait(accum_bar, 0);
+      tc_fence_after_sync();
+      const int krow = kb0 * 64 + warp * 32 + (t & 31);
+      const bool row_ok = krow < g.numKb * 64;
+      float* drow = p.dwt + static_cast<size_t>(row_ok ? krow : 0) * p.Nout + n0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < NT; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + c0 + j),
+                         "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])),
+                         "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                         : "memory");
+          }
+        }
+      }
+    } else {
+      constexpr uint32_t idesc = make_idesc_bf16(128, NT, 1, 1);
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        fence_proxy_async_smem();
+        tc_fence_after_sync();
+        if ((t & 31) == 0) {
+          const uint32_t stage = smem_u32(smem + s * STAGE_BYTES);
+          // MN-major: 64-wide panels PANEL bytes apart (LBO), 8-pixel groups 1024 B apart (SBO)
+          const uint64_t adesc = make_smem_desc_sw128(stage, PANEL, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(stage + 2 * PANEL, PANEL, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // K=16 pixels = two 8-pixel groups = 2048 B
+            umma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, idesc, (it | k) != 0);
+          }
+          umma_commit(&empty_bar[s]);
+          if (it == iters - 1) umma_commit(accum_bar);
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, NT);
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing / gradient unpacking (tiny, elementwise)
+// ---------------------------------------------------------------------------------------------
+// K index -> (ci, kt, kh, kw) of the PyTorch filter [Co][Ci][kt][kh][kw]; returns false for padding slots.
+__device__ __forceinline__ bool k_to_filter(int mode, int k, int Cs, int Ci, int kt, int kh, int kw, int pxs,
+                                            int& ci, int& a, int& b, int& c) {
+  if (mode == MODE_GENERIC) {
+    int tap = k / Cs;
+    ci = k - tap * Cs;
+    a = tap / (kh * kw);
+    int rem = tap - a * kh * kw;
+    b = rem / kw;
+    c = rem - b * kw;
+    return ci < Ci && a < kt;
+  }
+  int kb = k >> 6, e = k & 63;
+  int sub = e >> 2;
+  ci = e & 3;
+  int seg = sub / pxs, px = sub - seg * pxs;
+  int rr = kb * (16 / pxs) + seg;
+  a = rr / kh;
+  b = rr - a * kh;
+  c = px;
+  return ci < Ci && rr < kt * kh && px < kw;
+}
+
+// w fp32 [Co][Ci][kt][kh][kw] -> wp bf16 [CoPad][Kpad]  (fprop B operand)
+__global__ void pack_weight_fprop_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int mode, int Co,
+                                         int CoPad, int Ci, int Cs, int kt, int kh, int kw, int pxs, int Kpad) {
+  size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  size_t total = static_cast<size_t>(CoPad) * Kpad;
+  if (idx >= total) return;
+  int co = static_cast<int>(idx / Kpad), k = static_cast<int>(idx % Kpad);
+  int ci, a, b, c;
+  float v = 0.f;
+  if (co < Co && k_to_filter(mode, k, Cs, Ci, kt, kh, kw, pxs, ci, a, b, c))
+    v = w[(((static_cast<size_t>(co) * Ci + ci) * kt + a) * kh + b) * kw + c];
+  wp[idx] = __float2bfloat16(v);
+}
+
+// w fp32 [Co][Ci][kt][kh][kw] -> wd bf16 [CiPad][taps*CoPad]  (dgrad B operand: K index = tap*CoPad + co)
+__global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wd, int Co, int CoPad,
+                                         int Ci, int CiPad, int kt, int kh, int kw) {
+  size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  int taps = kt * kh * kw;
+  size_t K = static_cast<size_t>(taps) * CoPad;
+  size_t total = static_cast<size_t>(CiPad) * K;
+  if (idx >= total) return;
+  int ci = static_cast<int>(idx / K);
+  int k = static_cast<int>(idx % K);
+  int tap = k / CoPad, co = k - tap * CoPad;
+  float v = 0.f;
+  if (ci < Ci && co < Co) v = w[(static_cast<size_t>(co) * Ci + ci) * taps + tap];
+  wd[idx] = __float2bfloat16(v);
+}
+
+// dwt fp32 [Kpad][CoPad] -> dw fp32 [Co][Ci][kt][kh][kw]   (accumulate != 0: +=)
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwt, float* __restrict__ dw, int mode, int Co, int CoPad,
+                                    int Ci, int Cs, int kt, int kh, int kw, int pxs, int Kpad, int accumulate) {
+  size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  size_t total = static_cast<size_t>(CoPad) * Kpad;
+  if (idx >= total) return;
+  // co fastest so that reads of dwt are coalesced
+  int k = static_cast<int>(idx / CoPad), co = static_cast<int>(idx % CoPad);
+  int ci, a, b, c;
+  if (co >= Co || !k_to_filter(mode, k, Cs, Ci, kt, kh, kw, pxs, ci, a, b, c)) return;
+  size_t o = (((static_cast<size_t>(co) * Ci + ci) * kt + a) * kh + b) * kw + c;
+  float v = dwt[idx];
+  dw[o] = accumulate ? dw[o] + v : v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+static int fill_geom(GatherGeom& g, const rsp_conv3d_desc* d, int mode, int transposed) {
+  // forward geometry
+  const int To = (d->Ti + 2 * d->pt - d->kt) / d->st + 1;
+  const int Ho = (d->Hi + 2 * d->ph - d->kh) / d->sh + 1;
+  const int Wo = (d->Wi + 2 * d->pw - d->kw) / d->sw + 1;
+  RSP_REQUIRE(To > 0 && Ho > 0 && Wo > 0, "conv3d: empty output");
+  g.N = d->N;
+  g.kt = d->kt; g.kh = d->kh; g.kw = d->kw;
+  g.st = d->st; g.sh = d->sh; g.sw = d->sw;
+  g.pt = d->pt; g.ph = d->ph; g.pw = d->pw;
+  g.transposed = transposed;
+  g.pxs = 0;
+  if (!transposed) {
+    g.Ts = d->Ti; g.Hs = d->Hi; g.Ws = d->Wi; g.Cs = d->Ci;
+    g.Td = To; g.Hd = Ho; g.Wd = Wo;
+  } else {
+    RSP_REQUIRE(is_pow2(d->st) && is_pow2(d->sh) && is_pow2(d->sw), "conv3d dgrad: strides must be powers of two");
+    g.Ts = To; g.Hs = Ho; g.Ws = Wo; g.Cs = d->Co;
+    g.Td = d->Ti; g.Hd = d->Hi; g.Wd = d->Wi;
+  }
+  g.M = static_cast<long long>(g.N) * g.Td * g.Hd * g.Wd;
+  if (mode == MODE_GENERIC) {
+    RSP_REQUIRE(g.Cs % 64 == 0, "conv3d: gathered channel count %d must be a multiple of 64", g.Cs);
+    g.numKb = d->kt * d->kh * d->kw * (g.Cs / 64);
+  } else {
+    RSP_REQUIRE(!transposed, "conv3d: small-channel mode has no dgrad");
+    RSP_REQUIRE(g.Cs == 4, "conv3d: small-channel mode needs Ci == 4 (got %d)", g.Cs);
+    RSP_REQUIRE(d->kw <= 8, "conv3d: small-channel mode needs kw <= 8");
+    g.pxs = d->kw <= 4 ? 4 : 8;
+    const int segs = 16 / g.pxs;
+    g.numKb = (d->kt * d->kh + segs - 1) / segs;
+  }
+  RSP_REQUIRE(static_cast<long long>(g.N) * g.Ts * g.Hs * g.Ws < (1ll << 31) && g.M < (1ll << 31),
+              "conv3d: tensor too large");
+  return RSP_OK;
+}
+
+static int conv_mode(const rsp_conv3d_desc* d) { return d->Ci == 4 ? MODE_SMALLC : MODE_GENERIC; }
+
+template <int NT, int STAGES, int MODE>
+static int launch_igemm(const ConvParams& p, cudaStream_t stream) {
+  constexpr int smem = STAGES * (128 * 128 + NT * 128) + 1024 + 256;
+  auto kern = conv_igemm_kernel<NT, STAGES, MODE>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(conv_igemm): %s", cudaGetErrorString(e));
+    return RSP_ERR_CUDA;
+  }
+  dim3 grid(static_cast<unsigned>((p.g.M + 127) / 128), static_cast<unsigned>(p.Nout / NT));
+  kern<<<grid, kThreads, smem, stream>>>(p);
+  return check_launch("conv_igemm");
+}
+
+template <int MODE>
+static int dispatch_igemm(const ConvParams& p, cudaStream_t stream) {
+  if (p.Nout % 128 == 0) return launch_igemm<128, 3, MODE>(p, stream);
+  return launch_igemm<64, 4, MODE>(p, stream);
+}
+
+template <int NT, int STAGES, int MODE>
+static int launch_wgrad(WgradParams& p, int sm_count, cudaStream_t stream) {
+  constexpr int smem = STAGES * (2 + NT / 64) * 64 * 128 + 1024 + 256;
+  auto kern = conv_wgrad_kernel<NT, STAGES, MODE>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(conv_wgrad): %s", cudaGetErrorString(e));
+    return RSP_ERR_CUDA;
+  }
+  const int mt = (p.g.numKb + 1) / 2, nt = p.Nout / NT;
+  const long long totalPb = (p.g.M + 63) / 64;
+  // enough pixel splits for ~2 waves of CTAs (2 CTAs/SM), at least 8 pixel blocks per split
+  long long splits = (4ll * sm_count + mt * nt - 1) / (mt * nt);
+  if (splits > (totalPb + 7) / 8) splits = (totalPb + 7) / 8;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  p.pbPerSplit = static_cast<int>((totalPb + splits - 1) / splits);
+  splits = (totalPb + p.pbPerSplit - 1) / p.pbPerSplit;
+  dim3 grid(mt, nt, static_cast<unsigned>(splits));
+  kern<<<grid, kThreads, smem, stream>>>(p);
+  return check_launch("conv_wgrad");
+}
+
+template <int MODE>
+static int dispatch_wgrad(WgradParams& p, int sm_count, cudaStream_t stream) {
+  if (p.Nout % 128 == 0) return launch_wgrad<128, 3, MODE>(p, sm_count, stream);
+  return launch_wgrad<64, 4, MODE>(p, sm_count, stream);
+}
+
+int device_sm_count();
+
+}  // namespace rsp
+
+using namespace rsp;
+
+extern "C" {
+
+int rsp_conv3d_kpad(const rsp_conv3d_desc* d, int which) {
+  GatherGeom g{};
+  const int mode = conv_mode(d);
+  if (which == 1) {  // dgrad weights: K = taps * Co
+    return d->kt * d->kh * d->kw * d->Co;
+  }
+  if (fill_geom(g, d, mode, 0) != RSP_OK) return RSP_ERR_INVALID;
+  return g.numKb * 64;
+}
+
+int rsp_conv3d_pack_weight(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const float* w, void* wp,
+                           int which, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int mode = conv_mode(d);
+  if (which == 0) {
+    GatherGeom g{};
+    int rc = fill_geom(g, d, mode, 0);
+    if (rc != RSP_OK) return rc;
+    const int Kpad = g.numKb * 64;
+    size_t total = static_cast<size_t>(d->Co) * Kpad;
+    pack_weight_fprop_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+        w, static_cast<__nv_bfloat16*>(wp), mode, Co_logical, d->Co, Ci_logical, d->Ci, d->kt, d->kh, d->kw, g.pxs,
+        Kpad);
+    return check_launch("pack_weight_fprop");
+  }
+  RSP_REQUIRE(mode == MODE_GENERIC, "pack_weight(dgrad): small-channel convs have no dgrad");
+  size_t total = static_cast<size_t>(d->Ci) * d->kt * d->kh * d->kw * d->Co;
+  pack_weight_dgrad_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      w, static_cast<__nv_bfloat16*>(wp), Co_logical, d->Co, Ci_logical, d->Ci, d->kt, d->kh, d->kw);
+  return check_launch("pack_weight_dgrad");
+}
+
+int rsp_conv3d_fprop(const rsp_conv3d_desc* d, const void* x, const void* wp, const float* bias, void* y,
+                     void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int mode = conv_mode(d);
+  ConvParams p{};
+  int rc = fill_geom(p.g, d, mode, 0);
+  if (rc != RSP_OK) return rc;
+  RSP_REQUIRE(d->Co % 64 == 0, "conv3d fprop: Co=%d must be a multiple of 64", d->Co);
+  p.g.src = static_cast<const __nv_bfloat16*>(x);
+  p.wgt = static_cast<const __nv_bfloat16*>(wp);
+  p.out = static_cast<__nv_bfloat16*>(y);
+  p.bias = bias;
+  p.Nout = d->Co;
+  return mode == MODE_GENERIC ? dispatch_igemm<MODE_GENERIC>(p, stream) : dispatch_igemm<MODE_SMALLC>(p, stream);
+}
+
+int rsp_conv3d_dgrad(const rsp_conv3d_desc* d, const void* dy, const void* wd, void* dx, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ConvParams p{};
+  RSP_REQUIRE(d->Ci % 64 == 0 && d->Co % 64 == 0, "conv3d dgrad: Ci=%d, Co=%d must be multiples of 64", d->Ci, d->Co);
+  int rc = fill_geom(p.g, d, MODE_GENERIC, 1);
+  if (rc != RSP_OK) return rc;
+  p.g.src = static_cast<const __nv_bfloat16*>(dy);
+  p.wgt = static_cast<const __nv_bfloat16*>(wd);
+  p.out = static_cast<__nv_bfloat16*>(dx);
+  p.bias = nullptr;
+  p.Nout = d->Ci;
+  return dispatch_igemm<MODE_GENERIC>(p, stream);
+}
+
+int rsp_conv3d_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const void* x, const void* dy,
+                     float* dwt_workspace, float* dw, int accumulate, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int mode = conv_mode(d);
+  WgradParams p{};
+  int rc = fill_geom(p.g, d, mode, 0);
+  if (rc != RSP_OK) return rc;
+  RSP_REQUIRE(d->Co % 64 == 0, "conv3d wgrad: Co=%d must be a multiple of 64", d->Co);
+  p.g.src = static_cast<const __nv_bfloat16*>(x);
+  p.dy = static_cast<const __nv_bfloat16*>(dy);
+  p.dwt = dwt_workspace;
+  p.Nout = d->Co;
+  const int Kpad = p.g.numKb * 64;
+  cudaError_t e = cudaMemsetAsync(dwt_workspace, 0, static_cast<size_t>(Kpad) * d->Co * sizeof(float), stream);
+  if (e != cudaSuccess) {
+    set_error("wgrad memset: %s", cudaGetErrorString(e));
+    return RSP_ERR_CUDA;
+  }
+  const int sms = device_sm_count();
+  rc = mode == MODE_GENERIC ? dispatch_wgrad<MODE_GENERIC>(p, sms, stream) : dispatch_wgrad<MODE_SMALLC>(p, sms, stream);
+  if (rc != RSP_OK) return rc;
+  size_t total = static_cast<size_t>(d->Co) * Kpad;
+  unpack_wgrad_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      dwt_workspace, dw, mode, Co_logical, d->Co, Ci_logical, d->Ci, d->kt, d->kh, d->kw, p.g.pxs, Kpad, accumulate);
+  return check_launch("unpack_wgrad");
+}
+
+}  // extern "C"

@@ -1,0 +1,600 @@
+// HBM-bound activation kernels on bf16 NDHWC tensors: train-mode BatchNorm (+ReLU +residual), MaxPool3d,
+// the projection heads, and layout conversion.  All of them move 16-byte vectors (8 channels) per thread.
+// Reference call sites: models/resnet.py:54-75,137-139; models/c3d.py:22-50; moco/split_wrapper.py:128-169.
+#include "common.cuh"
+#include "rspnet_b200.h"
+
+namespace rsp {
+
+int device_sm_count();
+
+struct bf8 {
+  uint4 raw;
+};
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 v;
+  v.x = pack_bf16x2(f[0], f[1]);
+  v.y = pack_bf16x2(f[2], f[3]);
+  v.z = pack_bf16x2(f[4], f[5]);
+  v.w = pack_bf16x2(f[6], f[7]);
+  return v;
+}
+
+static inline unsigned ew_grid(size_t items, int block) {
+  size_t need = (items + block - 1) / block;
+  size_t cap = static_cast<size_t>(device_sm_count()) * 16;
+  if (need < 1) need = 1;
+  return static_cast<unsigned>(need < cap ? need : cap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-channel reductions: thread owns one 8-channel group, strides over rows
+// MODE 0: sum x, sum x^2.   MODE 1: sum dz, sum dz*xhat (BN backward)
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) channel_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ out,
+                                                             const uint4* __restrict__ dout,
+                                                             const float* __restrict__ mean,
+                                                             const float* __restrict__ invstd, int relu, size_t M,
+                                                             int C, float* __restrict__ r0, float* __restrict__ r1) {
+  const int G = C >> 3;             // channel groups per row (divides 256)
+  const int rows_per_iter = 256 / G;
+  const int g = threadIdx.x % G;
+  const int rsub = threadIdx.x / G;
+  float a[8], b[8], mu[8], is[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a[i] = b[i] = 0.f;
+    if (MODE == 1) {
+      mu[i] = mean[g * 8 + i];
+      is[i] = invstd[g * 8 + i];
+    }
+  }
+  for (size_t row = static_cast<size_t>(blockIdx.x) * rows_per_iter + rsub; row < M;
+       row += static_cast<size_t>(gridDim.x) * rows_per_iter) {
+    size_t o = row * G + g;
+    float xv[8];
+    unpack8(__ldg(x + o), xv);
+    if (MODE == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        a[i] += xv[i];
+        b[i] = fmaf(xv[i], xv[i], b[i]);
+      }
+    } else {
+      float dv[8], ov[8];
+      unpack8(__ldg(dout + o), dv);
+      if (relu) unpack8(__ldg(out + o), ov);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float dz = (relu && !(ov[i] > 0.f)) ? 0.f : dv[i];
+        a[i] += dz;
+        b[i] = fmaf(dz, (xv[i] - mu[i]) * is[i], b[i]);
+      }
+    }
+  }
+  // block reduce across the rows_per_iter threads sharing a channel group
+  __shared__ float sa[256 * 8];
+  __shared__ float sb[256 * 8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sa[threadIdx.x * 8 + i] = a[i];
+    sb[threadIdx.x * 8 + i] = b[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    int gg = c >> 3, i = c & 7;
+    float s0 = 0.f, s1 = 0.f;
+    for (int r = 0; r < rows_per_iter; ++r) {
+      s0 += sa[(r * G + gg) * 8 + i];
+      s1 += sb[(r * G + gg) * 8 + i];
+    }
+    atomicAdd(r0 + c, s0);
+    atomicAdd(r1 + c, s1);
+  }
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, float count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* __restrict__ rmean, float* __restrict__ rvar,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean,
+                                   float* __restrict__ invstd, int C, int Cl) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (c >= Cl) {
+    scale[c] = 0.f;
+    shift[c] = 0.f;
+    mean[c] = 0.f;
+    invstd[c] = 0.f;
+    return;
+  }
+  float mu = sum[c] / count;
+  float var = fmaxf(sumsq[c] / count - mu * mu, 0.f);
+  float is = rsqrtf(var + eps);
+  float sc = gamma[c] * is;
+  scale[c] = sc;
+  shift[c] = beta[c] - mu * sc;
+  mean[c] = mu;
+  invstd[c] = is;
+  if (rmean) rmean[c] = (1.f - momentum) * rmean[c] + momentum * mu;
+  if (rvar) {
+    float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
+    rvar[c] = (1.f - momentum) * rvar[c] + momentum * unbiased;
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ scale,
+                                                         const float* __restrict__ shift,
+                                                         const uint4* __restrict__ res, int relu,
+                                                         uint4* __restrict__ out, size_t nvec, int C) {
+  extern __shared__ float sm[];
+  float* ssc = sm;
+  float* ssh = sm + C;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    ssc[c] = scale[c];
+    ssh[c] = shift[c];
+  }
+  __syncthreads();
+  const int G = C >> 3;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < nvec;
+       i += static_cast<size_t>(gridDim.x) * 256) {
+    int g = static_cast<int>(i % G);
+    float xv[8], rv[8];
+    unpack8(__ldg(x + i), xv);
+    if (res) unpack8(__ldg(res + i), rv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float y = fmaf(xv[e], ssc[g * 8 + e], ssh[g * 8 + e]);
+      if (res) y += rv[e];
+      xv[e] = relu ? fmaxf(y, 0.f) : y;
+    }
+    out[i] = pack8(xv);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
+    const uint4* __restrict__ dout, const uint4* __restrict__ out, const uint4* __restrict__ x,
+    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+    const float* __restrict__ sum_dz, const float* __restrict__ sum_dz_xhat, int relu, uint4* __restrict__ dx,
+    uint4* __restrict__ dres, size_t nvec, int C, int Cl, float inv_m) {
+  extern __shared__ float sm[];
+  float* smu = sm;          // mean
+  float* sis = sm + C;      // invstd
+  float* sk = sm + 2 * C;   // gamma*invstd
+  float* s1 = sm + 3 * C;   // sum_dz / M
+  float* s2 = sm + 4 * C;   // sum_dz_xhat / M
+  for (int c = threadIdx.x; c < C; c += 256) {
+    bool live = c < Cl;
+    smu[c] = mean[c];
+    sis[c] = invstd[c];
+    sk[c] = live ? gamma[c] * invstd[c] : 0.f;
+    s1[c] = sum_dz[c] * inv_m;
+    s2[c] = sum_dz_xhat[c] * inv_m;
+  }
+  __syncthreads();
+  const int G = C >> 3;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < nvec;
+       i += static_cast<size_t>(gridDim.x) * 256) {
+    int g = static_cast<int>(i % G);
+    float dv[8], ov[8], xv[8], o[8];
+    unpack8(__ldg(dout + i), dv);
+    unpack8(__ldg(x + i), xv);
+    if (relu) unpack8(__ldg(out + i), ov);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      int c = g * 8 + e;
+      float dz = (relu && !(ov[e] > 0.f)) ? 0.f : dv[e];
+      dv[e] = dz;
+      float xh = (xv[e] - smu[c]) * sis[c];
+      o[e] = sk[c] * (dz - s1[c] - xh * s2[c]);
+    }
+    dx[i] = pack8(o);
+    if (dres) dres[i] = pack8(dv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// MaxPool3d
+// ------------------------------------------------------------------------------------------------
+struct PoolGeom {
+  int N, Ti, Hi, Wi, C, To, Ho, Wo;
+  int kt, kh, kw, st, sh, sw, pt, ph, pw;
+};
+
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
+                                                          uint2* __restrict__ idx, PoolGeom p, size_t total) {
+  const int G = p.C >> 3;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * 256) {
+    int g = static_cast<int>(i % G);
+    size_t pix = i / G;
+    int wo = static_cast<int>(pix % p.Wo);
+    size_t q = pix / p.Wo;
+    int ho = static_cast<int>(q % p.Ho);
+    q /= p.Ho;
+    int to = static_cast<int>(q % p.To);
+    int n = static_cast<int>(q / p.To);
+    float best[8];
+    unsigned bi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      best[e] = -INFINITY;
+      bi[e] = 0;
+    }
+    bool any = false;
+    for (int a = 0; a < p.kt; ++a) {
+      int ti = to * p.st - p.pt + a;
+      if (ti < 0 || ti >= p.Ti) continue;
+      for (int b = 0; b < p.kh; ++b) {
+        int hi = ho * p.sh - p.ph + b;
+        if (hi < 0 || hi >= p.Hi) continue;
+        for (int c = 0; c < p.kw; ++c) {
+          int wi = wo * p.sw - p.pw + c;
+          if (wi < 0 || wi >= p.Wi) continue;
+          size_t o = (((static_cast<size_t>(n) * p.Ti + ti) * p.Hi + hi) * p.Wi + wi) * G + g;
+          float v[8];
+          unpack8(__ldg(x + o), v);
+          unsigned lin = (a * p.kh + b) * p.kw + c;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            if (!any || v[e] > best[e]) {
+              best[e] = v[e];
+              bi[e] = lin;
+            }
+          }
+          any = true;
+        }
+      }
+    }
+    y[i] = pack8(best);
+    uint2 iv;
+    iv.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+    iv.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+    idx[i] = iv;
+  }
+}
+
+// gather form: every input element sums dy over the windows that selected it (deterministic, no atomics)
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx,
+                                                          uint4* __restrict__ dx, PoolGeom p, size_t total) {
+  const int G = p.C >> 3;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * 256) {
+    int g = static_cast<int>(i % G);
+    size_t pix = i / G;
+    int wi = static_cast<int>(pix % p.Wi);
+    size_t q = pix / p.Wi;
+    int hi = static_cast<int>(q % p.Hi);
+    q /= p.Hi;
+    int ti = static_cast<int>(q % p.Ti);
+    int n = static_cast<int>(q / p.Ti);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    // output positions o with o*s - p <= i <= o*s - p + k - 1
+    int to_lo = max(0, (ti + p.pt - p.kt + p.st) / p.st), to_hi = min(p.To - 1, (ti + p.pt) / p.st);
+    int ho_lo = max(0, (hi + p.ph - p.kh + p.sh) / p.sh), ho_hi = min(p.Ho - 1, (hi + p.ph) / p.sh);
+    int wo_lo = max(0, (wi + p.pw - p.kw + p.sw) / p.sw), wo_hi = min(p.Wo - 1, (wi + p.pw) / p.sw);
+    if (ti + p.pt - p.kt + 1 <= 0) to_lo = 0;
+    if (hi + p.ph - p.kh + 1 <= 0) ho_lo = 0;
+    if (wi + p.pw - p.kw + 1 <= 0) wo_lo = 0;
+    for (int to = to_lo; to <= to_hi; ++to) {
+      int a = ti + p.pt - to * p.st;
+      if (a < 0 || a >= p.kt) continue;
+      for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+        int b = hi + p.ph - ho * p.sh;
+        if (b < 0 || b >= p.kh) continue;
+        for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+          int c = wi + p.pw - wo * p.sw;
+          if (c < 0 || c >= p.kw) continue;
+          unsigned lin = (a * p.kh + b) * p.kw + c;
+          size_t o = (((static_cast<size_t>(n) * p.To + to) * p.Ho + ho) * p.Wo + wo) * G + g;
+          uint2 iv = __ldg(idx + o);
+          float d[8];
+          unpack8(__ldg(dy + o), d);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            unsigned sel = ((e < 4 ? iv.x : iv.y) >> (8 * (e & 3))) & 0xffu;
+            if (sel == lin) acc[e] += d[e];
+          }
+        }
+      }
+    }
+    dx[i] = pack8(acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// projection heads: avg-pool -> 2 x Linear -> L2 normalise. One block per sample.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+  for (int w = 0; w < (blockDim.x >> 5); ++w) s += red[w];
+  return s;
+}
+
+__global__ void __launch_bounds__(128) head_fwd_kernel(const __nv_bfloat16* __restrict__ feat, int S, int C, int Cl,
+                                                       int D, const float* __restrict__ w1,
+                                                       const float* __restrict__ b1, const float* __restrict__ w2,
+                                                       const float* __restrict__ b2, float* __restrict__ pooled,
+                                                       float* __restrict__ raw1, float* __restrict__ raw2,
+                                                       float* __restrict__ out1, float* __restrict__ out2) {
+  extern __shared__ float sm[];
+  float* sp = sm;  // [Cl]
+  __shared__ float red[4];
+  const int bidx = blockIdx.x;
+  const __nv_bfloat16* f = feat + static_cast<size_t>(bidx) * S * C;
+  for (int c = threadIdx.x; c < Cl; c += blockDim.x) {
+    float s = 0.f;
+    for (int i = 0; i < S; ++i) s += __bfloat162float(f[static_cast<size_t>(i) * C + c]);
+    s /= S;
+    sp[c] = s;
+    pooled[static_cast<size_t>(bidx) * Cl + c] = s;
+  }
+  __syncthreads();
+  for (int head = 0; head < 2; ++head) {
+    const float* w = head ? w2 : w1;
+    const float* bb = head ? b2 : b1;
+    float* raw = (head ? raw2 : raw1) + static_cast<size_t>(bidx) * D;
+    float* out = (head ? out2 : out1) + static_cast<size_t>(bidx) * D;
+    float sq = 0.f;
+    for (int j = threadIdx.x; j < D; j += blockDim.x) {
+      float acc = bb ? bb[j] : 0.f;
+      const float* wr = w + static_cast<size_t>(j) * Cl;
+      for (int c = 0; c < Cl; ++c) acc = fmaf(wr[c], sp[c], acc);
+      raw[j] = acc;
+      sq += acc * acc;
+    }
+    float nrm = fmaxf(sqrtf(block_sum(sq, red)), 1e-12f);
+    for (int j = threadIdx.x; j < D; j += blockDim.x) out[j] = raw[j] / nrm;
+  }
+}
+
+__global__ void __launch_bounds__(128) head_bwd_kernel(const float* __restrict__ dout1, const float* __restrict__ dout2,
+                                                       const float* __restrict__ pooled, const float* __restrict__ raw1,
+                                                       const float* __restrict__ raw2, int S, int C, int Cl, int D,
+                                                       const float* __restrict__ w1, const float* __restrict__ w2,
+                                                       float* __restrict__ dw1, float* __restrict__ db1,
+                                                       float* __restrict__ dw2, float* __restrict__ db2,
+                                                       __nv_bfloat16* __restrict__ dfeat) {
+  extern __shared__ float sm[];
+  float* dr1 = sm;          // [D] grad wrt raw1
+  float* dr2 = sm + D;      // [D]
+  float* sp = sm + 2 * D;   // [Cl] pooled
+  __shared__ float red[4];
+  const int bidx = blockIdx.x;
+  for (int c = threadIdx.x; c < Cl; c += blockDim.x) sp[c] = pooled[static_cast<size_t>(bidx) * Cl + c];
+  for (int head = 0; head < 2; ++head) {
+    const float* raw = (head ? raw2 : raw1) + static_cast<size_t>(bidx) * D;
+    const float* dout = (head ? dout2 : dout1) + static_cast<size_t>(bidx) * D;
+    float* dr = head ? dr2 : dr1;
+    float sq = 0.f, dot = 0.f;
+    for (int j = threadIdx.x; j < D; j += blockDim.x) {
+      sq += raw[j] * raw[j];
+      dot += raw[j] * dout[j];
+    }
+    float ss = block_sum(sq, red);
+    float dd = block_sum(dot, red);
+    float nrm = sqrtf(ss);
+    for (int j = threadIdx.x; j < D; j += blockDim.x) {
+      float g;
+      if (nrm > 1e-12f) {
+        // y = x/n: dx = dy/n - x * (x.dy) / n^3
+        g = dout[j] / nrm - raw[j] * dd / (nrm * nrm * nrm);
+      } else {
+        g = dout[j] / 1e-12f;
+      }
+      dr[j] = g;
+    }
+  }
+  __syncthreads();
+  // parameter gradients (accumulated over samples with atomics)
+  for (int j = threadIdx.x; j < D; j += blockDim.x) {
+    atomicAdd(db1 + j, dr1[j]);
+    atomicAdd(db2 + j, dr2[j]);
+  }
+  for (int i = threadIdx.x; i < D * Cl; i += blockDim.x) {
+    int j = i / Cl, c = i - j * Cl;
+    atomicAdd(dw1 + i, dr1[j] * sp[c]);
+    atomicAdd(dw2 + i, dr2[j] * sp[c]);
+  }
+  if (dfeat) {
+    __nv_bfloat16* df = dfeat + static_cast<size_t>(bidx) * S * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float acc = 0.f;
+      if (c < Cl) {
+        for (int j = 0; j < D; ++j)
+          acc += dr1[j] * w1[static_cast<size_t>(j) * Cl + c] + dr2[j] * w2[static_cast<size_t>(j) * Cl + c];
+        acc /= S;
+      }
+      __nv_bfloat16 v = __float2bfloat16(acc);
+      for (int i = 0; i < S; ++i) df[static_cast<size_t>(i) * C + c] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout conversion
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ncdhw_to_ndhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                             int C, int Cs, size_t THW, size_t total) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * 256) {
+    size_t n = i / THW, p = i - n * THW;
+    const float* s = x + n * C * THW + p;
+    __nv_bfloat16* o = y + i * Cs;
+    for (int c = 0; c < Cs; ++c) o[c] = __float2bfloat16(c < C ? s[c * THW] : 0.f);
+  }
+}
+__global__ void __launch_bounds__(256) ndhwc_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y,
+                                                             int C, int Cs, size_t THW, size_t total) {
+  // total = N*C*THW, output-major so that writes are coalesced
+  for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * 256) {
+    size_t p = i % THW;
+    size_t nc = i / THW;
+    size_t n = nc / C;
+    int c = static_cast<int>(nc - n * C);
+    y[i] = __bfloat162float(x[(n * THW + p) * Cs + c]);
+  }
+}
+
+static int check_c(int C, const char* what) {
+  RSP_REQUIRE(C >= 8 && C % 8 == 0 && 256 % (C / 8) == 0, "%s: channel count %d unsupported (need C/8 to divide 256)",
+              what, C);
+  return RSP_OK;
+}
+
+static int fill_pool(PoolGeom& g, const rsp_pool3d_desc* d) {
+  g.N = d->N; g.Ti = d->Ti; g.Hi = d->Hi; g.Wi = d->Wi; g.C = d->C;
+  g.kt = d->kt; g.kh = d->kh; g.kw = d->kw;
+  g.st = d->st; g.sh = d->sh; g.sw = d->sw;
+  g.pt = d->pt; g.ph = d->ph; g.pw = d->pw;
+  g.To = (d->Ti + 2 * d->pt - d->kt) / d->st + 1;
+  g.Ho = (d->Hi + 2 * d->ph - d->kh) / d->sh + 1;
+  g.Wo = (d->Wi + 2 * d->pw - d->kw) / d->sw + 1;
+  RSP_REQUIRE(g.To > 0 && g.Ho > 0 && g.Wo > 0, "maxpool3d: empty output");
+  RSP_REQUIRE(d->C % 8 == 0, "maxpool3d: C %% 8 != 0");
+  RSP_REQUIRE(d->kt * d->kh * d->kw <= 255, "maxpool3d: window too large for uint8 indices");
+  return RSP_OK;
+}
+
+}  // namespace rsp
+
+using namespace rsp;
+
+extern "C" {
+
+int rsp_bn_stats(const void* x, int64_t M, int32_t C, float* sum, float* sumsq, void* stream) {
+  int rc = check_c(C, "bn_stats");
+  if (rc != RSP_OK) return rc;
+  if (M == 0) return RSP_OK;
+  const int rows_per_iter = 256 / (C / 8);
+  unsigned grid = ew_grid(static_cast<size_t>((M + rows_per_iter - 1) / rows_per_iter) * 256 / 8 + 1, 256);
+  channel_reduce_kernel<0><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), nullptr, nullptr, nullptr, nullptr, 0, static_cast<size_t>(M), C, sum, sumsq);
+  return check_launch("bn_stats");
+}
+
+int rsp_bn_finalize(const float* sum, const float* sumsq, int64_t count, const float* gamma, const float* beta,
+                    float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                    float* mean, float* invstd, int32_t C, int32_t C_logical, void* stream) {
+  RSP_REQUIRE(count > 0 && C_logical <= C, "bn_finalize: bad count / channels");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      sum, sumsq, static_cast<float>(count), gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean,
+      invstd, C, C_logical);
+  return check_launch("bn_finalize");
+}
+
+int rsp_bn_act_fwd(const void* x, const float* scale, const float* shift, const void* residual, int relu, void* out,
+                   int64_t M, int32_t C, void* stream) {
+  RSP_REQUIRE(C % 8 == 0, "bn_act_fwd: C %% 8 != 0");
+  if (M == 0) return RSP_OK;
+  size_t nvec = static_cast<size_t>(M) * (C / 8);
+  bn_act_fwd_kernel<<<ew_grid(nvec, 256), 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), scale, shift, static_cast<const uint4*>(residual), relu, static_cast<uint4*>(out),
+      nvec, C);
+  return check_launch("bn_act_fwd");
+}
+
+int rsp_bn_act_bwd_reduce(const void* dout, const void* out, const void* x, const float* mean, const float* invstd,
+                          int relu, float* sum_dz, float* sum_dz_xhat, int64_t M, int32_t C, void* stream) {
+  int rc = check_c(C, "bn_act_bwd_reduce");
+  if (rc != RSP_OK) return rc;
+  if (M == 0) return RSP_OK;
+  const int rows_per_iter = 256 / (C / 8);
+  unsigned grid = ew_grid(static_cast<size_t>((M + rows_per_iter - 1) / rows_per_iter) * 256 / 8 + 1, 256);
+  channel_reduce_kernel<1><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), static_cast<const uint4*>(out), static_cast<const uint4*>(dout), mean, invstd, relu,
+      static_cast<size_t>(M), C, sum_dz, sum_dz_xhat);
+  return check_launch("bn_act_bwd_reduce");
+}
+
+int rsp_bn_act_bwd_apply(const void* dout, const void* out, const void* x, const float* mean, const float* invstd,
+                         const float* gamma, const float* sum_dz, const float* sum_dz_xhat, int relu, void* dx,
+                         void* dres, int64_t M, int32_t C, int32_t C_logical, void* stream) {
+  RSP_REQUIRE(C % 8 == 0 && C_logical <= C, "bn_act_bwd_apply: bad channels");
+  if (M == 0) return RSP_OK;
+  size_t nvec = static_cast<size_t>(M) * (C / 8);
+  bn_act_bwd_apply_kernel<<<ew_grid(nvec, 256), 256, 5 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(dout), static_cast<const uint4*>(out), static_cast<const uint4*>(x), mean, invstd,
+      gamma, sum_dz, sum_dz_xhat, relu, static_cast<uint4*>(dx), static_cast<uint4*>(dres), nvec, C, C_logical,
+      1.f / static_cast<float>(M));
+  return check_launch("bn_act_bwd_apply");
+}
+
+int rsp_maxpool3d_fwd(const rsp_pool3d_desc* d, const void* x, void* y, uint8_t* idx, void* stream) {
+  PoolGeom g;
+  int rc = fill_pool(g, d);
+  if (rc != RSP_OK) return rc;
+  size_t total = static_cast<size_t>(g.N) * g.To * g.Ho * g.Wo * (g.C / 8);
+  if (total == 0) return RSP_OK;
+  maxpool_fwd_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), static_cast<uint4*>(y), reinterpret_cast<uint2*>(idx), g, total);
+  return check_launch("maxpool3d_fwd");
+}
+
+int rsp_maxpool3d_bwd(const rsp_pool3d_desc* d, const void* dy, const uint8_t* idx, void* dx, void* stream) {
+  PoolGeom g;
+  int rc = fill_pool(g, d);
+  if (rc != RSP_OK) return rc;
+  size_t total = static_cast<size_t>(g.N) * g.Ti * g.Hi * g.Wi * (g.C / 8);
+  if (total == 0) return RSP_OK;
+  maxpool_bwd_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(dy), reinterpret_cast<const uint2*>(idx), static_cast<uint4*>(dx), g, total);
+  return check_launch("maxpool3d_bwd");
+}
+
+int rsp_head_fwd(const void* feat, int32_t B, int32_t S, int32_t C, int32_t C_logical, int32_t D, const float* w1,
+                 const float* b1, const float* w2, const float* b2, float* pooled, float* raw1, float* raw2,
+                 float* out1, float* out2, void* stream) {
+  RSP_REQUIRE(B > 0 && S > 0 && C_logical <= C && C_logical <= 8192, "head_fwd: bad sizes");
+  head_fwd_kernel<<<B, 128, C_logical * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(feat), S, C, C_logical, D, w1, b1, w2, b2, pooled, raw1, raw2, out1, out2);
+  return check_launch("head_fwd");
+}
+
+int rsp_head_bwd(const float* dout1, const float* dout2, const float* pooled, const float* raw1, const float* raw2,
+                 int32_t B, int32_t S, int32_t C, int32_t C_logical, int32_t D, const float* w1, const float* w2,
+                 float* dw1, float* db1, float* dw2, float* db2, void* dfeat, void* stream) {
+  RSP_REQUIRE(B > 0 && S > 0 && C_logical <= C && (2 * D + C_logical) * sizeof(float) <= 48 * 1024,
+              "head_bwd: bad sizes");
+  head_bwd_kernel<<<B, 128, (2 * D + C_logical) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      dout1, dout2, pooled, raw1, raw2, S, C, C_logical, D, w1, w2, dw1, db1, dw2, db2,
+      static_cast<__nv_bfloat16*>(dfeat));
+  return check_launch("head_bwd");
+}
+
+int rsp_ncdhw_to_ndhwc_bf16(const float* x, void* y, int32_t N, int32_t C, int32_t Cs, int64_t THW, void* stream) {
+  RSP_REQUIRE(Cs >= C, "layout: Cs < C");
+  size_t total = static_cast<size_t>(N) * THW;
+  if (total == 0) return RSP_OK;
+  ncdhw_to_ndhwc_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<__nv_bfloat16*>(y), C, Cs, static_cast<size_t>(THW), total);
+  return check_launch("ncdhw_to_ndhwc");
+}
+
+int rsp_ndhwc_bf16_to_ncdhw(const void* x, float* y, int32_t N, int32_t C, int32_t Cs, int64_t THW, void* stream) {
+  RSP_REQUIRE(Cs >= C, "layout: Cs < C");
+  size_t total = static_cast<size_t>(N) * C * THW;
+  if (total == 0) return RSP_OK;
+  ndhwc_to_ncdhw_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), y, C, Cs, static_cast<size_t>(THW), total);
+  return check_launch("ndhwc_to_ncdhw");
+}
+
+}  // extern "C"

@@ -1,0 +1,274 @@
+"""Thin, allocation-owning wrappers over the C ABI (one python function per kernel family).
+
+Tensors on the conv path are ``torch.bfloat16`` in NDHWC layout, stored as 5-D tensors ``[N, T, H, W, C]``.
+Nothing here falls back to ATen compute; torch only allocates outputs.
+"""
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, PoolDesc, call, ptr, stream_ptr
+import ctypes as C
+
+
+def _triple(v):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v, v, v)
+
+
+def pad_channels(c: int) -> int:
+    """Stored channel count of an activation with ``c`` logical channels."""
+    if c <= 4:
+        return 4
+    return (c + 63) // 64 * 64
+
+
+def conv_desc(x_shape, co: int, kernel, stride, padding) -> ConvDesc:
+    n, t, h, w, ci = x_shape
+    k, s, p = _triple(kernel), _triple(stride), _triple(padding)
+    return ConvDesc(n, t, h, w, ci, co, k[0], k[1], k[2], s[0], s[1], s[2], p[0], p[1], p[2])
+
+
+# ------------------------------------------------------------------------------------------------ conv
+def conv3d_pack_weight(desc: ConvDesc, weight: torch.Tensor, which: int = 0) -> torch.Tensor:
+    """fp32 ``[Co, Ci, kt, kh, kw]`` parameter -> packed bf16 operand (which=0 fprop/wgrad, 1 dgrad)."""
+    co_l, ci_l = weight.shape[0], weight.shape[1]
+    kpad = _lib.load().rsp_conv3d_kpad(C.byref(desc), which)
+    if kpad <= 0:
+        raise RuntimeError("rsp_conv3d_kpad failed: " + _lib.load().rsp_last_error().decode())
+    rows = desc.Co if which == 0 else desc.Ci
+    out = torch.empty((rows, kpad), dtype=torch.bfloat16, device=weight.device)
+    w = weight.detach().contiguous().float()
+    call("rsp_conv3d_pack_weight", C.byref(desc), ci_l, co_l, ptr(w), ptr(out), which, stream_ptr())
+    return out
+
+
+def conv3d_fprop(desc: ConvDesc, x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor] = None):
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    to, ho, wo = desc.out_dims()
+    y = torch.empty((desc.N, to, ho, wo, desc.Co), dtype=torch.bfloat16, device=x.device)
+    call("rsp_conv3d_fprop", C.byref(desc), ptr(x), ptr(wp), ptr(bias), ptr(y), stream_ptr())
+    return y
+
+
+def conv3d_dgrad(desc: ConvDesc, dy: torch.Tensor, wd: torch.Tensor):
+    assert dy.dtype == torch.bfloat16 and dy.is_contiguous()
+    dx = torch.empty((desc.N, desc.Ti, desc.Hi, desc.Wi, desc.Ci), dtype=torch.bfloat16, device=dy.device)
+    call("rsp_conv3d_dgrad", C.byref(desc), ptr(dy), ptr(wd), ptr(dx), stream_ptr())
+    return dx
+
+
+def conv3d_wgrad(desc: ConvDesc, x: torch.Tensor, dy: torch.Tensor, weight_shape, out: Optional[torch.Tensor] = None,
+                 accumulate: bool = False):
+    """Gradient of the fp32 parameter ``[Co, Ci, kt, kh, kw]``."""
+    co_l, ci_l = weight_shape[0], weight_shape[1]
+    kpad = _lib.load().rsp_conv3d_kpad(C.byref(desc), 0)
+    ws = torch.empty((kpad, desc.Co), dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty(tuple(weight_shape), dtype=torch.float32, device=x.device)
+        accumulate = False
+    call("rsp_conv3d_wgrad", C.byref(desc), ci_l, co_l, ptr(x), ptr(dy), ptr(ws), ptr(out), int(accumulate),
+         stream_ptr())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ batch norm
+def bn_stats(x: torch.Tensor):
+    c = x.shape[-1]
+    m = x.numel() // c
+    s = torch.zeros((2, c), dtype=torch.float32, device=x.device)
+    call("rsp_bn_stats", ptr(x), m, c, ptr(s[0]), ptr(s[1]), stream_ptr())
+    return s[0], s[1]
+
+
+def bn_finalize(s, ss, count, gamma, beta, eps, momentum, running_mean, running_var, c_stored):
+    dev = s.device
+    out = torch.empty((4, c_stored), dtype=torch.float32, device=dev)
+    call("rsp_bn_finalize", ptr(s), ptr(ss), count, ptr(gamma), ptr(beta), eps, momentum, ptr(running_mean),
+         ptr(running_var), ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(out[3]), c_stored, gamma.numel(), stream_ptr())
+    return out[0], out[1], out[2], out[3]  # scale, shift, mean, invstd
+
+
+def bn_act_fwd(x, scale, shift, residual, relu: bool):
+    c = x.shape[-1]
+    out = torch.empty_like(x)
+    call("rsp_bn_act_fwd", ptr(x), ptr(scale), ptr(shift), ptr(residual), int(relu), ptr(out), x.numel() // c, c,
+         stream_ptr())
+    return out
+
+
+def bn_act_bwd(dout, out, x, mean, invstd, gamma, relu: bool, want_dres: bool):
+    c = x.shape[-1]
+    m = x.numel() // c
+    sums = torch.zeros((2, c), dtype=torch.float32, device=x.device)
+    call("rsp_bn_act_bwd_reduce", ptr(dout), ptr(out), ptr(x), ptr(mean), ptr(invstd), int(relu), ptr(sums[0]),
+         ptr(sums[1]), m, c, stream_ptr())
+    dx = torch.empty_like(x)
+    dres = torch.empty_like(x) if want_dres else None
+    call("rsp_bn_act_bwd_apply", ptr(dout), ptr(out), ptr(x), ptr(mean), ptr(invstd), ptr(gamma), ptr(sums[0]),
+         ptr(sums[1]), int(relu), ptr(dx), ptr(dres), m, c, gamma.numel(), stream_ptr())
+    cl = gamma.numel()
+    return dx, dres, sums[1][:cl], sums[0][:cl]  # dx, dres, dgamma, dbeta
+
+
+# ------------------------------------------------------------------------------------------------ pooling
+def pool_desc(x_shape, kernel, stride, padding) -> PoolDesc:
+    n, t, h, w, c = x_shape
+    k, s, p = _triple(kernel), _triple(stride), _triple(padding)
+    return PoolDesc(n, t, h, w, c, k[0], k[1], k[2], s[0], s[1], s[2], p[0], p[1], p[2])
+
+
+def maxpool3d_fwd(desc: PoolDesc, x):
+    to, ho, wo = desc.out_dims()
+    y = torch.empty((desc.N, to, ho, wo, desc.C), dtype=torch.bfloat16, device=x.device)
+    idx = torch.empty((desc.N, to, ho, wo, desc.C), dtype=torch.uint8, device=x.device)
+    call("rsp_maxpool3d_fwd", C.byref(desc), ptr(x), ptr(y), ptr(idx), stream_ptr())
+    return y, idx
+
+
+def maxpool3d_bwd(desc: PoolDesc, dy, idx):
+    dx = torch.empty((desc.N, desc.Ti, desc.Hi, desc.Wi, desc.C), dtype=torch.bfloat16, device=dy.device)
+    call("rsp_maxpool3d_bwd", C.byref(desc), ptr(dy), ptr(idx), ptr(dx), stream_ptr())
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------ heads
+def head_fwd(feat, c_logical, w1, b1, w2, b2):
+    b = feat.shape[0]
+    c = feat.shape[-1]
+    s = feat.numel() // (b * c)
+    d = w1.shape[0]
+    dev = feat.device
+    pooled = torch.empty((b, c_logical), dtype=torch.float32, device=dev)
+    raw = torch.empty((2, b, d), dtype=torch.float32, device=dev)
+    out = torch.empty((2, b, d), dtype=torch.float32, device=dev)
+    call("rsp_head_fwd", ptr(feat), b, s, c, c_logical, d, ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(pooled),
+         ptr(raw[0]), ptr(raw[1]), ptr(out[0]), ptr(out[1]), stream_ptr())
+    return out[0], out[1], pooled, raw
+
+
+def head_bwd(dout1, dout2, pooled, raw, feat_shape, w1, w2, want_dfeat=True):
+    b = feat_shape[0]
+    c = feat_shape[-1]
+    s = 1
+    for v in feat_shape[1:-1]:
+        s *= v
+    d, cl = w1.shape
+    dev = w1.device
+    dw = torch.zeros((2, d, cl), dtype=torch.float32, device=dev)
+    db = torch.zeros((2, d), dtype=torch.float32, device=dev)
+    dfeat = torch.empty(tuple(feat_shape), dtype=torch.bfloat16, device=dev) if want_dfeat else None
+    call("rsp_head_bwd", ptr(dout1.contiguous()), ptr(dout2.contiguous()), ptr(pooled), ptr(raw[0]), ptr(raw[1]), b, s,
+         c, cl, d, ptr(w1), ptr(w2), ptr(dw[0]), ptr(db[0]), ptr(dw[1]), ptr(db[1]), ptr(dfeat), stream_ptr())
+    return dw[0], db[0], dw[1], db[1], dfeat
+
+
+# ------------------------------------------------------------------------------------------------ layout
+def to_ndhwc_bf16(x: torch.Tensor, c_stored: Optional[int] = None) -> torch.Tensor:
+    """fp32 NCDHW -> bf16 NDHWC with zero-padded channels."""
+    n, c, t, h, w = x.shape
+    cs = c_stored or pad_channels(c)
+    y = torch.empty((n, t, h, w, cs), dtype=torch.bfloat16, device=x.device)
+    xc = x.contiguous().float()
+    call("rsp_ncdhw_to_ndhwc_bf16", ptr(xc), ptr(y), n, c, cs, t * h * w, stream_ptr())
+    return y
+
+
+def to_ncdhw_f32(x: torch.Tensor, c_logical: int) -> torch.Tensor:
+    n, t, h, w, cs = x.shape
+    y = torch.empty((n, c_logical, t, h, w), dtype=torch.float32, device=x.device)
+    call("rsp_ndhwc_bf16_to_ncdhw", ptr(x), ptr(y), n, c_logical, cs, t * h * w, stream_ptr())
+    return y
+
+
+# ------------------------------------------------------------------------------------------------ MoCo
+def ema_update_(k_flat: torch.Tensor, q_flat: torch.Tensor, m: float):
+    """In place k = k*m + q*(1-m) (builder_diffspeed_diffloss.py:337-343)."""
+    call("rsp_ema_update", ptr(k_flat), ptr(q_flat), k_flat.numel(), float(m), float(1.0 - m), stream_ptr())
+
+
+def sgd_step_(p, grad, mom, lr, momentum, weight_decay, grad_scale=1.0, first_step=False):
+    call("rsp_sgd_step", ptr(p), ptr(grad), ptr(mom), p.numel(), float(lr), float(momentum), float(weight_decay),
+         float(grad_scale), int(first_step), stream_ptr())
+
+
+def speed_gather(im_q, im_k, perm, n_s1: int, d: int, layout: int):
+    """_diff_speed re-sampling. layout 0 -> fp32 NCDHW, 1 -> bf16 NDHWC(4)."""
+    b, c, t, h, w = im_q.shape
+    tr = t // d
+    dev = im_q.device
+    if layout == 0:
+        outs = [torch.empty((b, c, tr, h, w), dtype=torch.float32, device=dev) for _ in range(3)]
+    else:
+        outs = [torch.empty((b, tr, h, w, 4), dtype=torch.bfloat16, device=dev) for _ in range(3)]
+    call("rsp_speed_gather", ptr(im_q.contiguous()), ptr(im_k.contiguous()), ptr(perm), b, c, t, h, w, n_s1, d, layout,
+         ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), stream_ptr())
+    return outs
+
+
+def gather_rows(src: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
+    """dst[i] = src[index[i]] along dim 0."""
+    src = src.contiguous()
+    row_bytes = src[0].numel() * src.element_size() if src.shape[0] else 0
+    out = torch.empty((index.numel(),) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    if index.numel():
+        call("rsp_gather_rows", ptr(src), ptr(index), ptr(out), index.numel(), row_bytes, stream_ptr())
+    return out
+
+
+def queue_enqueue_(queue, keys, queue_ptr):
+    d, k = queue.shape
+    call("rsp_queue_enqueue", ptr(queue), ptr(keys.contiguous()), ptr(queue_ptr), d, k, keys.shape[0], stream_ptr())
+
+
+def moco_logits_fwd(q_a, q_m, k_a, k_m, kn_a, kn_m, queue, temperature: float, materialize: bool = True):
+    n, d = q_a.shape
+    k = queue.shape[1]
+    dev = q_a.device
+    logits = torch.empty((2, n, k + 1), dtype=torch.float32, device=dev) if materialize else None
+    rows = torch.empty((6, n), dtype=torch.float32, device=dev)  # lpos_m, lneg_m, lse1, lse2, pos1, pos2
+    ws = torch.empty((_lib.load().rsp_moco_logits_workspace(n, k) // 4,), dtype=torch.float32, device=dev)
+    call("rsp_moco_logits_fwd", ptr(q_a), ptr(q_m), ptr(k_a), ptr(k_m), ptr(kn_a), ptr(kn_m), ptr(queue), n, d, k,
+         float(temperature), ptr(logits[0]) if materialize else None, ptr(logits[1]) if materialize else None,
+         ptr(rows[0]), ptr(rows[1]), ptr(rows[2]), ptr(rows[3]), ptr(rows[4]), ptr(rows[5]), ptr(ws), stream_ptr())
+    return logits, rows
+
+
+def moco_logits_bwd(q_a, q_m, k_a, k_m, kn_a, kn_m, queue, temperature, rows, g_rows, g_logits1, g_logits2):
+    """rows = (lpos_m, lneg_m, lse1, lse2, pos1, pos2); g_rows same order."""
+    n, d = q_a.shape
+    k = queue.shape[1]
+    dq = torch.empty((2, n, d), dtype=torch.float32, device=q_a.device)
+    call("rsp_moco_logits_bwd", ptr(q_a), ptr(q_m), ptr(k_a), ptr(k_m), ptr(kn_a), ptr(kn_m), ptr(queue), n, d, k,
+         float(temperature), ptr(rows[4]), ptr(rows[5]), ptr(rows[2]), ptr(rows[3]), ptr(g_rows[2]), ptr(g_rows[3]),
+         ptr(g_rows[4]), ptr(g_rows[5]), ptr(g_rows[0]), ptr(g_rows[1]), ptr(g_logits1), ptr(g_logits2), ptr(dq[0]),
+         ptr(dq[1]), stream_ptr())
+    return dq[0], dq[1]
+
+
+def moco_loss_fwd(rows, margin, a, m):
+    out = torch.empty((3,), dtype=torch.float32, device=rows.device)
+    call("rsp_moco_loss_fwd", ptr(rows[2]), ptr(rows[3]), ptr(rows[4]), ptr(rows[5]), ptr(rows[0]), ptr(rows[1]),
+         rows.shape[1], float(margin), float(a), float(m), ptr(out), stream_ptr())
+    return out
+
+
+def moco_loss_bwd(rows, margin, a, m, g_out3):
+    g = torch.empty_like(rows)
+    call("rsp_moco_loss_bwd", ptr(rows[0]), ptr(rows[1]), rows.shape[1], float(margin), float(a), float(m),
+         ptr(g_out3), ptr(g[2]), ptr(g[3]), ptr(g[4]), ptr(g[5]), ptr(g[0]), ptr(g[1]), stream_ptr())
+    return g
+
+
+def ce0_fwd(logits):
+    n, l = logits.shape
+    lse = torch.empty((n,), dtype=torch.float32, device=logits.device)
+    call("rsp_ce0_fwd", ptr(logits), n, l, ptr(lse), stream_ptr())
+    return lse
+
+
+def ce0_bwd(logits, lse, g_scalar):
+    n, l = logits.shape
+    out = torch.empty_like(logits)
+    call("rsp_ce0_bwd", ptr(logits), ptr(lse), n, l, ptr(g_scalar), ptr(out), stream_ptr())
+    return out

@@ -1,0 +1,292 @@
+"""Per-kernel numerics on the B200: every C-ABI entry point against a plain PyTorch fp32 statement of the same
+operation (the path-level parity tests against the oracle live in test_parity_gpu.py)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+@pytest.fixture(autouse=True)
+def _strict_fp32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def _ops():
+    from rspnet_b200 import ops
+    return ops
+
+
+def rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+# ------------------------------------------------------------------------------------------------ MoCo kernels
+@pytest.mark.parametrize("n", [0, 1, 7, 4096, 1_000_003])
+def test_ema_bit_exact(n):
+    ops = _ops()
+    k, q = rand(n, seed=1), rand(n, seed=2)
+    m = 0.999
+    ref = k * m + q * (1.0 - m)  # the reference expression (builder:343)
+    ops.ema_update_(k, q, m)
+    assert torch.equal(k, ref)
+
+
+def test_sgd_matches_torch_optim():
+    ops = _ops()
+    n = 100_003
+    p0, g1, g2 = rand(n, seed=1), rand(n, seed=2), rand(n, seed=3)
+    pr = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.SGD([pr], lr=0.1, momentum=0.9, weight_decay=1e-4)
+    p = p0.clone()
+    mom = torch.zeros_like(p)
+    for i, g in enumerate((g1, g2)):
+        pr.grad = g.clone()
+        opt.step()
+        ops.sgd_step_(p, g, mom, 0.1, 0.9, 1e-4, 1.0, first_step=(i == 0))
+    torch.testing.assert_close(p, pr.data, rtol=1e-5, atol=1e-6)
+
+
+def _diff_speed_ref(im_q, im_k, perm, n_s1, d):
+    b, c, t, h, w = im_q.shape
+    tr = t // d
+    s1, s2 = perm[:n_s1], perm[n_s1:]
+    sp1 = torch.arange(0, t, 1, device=DEV)[:tr]
+    sp2 = torch.arange(0, t, d, device=DEV)[:tr]
+    q = torch.empty(b, c, tr, h, w, device=DEV)
+    k = torch.empty_like(q)
+    kn = torch.empty_like(q)
+    q[s1] = im_q.index_select(0, s1).index_select(2, sp1)
+    q[s2] = im_q.index_select(0, s2).index_select(2, sp2)
+    k[s1] = im_k.index_select(0, s1).index_select(2, sp1)
+    k[s2] = im_k.index_select(0, s2).index_select(2, sp2)
+    kn[s1] = im_k.index_select(0, s1).index_select(2, sp2)
+    kn[s2] = im_k.index_select(0, s2).index_select(2, sp1)
+    return q, k, kn
+
+
+@pytest.mark.parametrize("b,t,hw,d", [(4, 8, 6, 2), (5, 12, 7, 2), (1, 4, 5, 2), (6, 8, 8, 4)])
+def test_speed_gather(b, t, hw, d):
+    ops = _ops()
+    im_q, im_k = rand(b, 3, t, hw, hw, seed=1), rand(b, 3, t, hw, hw, seed=2)
+    perm = torch.randperm(b, generator=torch.Generator().manual_seed(3)).to(DEV)
+    n_s1 = int(b * 0.5)
+    ref = _diff_speed_ref(im_q, im_k, perm, n_s1, d)
+    got = ops.speed_gather(im_q, im_k, perm, n_s1, d, 0)
+    for g, r in zip(got, ref):
+        assert torch.equal(g, r)
+    got1 = ops.speed_gather(im_q, im_k, perm, n_s1, d, 1)
+    for g, r in zip(got1, ref):
+        exp = r.permute(0, 2, 3, 4, 1).bfloat16()
+        assert torch.equal(g[..., :3], exp)
+        assert torch.count_nonzero(g[..., 3]) == 0
+
+
+def test_gather_rows_and_layout_roundtrip():
+    ops = _ops()
+    src = rand(10, 3, 4, 8, seed=1)
+    idx = torch.tensor([9, 0, 3, 3, 7], device=DEV)
+    assert torch.equal(ops.gather_rows(src, idx), src[idx])
+    x = rand(2, 3, 4, 5, 6, seed=2)
+    y = ops.to_ndhwc_bf16(x)
+    assert y.shape == (2, 4, 5, 6, 4)
+    assert torch.equal(ops.to_ncdhw_f32(y, 3), x.bfloat16().float())
+
+
+def test_queue_enqueue_ring():
+    ops = _ops()
+    d, k, n = 128, 1024, 64
+    queue = rand(d, k, seed=1)
+    ref = queue.clone()
+    ptr = torch.zeros(1, dtype=torch.long, device=DEV)
+    p = 0
+    for step in range(k // n + 2):  # wraps around
+        keys = rand(n, d, seed=10 + step)
+        ops.queue_enqueue_(queue, keys, ptr)
+        ref[:, p:p + n] = keys.T
+        p = (p + n) % k
+        assert int(ptr) == p
+    assert torch.equal(queue, ref)
+
+
+def _logits_ref(q_a, q_m, k_a, k_m, kn_a, kn_m, queue, T):
+    l_pos_a1 = torch.einsum("nc,nc->n", q_a, k_a).unsqueeze(-1) / T
+    l_pos_a2 = torch.einsum("nc,nc->n", q_a, kn_a).unsqueeze(-1) / T
+    l_pos_m = torch.einsum("nc,nc->n", q_m, k_m).unsqueeze(-1) / T
+    l_neg_a = torch.einsum("nc,ck->nk", q_a, queue) / T
+    l_neg_m = torch.einsum("nc,nc->n", q_m, kn_m).unsqueeze(-1) / T
+    return torch.cat([l_pos_a1, l_neg_a], 1), torch.cat([l_pos_a2, l_neg_a], 1), l_pos_m, l_neg_m
+
+
+@pytest.mark.parametrize("n,k", [(4, 512), (64, 16384), (5, 300)])
+def test_moco_logits_loss_fwd_bwd(n, k):
+    ops = _ops()
+    d, T, margin, A, M = 128, 0.07, 2.0, 1.0, 0.5
+    feats = [F.normalize(rand(n, d, seed=s), dim=1) for s in range(6)]
+    queue = F.normalize(rand(d, k, seed=9), dim=0)
+    q_a, q_m = feats[0].clone().requires_grad_(True), feats[1].clone().requires_grad_(True)
+    l1, l2, lpm, lnm = _logits_ref(q_a, q_m, *feats[2:], queue, T)
+    tgt = torch.zeros(n, dtype=torch.long, device=DEV)
+    ce = F.cross_entropy(l1, tgt) + F.cross_entropy(l2, tgt)
+    rank = torch.clamp(-(lpm - lnm) + margin, min=0).mean()
+    loss = A * ce + M * rank
+    loss.backward()
+
+    logits, rows = ops.moco_logits_fwd(feats[0], feats[1], *feats[2:], queue, T, materialize=True)
+    torch.testing.assert_close(logits[0], l1.detach(), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(logits[1], l2.detach(), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(rows[0], lpm.detach().squeeze(1), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(rows[1], lnm.detach().squeeze(1), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(rows[2], torch.logsumexp(l1.detach(), 1), rtol=1e-5, atol=1e-4)
+    out3 = ops.moco_loss_fwd(rows, margin, A, M)
+    torch.testing.assert_close(out3, torch.stack([loss, ce, rank]).detach(), rtol=1e-3, atol=1e-5)
+
+    g3 = torch.tensor([1.0, 0.0, 0.0], device=DEV)
+    g_rows = ops.moco_loss_bwd(rows, margin, A, M, g3)
+    dq_a, dq_m = ops.moco_logits_bwd(feats[0], feats[1], *feats[2:], queue, T, rows, g_rows, None, None)
+    torch.testing.assert_close(dq_a, q_a.grad, rtol=1e-3, atol=1e-5)
+    torch.testing.assert_close(dq_m, q_m.grad, rtol=1e-3, atol=1e-5)
+
+    # dense path: gradient arriving through the materialised logits (a caller doing its own CE)
+    lse = ops.ce0_fwd(logits[0])
+    torch.testing.assert_close(lse, torch.logsumexp(l1.detach(), 1), rtol=1e-5, atol=1e-4)
+    one = torch.ones(1, device=DEV)
+    dl1 = ops.ce0_bwd(logits[0], lse, one)
+    dl2 = ops.ce0_bwd(logits[1], ops.ce0_fwd(logits[1]), one)
+    zero_rows = torch.zeros_like(rows)
+    dq_a2, _ = ops.moco_logits_bwd(feats[0], feats[1], *feats[2:], queue, T, rows, zero_rows, dl1, dl2)
+    q_a2 = feats[0].clone().requires_grad_(True)
+    r1, r2, _, _ = _logits_ref(q_a2, feats[1], *feats[2:], queue, T)
+    (F.cross_entropy(r1, tgt) + F.cross_entropy(r2, tgt)).backward()
+    torch.testing.assert_close(dq_a2, q_a2.grad, rtol=1e-3, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ BN / pool / head
+@pytest.mark.parametrize("c,relu,res", [(64, True, False), (128, True, True), (512, False, False), (256, True, True)])
+def test_bn_act_fwd_bwd(c, relu, res):
+    ops = _ops()
+    n, t, h, w = 2, 3, 5, 7
+    x = rand(n, c, t, h, w, seed=1) * 2 + 0.5
+    gamma, beta = rand(c, seed=2).abs() + 0.5, rand(c, seed=3)
+    r = rand(n, c, t, h, w, seed=4) if res else None
+    xb = x.bfloat16().float().requires_grad_(True)
+    rb = r.bfloat16().float().requires_grad_(True) if res else None
+    rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y = F.batch_norm(xb, rm, rv, gr, br, True, 0.1, 1e-5)
+    if res:
+        y = y + rb
+    if relu:
+        y = F.relu(y)
+    dy = rand(n, c, t, h, w, seed=5)
+    y.backward(dy.bfloat16().float())
+
+    xn = ops.to_ndhwc_bf16(x, c)
+    s, ss = ops.bn_stats(xn)
+    rm2, rv2 = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+    scale, shift, mean, invstd = ops.bn_finalize(s, ss, xn.numel() // c, gamma, beta, 1e-5, 0.1, rm2, rv2, c)
+    torch.testing.assert_close(rm2, rm, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(rv2, rv, rtol=1e-4, atol=1e-5)
+    rn = ops.to_ndhwc_bf16(r, c) if res else None
+    out = ops.bn_act_fwd(xn, scale, shift, rn, relu)
+    torch.testing.assert_close(ops.to_ncdhw_f32(out, c), y.detach(), rtol=2e-2, atol=2e-2)
+    dyn = ops.to_ndhwc_bf16(dy, c)
+    dx, dres, dgamma, dbeta = ops.bn_act_bwd(dyn, out, xn, mean, invstd, gamma, relu, res)
+    torch.testing.assert_close(ops.to_ncdhw_f32(dx, c), xb.grad, rtol=3e-2, atol=3e-2)
+    # ReLU masks are decided on bf16-rounded outputs: compare the reductions with a loose tolerance
+    torch.testing.assert_close(dgamma, gr.grad, rtol=5e-2, atol=0.3)
+    torch.testing.assert_close(dbeta, br.grad, rtol=5e-2, atol=0.3)
+    if res:
+        torch.testing.assert_close(ops.to_ncdhw_f32(dres, c), rb.grad, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("k,s,p,shape", [((3, 3, 3), (2, 2, 2), (1, 1, 1), (2, 64, 6, 10, 10)),
+                                          ((1, 2, 2), (1, 2, 2), (0, 0, 0), (2, 64, 4, 8, 8)),
+                                          ((2, 2, 2), (2, 2, 2), (0, 0, 0), (1, 128, 4, 6, 6)),
+                                          ((3, 3, 3), (1, 1, 1), (1, 1, 1), (1, 64, 3, 5, 5))])
+def test_maxpool_fwd_bwd(k, s, p, shape):
+    ops = _ops()
+    x = rand(*shape, seed=1)
+    x = torch.where(x < 0, torch.zeros_like(x), x)  # post-ReLU style ties at 0
+    xb = x.bfloat16().float().requires_grad_(True)
+    y = F.max_pool3d(xb, k, s, p)
+    dy = rand(*y.shape, seed=2)
+    y.backward(dy.bfloat16().float())
+    c = shape[1]
+    xn = ops.to_ndhwc_bf16(x, c)
+    desc = ops.pool_desc(xn.shape, k, s, p)
+    yo, idx = ops.maxpool3d_fwd(desc, xn)
+    assert torch.equal(ops.to_ncdhw_f32(yo, c), y.detach())
+    dx = ops.maxpool3d_bwd(desc, ops.to_ndhwc_bf16(dy, c), idx)
+    torch.testing.assert_close(ops.to_ncdhw_f32(dx, c), xb.grad, rtol=1e-2, atol=1e-2)
+
+
+def test_head_fwd_bwd():
+    ops = _ops()
+    b, c, d = 5, 512, 128
+    feat = rand(b, c, 1, 4, 4, seed=1).abs()
+    w1, b1, w2, b2 = rand(d, c, seed=2, scale=0.05), rand(d, seed=3), rand(d, c, seed=4, scale=0.05), rand(d, seed=5)
+    fb = feat.bfloat16().float().requires_grad_(True)
+    params = [t.clone().requires_grad_(True) for t in (w1, b1, w2, b2)]
+    pooled = fb.mean(dim=(2, 3, 4))
+    o1 = F.normalize(F.linear(pooled, params[0], params[1]), dim=1)
+    o2 = F.normalize(F.linear(pooled, params[2], params[3]), dim=1)
+    g1, g2 = rand(b, d, seed=6), rand(b, d, seed=7)
+    (o1 * g1).sum().backward(retain_graph=True)
+    (o2 * g2).sum().backward()
+    fn = ops.to_ndhwc_bf16(feat, c)
+    out1, out2, pl, raw = ops.head_fwd(fn, c, w1, b1, w2, b2)
+    torch.testing.assert_close(out1, o1.detach(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(out2, o2.detach(), rtol=1e-4, atol=1e-5)
+    dw1, db1, dw2, db2, dfeat = ops.head_bwd(g1, g2, pl, raw, fn.shape, w1, w2)
+    for got, ref in zip((dw1, db1, dw2, db2), params):
+        torch.testing.assert_close(got, ref.grad, rtol=1e-3, atol=1e-5)
+    torch.testing.assert_close(ops.to_ncdhw_f32(dfeat, c), fb.grad, rtol=2e-2, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ conv (tcgen05)
+CONV_CASES = [
+    (2, 64, 64, (4, 8, 8), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (1, 64, 128, (3, 9, 7), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (2, 128, 128, (4, 10, 10), (3, 3, 3), (2, 2, 2), (1, 1, 1)),
+    (2, 64, 128, (4, 8, 8), (1, 1, 1), (2, 2, 2), (0, 0, 0)),
+    (2, 128, 256, (2, 6, 6), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (1, 3, 64, (6, 20, 20), (7, 7, 7), (1, 2, 2), (3, 3, 3)),
+    (2, 3, 64, (4, 12, 12), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (3, 256, 512, (2, 7, 7), (3, 3, 3), (2, 2, 2), (1, 1, 1)),
+]
+
+
+@pytest.mark.parametrize("n,ci,co,dims,k,s,p", CONV_CASES)
+def test_conv3d_fprop_dgrad_wgrad(n, ci, co, dims, k, s, p):
+    """bf16 inputs, fp32 accumulation: tolerance = 1e-2 of the tensor's max magnitude (bf16 output rounding is 2^-9)."""
+    ops = _ops()
+    x = rand(n, ci, *dims, seed=1)
+    w = rand(co, ci, *k, seed=2, scale=(ci * k[0] * k[1] * k[2]) ** -0.5)
+    bias = rand(co, seed=3)
+    xr = x.bfloat16().float().requires_grad_(True)
+    wr = w.bfloat16().float().requires_grad_(True)
+    yref = F.conv3d(xr, wr, bias, s, p)
+    dy = rand(*yref.shape, seed=4)
+    yref.backward(dy.bfloat16().float())
+
+    def close(got, ref, tol):
+        err = (got.float() - ref.float()).abs().max().item()
+        assert err <= tol * (ref.abs().max().item() + 1e-6), f"max err {err} vs scale {ref.abs().max().item()}"
+
+    cis, cos = ops.pad_channels(ci), ops.pad_channels(co)
+    xn = ops.to_ndhwc_bf16(x, cis)
+    desc = ops.conv_desc(xn.shape, cos, k, s, p)
+    y = ops.conv3d_fprop(desc, xn, ops.conv3d_pack_weight(desc, w, 0), bias)
+    close(ops.to_ncdhw_f32(y, co), yref.detach(), 1e-2)
+    dyn = ops.to_ndhwc_bf16(dy, cos)
+    dw = ops.conv3d_wgrad(desc, xn, dyn, w.shape)
+    close(dw, wr.grad, 1e-2)
+    if cis % 64 == 0:
+        dx = ops.conv3d_dgrad(desc, dyn, ops.conv3d_pack_weight(desc, w, 1))
+        close(ops.to_ncdhw_f32(dx, ci), xr.grad, 1e-2)
