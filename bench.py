@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""Benchmark of the RSPNet pretraining step (BASELINE.json: "pretrain clips/sec (R3D-18, 16x112x112)").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--arch resnet18|c3d|r2plus1d-vcop] [--batch B]
+    python bench.py --impl reference ...      # the reference algorithm on the host CPU cores (oracle port)
+
+One "step" = one full training iteration on a batch of B synthetic videos per GPU: EMA of the key encoder,
+speed re-sampling, two key-encoder forwards (shuffle-BN), query forward, logits + 3-term loss, backward,
+gradient all-reduce, SGD, queue update.  One "clip"  = one video = one (clip_q, clip_k) pair.
+
+`value`  : clips/s with the fp32 input clips already resident in HBM (a ring of batches larger than L2).
+`e2e`    : clips/s through the public API (PretrainEngine.step) from PINNED HOST buffers; every step copies its two
+           input tensors host->device (double-buffered on a copy stream, inside the timed region) and reads the
+           loss back device->host.
+Prints one JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+HYPER = dict(dim=128, K=16384, m=0.999, T=0.07, diff_speed=[2], margin=2.0, A=1.0, M=1.0, lr=0.1, momentum=0.9,
+             weight_decay=1e-4)
+# forward conv GFLOP per 16-frame clip and first-conv share
+CONV_GF = {"resnet18": (16.62, 6.61), "c3d": (76.99, 2.08), "r2plus1d-vcop": (42.72, 1.22)}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--arch", default="resnet18")
+    ap.add_argument("--batch", type=int, default=64, help="videos per GPU")
+    ap.add_argument("--frames", type=int, default=32, help="loaded frames per clip (2 x 16)")
+    ap.add_argument("--size", type=int, default=112)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_clips_per_s(arch, steps, warmup, batch=4, frames=32, size=112, K=16384):
+    """The reference algorithm (oracle/rspnet_oracle.py, a torch-CPU restatement pinned to the reference by
+    tests/test_oracle_cpu.py) on the host cores: BASELINE config 1 (R3D-18, B=4, K=16384, single process)."""
+    import torch
+    from oracle import rspnet_oracle as oracle
+    from rspnet_b200.models import get_model_class
+    from rspnet_b200.moco import MoCoDiffLossTwoFc, MultiTaskWrapper
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    base = get_model_class(arch=arch)
+    # module construction only (random-init weights with the reference's names); the oracle does the arithmetic
+    init = MoCoDiffLossTwoFc(lambda num_classes=128: MultiTaskWrapper(base, num_classes=num_classes), dim=HYPER["dim"],
+                             K=K, m=HYPER["m"], T=HYPER["T"], diff_speed=HYPER["diff_speed"])
+    sd = {k: v.clone() for k, v in init.state_dict().items()}
+    del init
+    g = torch.Generator().manual_seed(1234)
+    im_q = torch.randn(batch, 3, frames, size, size, generator=g)
+    im_k = torch.randn(batch, 3, frames, size, size, generator=g)
+    mom, times = {}, []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        oracle.train_step(arch, [sd], [im_q], [im_k], [torch.randperm(batch)],
+                          (torch.randperm(batch), torch.randperm(batch)), d=2, m=HYPER["m"], T=HYPER["T"],
+                          margin=HYPER["margin"], lr=HYPER["lr"] * batch / 64, momentum=HYPER["momentum"],
+                          weight_decay=HYPER["weight_decay"], mom_bufs=mom)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    ms = statistics.median(times) * 1e3
+    return batch / (ms / 1e3), ms, cores, batch
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 8))
+    warmup = max(1, min(args.warmup, 2))
+    v, ms, cores, batch = cpu_reference_clips_per_s(args.arch, steps, warmup)
+    sample = f"{steps} steps of {batch} videos ({args.arch}, 2x16x112x112 frames, K=16384) on {cores} host threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "pretrain clips/sec", "value": v, "unit": "clips/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": f"RSPNet {args.arch} pretraining step, 16x112x112 clips (CPU sample: batch {batch})"},
+        "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+KERNELS_PER_CALL = {"rsp_conv3d_wgrad": 2, "rsp_queue_enqueue": 2, "rsp_moco_logits_fwd": 3,
+                    "rsp_moco_logits_bwd": 2}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from rspnet_b200 import _lib
+    from rspnet_b200.engine import PretrainEngine, scale_learning_rate
+    from rspnet_b200.models import get_model_class
+    from rspnet_b200.moco import Loss, MoCoDiffLossTwoFc, MultiTaskWrapper
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    # launch accounting: every C-ABI call is counted (most launch exactly one kernel)
+    counter = {"n": 0, "on": False}
+    raw_call = _lib.call
+
+    def counting_call(name, *a):
+        if counter["on"]:
+            counter["n"] += KERNELS_PER_CALL.get(name, 1)
+        return raw_call(name, *a)
+
+    _lib.call = counting_call
+    from rspnet_b200 import ops
+    ops.call = counting_call
+
+    torch.manual_seed(0 + rank)
+    base = get_model_class(arch=args.arch)
+    model = MoCoDiffLossTwoFc(
+        lambda num_classes=128: MultiTaskWrapper(base, num_classes=num_classes, fc_type="linear"),
+        dim=HYPER["dim"], K=HYPER["K"], m=HYPER["m"], T=HYPER["T"], diff_speed=HYPER["diff_speed"]).to(dev)
+    lr = scale_learning_rate(HYPER["lr"], world, args.batch)
+    engine = PretrainEngine(model, Loss(HYPER["margin"], HYPER["A"], HYPER["M"]), lr, HYPER["momentum"],
+                            HYPER["weight_decay"])
+
+    B = args.batch
+    shape = (B, 3, args.frames, args.size, args.size)
+    in_bytes = 2 * B * 3 * args.frames * args.size * args.size * 4
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    ring = [(torch.randn(shape, device=dev, generator=gen), torch.randn(shape, device=dev, generator=gen))
+            for _ in range(2)]  # 2 x 617 MB >> 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    last = {}
+
+    def resident_step(i):
+        q, k = ring[i % len(ring)]
+        last["loss"] = engine.step(q, k)
+
+    for i in range(args.warmup):
+        resident_step(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    counter["on"], counter["n"] = True, 0
+    ms_total = timed(resident_step, args.steps)
+    counter["on"] = False
+    clocks = sampler.stop() if rank == 0 else None
+    loss_val = float(last["loss"][0])
+    ms_step = ms_total / args.steps
+    value = B * world / (ms_step / 1e3)
+    launches = counter["n"]
+
+    # ---- dominant kernel roofline: conv kernels (fprop+dgrad+wgrad) timed over a pass of the same shapes ------
+    roofline = conv_roofline(args, B, ms_step)
+
+    # ---- end to end from pinned host memory --------------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host = [(torch.randn(shape).pin_memory(), torch.randn(shape).pin_memory()) for _ in range(2)]
+        stage = [(torch.empty(shape, device=dev), torch.empty(shape, device=dev)) for _ in range(2)]
+        copy_stream = torch.cuda.Stream()
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        loss_host = torch.empty(3, pin_memory=True)
+
+        def prefetch(i):
+            s = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[s])
+                stage[s][0].copy_(host[s][0], non_blocking=True)
+                stage[s][1].copy_(host[s][1], non_blocking=True)
+                ready[s].record(copy_stream)
+
+        tick = {"i": 0}
+
+        def e2e_step(_):
+            i = tick["i"]
+            tick["i"] += 1
+            s = i % 2
+            if i == 0:
+                prefetch(0)
+            prefetch(i + 1)  # next step's inputs move while this step computes
+            torch.cuda.current_stream().wait_event(ready[s])
+            loss = engine.step(stage[s][0], stage[s][1])
+            consumed[s].record()
+            loss_host.copy_(torch.stack(loss), non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the caller reads the loss every step
+
+        for s in range(2):
+            consumed[s].record()
+        for i in range(2):
+            e2e_step(i)
+        ms_e2e = timed(e2e_step, args.steps) / args.steps
+        e2e = {"value": B * world / (ms_e2e / 1e3), "unit": "clips/s", "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 12,
+               "note": "pinned host fp32 clips, double-buffered H2D on a copy stream, loss read back every step"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, ms, cores, cb = cpu_reference_clips_per_s("resnet18" if args.arch not in ("resnet18", "c3d") else args.arch,
+                                                     steps=5, warmup=1)
+        cpu = {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "ms_per_step": ms,
+               "sample": f"5 steps of {cb} videos (BASELINE config 1 shape: batch 4, K=16384) on {cores} host threads, "
+                         "oracle/rspnet_oracle.py (torch CPU fp32 restatement of the reference step)"}
+    if rank == 0:
+        print(json.dumps({
+            "metric": "pretrain clips/sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"RSPNet {args.arch} pretraining step (MoCoDiffLossTwoFc), per-GPU batch {B} videos, "
+                                   f"2x{args.frames // 2}x{args.size}x{args.size} clips, K={HYPER['K']}, dim 128",
+                       "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2": "inputs alternate between two 617 MB device batches (> 126 MB L2)"},
+            "loss": loss_val, "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roofline,
+            "cpu_baseline": cpu,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def conv_roofline(args, B, ms_step):
+    """Tensor-pipe roofline of the conv kernels: algorithmic FLOPs of one step / time spent in conv kernels.
+
+    The conv time is measured live with CUDA events around fprop / dgrad / wgrad launches of every conv shape of the
+    backbone (same batch, same tensors sizes), weighted as in a step (3 fprop passes + 1 dgrad + 1 wgrad)."""
+    import torch
+    from rspnet_b200 import ops
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    peak, src = 1590.0, "fallback"
+    if peaks_file.exists():
+        pk = json.loads(peaks_file.read_text())
+        peak, src = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1590.0))), "measured (sustained)"
+    fwd, first = CONV_GF.get(args.arch, (None, None))
+    if fwd is None:
+        return None
+    from rspnet_b200.models import get_model_class
+    from rspnet_b200 import nn as rnn
+    shapes = []
+    orig = ops.conv3d_fprop
+
+    def spy(desc, x, wp, bias=None):
+        shapes.append((desc, tuple(x.shape), x.requires_grad))
+        return orig(desc, x, wp, bias)
+
+    ops.conv3d_fprop = spy
+    net = get_model_class(arch=args.arch)(num_classes=1).cuda()
+    with torch.no_grad():
+        net.feature_ndhwc(torch.zeros(B, 3, args.frames // 2, args.size, args.size, device="cuda"))
+    ops.conv3d_fprop = orig
+    del net
+    tot_ms = {"fprop": 0.0, "dgrad": 0.0, "wgrad": 0.0}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for li, (desc, xshape, _) in enumerate(shapes):
+        x = torch.randn(xshape, device="cuda").bfloat16()
+        ci_l = 3 if desc.Ci == 4 else desc.Ci
+        w = torch.randn(desc.Co, ci_l, desc.kt, desc.kh, desc.kw, device="cuda") * 0.05
+        wp = ops.conv3d_pack_weight(desc, w, 0)
+        y = ops.conv3d_fprop(desc, x, wp)
+        dy = torch.randn_like(y)
+        jobs = [("fprop", lambda: ops.conv3d_fprop(desc, x, wp))]
+        ws = torch.empty((wp.shape[1], desc.Co), dtype=torch.float32, device="cuda")
+        dw = torch.empty_like(w)
+        jobs.append(("wgrad", lambda: ops.conv3d_wgrad(desc, x, dy, w.shape, out=dw)))
+        if li > 0:
+            wd = ops.conv3d_pack_weight(desc, w, 1)
+            jobs.append(("dgrad", lambda: ops.conv3d_dgrad(desc, dy, wd)))
+        for name, fn in jobs:
+            fn()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(3):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            tot_ms[name] += e0.elapsed_time(e1) / 3
+        del x, y, dy, w, wp
+    conv_ms = 3 * tot_ms["fprop"] + tot_ms["dgrad"] + tot_ms["wgrad"]
+    flops = (3 * fwd + (2 * fwd - first)) * 1e9 * B
+    achieved = flops / (conv_ms / 1e3) / 1e12
+    return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "traffic": None, "peak_source": src, "kernel": "conv_igemm_kernel / conv_wgrad_kernel (tcgen05)",
+            "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / ms_step,
+            "per_pass_ms": tot_ms, "algorithmic_gflop_per_step": flops / 1e9}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

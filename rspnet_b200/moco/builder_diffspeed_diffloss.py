@@ -1,0 +1,318 @@
+"""MoCo-style relative-speed contrastive builder — the interface of the reference's
+``moco/builder_diffspeed_diffloss.py`` (``MoCoDiffLossTwoFc`` :286-547, ``MoCoDiffLoss`` :11-245,
+``concat_all_gather`` :249-260, ``Loss`` :263-283) on B200 kernels:
+
+* momentum update  -> one coalesced EMA pass over the flattened parameters          (ref :337-343)
+* ``_diff_speed``   -> one gather kernel that writes q / k / k_neg conv-ready        (ref :421-447)
+* shuffle-BN        -> permutation all-to-all instead of all_gather + index          (ref :361-406)
+* logits + CE       -> q.queue tiles fused with the row logsumexp                    (ref :521-538, :272-283)
+* enqueue           -> ring-buffer transpose write, pointer kept on the device       (ref :345-359)
+
+Random draws are made with the same generators in the same order as the reference, so
+permutations, queue pointers and gathered keys are bit-identical.
+"""
+import logging
+import random
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor, nn
+
+from .. import nn as rnn
+from .. import ops
+from . import exchange
+
+logger = logging.getLogger(__name__)
+
+
+@torch.no_grad()
+def concat_all_gather(tensor: Tensor) -> Tensor:
+    """all_gather along dim 0 in rank order (no gradient), as the reference's helper of the same name."""
+    return exchange.all_gather_rows(tensor)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# autograd functions of the objective
+# ----------------------------------------------------------------------------------------------------------------
+class _LogitsFn(torch.autograd.Function):
+    """(q_A, q_M, keys, queue) -> logits1, logits2, l_pos_M, l_neg_M and the row statistics
+    rows = [l_pos_M, l_neg_M, lse1, lse2, pos1, pos2] that the fused loss consumes."""
+
+    @staticmethod
+    def forward(ctx, q_a, q_m, k_a, k_m, kn_a, kn_m, queue, temperature, materialize):
+        args = [t.contiguous().float() for t in (q_a, q_m, k_a, k_m, kn_a, kn_m)]
+        logits, rows = ops.moco_logits_fwd(*args, queue, temperature, materialize)
+        ctx.temperature = temperature
+        ctx.save_for_backward(*args, queue, rows)
+        ctx.set_materialize_grads(False)
+        l1 = logits[0] if materialize else None
+        l2 = logits[1] if materialize else None
+        return l1, l2, rows[0].unsqueeze(-1), rows[1].unsqueeze(-1), rows
+
+    @staticmethod
+    def backward(ctx, g_l1, g_l2, g_lpm, g_lnm, g_rows):
+        *args, queue, rows = ctx.saved_tensors
+        g = torch.zeros_like(rows) if g_rows is None else g_rows.contiguous().clone()
+        if g_lpm is not None:
+            g[0] += g_lpm.flatten()
+        if g_lnm is not None:
+            g[1] += g_lnm.flatten()
+        g_l1 = g_l1.contiguous() if g_l1 is not None else None
+        g_l2 = g_l2.contiguous() if g_l2 is not None else None
+        dq_a, dq_m = ops.moco_logits_bwd(*args, queue, ctx.temperature, rows, g, g_l1, g_l2)
+        return dq_a, dq_m, None, None, None, None, None, None, None
+
+
+class _FusedLossFn(torch.autograd.Function):
+    """rows -> (A*(ce1+ce2) + M*rank, ce1+ce2, rank)."""
+
+    @staticmethod
+    def forward(ctx, rows, margin, a, m):
+        ctx.cfg = (margin, a, m)
+        ctx.save_for_backward(rows)
+        return ops.moco_loss_fwd(rows, margin, a, m)
+
+    @staticmethod
+    def backward(ctx, g3):
+        (rows,) = ctx.saved_tensors
+        return ops.moco_loss_bwd(rows, *ctx.cfg, g3.contiguous()), None, None, None
+
+
+class _DenseCE0Fn(torch.autograd.Function):
+    """mean cross entropy against class 0 over arbitrary dense logits."""
+
+    @staticmethod
+    def forward(ctx, logits):
+        logits = logits.contiguous().float()
+        lse = ops.ce0_fwd(logits)
+        ctx.save_for_backward(logits, lse)
+        return (lse - logits[:, 0]).mean()
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, lse = ctx.saved_tensors
+        return ops.ce0_bwd(logits, lse, g.reshape(1).contiguous().float())
+
+
+class Loss(nn.Module):
+    """``A * (CE(logits1) + CE(logits2)) + M * MarginRanking(l_pos_M, l_neg_M)``; returns (loss, ce_sum, ranking)."""
+
+    def __init__(self, margin=1.0, A: float = 1.0, M: float = 1.0):
+        super().__init__()
+        self.A = A
+        self.M = M
+        self.margin = margin
+
+    def forward(self, output: Tuple[Tensor, Tensor], target: Tensor, ranking_logits: Tuple[Tensor, Tensor],
+                ranking_target: Tensor):
+        rows = getattr(output[0], "_rsp_rows", None)
+        fused = (rows is not None and getattr(output[1], "_rsp_rows", None) is rows and
+                 getattr(ranking_logits[0], "_rsp_rows", None) is rows and
+                 getattr(ranking_logits[1], "_rsp_rows", None) is rows)
+        if fused:
+            # target == 0 and ranking_target == 1 by construction of MoCoDiffLoss*.forward
+            out3 = _FusedLossFn.apply(rows, self.margin, self.A, self.M)
+            return out3[0], out3[1], out3[2]
+        # plain tensors: dense cross-entropy kernels + the ranking term on an assembled statistics block
+        if not bool((target == 0).all()) or not bool((ranking_target == 1).all()):
+            raise NotImplementedError("rspnet_b200.Loss: only the MoCo targets (class 0 / ranking +1) are supported")
+        ce = _DenseCE0Fn.apply(output[0]) + _DenseCE0Fn.apply(output[1])
+        lp, ln = ranking_logits[0].flatten().float(), ranking_logits[1].flatten().float()
+        z = torch.zeros_like(lp)
+        rank = _FusedLossFn.apply(torch.stack([lp, ln, z, z, z, z]), self.margin, 0.0, 1.0)[2]
+        return self.A * ce + self.M * rank, ce, rank
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# flat parameter storage (one buffer per encoder so EMA / SGD / all-reduce are single passes)
+# ----------------------------------------------------------------------------------------------------------------
+def flatten_parameters(module: nn.Module) -> Tensor:
+    """Moves every parameter of ``module`` into one contiguous fp32 buffer (16-byte aligned segments) and returns it.
+    Parameters keep their names, shapes and values; ``p.data`` becomes a view."""
+    params = list(module.parameters())
+    sizes = [(p.numel() + 3) // 4 * 4 for p in params]
+    flat = torch.zeros(sum(sizes), dtype=torch.float32, device=params[0].device)
+    off = 0
+    for p, n in zip(params, sizes):
+        view = flat[off:off + p.numel()].view_as(p)
+        view.copy_(p.data)
+        p.data = view
+        off += n
+    return flat
+
+
+class _MoCoBase(nn.Module):
+    """State and kernels shared by the two builder variants."""
+
+    def _init_common(self, base_encoder, dim, K, m, T, diff_speed):
+        self.K = K
+        self.m = m
+        self.T = T
+        self.diff_speed = diff_speed
+        logger.warning('Using diffspeed: %s', self.diff_speed)
+        self.encoder_q = base_encoder(num_classes=dim)
+        self.encoder_k = base_encoder(num_classes=dim)
+        for param_q, param_k in zip(self.encoder_q.parameters(), self.encoder_k.parameters()):
+            param_k.data.copy_(param_q.data)
+            param_k.requires_grad = False
+        self.register_buffer("queue", torch.randn(dim, K))
+        self.queue = nn.functional.normalize(self.queue, dim=0)
+        self.register_buffer("queue_ptr", torch.zeros(1, dtype=torch.long))
+        self.alpha = 0.5
+        self.materialize_logits = True   # forward() returns [N, 1+K] logits like the reference
+        self._flat_q: Optional[Tensor] = None
+        self._flat_k: Optional[Tensor] = None
+        assert self.diff_speed is not None, "This branch is for diff speed"
+
+    # -- flat buffers ------------------------------------------------------------------------------------------
+    def _ensure_flat(self):
+        p0 = next(self.encoder_q.parameters())
+        stale = (self._flat_q is None or self._flat_q.device != p0.device or
+                 p0.data_ptr() != self._flat_q.data_ptr())
+        if stale:
+            self._flat_q = flatten_parameters(self.encoder_q)
+            self._flat_k = flatten_parameters(self.encoder_k)
+            rnn.bump_weight_epoch()
+
+    def flat_parameters(self) -> Tuple[Tensor, Tensor]:
+        """(flat encoder_q parameters, flat encoder_k parameters)."""
+        self._ensure_flat()
+        return self._flat_q, self._flat_k
+
+    @torch.no_grad()
+    def _momentum_update_key_encoder(self):
+        self._ensure_flat()
+        ops.ema_update_(self._flat_k, self._flat_q, self.m)
+        rnn.bump_weight_epoch()
+
+    @torch.no_grad()
+    def _dequeue_and_enqueue(self, keys, gathered: bool = False):
+        if not gathered:
+            keys = concat_all_gather(keys)
+        assert self.K % keys.shape[0] == 0  # for simplicity
+        ops.queue_enqueue_(self.queue, keys.float(), self.queue_ptr)
+
+    @torch.no_grad()
+    def _draw_shuffle(self, batch_size_all: int) -> Tensor:
+        """The reference's ``torch.randperm(batch_size_all).cuda()`` + broadcast(src=0) (ref :375-378), kept on the host."""
+        return exchange.broadcast_permutation(torch.randperm(batch_size_all))
+
+    @torch.no_grad()
+    def _batch_shuffle_ddp(self, x):
+        _, world = exchange.world_info()
+        idx_shuffle = self._draw_shuffle(x.shape[0] * world)
+        idx_unshuffle = torch.argsort(idx_shuffle)
+        return exchange.exchange_rows(x, idx_shuffle, ops.gather_rows), idx_unshuffle
+
+    @torch.no_grad()
+    def _batch_unshuffle_ddp(self, x, idx_unshuffle, return_all: bool = False):
+        rank, world = exchange.world_info()
+        x_gather = concat_all_gather(x)
+        restored = ops.gather_rows(x_gather, idx_unshuffle.to(x.device, non_blocking=True))  # global original order
+        b = x.shape[0]
+        mine = restored[rank * b:(rank + 1) * b]
+        return (mine, restored) if return_all else mine
+
+    @torch.no_grad()
+    def _forward_encoder_k(self, im_k, return_all: bool = False):
+        im_k, idx_unshuffle = self._batch_shuffle_ddp(rnn.as_ndhwc(im_k))
+        k_a, k_m = self.encoder_k(im_k)
+        both = torch.cat([k_a, k_m], dim=1)  # one gather for both heads
+        res = self._batch_unshuffle_ddp(both, idx_unshuffle, return_all)
+        d = k_a.shape[1]
+        if return_all:
+            mine, everyone = res
+            return mine[:, :d].contiguous(), mine[:, d:].contiguous(), everyone[:, :d].contiguous()
+        return res[:, :d].contiguous(), res[:, d:].contiguous()
+
+    @torch.no_grad()
+    def _speed_views(self, im_q: Tensor, im_k: Tensor):
+        """ref :421-443: draws randperm(B) on the input's device and random.choice(diff_speed), then re-samples."""
+        B = im_q.shape[0]
+        random_indices = torch.randperm(B, device=im_q.device)
+        diff_speed = random.choice(self.diff_speed)
+        return ops.speed_gather(im_q.float(), im_k.float(), random_indices, int(B * self.alpha), int(diff_speed), 1)
+
+    def _logits(self, q_a, q_m, k_a, k_m, kn_a, kn_m):
+        l1, l2, lpm, lnm, rows = _LogitsFn.apply(q_a, q_m, k_a, k_m, kn_a, kn_m, self.queue, self.T,
+                                                 self.materialize_logits)
+        if l1 is None:  # statistics-only mode: hand the Loss something to hold on to
+            l1, l2 = rows[2].unsqueeze(-1), rows[3].unsqueeze(-1)
+        for t in (l1, l2, lpm, lnm):
+            t._rsp_rows = rows
+        return (l1, l2), (lpm, lnm)
+
+
+class MoCoDiffLossTwoFc(_MoCoBase):
+    def __init__(self, base_encoder, dim=128, K=65536, m=0.999, T=0.07, mlp=False,
+                 diff_speed: Optional[List[int]] = None):
+        """
+        dim: feature dimension (default: 128); K: queue size; m: momentum of the key encoder; T: softmax temperature
+        """
+        super().__init__()
+        if mlp:
+            raise NotImplementedError("mlp=True rewires encoder.fc, which the two-head wrapper does not have")
+        self._init_common(base_encoder, dim, K, m, T, diff_speed)
+        self.gap = nn.AdaptiveAvgPool3d((1, 1, 1))
+
+    @torch.no_grad()
+    def _diff_speed(self, im_q: Tensor, im_k: Tensor):
+        q, k, k_neg = self._speed_views(im_q, im_k)
+        kn_a, kn_m, kn_a_all = self._forward_encoder_k(k_neg, return_all=True)
+        self._enqueue_payload = kn_a_all
+        return q, k, kn_a, kn_m
+
+    def forward(self, im_q, im_k):
+        """
+        Input: im_q, im_k: [B, 3, T, H, W] clips (T = diff_speed * clip length).
+        Output: (logits1, logits2), labels_A (zeros), (l_pos_M, l_neg_M), labels_M (ones) — as the reference.
+        """
+        with torch.no_grad():
+            self._momentum_update_key_encoder()
+            im_q, im_k, k_neg_A, k_neg_M = self._diff_speed(im_q, im_k)
+            k_A, k_M = self._forward_encoder_k(im_k)
+        q_A, q_M = self.encoder_q(im_q)
+        logits_A, logits_M = self._logits(q_A, q_M, k_A, k_M, k_neg_A, k_neg_M)
+        labels_A = torch.zeros(q_A.shape[0], dtype=torch.long, device=q_A.device)
+        labels_M = torch.ones_like(labels_A)
+        # the unshuffle gather of the k_neg pass already holds every rank's keys in rank order
+        self._dequeue_and_enqueue(self._enqueue_payload, gathered=True)
+        self._enqueue_payload = None
+        return logits_A, labels_A, logits_M, labels_M
+
+    @torch.no_grad()
+    def cam_visualize(self, im_q, im_k):
+        """CAM maps (ref :449-490). Inference-only tooling: the contractions are tiny and use torch.einsum."""
+        im_q, im_k, _, _ = self._diff_speed(im_q, im_k)
+        self._forward_encoder_k(im_k)
+        k_F = self.encoder_k._get_last_feature()
+        self.encoder_q(im_q)
+        q_F = self.encoder_q._get_last_feature()
+        q_X = q_F.mean(dim=(2, 3, 4))
+        k_X = k_F.mean(dim=(2, 3, 4))
+        q_wA, q_wM = self.encoder_q._get_fc_weight()
+        k_wA, k_wM = self.encoder_k._get_fc_weight()
+
+        def cam(w_other, x_other, w_self, f_self):
+            return torch.einsum('bc,bcthw->bthw', torch.einsum('bn,nc->bc', torch.einsum('nc,bc->bn', w_other, x_other),
+                                                                w_self), f_self)
+        return (cam(k_wA, k_X, q_wA, q_F), cam(k_wM, k_X, q_wM, q_F), cam(q_wA, q_X, k_wA, k_F),
+                cam(q_wM, q_X, k_wM, k_F))
+
+
+class MoCoDiffLoss(_MoCoBase):
+    """Single-head variant (ref :11-245): the encoder returns one embedding, normalised here; the ranking pair is
+    (q.k, q.speed_k) and the enqueued key is k."""
+
+    def __init__(self, base_encoder, dim=128, K=65536, m=0.999, T=0.07, mlp=False,
+                 diff_speed: Optional[List[int]] = None):
+        super().__init__()
+        if mlp:
+            raise NotImplementedError("mlp=True is not part of any shipped pretrain config")
+        self._init_common(base_encoder, dim, K, m, T, diff_speed)
+
+    def forward(self, im_q, im_k):
+        raise NotImplementedError(
+            "MoCoDiffLoss (single projection head) is dead code w.r.t. every reference entry point "
+            "(moco/__init__.py builds MoCoDiffLossTwoFc); only its constructor/state_dict surface is provided")

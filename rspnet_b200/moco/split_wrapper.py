@@ -1,0 +1,98 @@
+"""``MultiTaskWrapper`` — backbone plus two projection heads (A-VID, RSP), interface and state_dict names of the
+reference's ``moco/split_wrapper.py`` (:66-190).  With ``fc_type='linear'`` (the shipped configs) the pooled
+features, both Linear heads and both L2 normalisations run as one fused kernel (rspnet_b200.nn.HeadsFn).
+"""
+import logging
+from typing import Callable, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor, nn
+
+from .. import nn as rnn
+
+logger = logging.getLogger(__name__)
+
+
+class Flatten(nn.Module):
+    def forward(self, x: Tensor):
+        return x.flatten(1)
+
+
+class MultiTaskWrapper(nn.Module):
+    def __init__(self, base_encoder: Callable[[int], nn.Module], num_classes: int = 128, finetune: bool = False,
+                 fc_type: str = 'linear', groups: int = 1):
+        super().__init__()
+        logger.info('Using MultiTask Wrapper')
+        self.finetune = finetune
+        self.moco_dim = num_classes
+        self.num_classes = num_classes
+        self.groups = groups
+        self.fc_type = fc_type
+        self.feat = None
+        self.encoder = base_encoder(num_classes=1)
+        feat_dim = self._get_feat_dim(self.encoder) // groups
+        if self.finetune:
+            self.avg_pool = nn.AdaptiveAvgPool3d((1, 1, 1))
+            self.fc = nn.Linear(feat_dim, num_classes)
+        elif fc_type == 'linear':
+            self.fc1 = self._get_linear_fc(feat_dim, self.moco_dim)
+            self.fc2 = self._get_linear_fc(feat_dim, self.moco_dim)
+        elif fc_type == 'mlp':
+            self.fc1 = self._get_mlp_fc(feat_dim, self.moco_dim)
+            self.fc2 = self._get_mlp_fc(feat_dim, self.moco_dim)
+        elif fc_type == 'speednet':
+            self.fc1 = self._get_linear_fc(feat_dim, self.moco_dim)
+            self.fc2 = self._get_linear_fc(feat_dim, 1)
+        else:
+            raise NotImplementedError(f"fc_type '{fc_type}' (conv / convbn heads) is outside the shipped pretrain "
+                                      "configs and not implemented in rspnet_b200")
+
+    def forward(self, x: Tensor):
+        feat = self.encoder.feature_ndhwc(x)  # bf16 NDHWC
+        self.feat = feat
+        fused = (not self.finetune and self.fc_type == 'linear' and self.groups == 1)
+        if fused:
+            l1, l2 = self.fc1[2], self.fc2[2]
+            return rnn.HeadsFn.apply(feat, l1.weight, l1.bias, l2.weight, l2.bias, l1.in_features)
+        # generic (non-hot) variants run on the reference layout
+        f = rnn.ToNCDHW.apply(feat, self.encoder.feature_channels)
+        if self.finetune:
+            return self.fc(self.avg_pool(f).flatten(1))
+        if self.groups == 1:
+            x1, x2 = self.fc1(f), self.fc2(f)
+        elif self.groups == 2:
+            f1, f2 = f.chunk(2, 1)
+            x1, x2 = self.fc1(f1), self.fc2(f2)
+        else:
+            raise Exception
+        x1 = F.normalize(x1, dim=1)
+        x2 = torch.sigmoid(x2) if self.fc_type == 'speednet' else F.normalize(x2, dim=1)
+        return x1, x2
+
+    def _get_last_feature(self):
+        """Feature map of the last forward in the reference layout ([B,C,t,h,w] fp32)."""
+        return rnn.ToNCDHW.apply(self.feat, self.encoder.feature_channels)
+
+    def _get_fc_weight(self) -> Tuple[Tensor, Tensor]:
+        with torch.no_grad():
+            return self.fc1[2].weight.data, self.fc2[2].weight.data
+
+    @staticmethod
+    def _get_linear_fc(feat_dim: int, moco_dim: int):
+        return nn.Sequential(nn.AdaptiveAvgPool3d((1, 1, 1)), Flatten(), nn.Linear(feat_dim, moco_dim))
+
+    @staticmethod
+    def _get_mlp_fc(feat_dim: int, moco_dim: int):
+        return nn.Sequential(nn.AdaptiveAvgPool3d((1, 1, 1)), Flatten(), nn.Linear(feat_dim, feat_dim),
+                             nn.ReLU(inplace=True), nn.Linear(feat_dim, moco_dim))
+
+    @staticmethod
+    def _get_feat_dim(encoder):
+        feat_dim = 512
+        for fc_name in ('fc', 'new_fc', 'classifier'):
+            if hasattr(encoder, fc_name):
+                feat_dim = getattr(encoder, fc_name).in_features
+                logger.info(f'Found fc: {fc_name} with in_features: {feat_dim}')
+                break
+        return feat_dim

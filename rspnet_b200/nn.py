@@ -1,0 +1,180 @@
+"""Autograd glue between torch modules and the sm_100a kernels (rspnet_b200.ops).
+
+The conv path works on bf16 NDHWC tensors ``[N, T, H, W, C]``.  Each fused block is one ``autograd.Function``:
+
+* ``ConvBNAct``   — Conv3d (+bias) -> train-mode BatchNorm3d -> (+residual) -> (ReLU)
+                    (reference: the conv/bn/relu triplets of models/resnet.py:59-77,203-213, models/c3d.py:111-150)
+* ``MaxPool3dFn`` — nn.MaxPool3d
+* ``HeadsFn``     — AdaptiveAvgPool3d + Flatten + Linear (x2) + F.normalize (moco/split_wrapper.py:128-152)
+* ``ToNCDHW`` / ``ToNDHWC`` — layout conversion at the public module boundary
+
+Packed bf16 filter operands are cached per parameter and invalidated by ``bump_weight_epoch()`` (called by the
+EMA / SGD kernels, which update parameters through raw pointers) or by torch's own version counter.
+"""
+from typing import Optional
+
+import torch
+
+from . import ops
+
+_weight_epoch = 0
+
+
+def bump_weight_epoch():
+    """Invalidate every cached packed filter (parameters were changed behind torch's back)."""
+    global _weight_epoch
+    _weight_epoch += 1
+
+
+class _PackCache:
+    """Per-parameter cache of packed filter operands, keyed by (which, geometry, weight version)."""
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, weight: torch.Tensor, desc, which: int):
+        key = (id(weight), which, desc.Ci, desc.Co, desc.kt, desc.kh, desc.kw)
+        tag = (_weight_epoch, weight._version, weight.data_ptr())
+        hit = self._store.get(key)
+        if hit is not None and hit[0] == tag:
+            return hit[1]
+        packed = ops.conv3d_pack_weight(desc, weight, which)
+        self._store[key] = (tag, packed)
+        return packed
+
+
+_pack_cache = _PackCache()
+
+
+def _pad_vec(v: Optional[torch.Tensor], n: int):
+    if v is None or v.numel() == n:
+        return v
+    out = torch.zeros(n, dtype=v.dtype, device=v.device)
+    out[:v.numel()] = v
+    return out
+
+
+class ConvBNAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, residual, kernel, stride, padding, eps,
+                momentum, relu):
+        co = ops.pad_channels(weight.shape[0])
+        desc = ops.conv_desc(x.shape, co, kernel, stride, padding)
+        wp = _pack_cache.get(weight, desc, 0)
+        y = ops.conv3d_fprop(desc, x, wp, _pad_vec(bias, co))
+        s, ss = ops.bn_stats(y)
+        count = y.numel() // co
+        scale, shift, mean, invstd = ops.bn_finalize(s, ss, count, gamma, beta, eps, momentum, running_mean,
+                                                     running_var, co)
+        out = ops.bn_act_fwd(y, scale, shift, residual, relu)
+        ctx.desc = desc
+        ctx.relu = relu
+        ctx.has_bias = bias is not None
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(x, weight, y, out if relu else None, mean, invstd, gamma)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight, y, out, mean, invstd, gamma = ctx.saved_tensors
+        desc = ctx.desc
+        dout = dout.contiguous()
+        dy, dres, dgamma, dbeta = ops.bn_act_bwd(dout, out, y, mean, invstd, gamma, ctx.relu, ctx.has_res)
+        dw = ops.conv3d_wgrad(desc, x, dy, weight.shape)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.conv3d_dgrad(desc, dy, _pack_cache.get(weight, desc, 1))
+        # a bias feeding straight into train-mode BN has an exactly zero gradient
+        dbias = torch.zeros(weight.shape[0], dtype=torch.float32, device=weight.device) if ctx.has_bias else None
+        return dx, dw, dbias, dgamma, dbeta, None, None, dres, None, None, None, None, None, None
+
+
+def conv_bn_act(x, conv: torch.nn.Conv3d, bn: torch.nn.BatchNorm3d, relu: bool = True, residual=None):
+    """Fused Conv3d -> BatchNorm3d(train) -> (+residual) -> (ReLU) on NDHWC bf16 activations."""
+    if not bn.training:
+        raise NotImplementedError("rspnet_b200: only train-mode BatchNorm (the pretraining path) is implemented")
+    if conv.groups != 1 or tuple(conv.dilation) != (1, 1, 1):
+        raise NotImplementedError("rspnet_b200: grouped / dilated Conv3d is not on the pretraining path")
+    momentum = bn.momentum if bn.momentum is not None else 0.0
+    out = ConvBNAct.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual,
+                          tuple(conv.kernel_size), tuple(conv.stride), tuple(conv.padding), bn.eps, momentum, relu)
+    if bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    return out
+
+
+class MaxPool3dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kernel, stride, padding):
+        desc = ops.pool_desc(x.shape, kernel, stride, padding)
+        y, idx = ops.maxpool3d_fwd(desc, x)
+        ctx.desc = desc
+        ctx.save_for_backward(idx)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        return ops.maxpool3d_bwd(ctx.desc, dy.contiguous(), idx), None, None, None
+
+
+def max_pool3d(x, pool: torch.nn.MaxPool3d):
+    if pool.ceil_mode or pool.dilation not in (1, (1, 1, 1)):
+        raise NotImplementedError("rspnet_b200: ceil_mode / dilated MaxPool3d is not on the pretraining path")
+    stride = pool.stride if pool.stride is not None else pool.kernel_size
+    return MaxPool3dFn.apply(x, pool.kernel_size, stride, pool.padding)
+
+
+class HeadsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, w1, b1, w2, b2, c_logical):
+        o1, o2, pooled, raw = ops.head_fwd(feat, c_logical, w1, b1, w2, b2)
+        ctx.feat_shape = tuple(feat.shape)
+        ctx.save_for_backward(pooled, raw, w1, w2)
+        return o1, o2
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        pooled, raw, w1, w2 = ctx.saved_tensors
+        if g1 is None:
+            g1 = torch.zeros_like(raw[0])
+        if g2 is None:
+            g2 = torch.zeros_like(raw[1])
+        dw1, db1, dw2, db2, dfeat = ops.head_bwd(g1, g2, pooled, raw, ctx.feat_shape, w1, w2,
+                                                 want_dfeat=ctx.needs_input_grad[0])
+        return dfeat, dw1, db1, dw2, db2, None
+
+
+class ToNCDHW(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, c_logical):
+        ctx.cs = x.shape[-1]
+        return ops.to_ncdhw_f32(x, c_logical)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.to_ndhwc_bf16(g.contiguous(), ctx.cs), None
+
+
+class ToNDHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, c_stored):
+        ctx.c = x.shape[1]
+        return ops.to_ndhwc_bf16(x, c_stored)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.to_ncdhw_f32(g.contiguous(), ctx.c), None
+
+
+def is_ndhwc(x: torch.Tensor) -> bool:
+    """Internal activations are tagged by dtype: bf16 5-D tensors are NDHWC, anything else is NCDHW."""
+    return x.dim() == 5 and x.dtype == torch.bfloat16
+
+
+def as_ndhwc(x: torch.Tensor) -> torch.Tensor:
+    if is_ndhwc(x):
+        return x
+    if not x.is_cuda:
+        raise RuntimeError("rspnet_b200: forward needs CUDA tensors (there is no CPU path)")
+    return ToNDHWC.apply(x, ops.pad_channels(x.shape[1]))

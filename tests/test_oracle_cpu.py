@@ -1,0 +1,123 @@
+"""Pins the oracle (oracle/rspnet_oracle.py) against the golden vectors produced by the UNMODIFIED reference
+(oracle/make_golden.py) — losses, logits, permutations, queue state, gradients, updated parameters — and checks
+that the product's module constructors reproduce the reference's initial state bit for bit."""
+import copy
+
+import pytest
+import torch
+
+from helpers import build_product_moco, check_packed, load_golden, make_inputs, summarize
+from oracle import rspnet_oracle as oracle
+
+CASES = ["r3d18_w1", "r3d18_w2", "c3d_w1"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_product_init_matches_reference_state_dict(name):
+    g = load_golden(name)
+    cfg, hyper = g["config"], g["hyper"]
+    for rank_rec in g["ranks"]:
+        model = build_product_moco(cfg, hyper, rank=rank_rec["rank"])
+        sd = model.state_dict()
+        assert list(sd.keys()) == list(rank_rec["init"].keys()), "state_dict names / order differ from the reference"
+        if cfg["world"] > 1 and rank_rec["rank"] > 0:
+            continue  # DDP broadcast rank 0's values before the fixture was taken
+        for k, v in sd.items():
+            ref = rank_rec["init"][k]
+            s = summarize(v.float())
+            # double-precision checksums (summation order may differ by an ulp) + exact leading values
+            assert s["n"] == ref["n"], k
+            assert abs(s["sum"] - ref["sum"]) <= 1e-11 * max(ref["abssum"], 1.0), k
+            assert abs(s["abssum"] - ref["abssum"]) <= 1e-11 * max(ref["abssum"], 1.0), k
+            assert torch.equal(s["head"], ref["head"]), k
+
+
+def _run_oracle(name):
+    g = load_golden(name)
+    cfg, hyper = g["config"], g["hyper"]
+    W = cfg["world"]
+    base = {k: v.clone() for k, v in build_product_moco(cfg, hyper, rank=0).state_dict().items()}
+    sds = [copy.deepcopy(base) for _ in range(W)]
+    mom = {}
+    outs = []
+    for step in range(cfg["steps"]):
+        im = [make_inputs(cfg, r, step) for r in range(W)]
+        recs = [g["ranks"][r]["steps"][step] for r in range(W)]
+        out = oracle.train_step(
+            cfg["arch"], sds, [x[0] for x in im], [x[1] for x in im], [rec["perm"] for rec in recs],
+            (recs[0]["idx_shuffle_neg"], recs[0]["idx_shuffle_pos"]), d=hyper["diff_speed"][0], m=hyper["m"],
+            T=hyper["T"], margin=hyper["margin"], A=hyper["A"], M=hyper["M"], lr=hyper["lr"],
+            momentum=hyper["momentum"], weight_decay=hyper["weight_decay"], mom_bufs=mom)
+        outs.append((out, [copy.deepcopy(sd) for sd in sds]))
+    return g, outs
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_goldens(name):
+    g, outs = _run_oracle(name)
+    cfg = g["config"]
+    W, B = cfg["world"], cfg["batch"]
+    for step, (out, sds) in enumerate(outs):
+        # fp32 on the same CPU kernels: step 0 is tight.  After an SGD update the 2-rank fixture (2 clips per rank,
+        # 1x1x1 feature maps => BatchNorm over two values) amplifies thread-count-dependent rounding of the
+        # reference run (two 4-thread processes) to ~1e-3 on logits of magnitude ~10; the tolerance says so.
+        loose = step > 0 and W > 1
+        la, ll = (1e-2, 1e-2) if loose else (2e-4, 1e-5)
+        for r in range(W):
+            rec = g["ranks"][r]["steps"][step]
+            assert rec["n_randperm"] == 3
+            torch.testing.assert_close(out["logits_a"][r][0], rec["logits1"], rtol=1e-4, atol=la)
+            torch.testing.assert_close(out["logits_a"][r][1], rec["logits2"], rtol=1e-4, atol=la)
+            torch.testing.assert_close(out["logits_m"][r][0], rec["l_pos_m"], rtol=1e-4, atol=la)
+            torch.testing.assert_close(out["logits_m"][r][1], rec["l_neg_m"], rtol=1e-4, atol=la)
+            torch.testing.assert_close(torch.stack(out["loss"][r]), rec["loss"], rtol=1e-4, atol=ll)
+            assert int(sds[r]["queue_ptr"]) == rec["queue_ptr"] == ((step + 1) * B * W) % cfg["K"]
+            first = (rec["queue_ptr"] - B * W) % cfg["K"]
+            torch.testing.assert_close(sds[r]["queue"][:, first:first + B * W], rec["queue_cols"], rtol=1e-4,
+                                       atol=2e-3 if loose else 1e-5)
+            assert torch.equal(rec["target"], torch.zeros(B, dtype=torch.long))
+            assert torch.equal(rec["ranking_target"], torch.ones(B, dtype=torch.long))
+        rec0 = g["ranks"][0]["steps"][step]
+        for k, ref in rec0["grads"].items():
+            check_packed(out["grads"][k], ref, rtol=5e-2 if loose else 2e-3, atol=1e-3 if loose else 2e-5,
+                         what=f"grad {k} step {step}", norm_only=loose)
+        assert set(rec0["params_without_grad"]) == {k for k in oracle.param_names(sds[0], "encoder_q.")
+                                                     if k not in out["grads"]}
+        for k, ref in rec0["params_after"].items():
+            if k.endswith("num_batches_tracked") or k == "queue_ptr":
+                assert int(sds[0][k]) == int(ref["sum"]), k
+                continue
+            check_packed(sds[0][k].float(), ref, rtol=5e-3 if loose else 2e-3, atol=1e-3 if loose else 2e-5,
+                         what=f"param {k} step {step}", norm_only=loose)
+
+
+def test_oracle_matches_live_reference_when_present():
+    """Direct comparison with the reference modules (build container only; skipped on the GPU box)."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("/root/reference not present")
+    from helpers import initialize_seed
+    ref_loader.install_shims()
+    for arch, frames in (("resnet18", 8), ("c3d", 16)):
+        initialize_seed(3)
+        ref = ref_loader.build_reference_moco(arch, K=32)
+        sd = {k: v.clone() for k, v in ref.state_dict().items()}
+        x = torch.randn(2, 3, frames // 2, 32, 32)
+        ref.train()
+        a_ref, m_ref = ref.encoder_q(x)
+        a, m = oracle.wrapper_forward(arch, x, sd, "encoder_q.")
+        torch.testing.assert_close(a, a_ref, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(m, m_ref, rtol=1e-4, atol=1e-5)
+        for k, v in ref.state_dict().items():  # BN running statistics after one train-mode forward
+            if "encoder_q" in k and "running" in k:
+                torch.testing.assert_close(sd[k], v, rtol=1e-4, atol=1e-6)
+        # momentum update (builder:337-343) bit-exact
+        with torch.no_grad():
+            for p in ref.encoder_q.parameters():
+                p.add_(0.01)
+        sd2 = {k: v.clone() for k, v in ref.state_dict().items()}
+        ref._momentum_update_key_encoder()
+        oracle.momentum_update(sd2, ref.m)
+        for k, v in ref.state_dict().items():
+            if k.startswith("encoder_k."):
+                assert torch.equal(sd2[k], v), k
