@@ -18,6 +18,15 @@ import torch.nn.functional as F
 
 State = Dict[str, torch.Tensor]
 
+# When True the restatement rounds to bf16 at exactly the points where the B200 path stores bf16 (network input,
+# conv operands, conv output, output of every fused BN(+residual)(+ReLU)); accumulation stays fp32.  This separates
+# "precision of the stated bf16 conv path" from "logic" in the GPU parity tests.  Default: exact fp32 reference math.
+EMULATE_BF16 = False
+
+
+def _r(x):
+    return x.bfloat16().float() if EMULATE_BF16 else x
+
 
 # --------------------------------------------------------------------------------------------------------------
 # building blocks
@@ -32,13 +41,13 @@ def _bn(x, sd: State, name: str, train: bool, eps=1e-5, momentum=0.1):
 
 
 def _conv(x, sd: State, name: str, stride, padding):
-    return F.conv3d(x, sd[name + ".weight"], sd.get(name + ".bias"), stride, padding)
+    return _r(F.conv3d(_r(x), _r(sd[name + ".weight"]), sd.get(name + ".bias"), stride, padding))
 
 
 def resnet18_feature(x, sd: State, p: str, train=True):
     """models/resnet.py:203-213 (get_feature) with BasicBlock (:59-77), layers [2,2,2,2], shortcut B (:170-175)."""
     x = _conv(x, sd, p + "conv1", (1, 2, 2), (3, 3, 3))
-    x = F.relu(_bn(x, sd, p + "bn1", train))
+    x = _r(F.relu(_bn(x, sd, p + "bn1", train)))
     x = F.max_pool3d(x, 3, 2, 1)
     for li, planes in enumerate((64, 128, 256, 512), start=1):
         for bi in range(2):
@@ -46,20 +55,20 @@ def resnet18_feature(x, sd: State, p: str, train=True):
             stride = 2 if (li > 1 and bi == 0) else 1
             residual = x
             out = _conv(x, sd, b + "conv1", stride, 1)
-            out = F.relu(_bn(out, sd, b + "bn1", train))
+            out = _r(F.relu(_bn(out, sd, b + "bn1", train)))
             out = _conv(out, sd, b + "conv2", 1, 1)
             out = _bn(out, sd, b + "bn2", train)
             if (b + "downsample.0.weight") in sd:
                 residual = _conv(x, sd, b + "downsample.0", stride, 0)
-                residual = _bn(residual, sd, b + "downsample.1", train)
-            x = F.relu(out + residual)
+                residual = _r(_bn(residual, sd, b + "downsample.1", train))
+            x = _r(F.relu(out + residual))
     return x
 
 
 def c3d_feature(x, sd: State, p: str, train=True):
     """models/c3d.py:111-150 (get_feature, return_conv=False): 8 conv(bias)+BN+ReLU, pools 1-4, no pool5."""
     def cbr(x, c, b):
-        return F.relu(_bn(_conv(x, sd, p + c, 1, 1), sd, p + b, train))
+        return _r(F.relu(_bn(_conv(x, sd, p + c, 1, 1), sd, p + b, train)))
     x = F.max_pool3d(cbr(x, "conv1", "bn1"), (1, 2, 2), (1, 2, 2))
     x = F.max_pool3d(cbr(x, "conv2", "bn2"), 2, 2)
     x = F.max_pool3d(cbr(cbr(x, "conv3a", "bn3a"), "conv3b", "bn3b"), 2, 2)
@@ -73,7 +82,7 @@ FEATURES = {"resnet18": resnet18_feature, "c3d": c3d_feature}
 
 def wrapper_forward(arch: str, x, sd: State, p: str, train=True):
     """moco/split_wrapper.py:128-152 with fc_type='linear' (:164-169), groups=1: two pooled linear heads, L2-normalised."""
-    feat = FEATURES[arch](x, sd, p + "encoder.", train)
+    feat = FEATURES[arch](_r(x), sd, p + "encoder.", train)
     pooled = feat.mean(dim=(2, 3, 4))
     x1 = F.linear(pooled, sd[p + "fc1.2.weight"], sd[p + "fc1.2.bias"])
     x2 = F.linear(pooled, sd[p + "fc2.2.weight"], sd[p + "fc2.2.bias"])

@@ -56,6 +56,27 @@ def test_step_matches_reference_golden(name):
     loss, ce, rank = crit(output, target, ranking_logits, ranking_target)
     loss.backward()
     torch.cuda.synchronize()
+    # (1) logic check: the oracle with bf16 rounding at the product's storage points must agree tightly
+    sd = {k: v.clone() for k, v in build_product_moco(cfg, hyper, rank=0).state_dict().items()}
+    oracle.EMULATE_BF16 = True
+    try:
+        emu = oracle.train_step(cfg["arch"], [sd], [im_q], [im_k], [draws[0]], (draws[1], draws[2]),
+                                d=hyper["diff_speed"][0], m=hyper["m"], T=hyper["T"], margin=hyper["margin"],
+                                A=hyper["A"], M=hyper["M"], do_update=False)
+    finally:
+        oracle.EMULATE_BF16 = False
+    d_emu = (output[0].detach().cpu() - emu["logits_a"][0][0]).abs().max().item()
+    d_ref = (output[0].detach().cpu() - rec["logits1"]).abs().max().item()
+    print(f"[{name}] max|logits - bf16-emulating oracle| = {d_emu:.4f}; max|logits - fp32 reference| = {d_ref:.4f}")
+    assert d_emu < 0.12, d_emu
+    assert (torch.stack([loss, ce, rank]).detach().cpu() - torch.stack(emu["loss"][0])).abs().max() < 0.05
+    named = dict(model.named_parameters())
+    for k, gref in emu["grads"].items():
+        if gref.abs().max() < 1e-6:
+            continue
+        c = _cos(named[k].grad.cpu(), gref)
+        assert c > 0.99, (k, c)
+    # (2) precision check against the fp32 fixtures of the unmodified reference: stated bf16 tolerance
     # bit-exact integer state
     assert torch.equal(target.cpu(), rec["target"]) and torch.equal(ranking_target.cpu(), rec["ranking_target"])
     assert int(model.queue_ptr) == rec["queue_ptr"]
