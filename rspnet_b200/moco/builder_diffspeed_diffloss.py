@@ -42,6 +42,10 @@ class _LogitsFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q_a, q_m, k_a, k_m, kn_a, kn_m, queue, temperature, materialize):
         args = [t.contiguous().float() for t in (q_a, q_m, k_a, k_m, kn_a, kn_m)]
+        if any(ctx.needs_input_grad[:2]):
+            # the queue is overwritten in place by _dequeue_and_enqueue before backward runs; backward recomputes the
+            # negative logits, so it needs the queue as it was (the reference clones it for the same reason, :529)
+            queue = queue.clone()
         logits, rows = ops.moco_logits_fwd(*args, queue, temperature, materialize)
         ctx.temperature = temperature
         ctx.save_for_backward(*args, queue, rows)
