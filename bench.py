@@ -342,7 +342,6 @@ def conv_roofline(args, B, ms_step):
         y = ops.conv3d_fprop(desc, x, wp)
         dy = torch.randn_like(y)
         jobs = [("fprop", lambda: ops.conv3d_fprop(desc, x, wp))]
-        ws = torch.empty((wp.shape[1], desc.Co), dtype=torch.float32, device="cuda")
         dw = torch.empty_like(w)
         jobs.append(("wgrad", lambda: ops.conv3d_wgrad(desc, x, dy, w.shape, out=dw)))
         if li > 0:

@@ -44,8 +44,11 @@ typedef struct rsp_conv3d_desc {
 /* which = 0: K extent (elements per output channel) of the packed fprop filter;
  * which = 1: K extent of the packed dgrad filter. Negative on error. */
 int rsp_conv3d_kpad(const rsp_conv3d_desc* d, int which);
+/* Number of bf16 elements of the packed operand (which = 0 may carry extra direct-conv slabs for the RGB stem). */
+int64_t rsp_conv3d_packed_elems(const rsp_conv3d_desc* d, int which);
 /* w: fp32 [Co_logical][Ci_logical][kt][kh][kw] (the nn.Conv3d parameter).
- * which = 0 -> wp bf16 [Co][kpad(0)]  (fprop / wgrad K order);  which = 1 -> wd bf16 [Ci][kpad(1)] (dgrad). */
+ * which = 0 -> wp bf16 [Co][kpad(0)] (+ stem slabs)  (fprop / wgrad K order);  which = 1 -> wd bf16 [Ci][kpad(1)]
+ * (dgrad).  wp must hold rsp_conv3d_packed_elems(d, which) elements. */
 int rsp_conv3d_pack_weight(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const float* w, void* wp,
                            int which, void* stream);
 /* y[N,To,Ho,Wo,Co] = conv(x[N,Ti,Hi,Wi,Ci], wp) (+ bias[Co] fp32, may be NULL). */

@@ -42,6 +42,7 @@ SIGNATURES = {
     "rsp_init": (c_i32, []),
     "rsp_last_error": (C.c_char_p, []),
     "rsp_conv3d_kpad": (c_i32, [C.POINTER(ConvDesc), c_i32]),
+    "rsp_conv3d_packed_elems": (c_i64, [C.POINTER(ConvDesc), c_i32]),
     "rsp_conv3d_pack_weight": (c_i32, [C.POINTER(ConvDesc), c_i32, c_i32, _P, _P, c_i32, _P]),
     "rsp_conv3d_fprop": (c_i32, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P]),
     "rsp_conv3d_dgrad": (c_i32, [C.POINTER(ConvDesc), _P, _P, _P, _P]),

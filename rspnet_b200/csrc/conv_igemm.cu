@@ -577,6 +577,13 @@ static int dispatch_wgrad(WgradParams& p, int sm_count, cudaStream_t stream) {
 }
 
 int device_sm_count();
+bool stem_supported(const rsp_conv3d_desc* d);
+int launch_stem(const rsp_conv3d_desc* d, const void* x, const void* wst, const float* bias, void* y, int sm_count,
+                cudaStream_t stream);
+int pack_stem(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const float* w, void* wst,
+              cudaStream_t stream);
+int launch_stem_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const void* x, const void* dy,
+                      float* dw, int accumulate, int sm_count, cudaStream_t stream);
 
 }  // namespace rsp
 
@@ -594,6 +601,15 @@ int rsp_conv3d_kpad(const rsp_conv3d_desc* d, int which) {
   return g.numKb * 64;
 }
 
+int64_t rsp_conv3d_packed_elems(const rsp_conv3d_desc* d, int which) {
+  const int kpad = rsp_conv3d_kpad(d, which);
+  if (kpad < 0) return kpad;
+  if (which == 1) return static_cast<int64_t>(d->Ci) * kpad;
+  int64_t n = static_cast<int64_t>(d->Co) * kpad;
+  if (stem_supported(d)) n += static_cast<int64_t>(d->kt) * d->kh * 2048;  // direct-conv filter slabs appended
+  return n;
+}
+
 int rsp_conv3d_pack_weight(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const float* w, void* wp,
                            int which, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -607,7 +623,11 @@ int rsp_conv3d_pack_weight(const rsp_conv3d_desc* d, int Ci_logical, int Co_logi
     pack_weight_fprop_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
         w, static_cast<__nv_bfloat16*>(wp), mode, Co_logical, d->Co, Ci_logical, d->Ci, d->kt, d->kh, d->kw, g.pxs,
         Kpad);
-    return check_launch("pack_weight_fprop");
+    rc = check_launch("pack_weight_fprop");
+    if (rc != RSP_OK) return rc;
+    if (stem_supported(d))
+      return pack_stem(d, Ci_logical, Co_logical, w, static_cast<__nv_bfloat16*>(wp) + total, stream);
+    return RSP_OK;
   }
   RSP_REQUIRE(mode == MODE_GENERIC, "pack_weight(dgrad): small-channel convs have no dgrad");
   size_t total = static_cast<size_t>(d->Ci) * d->kt * d->kh * d->kw * d->Co;
@@ -624,6 +644,10 @@ int rsp_conv3d_fprop(const rsp_conv3d_desc* d, const void* x, const void* wp, co
   int rc = fill_geom(p.g, d, mode, 0);
   if (rc != RSP_OK) return rc;
   RSP_REQUIRE(d->Co % 64 == 0, "conv3d fprop: Co=%d must be a multiple of 64", d->Co);
+  if (stem_supported(d)) {
+    const __nv_bfloat16* wst = static_cast<const __nv_bfloat16*>(wp) + static_cast<size_t>(d->Co) * p.g.numKb * 64;
+    return launch_stem(d, x, wst, bias, y, device_sm_count(), stream);
+  }
   p.g.src = static_cast<const __nv_bfloat16*>(x);
   p.wgt = static_cast<const __nv_bfloat16*>(wp);
   p.out = static_cast<__nv_bfloat16*>(y);
@@ -654,6 +678,8 @@ int rsp_conv3d_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, c
   int rc = fill_geom(p.g, d, mode, 0);
   if (rc != RSP_OK) return rc;
   RSP_REQUIRE(d->Co % 64 == 0, "conv3d wgrad: Co=%d must be a multiple of 64", d->Co);
+  if (stem_supported(d) && d->kh * 2 * 32 <= 448)
+    return launch_stem_wgrad(d, Ci_logical, Co_logical, x, dy, dw, accumulate, device_sm_count(), stream);
   p.g.src = static_cast<const __nv_bfloat16*>(x);
   p.dy = static_cast<const __nv_bfloat16*>(dy);
   p.dwt = dwt_workspace;

@@ -1,0 +1,456 @@
+// Direct (im2col-free) tcgen05 convolution for the RGB stem: kt x kh x 7 filters, stride (st, sh, 2), 4 stored input
+// channels (RGB + pad), 64 output channels  (reference: models/resnet.py:130-136 conv1 7x7x7 s(1,2,2);
+// models/r2plus1d_vcop.py conv1.spatial_conv 1x7x7 s(1,2,2)).
+//
+// Observation: with 8 B per input pixel and a w-stride of 2, the patches of two neighbouring output pixels start
+// exactly 16 B apart inside a raw input row.  That is the row pitch of the *non-swizzled K-major* UMMA operand layout
+// (core matrix = 8 rows x 16 B), so a raw input row sitting in shared memory already IS the A operand of
+//   D[ow, co] += sum_{q<8 px, c<4} X[row, 2*ow - 4 + q, c] * W[co, c, a, b, q-1]
+// (rows overlap, which a descriptor does not mind): descriptor start = row address, LBO = 16 B (next 2 pixels),
+// SBO = 128 B (next 8 output pixels).  Rows are stored 1024 B apart per h-stride phase so that output row ho+1
+// (input row + sh) is the second half of an M=128 tile.  No gather, no index math, no im2col traffic: each input
+// row is read once per (tile, frame tap) with plain 16 B cp.async, the filter slab of one frame tap (kh*4 KB) arrives
+// with one bulk-TMA copy.
+//
+// CTA (persistent, 1/SM): 4 producer warps, 4 epilogue warps, 1 MMA warp.  One iteration = 4 output rows of one
+// (n, to) = two 128x64 accumulators in TMEM, double buffered (256 columns) so the epilogue of iteration i overlaps the
+// MMAs of i+1.  Pipeline stage = one frame tap a: {13 input rows, kh*4 KB filter slab}, 4 stages.
+#include "common.cuh"
+#include "rspnet_b200.h"
+
+namespace rsp {
+
+struct StemParams {
+  const __nv_bfloat16* x;    // [N][Ti][Hi][Wi][4]
+  const __nv_bfloat16* wst;  // [kt][kh][4 kchunk][8 co-group][8 co][8 k] bf16
+  __nv_bfloat16* y;          // [N][To][Ho][Wo][64]
+  const float* bias;
+  int N, Ti, Hi, Wi, To, Ho, Wo;
+  int kt, kh, st, sh, pt, ph;
+  int hq;        // ceil(Ho / 4)
+  int numIters;  // N * To * hq
+};
+
+constexpr int kStemThreads = 288;
+constexpr int kStemStages = 4;
+constexpr int kStemRowBytes = 1024;   // 128 pixel slots of 8 B; slot s holds input pixel s - 4
+constexpr int kStemMaxRows = 14;      // rows per A slab (two h-phases x 7)
+constexpr int kStemASlab = kStemMaxRows * kStemRowBytes;
+constexpr int kStemBSlabMax = 7 * 4096;
+constexpr int kStemStageBytes = kStemASlab + kStemBSlabMax;
+
+__device__ __forceinline__ uint64_t make_smem_desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  return d;  // layout type 0: no swizzle
+}
+
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStemStages * kStemStageBytes);
+  uint64_t* empty_bar = full_bar + kStemStages;
+  uint64_t* acc_full = empty_bar + kStemStages;   // [2]
+  uint64_t* acc_empty = acc_full + 2;             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int t = threadIdx.x;
+  const int warp = t >> 5;
+  const int rowsA = 3 * p.sh + p.kh;              // input rows feeding 4 output rows
+  const int perPhase = (rowsA + p.sh - 1) / p.sh; // rows of one h-phase, stored 1024 B apart
+  const uint32_t bslab_bytes = static_cast<uint32_t>(p.kh) * 4096u;
+
+  // zero the A slabs once: halo pixel slots are never written afterwards
+  for (int i = t; i < kStemStages * kStemStageBytes / 16; i += kStemThreads)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (t == 0) {
+    for (int s = 0; s < kStemStages; ++s) {
+      mbar_init(&full_bar[s], 128 + 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, 256);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ producers
+    uint32_t stage_ctr = 0;
+    const int chunksPerRow = p.Wi >> 1;           // 16 B = 2 pixels
+    const int totalChunks = rowsA * chunksPerRow;
+    for (int it = blockIdx.x; it < p.numIters; it += gridDim.x) {
+      const int hq = it % p.hq;
+      const int q = it / p.hq;
+      const int to = q % p.To, n = q / p.To;
+      const int hi0 = hq * 4 * p.sh - p.ph;
+      for (int a = 0; a < p.kt; ++a, ++stage_ctr) {
+        const int s = stage_ctr % kStemStages;
+        const uint32_t ph = (stage_ctr / kStemStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* aslab = smem + s * kStemStageBytes;
+        if (t == 0) {
+          mbar_arrive_expect_tx(&full_bar[s], bslab_bytes);
+          bulk_copy_g2s(smem_u32(aslab + kStemASlab), p.wst + static_cast<size_t>(a) * p.kh * 2048, bslab_bytes,
+                        &full_bar[s]);
+        }
+        const int ti = to * p.st - p.pt + a;
+        const bool tok = ti >= 0 && ti < p.Ti;
+        const __nv_bfloat16* frame = p.x + (static_cast<size_t>(n) * p.Ti + (tok ? ti : 0)) * p.Hi * p.Wi * 4;
+        for (int idx = t; idx < totalChunks; idx += 128) {
+          const int j = idx / chunksPerRow, c = idx - j * chunksPerRow;
+          const int hi = hi0 + j;
+          const bool ok = tok && hi >= 0 && hi < p.Hi;
+          const uint32_t dst = smem_u32(aslab) + ((j % p.sh) * perPhase + j / p.sh) * kStemRowBytes + 32 + c * 16;
+          const __nv_bfloat16* src = frame + (static_cast<size_t>(ok ? hi : 0) * p.Wi) * 4 + c * 8;
+          cp_async16(dst, src, ok ? 16u : 0u);
+        }
+        cp_async_mbar_arrive(&full_bar[s]);
+        mbar_arrive(&full_bar[s]);
+      }
+    }
+  } else if (warp < 8) {
+    // ------------------------------------------------------------------ epilogue
+    const int ew = warp - 4;          // TMEM lane quarter
+    const int lane = t & 31;
+    uint32_t iter_ctr = 0;
+    for (int it = blockIdx.x; it < p.numIters; it += gridDim.x, ++iter_ctr) {
+      const int buf = iter_ctr & 1;
+      const uint32_t ph = (iter_ctr >> 1) & 1;
+      const int hq = it % p.hq;
+      const int q = it / p.hq;
+      const int to = q % p.To, n = q / p.To;
+      mbar_wait(&acc_full[buf], ph);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int m = 0; m < 2; ++m) {
+        const int ho = hq * 4 + 2 * m + (ew >> 1);
+        const int ow = (ew & 1) * 32 + lane;
+        const bool ok = ho < p.Ho && ow < p.Wo;
+        __nv_bfloat16* orow =
+            p.y + ((((static_cast<size_t>(n) * p.To + to) * p.Ho + (ok ? ho : 0)) * p.Wo) + (ok ? ow : 0)) * 64;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * 128 + m * 64 + c0, v);
+          tmem_ld_wait();
+          if (ok) {
+#pragma unroll
+            for (int jx = 0; jx < 32; jx += 8) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                f[e] = __uint_as_float(v[jx + e]);
+                if (p.bias) f[e] += __ldg(p.bias + c0 + jx + e);
+              }
+              uint4 o;
+              o.x = pack_bf16x2(f[0], f[1]);
+              o.y = pack_bf16x2(f[2], f[3]);
+              o.z = pack_bf16x2(f[4], f[5]);
+              o.w = pack_bf16x2(f[6], f[7]);
+              *reinterpret_cast<uint4*>(orow + c0 + jx) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&acc_empty[buf]);
+    }
+  } else {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+    uint32_t stage_ctr = 0, iter_ctr = 0;
+    for (int it = blockIdx.x; it < p.numIters; it += gridDim.x, ++iter_ctr) {
+      const int buf = iter_ctr & 1;
+      const uint32_t aph = (iter_ctr >> 1) & 1;
+      mbar_wait(&acc_empty[buf], aph ^ 1);
+      tc_fence_after_sync();
+      for (int a = 0; a < p.kt; ++a, ++stage_ctr) {
+        const int s = stage_ctr % kStemStages;
+        const uint32_t ph = (stage_ctr / kStemStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        fence_proxy_async_smem();
+        tc_fence_after_sync();
+        if ((t & 31) == 0) {
+          const uint32_t aslab = smem_u32(smem + s * kStemStageBytes);
+          const uint32_t bslab = aslab + kStemASlab;
+          for (int b = 0; b < p.kh; ++b) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+              const int j = 2 * m * p.sh + b;  // input row (relative) of the tile's first output row
+              const uint32_t arow = aslab + ((j % p.sh) * perPhase + j / p.sh) * kStemRowBytes;
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint64_t adesc = make_smem_desc_nosw(arow + ks * 32, 16, 128);
+                const uint64_t bdesc = make_smem_desc_nosw(bslab + b * 4096 + ks * 2048, 1024, 128);
+                umma_bf16(tmem_base + buf * 128 + m * 64, adesc, bdesc, idesc, (a | b | ks) != 0);
+              }
+            }
+          }
+          umma_commit(&empty_bar[s]);
+          if (a == p.kt - 1) umma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, 256);
+}
+
+// w fp32 [64][Ci<=4][kt][kh][7] -> wst bf16 [kt][kh][4][8][8][8]; K slot q = kchunk*8 + e: pixel slot q/4 (kw = slot-1), ch q%4
+__global__ void pack_weight_stem_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wst, int Co, int Ci,
+                                        int kt, int kh, int kw) {
+  size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  size_t total = static_cast<size_t>(kt) * kh * 2048;
+  if (idx >= total) return;
+  int e = idx & 7, r = (idx >> 3) & 7, g = (idx >> 6) & 7, j = (idx >> 9) & 3;
+  int ab = static_cast<int>(idx >> 11);
+  int a = ab / kh, b = ab - a * kh;
+  int co = g * 8 + r;
+  int qk = j * 8 + e;
+  int slot = qk >> 2, ch = qk & 3;
+  int c = slot - 1;
+  float v = 0.f;
+  if (co < Co && ch < Ci && c >= 0 && c < kw)
+    v = w[(((static_cast<size_t>(co) * Ci + ch) * kt + a) * kh + b) * kw + c];
+  wst[idx] = __float2bfloat16(v);
+}
+
+bool stem_supported(const rsp_conv3d_desc* d) {
+  const int Wo = (d->Wi + 2 * d->pw - d->kw) / d->sw + 1;
+  return d->Ci == 4 && d->Co == 64 && d->kw == 7 && d->sw == 2 && d->pw == 3 && d->kh <= 7 && d->sh >= 1 &&
+         d->sh <= 2 && (d->Wi % 2) == 0 && d->Wi + 4 <= 124 && Wo <= 64 && (3 * d->sh + d->kh) <= kStemMaxRows;
+}
+
+int launch_stem(const rsp_conv3d_desc* d, const void* x, const void* wst, const float* bias, void* y, int sm_count,
+                cudaStream_t stream) {
+  StemParams p{};
+  p.x = static_cast<const __nv_bfloat16*>(x);
+  p.wst = static_cast<const __nv_bfloat16*>(wst);
+  p.y = static_cast<__nv_bfloat16*>(y);
+  p.bias = bias;
+  p.N = d->N; p.Ti = d->Ti; p.Hi = d->Hi; p.Wi = d->Wi;
+  p.To = (d->Ti + 2 * d->pt - d->kt) / d->st + 1;
+  p.Ho = (d->Hi + 2 * d->ph - d->kh) / d->sh + 1;
+  p.Wo = (d->Wi + 2 * d->pw - d->kw) / d->sw + 1;
+  p.kt = d->kt; p.kh = d->kh; p.st = d->st; p.sh = d->sh; p.pt = d->pt; p.ph = d->ph;
+  p.hq = (p.Ho + 3) / 4;
+  p.numIters = p.N * p.To * p.hq;
+  constexpr int smem = kStemStages * kStemStageBytes + 1024 + 256;
+  cudaError_t e = cudaFuncSetAttribute(conv_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(conv_stem): %s", cudaGetErrorString(e));
+    return RSP_ERR_CUDA;
+  }
+  int grid = p.numIters < sm_count ? p.numIters : sm_count;
+  conv_stem_kernel<<<grid, kStemThreads, smem, stream>>>(p);
+  return check_launch("conv_stem");
+}
+
+int pack_stem(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const float* w, void* wst,
+              cudaStream_t stream) {
+  size_t total = static_cast<size_t>(d->kt) * d->kh * 2048;
+  pack_weight_stem_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      w, static_cast<__nv_bfloat16*>(wst), Co_logical, Ci_logical, d->kt, d->kh, d->kw);
+  return check_launch("pack_weight_stem");
+}
+
+
+// =====================================================================================================================
+// Stem wgrad with the same raw-row trick:  dW[co][c][a][b][kw] = sum_pixels dY[pixel][co] * X[patch(pixel)][kw, c].
+//   A = dY row panel   [64 px (K)] x [64 co (M)]   MN-major, 128 B swizzle (one pixel = one 128 B row)
+//   B = raw input row  [64 px (K)] x [32 k-slots (N)] MN-major, no swizzle: pixel pitch 16 B (K), 8-element N chunks 16 B
+//       apart (overlapping windows), 8-pixel K groups 128 B apart
+//   D = [64 co] x [32] per filter row (a, b); one CTA keeps the accumulators of two frame taps (2*kh*32 <= 448 TMEM
+//       columns) while it streams output rows, then adds them into dW with fp32 atomics.
+// grid: x = workers over output rows, y = pairs of frame taps.
+// =====================================================================================================================
+struct StemWgradParams {
+  const __nv_bfloat16* x;   // [N][Ti][Hi][Wi][4]
+  const __nv_bfloat16* dy;  // [N][To][Ho][Wo][64]
+  float* dw;                // [Co][Ci][kt][kh][kw] fp32, accumulated atomically
+  int N, Ti, Hi, Wi, To, Ho, Wo;
+  int kt, kh, kw, st, sh, pt, ph;
+  int Co, Ci;               // logical
+  int numRows;              // N*To*Ho
+};
+
+constexpr int kSWStages = 6;
+constexpr int kSWDyBytes = 64 * 128;
+constexpr int kSWRowsMax = 14;
+constexpr int kSWStageBytes = kSWDyBytes + kSWRowsMax * kStemRowBytes;
+
+__global__ void __launch_bounds__(160, 1) conv_stem_wgrad_kernel(const StemWgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kSWStages * kSWStageBytes);
+  uint64_t* empty_bar = full_bar + kSWStages;
+  uint64_t* accum_bar = empty_bar + kSWStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int t = threadIdx.x;
+  const int warp = t >> 5;
+  const int a0 = blockIdx.y * 2;                       // first frame tap of this CTA
+  const int na = (p.kt - a0) < 2 ? (p.kt - a0) : 2;    // frame taps handled (1 or 2)
+  const int nrows = na * p.kh;                         // filter rows = accumulators
+  int iters = 0;
+  for (int r = blockIdx.x; r < p.numRows; r += gridDim.x) ++iters;
+
+  for (int i = t; i < kSWStages * kSWStageBytes / 16; i += 160) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (t == 0) {
+    for (int s = 0; s < kSWStages; ++s) {
+      mbar_init(&full_bar[s], 128);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, 512);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (iters > 0) {
+    if (warp < 4) {
+      const int chunksPerRow = p.Wi >> 1;
+      int it = 0;
+      for (int r = blockIdx.x; r < p.numRows; r += gridDim.x, ++it) {
+        const int s = it % kSWStages;
+        const uint32_t ph = (it / kSWStages) & 1;
+        const int ho = r % p.Ho;
+        const int q = r / p.Ho;
+        const int to = q % p.To, n = q / p.To;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const uint32_t stage = smem_u32(smem + s * kSWStageBytes);
+        // dY row -> 128B-swizzled panel (pixel rows beyond Wo are zero so that garbage B rows contribute nothing)
+        const __nv_bfloat16* dyrow = p.dy + static_cast<size_t>(r) * p.Wo * 64;
+        for (int idx = t; idx < 64 * 8; idx += 128) {
+          const int row = idx >> 3, ch = idx & 7;
+          const bool ok = row < p.Wo;
+          cp_async16(stage + row * 128 + ((ch ^ (row & 7)) << 4), dyrow + (ok ? row * 64 + ch * 8 : 0), ok ? 16u : 0u);
+        }
+        // raw input rows of the filter rows (a, b)
+        const int total = nrows * chunksPerRow;
+        for (int idx = t; idx < total; idx += 128) {
+          const int fr = idx / chunksPerRow, c = idx - fr * chunksPerRow;
+          const int al = fr / p.kh, b = fr - al * p.kh;
+          const int ti = to * p.st - p.pt + a0 + al;
+          const int hi = ho * p.sh - p.ph + b;
+          const bool ok = ti >= 0 && ti < p.Ti && hi >= 0 && hi < p.Hi;
+          const __nv_bfloat16* src =
+              p.x + (((static_cast<size_t>(n) * p.Ti + (ok ? ti : 0)) * p.Hi + (ok ? hi : 0)) * p.Wi) * 4 + c * 8;
+          cp_async16(stage + kSWDyBytes + fr * kStemRowBytes + 32 + c * 16, src, ok ? 16u : 0u);
+        }
+        cp_async_mbar_arrive(&full_bar[s]);
+        mbar_arrive(&full_bar[s]);
+      }
+      // ---------------- epilogue: TMEM lanes of an M=64 accumulator: co = 16*warp + lane, lanes 16..31 unused
+      mbar_wait(accum_bar, 0);
+      tc_fence_after_sync();
+      const int lane = t & 31;
+      const int co = warp * 16 + lane;
+      for (int fr = 0; fr < nrows; ++fr) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + fr * 32, v);
+        tmem_ld_wait();
+        if (lane < 16 && co < p.Co) {
+          const int a = a0 + fr / p.kh, b = fr % p.kh;
+#pragma unroll
+          for (int qk = 0; qk < 32; ++qk) {
+            const int slot = qk >> 2, ch = qk & 3, c = slot - 1;
+            if (ch < p.Ci && c >= 0 && c < p.kw)
+              atomicAdd(p.dw + (((static_cast<size_t>(co) * p.Ci + ch) * p.kt + a) * p.kh + b) * p.kw + c,
+                        __uint_as_float(v[qk]));
+          }
+        }
+      }
+    } else {
+      constexpr uint32_t idesc = make_idesc_bf16(64, 32, 1, 1);
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % kSWStages;
+        const uint32_t ph = (it / kSWStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        fence_proxy_async_smem();
+        tc_fence_after_sync();
+        if ((t & 31) == 0) {
+          const uint32_t stage = smem_u32(smem + s * kSWStageBytes);
+          for (int fr = 0; fr < nrows; ++fr) {
+            const uint32_t brow = stage + kSWDyBytes + fr * kStemRowBytes;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              // A: 16 pixels = two 8-row groups of the swizzled panel; B: 16 pixels = 256 B along the raw row
+              const uint64_t adesc = make_smem_desc_sw128(stage + ks * 2048, 8192, 1024);
+              const uint64_t bdesc = make_smem_desc_nosw(brow + ks * 256, 128, 16);
+              umma_bf16(tmem_base + fr * 32, adesc, bdesc, idesc, (it | ks) != 0);
+            }
+          }
+          umma_commit(&empty_bar[s]);
+          if (it == iters - 1) umma_commit(accum_bar);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 512);
+}
+
+int launch_stem_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const void* x, const void* dy,
+                      float* dw, int accumulate, int sm_count, cudaStream_t stream) {
+  StemWgradParams p{};
+  p.x = static_cast<const __nv_bfloat16*>(x);
+  p.dy = static_cast<const __nv_bfloat16*>(dy);
+  p.dw = dw;
+  p.N = d->N; p.Ti = d->Ti; p.Hi = d->Hi; p.Wi = d->Wi;
+  p.To = (d->Ti + 2 * d->pt - d->kt) / d->st + 1;
+  p.Ho = (d->Hi + 2 * d->ph - d->kh) / d->sh + 1;
+  p.Wo = (d->Wi + 2 * d->pw - d->kw) / d->sw + 1;
+  p.kt = d->kt; p.kh = d->kh; p.kw = d->kw; p.st = d->st; p.sh = d->sh; p.pt = d->pt; p.ph = d->ph;
+  p.Co = Co_logical; p.Ci = Ci_logical;
+  p.numRows = p.N * p.To * p.Ho;
+  const size_t nw = static_cast<size_t>(Co_logical) * Ci_logical * d->kt * d->kh * d->kw;
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(dw, 0, nw * sizeof(float), stream);
+    if (e != cudaSuccess) {
+      set_error("stem wgrad memset: %s", cudaGetErrorString(e));
+      return RSP_ERR_CUDA;
+    }
+  }
+  constexpr int smem = kSWStages * kSWStageBytes + 1024 + 256;
+  cudaError_t e = cudaFuncSetAttribute(conv_stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(conv_stem_wgrad): %s", cudaGetErrorString(e));
+    return RSP_ERR_CUDA;
+  }
+  const int groups = (d->kt + 1) / 2;
+  int workers = sm_count / groups;
+  if (workers < 1) workers = 1;
+  if (workers > p.numRows) workers = p.numRows;
+  dim3 grid(workers, groups);
+  conv_stem_wgrad_kernel<<<grid, 160, smem, stream>>>(p);
+  return check_launch("conv_stem_wgrad");
+}
+
+}  // namespace rsp

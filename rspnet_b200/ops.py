@@ -36,8 +36,8 @@ def conv3d_pack_weight(desc: ConvDesc, weight: torch.Tensor, which: int = 0) -> 
     kpad = _lib.load().rsp_conv3d_kpad(C.byref(desc), which)
     if kpad <= 0:
         raise RuntimeError("rsp_conv3d_kpad failed: " + _lib.load().rsp_last_error().decode())
-    rows = desc.Co if which == 0 else desc.Ci
-    out = torch.empty((rows, kpad), dtype=torch.bfloat16, device=weight.device)
+    n_elems = _lib.load().rsp_conv3d_packed_elems(C.byref(desc), which)
+    out = torch.empty((n_elems,), dtype=torch.bfloat16, device=weight.device)
     w = weight.detach().contiguous().float()
     call("rsp_conv3d_pack_weight", C.byref(desc), ci_l, co_l, ptr(w), ptr(out), which, stream_ptr())
     return out
