@@ -35,7 +35,47 @@ struct GatherGeom {
   int pxs;                   // SMALLC: w-pixels per (kt,kh) segment (4 or 8)
   int numKb;                 // number of 64-wide K blocks
   long long M;               // N*Td*Hd*Wd
+  int fast;                  // 1: source offset is linear in the tap (fprop, or dgrad with unit strides) and k <= 8
+  unsigned long long mulW, mulH, mulT;  // ceil(2^sh / d) for row decoding without integer division
+  int shW, shH, shT;
 };
+
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, unsigned long long mul, int sh) {
+  return static_cast<uint32_t>((static_cast<unsigned long long>(n) * mul) >> sh);
+}
+
+// (n, td, hd, wd) of GEMM row m (< 2^31) using the precomputed reciprocals
+__device__ __forceinline__ void decode_fast(const GatherGeom& g, uint32_t m, int& n, int& td, int& hd, int& wd) {
+  uint32_t q = fdiv(m, g.mulW, g.shW);
+  wd = static_cast<int>(m - q * g.Wd);
+  uint32_t q2 = fdiv(q, g.mulH, g.shH);
+  hd = static_cast<int>(q - q2 * g.Hd);
+  uint32_t q3 = fdiv(q2, g.mulT, g.shT);
+  td = static_cast<int>(q2 - q3 * g.Td);
+  n = static_cast<int>(q3);
+}
+
+// Per-row gather state of the fast path: element offset of the row's (n, t0, h0, w0, chunk) and per-tap validity bits
+// (bit a: t tap a in range; bit 8+b: h tap b; bit 16+c: w tap c).  Source of tap (a,b,c) = base + dir*((a*Hs+b)*Ws+c)*Cs.
+__device__ __forceinline__ void row_state(const GatherGeom& g, long long m, int chunk, int& base, uint32_t& mask) {
+  if (m >= g.M) {
+    base = 0;
+    mask = 0;
+    return;
+  }
+  int n, td, hd, wd;
+  decode_fast(g, static_cast<uint32_t>(m), n, td, hd, wd);
+  const int dir = g.transposed ? -1 : 1;
+  const int t0 = g.transposed ? td + g.pt : td * g.st - g.pt;
+  const int h0 = g.transposed ? hd + g.ph : hd * g.sh - g.ph;
+  const int w0 = g.transposed ? wd + g.pw : wd * g.sw - g.pw;
+  uint32_t mk = 0;
+  for (int a = 0; a < g.kt; ++a) mk |= (static_cast<unsigned>(t0 + dir * a) < static_cast<unsigned>(g.Ts)) << a;
+  for (int b = 0; b < g.kh; ++b) mk |= (static_cast<unsigned>(h0 + dir * b) < static_cast<unsigned>(g.Hs)) << (8 + b);
+  for (int c = 0; c < g.kw; ++c) mk |= (static_cast<unsigned>(w0 + dir * c) < static_cast<unsigned>(g.Ws)) << (16 + c);
+  mask = mk;
+  base = (((n * g.Ts + t0) * g.Hs + h0) * g.Ws + w0) * g.Cs + chunk * 8;
+}
 
 struct ConvParams {
   GatherGeom g;
@@ -217,23 +257,67 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvParams p
 
   if (warp < 4) {
     // ---------------- producers ----------------
-    RowCoord rows[ROWS_PER_THREAD];
-#pragma unroll
-    for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-      int row = (MODE == MODE_GENERIC) ? (t >> 3) + 16 * i : (t >> 4) + 8 * i;
-      rows[i] = decode_row(g, m0 + row);
-    }
     const size_t ldw = static_cast<size_t>(numKb) * 64;
-    for (int kb = 0; kb < numKb; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (kb / STAGES) & 1;
-      mbar_wait(&empty_bar[s], ph ^ 1);
-      const uint32_t a_panel = smem_u32(smem + s * STAGE_BYTES);
-      const uint32_t b_panel = a_panel + A_BYTES;
-      gather_panel<MODE, 128>(g, a_panel, kb, t, rows);
-      load_rows<NT>(b_panel, p.wgt + static_cast<size_t>(kb) * 64, n0, p.Nout, ldw, t);
-      cp_async_mbar_arrive(&full_bar[s]);
-      mbar_arrive(&full_bar[s]);
+    if (MODE == MODE_GENERIC && g.fast) {
+      // fast path: ~10 instructions per 16 B copy (row state precomputed, taps advanced incrementally)
+      const int chunk = t & 7;
+      int rbase[8];
+      uint32_t rmask[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) row_state(g, m0 + (t >> 3) + 16 * i, chunk, rbase[i], rmask[i]);
+      const uint32_t dst0 = swz(t >> 3, chunk * 16);  // rows (t>>3)+16i share the swizzle phase: + i*2048
+      const __nv_bfloat16* wrow = p.wgt + static_cast<size_t>(n0 + (t >> 3)) * ldw + chunk * 8;
+      const size_t wstep = 16 * ldw;
+      const int dirCs = g.transposed ? -g.Cs : g.Cs;
+      const int cchunks = g.Cs >> 6;
+      int a = 0, b = 0, c = 0, cc = 0;
+      for (int kb = 0; kb < numKb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        const int koff = ((a * g.Hs + b) * g.Ws + c) * dirCs + cc * 64;
+        const int sb = 8 + b, sc = 16 + c;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const uint32_t a_panel = smem_u32(smem + s * STAGE_BYTES) + dst0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t v = (rmask[i] >> a) & (rmask[i] >> sb) & (rmask[i] >> sc) & 1u;
+          const __nv_bfloat16* src = g.src + (v ? static_cast<ptrdiff_t>(rbase[i] + koff) : 0);
+          cp_async16(a_panel + i * 2048, src, v << 4);
+        }
+        const __nv_bfloat16* wsrc = wrow + static_cast<size_t>(kb) * 64;
+#pragma unroll
+        for (int i = 0; i < NT / 16; ++i) cp_async16(a_panel + A_BYTES + i * 2048, wsrc + i * wstep, 16u);
+        cp_async_mbar_arrive(&full_bar[s]);
+        mbar_arrive(&full_bar[s]);
+        if (++cc == cchunks) {
+          cc = 0;
+          if (++c == g.kw) {
+            c = 0;
+            if (++b == g.kh) {
+              b = 0;
+              ++a;
+            }
+          }
+        }
+      }
+    } else {
+      RowCoord rows[ROWS_PER_THREAD];
+#pragma unroll
+      for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+        int row = (MODE == MODE_GENERIC) ? (t >> 3) + 16 * i : (t >> 4) + 8 * i;
+        rows[i] = decode_row(g, m0 + row);
+      }
+      for (int kb = 0; kb < numKb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const uint32_t a_panel = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t b_panel = a_panel + A_BYTES;
+        gather_panel<MODE, 128>(g, a_panel, kb, t, rows);
+        load_rows<NT>(b_panel, p.wgt + static_cast<size_t>(kb) * 64, n0, p.Nout, ldw, t);
+        cp_async_mbar_arrive(&full_bar[s]);
+        mbar_arrive(&full_bar[s]);
+      }
     }
     // ---------------- epilogue ----------------
     mbar_wait(accum_bar, 0);
@@ -340,6 +424,64 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const WgradParams 
 
   if (iters > 0) {
     if (warp < 4) {
+      if (MODE == MODE_GENERIC && !g.transposed && g.fast) {
+        const int chunk = t & 7;
+        const uint32_t dst0 = swz(t >> 3, chunk * 16);
+        const int cchunks = g.Cs >> 6;
+        int ta[2], tb[2], tc[2], koff[2];
+        bool kbok[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int kb = kb0 + j;
+          kbok[j] = kb < g.numKb;
+          const int tap = kb / cchunks, cc = kb - tap * cchunks;
+          ta[j] = tap / (g.kh * g.kw);
+          const int rem = tap - ta[j] * g.kh * g.kw;
+          tb[j] = rem / g.kw;
+          tc[j] = rem - tb[j] * g.kw;
+          koff[j] = ((ta[j] * g.Hs + tb[j]) * g.Ws + tc[j]) * g.Cs + cc * 64;
+        }
+        const __nv_bfloat16* dybase = p.dy + n0 + chunk * 8;
+        for (int it = 0; it < iters; ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          const uint32_t prow0 = static_cast<uint32_t>((pbBegin + it) * 64) + (t >> 3);
+          int base[4], t0[4], h0[4], w0[4];
+          bool ok[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t m = prow0 + 16 * i;
+            ok[i] = m < static_cast<uint32_t>(g.M);
+            int n, td, hd, wd;
+            decode_fast(g, ok[i] ? m : 0u, n, td, hd, wd);
+            t0[i] = td * g.st - g.pt;
+            h0[i] = hd * g.sh - g.ph;
+            w0[i] = wd * g.sw - g.pw;
+            base[i] = (((n * g.Ts + t0[i]) * g.Hs + h0[i]) * g.Ws + w0[i]) * g.Cs + chunk * 8;
+          }
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          const uint32_t stage = smem_u32(smem + s * STAGE_BYTES) + dst0;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const bool v = ok[i] && kbok[j] && static_cast<unsigned>(t0[i] + ta[j]) < static_cast<unsigned>(g.Ts) &&
+                             static_cast<unsigned>(h0[i] + tb[j]) < static_cast<unsigned>(g.Hs) &&
+                             static_cast<unsigned>(w0[i] + tc[j]) < static_cast<unsigned>(g.Ws);
+              cp_async16(stage + j * PANEL + i * 2048, g.src + (v ? static_cast<ptrdiff_t>(base[i] + koff[j]) : 0),
+                         v ? 16u : 0u);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat16* dsrc = dybase + (ok[i] ? static_cast<size_t>(prow0 + 16 * i) * p.Nout : 0);
+#pragma unroll
+            for (int j = 0; j < NB; ++j) cp_async16(stage + (2 + j) * PANEL + i * 2048, dsrc + j * 64, ok[i] ? 16u : 0u);
+          }
+          cp_async_mbar_arrive(&full_bar[s]);
+          mbar_arrive(&full_bar[s]);
+        }
+      } else
       for (int it = 0; it < iters; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
@@ -520,8 +662,19 @@ static int fill_geom(GatherGeom& g, const rsp_conv3d_desc* d, int mode, int tran
     const int segs = 16 / g.pxs;
     g.numKb = (d->kt * d->kh + segs - 1) / segs;
   }
-  RSP_REQUIRE(static_cast<long long>(g.N) * g.Ts * g.Hs * g.Ws < (1ll << 31) && g.M < (1ll << 31),
+  RSP_REQUIRE(static_cast<long long>(g.N) * g.Ts * g.Hs * g.Ws * g.Cs < (1ll << 31) && g.M < (1ll << 31),
               "conv3d: tensor too large");
+  auto recip = [](int d, unsigned long long& mul, int& sh) {
+    int l = 0;
+    while ((1ll << l) < d) ++l;
+    sh = 32 + l;  // exact for dividends < 2^31 (Granlund-Montgomery: shift >= 31 + ceil(log2 d))
+    mul = ((1ull << sh) + d - 1) / d;
+  };
+  recip(g.Wd, g.mulW, g.shW);
+  recip(g.Hd, g.mulH, g.shH);
+  recip(g.Td, g.mulT, g.shT);
+  g.fast = (mode == MODE_GENERIC) && d->kt <= 8 && d->kh <= 8 && d->kw <= 8 &&
+           (!transposed || (d->st == 1 && d->sh == 1 && d->sw == 1));
   return RSP_OK;
 }
 
