@@ -306,7 +306,9 @@ constexpr int kSWStageBytes = kSWDyBytes + kSWRowsMax * kStemRowBytes;
 __global__ void __launch_bounds__(160, 1) conv_stem_wgrad_kernel(const StemWgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kSWStages * kSWStageBytes);
+  // 1 KB of zeros follows the stages: pixels ow >= Wo of the last raw row are read (and multiplied by zero dY rows),
+  // so whatever lies behind it must be finite bf16 data, never barrier words
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kSWStages * kSWStageBytes + 1024);
   uint64_t* empty_bar = full_bar + kSWStages;
   uint64_t* accum_bar = empty_bar + kSWStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
@@ -319,7 +321,8 @@ __global__ void __launch_bounds__(160, 1) conv_stem_wgrad_kernel(const StemWgrad
   int iters = 0;
   for (int r = blockIdx.x; r < p.numRows; r += gridDim.x) ++iters;
 
-  for (int i = t; i < kSWStages * kSWStageBytes / 16; i += 160) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = t; i < (kSWStages * kSWStageBytes + 1024) / 16; i += 160)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (t == 0) {
     for (int s = 0; s < kSWStages; ++s) {
       mbar_init(&full_bar[s], 128);
@@ -374,23 +377,31 @@ __global__ void __launch_bounds__(160, 1) conv_stem_wgrad_kernel(const StemWgrad
       tc_fence_after_sync();
       const int lane = t & 31;
       const int co = warp * 16 + lane;
-      for (int fr = 0; fr < nrows; ++fr) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + fr * 32, v);
-        tmem_ld_wait();
-        if (lane < 16 && co < p.Co) {
-          const int a = a0 + fr / p.kh, b = fr % p.kh;
+      const int ncol = nrows * 8;
+      for (int j = 0; j < 4; ++j) {
+        for (int c0 = 0; c0 < ncol; c0 += 8) {
+          uint32_t v[8];
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                       : "r"(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + j * ncol + c0)
+                       : "memory");
+          tmem_ld_wait();
+          if (lane < 16 && co < p.Co) {
+            const int fr = c0 >> 3;
+            const int a = a0 + fr / p.kh, b = fr % p.kh;
 #pragma unroll
-          for (int qk = 0; qk < 32; ++qk) {
-            const int slot = qk >> 2, ch = qk & 3, c = slot - 1;
-            if (ch < p.Ci && c >= 0 && c < p.kw)
-              atomicAdd(p.dw + (((static_cast<size_t>(co) * p.Ci + ch) * p.kt + a) * p.kh + b) * p.kw + c,
-                        __uint_as_float(v[qk]));
+            for (int e = 0; e < 8; ++e) {
+              const int slot = 2 * j + (e >> 2), ch = e & 3, c = slot - 1;
+              if (ch < p.Ci && c >= 0 && c < p.kw)
+                atomicAdd(p.dw + (((static_cast<size_t>(co) * p.Ci + ch) * p.kt + a) * p.kh + b) * p.kw + c,
+                          __uint_as_float(v[e]));
+            }
           }
         }
       }
     } else {
-      constexpr uint32_t idesc = make_idesc_bf16(64, 32, 1, 1);
+      const int ncol = nrows * 8;                                    // accumulator columns per pixel-pair window
+      const uint32_t idesc = make_idesc_bf16(64, ncol, 1, 1);
       for (int it = 0; it < iters; ++it) {
         const int s = it % kSWStages;
         const uint32_t ph = (it / kSWStages) & 1;
@@ -399,18 +410,17 @@ __global__ void __launch_bounds__(160, 1) conv_stem_wgrad_kernel(const StemWgrad
         tc_fence_after_sync();
         if ((t & 31) == 0) {
           const uint32_t stage = smem_u32(smem + s * kSWStageBytes);
-          // A: 16 pixels = two 8-row groups of the swizzled panel; B: 16 pixels = 256 B along the raw row
+          // A: 16 pixels = two 8-row groups of the swizzled dY panel.
+          // B: N chunk = the same 2-pixel window (16 B) of every filter row (rows are 1 KB apart -> SBO = 1024), so one
+          //    instruction covers all nrows filter rows (N = 8*nrows <= 112); K: 8-pixel groups 128 B apart (LBO).
           const uint64_t abase = make_smem_desc_sw128(stage, 8192, 1024);
-          const uint64_t bbase = make_smem_desc_nosw(stage + kSWDyBytes, 128, 16);
-          for (int al = 0; al < na; ++al) {
+          const uint64_t bbase = make_smem_desc_nosw(stage + kSWDyBytes, 128, kStemRowBytes);
 #pragma unroll
-            for (int b = 0; b < 7; ++b) {
-              const int fr = al * 7 + b;
+          for (int j = 0; j < 4; ++j) {
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                umma_bf16(tmem_base + fr * 32, abase + static_cast<uint64_t>((ks * 2048) >> 4),
-                          bbase + static_cast<uint64_t>((fr * kStemRowBytes + ks * 256) >> 4), idesc, (it | ks) != 0);
-              }
+            for (int ks = 0; ks < 4; ++ks) {
+              umma_bf16(tmem_base + j * ncol, abase + static_cast<uint64_t>((ks * 2048) >> 4),
+                        bbase + static_cast<uint64_t>((j * 16 + ks * 256) >> 4), idesc, (it | ks) != 0);
             }
           }
           umma_commit(&empty_bar[s]);
@@ -446,7 +456,7 @@ int launch_stem_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, 
       return RSP_ERR_CUDA;
     }
   }
-  constexpr int smem = kSWStages * kSWStageBytes + 1024 + 256;
+  constexpr int smem = kSWStages * kSWStageBytes + 1024 + 1024 + 256;
   cudaError_t e = cudaFuncSetAttribute(conv_stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(conv_stem_wgrad): %s", cudaGetErrorString(e));
