@@ -106,9 +106,9 @@ def test_step_matches_reference_golden(name):
     assert (torch.stack([loss, ce, rank]).cpu() - rec["loss"]).abs().max() < 0.15
     first = (rec["queue_ptr"] - cfg["batch"]) % cfg["K"]
     assert (model.queue[:, first:first + cfg["batch"]].cpu() - rec["queue_cols"]).abs().max() < 0.03
-    # gradients of small tensors are stored in full in the fixture
-    named = dict(model.named_parameters())
-    checked = 0
+    # gradients of small tensors are stored in full in the fixture: per-tensor direction >= 0.80 (ill-conditioned at
+    # random init, see above) and direction of all of them taken together >= 0.95
+    checked, gots, refs = 0, [], []
     for k, ref in rec["grads"].items():
         if isinstance(ref, dict):
             continue
@@ -116,9 +116,14 @@ def test_step_matches_reference_golden(name):
         if ref.abs().max() < 1e-6:   # mathematically-zero gradients (conv bias before BN)
             assert got is None or got.abs().max() < 1e-3
             continue
-        assert _cos(got.cpu(), ref) > 0.90, (k, _cos(got.cpu(), ref))
+        assert _cos(got.cpu(), ref) > 0.80, (k, _cos(got.cpu(), ref))
+        gots.append(got.cpu().flatten())
+        refs.append(ref.flatten())
         checked += 1
     assert checked >= 10
+    overall = _cos(torch.cat(gots), torch.cat(refs))
+    print(f"[{name}] gradient cosine vs fp32 reference fixture over {checked} tensors: {overall:.4f}")
+    assert overall > 0.95, overall
     for k in rec["params_without_grad"]:
         assert named[k].grad is None, k
 
