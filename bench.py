@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--size", type=int, default=112)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
     return ap.parse_args()
 
 
@@ -235,7 +236,7 @@ def run_b200(args):
     launches = counter["n"]
 
     # ---- dominant kernel roofline: conv kernels (fprop+dgrad+wgrad) timed over a pass of the same shapes ------
-    roofline = conv_roofline(args, B, ms_step)
+    roofline = None if args.no_roofline else conv_roofline(args, B, ms_step)
 
     # ---- end to end from pinned host memory --------------------------------------------------------------------
     e2e = None

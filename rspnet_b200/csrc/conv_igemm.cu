@@ -38,6 +38,11 @@ struct GatherGeom {
   int fast;                  // 1: source offset is linear in the tap (fprop, or dgrad with unit strides) and k <= 8
   unsigned long long mulW, mulH, mulT;  // ceil(2^sh / d) for row decoding without integer division
   int shW, shH, shT;
+  // strided dgrad runs once per parity class of the destination grid (unit-stride problem in class space):
+  int cls;                   // 1: the fields below are active
+  int wa0, was, wb0, wbs, wc0, wcs, wkh, wkw;   // class tap (a,b,c) -> real filter tap (wa0+was*a, ...), real kh / kw
+  int oT, oH, oW;            // full destination grid
+  int ost, osh, osw, oot, ooh, oow;             // class pixel (t,h,w) -> real pixel (ost*t + oot, ...)
 };
 
 __device__ __forceinline__ uint32_t fdiv(uint32_t n, unsigned long long mul, int sh) {
@@ -83,6 +88,7 @@ struct ConvParams {
   __nv_bfloat16* out;        // [M][Nout]
   const float* bias;         // [Nout] or null
   int Nout;
+  int wgtKb;                 // K blocks per filter row of `wgt` (== g.numKb unless a parity class uses a tap subset)
 };
 
 struct WgradParams {
@@ -257,7 +263,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvParams p
 
   if (warp < 4) {
     // ---------------- producers ----------------
-    const size_t ldw = static_cast<size_t>(numKb) * 64;
+    const size_t ldw = static_cast<size_t>(p.wgtKb) * 64;
     if (MODE == MODE_GENERIC && g.fast) {
       // fast path: ~10 instructions per 16 B copy (row state precomputed, taps advanced incrementally)
       const int chunk = t & 7;
@@ -284,7 +290,10 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvParams p
           const __nv_bfloat16* src = g.src + (v ? static_cast<ptrdiff_t>(rbase[i] + koff) : 0);
           cp_async16(a_panel + i * 2048, src, v << 4);
         }
-        const __nv_bfloat16* wsrc = wrow + static_cast<size_t>(kb) * 64;
+        const int kbw = g.cls ? (((g.wa0 + g.was * a) * g.wkh + (g.wb0 + g.wbs * b)) * g.wkw + (g.wc0 + g.wcs * c)) *
+                                        cchunks + cc
+                              : kb;
+        const __nv_bfloat16* wsrc = wrow + static_cast<size_t>(kbw) * 64;
 #pragma unroll
         for (int i = 0; i < NT / 16; ++i) cp_async16(a_panel + A_BYTES + i * 2048, wsrc + i * wstep, 16u);
         cp_async_mbar_arrive(&full_bar[s]);
@@ -324,7 +333,14 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvParams p
     tc_fence_after_sync();
     const long long row = m0 + warp * 32 + (t & 31);
     const bool row_ok = row < g.M;
-    __nv_bfloat16* orow = p.out + static_cast<size_t>(row_ok ? row : 0) * p.Nout + n0;
+    size_t opix = static_cast<size_t>(row_ok ? row : 0);
+    if (g.cls && row_ok) {
+      int n, td, hd, wd;
+      decode_fast(g, static_cast<uint32_t>(row), n, td, hd, wd);
+      opix = ((static_cast<size_t>(n) * g.oT + td * g.ost + g.oot) * g.oH + hd * g.osh + g.ooh) * g.oW + wd * g.osw +
+             g.oow;
+    }
+    __nv_bfloat16* orow = p.out + opix * p.Nout + n0;
 #pragma unroll 1
     for (int c0 = 0; c0 < NT; c0 += 32) {
       uint32_t v[32];
@@ -682,6 +698,7 @@ static int conv_mode(const rsp_conv3d_desc* d) { return d->Ci == 4 ? MODE_SMALLC
 
 template <int NT, int STAGES, int MODE>
 static int launch_igemm(const ConvParams& p, cudaStream_t stream) {
+  if (p.g.M == 0) return RSP_OK;
   constexpr int smem = STAGES * (128 * 128 + NT * 128) + 1024 + 256;
   auto kern = conv_igemm_kernel<NT, STAGES, MODE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -695,7 +712,8 @@ static int launch_igemm(const ConvParams& p, cudaStream_t stream) {
 }
 
 template <int MODE>
-static int dispatch_igemm(const ConvParams& p, cudaStream_t stream) {
+static int dispatch_igemm(ConvParams& p, cudaStream_t stream, int wgtKb = 0) {
+  p.wgtKb = wgtKb > 0 ? wgtKb : p.g.numKb;
   if (p.Nout % 128 == 0) return launch_igemm<128, 3, MODE>(p, stream);
   return launch_igemm<64, 4, MODE>(p, stream);
 }
@@ -809,10 +827,87 @@ int rsp_conv3d_fprop(const rsp_conv3d_desc* d, const void* x, const void* wp, co
   return mode == MODE_GENERIC ? dispatch_igemm<MODE_GENERIC>(p, stream) : dispatch_igemm<MODE_SMALLC>(p, stream);
 }
 
+// One parity class of a strided dgrad: destination pixels (st*t'+par_t, ...) only see the taps a = a0 + st*i with
+// a0 = (par_t + pt) % st, and source (dY) index t' + (par_t + pt - a0)/st - i: a unit-stride transposed conv in class space.
+static int dgrad_class(const rsp_conv3d_desc* d, const int par[3], const void* dy, const void* wd, void* dx,
+                       cudaStream_t stream) {
+  const int k[3] = {d->kt, d->kh, d->kw}, s[3] = {d->st, d->sh, d->sw}, pd[3] = {d->pt, d->ph, d->pw};
+  const int in[3] = {d->Ti, d->Hi, d->Wi};
+  int a0[3], na[3], off[3], cd[3];
+  for (int i = 0; i < 3; ++i) {
+    a0[i] = (par[i] + pd[i]) % s[i];
+    na[i] = a0[i] < k[i] ? (k[i] - a0[i] + s[i] - 1) / s[i] : 0;
+    off[i] = (par[i] + pd[i] - a0[i]) / s[i];
+    cd[i] = in[i] > par[i] ? (in[i] - par[i] + s[i] - 1) / s[i] : 0;
+    if (na[i] == 0 || cd[i] == 0) return RSP_OK;  // no tap reaches this class: dx stays zero (memset by the caller)
+  }
+  ConvParams p{};
+  GatherGeom& g = p.g;
+  g.N = d->N;
+  g.Ts = (d->Ti + 2 * d->pt - d->kt) / d->st + 1;
+  g.Hs = (d->Hi + 2 * d->ph - d->kh) / d->sh + 1;
+  g.Ws = (d->Wi + 2 * d->pw - d->kw) / d->sw + 1;
+  g.Cs = d->Co;
+  g.Td = cd[0]; g.Hd = cd[1]; g.Wd = cd[2];
+  g.kt = na[0]; g.kh = na[1]; g.kw = na[2];
+  g.st = g.sh = g.sw = 1;
+  g.pt = off[0]; g.ph = off[1]; g.pw = off[2];
+  g.transposed = 1;
+  g.pxs = 0;
+  g.M = static_cast<long long>(g.N) * g.Td * g.Hd * g.Wd;
+  g.numKb = na[0] * na[1] * na[2] * (g.Cs / 64);
+  auto recip = [](int dd, unsigned long long& mul, int& sh) {
+    int l = 0;
+    while ((1ll << l) < dd) ++l;
+    sh = 32 + l;
+    mul = ((1ull << sh) + dd - 1) / dd;
+  };
+  recip(g.Wd, g.mulW, g.shW);
+  recip(g.Hd, g.mulH, g.shH);
+  recip(g.Td, g.mulT, g.shT);
+  g.fast = 1;
+  g.cls = 1;
+  g.wa0 = a0[0]; g.was = s[0]; g.wb0 = a0[1]; g.wbs = s[1]; g.wc0 = a0[2]; g.wcs = s[2];
+  g.wkh = d->kh; g.wkw = d->kw;
+  g.oT = d->Ti; g.oH = d->Hi; g.oW = d->Wi;
+  g.ost = s[0]; g.osh = s[1]; g.osw = s[2];
+  g.oot = par[0]; g.ooh = par[1]; g.oow = par[2];
+  g.src = static_cast<const __nv_bfloat16*>(dy);
+  p.wgt = static_cast<const __nv_bfloat16*>(wd);
+  p.out = static_cast<__nv_bfloat16*>(dx);
+  p.bias = nullptr;
+  p.Nout = d->Ci;
+  // the kernel addresses filter rows with the full K extent of the dgrad operand
+  return dispatch_igemm<MODE_GENERIC>(p, stream, d->kt * d->kh * d->kw * (d->Co / 64));
+}
+
 int rsp_conv3d_dgrad(const rsp_conv3d_desc* d, const void* dy, const void* wd, void* dx, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ConvParams p{};
   RSP_REQUIRE(d->Ci % 64 == 0 && d->Co % 64 == 0, "conv3d dgrad: Ci=%d, Co=%d must be multiples of 64", d->Ci, d->Co);
+  if ((d->st > 1 || d->sh > 1 || d->sw > 1) && d->kt <= 8 && d->kh <= 8 && d->kw <= 8) {
+    const long long To = (d->Ti + 2 * d->pt - d->kt) / d->st + 1, Ho = (d->Hi + 2 * d->ph - d->kh) / d->sh + 1,
+                    Wo = (d->Wi + 2 * d->pw - d->kw) / d->sw + 1;
+    RSP_REQUIRE(To > 0 && Ho > 0 && Wo > 0, "conv3d dgrad: empty output");
+    RSP_REQUIRE(static_cast<long long>(d->N) * To * Ho * Wo * d->Co < (1ll << 31) &&
+                    static_cast<long long>(d->N) * d->Ti * d->Hi * d->Wi < (1ll << 31),
+                "conv3d dgrad: tensor too large");
+    if (d->kt < d->st || d->kh < d->sh || d->kw < d->sw) {  // some parity classes receive nothing
+      cudaError_t e = cudaMemsetAsync(dx, 0, static_cast<size_t>(d->N) * d->Ti * d->Hi * d->Wi * d->Ci * 2, stream);
+      if (e != cudaSuccess) {
+        set_error("dgrad memset: %s", cudaGetErrorString(e));
+        return RSP_ERR_CUDA;
+      }
+    }
+    for (int a = 0; a < d->st; ++a)
+      for (int b = 0; b < d->sh; ++b)
+        for (int c = 0; c < d->sw; ++c) {
+          const int par[3] = {a, b, c};
+          int rc = dgrad_class(d, par, dy, wd, dx, stream);
+          if (rc != RSP_OK) return rc;
+        }
+    return RSP_OK;
+  }
   int rc = fill_geom(p.g, d, MODE_GENERIC, 1);
   if (rc != RSP_OK) return rc;
   p.g.src = static_cast<const __nv_bfloat16*>(dy);
