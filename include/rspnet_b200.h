@@ -51,11 +51,15 @@ int64_t rsp_conv3d_packed_elems(const rsp_conv3d_desc* d, int which);
  * (dgrad).  wp must hold rsp_conv3d_packed_elems(d, which) elements. */
 int rsp_conv3d_pack_weight(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const float* w, void* wp,
                            int which, void* stream);
+/* Bytes of the fp32 split-K accumulation buffer fprop (which = 0) / dgrad (which = 1) want for this geometry
+ * (0: the K loop is not split). Passing NULL as workspace is always legal and disables split-K. */
+int64_t rsp_conv3d_workspace_bytes(const rsp_conv3d_desc* d, int which);
 /* y[N,To,Ho,Wo,Co] = conv(x[N,Ti,Hi,Wi,Ci], wp) (+ bias[Co] fp32, may be NULL). */
 int rsp_conv3d_fprop(const rsp_conv3d_desc* d, const void* x, const void* wp, const float* bias, void* y,
-                     void* stream);
+                     void* workspace, void* stream);
 /* dx[N,Ti,Hi,Wi,Ci] = conv_transpose(dy[N,To,Ho,Wo,Co], wd). Strides must be powers of two. */
-int rsp_conv3d_dgrad(const rsp_conv3d_desc* d, const void* dy, const void* wd, void* dx, void* stream);
+int rsp_conv3d_dgrad(const rsp_conv3d_desc* d, const void* dy, const void* wd, void* dx, void* workspace,
+                     void* stream);
 /* dw fp32 [Co_logical][Ci_logical][kt][kh][kw] (=, or += when accumulate) from x and dy.
  * dwt_workspace: fp32 [kpad(0)][Co], overwritten. */
 int rsp_conv3d_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const void* x, const void* dy,

@@ -21,6 +21,8 @@
 
 namespace rsp {
 
+int device_sm_count();
+
 constexpr int kProducerThreads = 128;
 constexpr int kThreads = 160;  // 4 producer/epilogue warps + 1 MMA warp
 
@@ -89,6 +91,8 @@ struct ConvParams {
   const float* bias;         // [Nout] or null
   int Nout;
   int wgtKb;                 // K blocks per filter row of `wgt` (== g.numKb unless a parity class uses a tap subset)
+  float* acc;                // split-K: fp32 [M][Nout] accumulation buffer (zeroed by the host), else null
+  int kbPerSplit;            // K blocks handled by one z-slice
 };
 
 struct WgradParams {
@@ -245,7 +249,9 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvParams p
   const long long m0 = static_cast<long long>(blockIdx.x) * 128;
   const int n0 = blockIdx.y * NT;
   const GatherGeom& g = p.g;
-  const int numKb = g.numKb;
+  // split-K: z-slice handles K blocks [kbBegin, kbBegin + numKb)
+  const int kbBegin = blockIdx.z * p.kbPerSplit;
+  const int numKb = (g.numKb - kbBegin) < p.kbPerSplit ? (g.numKb - kbBegin) : p.kbPerSplit;
 
   if (t == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -276,7 +282,12 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvParams p
       const size_t wstep = 16 * ldw;
       const int dirCs = g.transposed ? -g.Cs : g.Cs;
       const int cchunks = g.Cs >> 6;
-      int a = 0, b = 0, c = 0, cc = 0;
+      int cc = kbBegin % cchunks;
+      int tap = kbBegin / cchunks;
+      int c = tap % g.kw;
+      tap /= g.kw;
+      int b = tap % g.kh;
+      int a = tap / g.kh;
       for (int kb = 0; kb < numKb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -292,7 +303,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvParams p
         }
         const int kbw = g.cls ? (((g.wa0 + g.was * a) * g.wkh + (g.wb0 + g.wbs * b)) * g.wkw + (g.wc0 + g.wcs * c)) *
                                         cchunks + cc
-                              : kb;
+                              : kbBegin + kb;
         const __nv_bfloat16* wsrc = wrow + static_cast<size_t>(kbw) * 64;
 #pragma unroll
         for (int i = 0; i < NT / 16; ++i) cp_async16(a_panel + A_BYTES + i * 2048, wsrc + i * wstep, 16u);
@@ -322,8 +333,8 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvParams p
         mbar_wait(&empty_bar[s], ph ^ 1);
         const uint32_t a_panel = smem_u32(smem + s * STAGE_BYTES);
         const uint32_t b_panel = a_panel + A_BYTES;
-        gather_panel<MODE, 128>(g, a_panel, kb, t, rows);
-        load_rows<NT>(b_panel, p.wgt + static_cast<size_t>(kb) * 64, n0, p.Nout, ldw, t);
+        gather_panel<MODE, 128>(g, a_panel, kbBegin + kb, t, rows);
+        load_rows<NT>(b_panel, p.wgt + static_cast<size_t>(kbBegin + kb) * 64, n0, p.Nout, ldw, t);
         cp_async_mbar_arrive(&full_bar[s]);
         mbar_arrive(&full_bar[s]);
       }
@@ -346,7 +357,15 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvParams p
       uint32_t v[32];
       tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
       tmem_ld_wait();
-      if (row_ok) {
+      if (row_ok && p.acc) {
+        float* arow = p.acc + opix * p.Nout + n0 + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(arow + j), "f"(__uint_as_float(v[j])),
+                       "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                       : "memory");
+        }
+      } else if (row_ok) {
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           float f[8];
@@ -696,9 +715,49 @@ static int fill_geom(GatherGeom& g, const rsp_conv3d_desc* d, int mode, int tran
 
 static int conv_mode(const rsp_conv3d_desc* d) { return d->Ci == 4 ? MODE_SMALLC : MODE_GENERIC; }
 
+// split-K finalize: out = bf16(acc + bias)
+__global__ void __launch_bounds__(256) splitk_finalize_kernel(const float4* __restrict__ acc,
+                                                              const float* __restrict__ bias,
+                                                              uint2* __restrict__ out, size_t n4, int Nout) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * 256) {
+    float4 v = acc[i];
+    if (bias) {
+      int c = static_cast<int>((i * 4) % Nout);
+      v.x += bias[c]; v.y += bias[c + 1]; v.z += bias[c + 2]; v.w += bias[c + 3];
+    }
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    out[i] = o;
+  }
+}
+
+static int choose_splits(long long M, int Nout, int NT, int numKb, int sm_count) {
+  const long long ctas = ((M + 127) / 128) * (Nout / NT);
+  if (ctas * 2 > sm_count || numKb < 16) return 1;     // at least half a wave already, or K too short to split
+  long long s = (2ll * sm_count + ctas - 1) / ctas;    // aim at ~2 CTAs per SM
+  if (s > numKb / 8) s = numKb / 8;
+  if (s > 16) s = 16;
+  return s < 1 ? 1 : static_cast<int>(s);
+}
+
 template <int NT, int STAGES, int MODE>
-static int launch_igemm(const ConvParams& p, cudaStream_t stream) {
+static int launch_igemm(ConvParams& p, cudaStream_t stream) {
   if (p.g.M == 0) return RSP_OK;
+  int splits = 1;
+  if (p.acc && !p.g.cls) splits = choose_splits(p.g.M, p.Nout, NT, p.g.numKb, device_sm_count());
+  float* acc = splits > 1 ? p.acc : nullptr;
+  p.acc = acc;
+  p.kbPerSplit = (p.g.numKb + splits - 1) / splits;
+  splits = (p.g.numKb + p.kbPerSplit - 1) / p.kbPerSplit;
+  if (acc) {
+    cudaError_t e = cudaMemsetAsync(acc, 0, static_cast<size_t>(p.g.M) * p.Nout * sizeof(float), stream);
+    if (e != cudaSuccess) {
+      set_error("split-K memset: %s", cudaGetErrorString(e));
+      return RSP_ERR_CUDA;
+    }
+  }
   constexpr int smem = STAGES * (128 * 128 + NT * 128) + 1024 + 256;
   auto kern = conv_igemm_kernel<NT, STAGES, MODE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -706,9 +765,17 @@ static int launch_igemm(const ConvParams& p, cudaStream_t stream) {
     set_error("cudaFuncSetAttribute(conv_igemm): %s", cudaGetErrorString(e));
     return RSP_ERR_CUDA;
   }
-  dim3 grid(static_cast<unsigned>((p.g.M + 127) / 128), static_cast<unsigned>(p.Nout / NT));
+  dim3 grid(static_cast<unsigned>((p.g.M + 127) / 128), static_cast<unsigned>(p.Nout / NT),
+            static_cast<unsigned>(splits));
   kern<<<grid, kThreads, smem, stream>>>(p);
-  return check_launch("conv_igemm");
+  int rc = check_launch("conv_igemm");
+  if (rc != RSP_OK || !acc) return rc;
+  const size_t n4 = static_cast<size_t>(p.g.M) * p.Nout / 4;
+  unsigned fg = static_cast<unsigned>((n4 + 255) / 256);
+  if (fg > 148u * 8) fg = 148u * 8;
+  splitk_finalize_kernel<<<fg, 256, 0, stream>>>(reinterpret_cast<const float4*>(acc), p.bias,
+                                                 reinterpret_cast<uint2*>(p.out), n4, p.Nout);
+  return check_launch("splitk_finalize");
 }
 
 template <int MODE>
@@ -807,8 +874,23 @@ int rsp_conv3d_pack_weight(const rsp_conv3d_desc* d, int Ci_logical, int Co_logi
   return check_launch("pack_weight_dgrad");
 }
 
+int64_t rsp_conv3d_workspace_bytes(const rsp_conv3d_desc* d, int which) {
+  // which = 0: fprop (M = output pixels, N = Co); which = 1: dgrad (M = input pixels, N = Ci). 0 when split-K is unused.
+  const long long To = (d->Ti + 2 * d->pt - d->kt) / d->st + 1, Ho = (d->Hi + 2 * d->ph - d->kh) / d->sh + 1,
+                  Wo = (d->Wi + 2 * d->pw - d->kw) / d->sw + 1;
+  const long long M = which == 0 ? d->N * To * Ho * Wo : static_cast<long long>(d->N) * d->Ti * d->Hi * d->Wi;
+  const int Nout = which == 0 ? d->Co : d->Ci;
+  const int Cs = which == 0 ? d->Ci : d->Co;
+  if (Cs % 64 != 0 || Nout % 64 != 0) return 0;
+  if (which == 1 && (d->st > 1 || d->sh > 1 || d->sw > 1)) return 0;
+  const int NT = Nout % 128 == 0 ? 128 : 64;
+  const int numKb = d->kt * d->kh * d->kw * (Cs / 64);
+  if (choose_splits(M, Nout, NT, numKb, device_sm_count()) <= 1) return 0;
+  return M * Nout * static_cast<long long>(sizeof(float));
+}
+
 int rsp_conv3d_fprop(const rsp_conv3d_desc* d, const void* x, const void* wp, const float* bias, void* y,
-                     void* stream_) {
+                     void* workspace, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int mode = conv_mode(d);
   ConvParams p{};
@@ -824,6 +906,7 @@ int rsp_conv3d_fprop(const rsp_conv3d_desc* d, const void* x, const void* wp, co
   p.out = static_cast<__nv_bfloat16*>(y);
   p.bias = bias;
   p.Nout = d->Co;
+  p.acc = mode == MODE_GENERIC ? static_cast<float*>(workspace) : nullptr;
   return mode == MODE_GENERIC ? dispatch_igemm<MODE_GENERIC>(p, stream) : dispatch_igemm<MODE_SMALLC>(p, stream);
 }
 
@@ -881,7 +964,8 @@ static int dgrad_class(const rsp_conv3d_desc* d, const int par[3], const void* d
   return dispatch_igemm<MODE_GENERIC>(p, stream, d->kt * d->kh * d->kw * (d->Co / 64));
 }
 
-int rsp_conv3d_dgrad(const rsp_conv3d_desc* d, const void* dy, const void* wd, void* dx, void* stream_) {
+int rsp_conv3d_dgrad(const rsp_conv3d_desc* d, const void* dy, const void* wd, void* dx, void* workspace,
+                     void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ConvParams p{};
   RSP_REQUIRE(d->Ci % 64 == 0 && d->Co % 64 == 0, "conv3d dgrad: Ci=%d, Co=%d must be multiples of 64", d->Ci, d->Co);
@@ -915,6 +999,7 @@ int rsp_conv3d_dgrad(const rsp_conv3d_desc* d, const void* dy, const void* wd, v
   p.out = static_cast<__nv_bfloat16*>(dx);
   p.bias = nullptr;
   p.Nout = d->Ci;
+  p.acc = static_cast<float*>(workspace);
   return dispatch_igemm<MODE_GENERIC>(p, stream);
 }
 

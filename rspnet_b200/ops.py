@@ -43,18 +43,27 @@ def conv3d_pack_weight(desc: ConvDesc, weight: torch.Tensor, which: int = 0) -> 
     return out
 
 
+def _splitk_workspace(desc: ConvDesc, which: int, device):
+    """fp32 accumulation buffer for split-K on small-M layers (None when the library does not want one)."""
+    _lib._ensure_device()
+    n = _lib.load().rsp_conv3d_workspace_bytes(C.byref(desc), which)
+    return torch.empty((n // 4,), dtype=torch.float32, device=device) if n > 0 else None
+
+
 def conv3d_fprop(desc: ConvDesc, x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor] = None):
     assert x.dtype == torch.bfloat16 and x.is_contiguous()
     to, ho, wo = desc.out_dims()
     y = torch.empty((desc.N, to, ho, wo, desc.Co), dtype=torch.bfloat16, device=x.device)
-    call("rsp_conv3d_fprop", C.byref(desc), ptr(x), ptr(wp), ptr(bias), ptr(y), stream_ptr())
+    ws = _splitk_workspace(desc, 0, x.device)
+    call("rsp_conv3d_fprop", C.byref(desc), ptr(x), ptr(wp), ptr(bias), ptr(y), ptr(ws), stream_ptr())
     return y
 
 
 def conv3d_dgrad(desc: ConvDesc, dy: torch.Tensor, wd: torch.Tensor):
     assert dy.dtype == torch.bfloat16 and dy.is_contiguous()
     dx = torch.empty((desc.N, desc.Ti, desc.Hi, desc.Wi, desc.Ci), dtype=torch.bfloat16, device=dy.device)
-    call("rsp_conv3d_dgrad", C.byref(desc), ptr(dy), ptr(wd), ptr(dx), stream_ptr())
+    ws = _splitk_workspace(desc, 1, dy.device)
+    call("rsp_conv3d_dgrad", C.byref(desc), ptr(dy), ptr(wd), ptr(dx), ptr(ws), stream_ptr())
     return dx
 
 
