@@ -113,10 +113,37 @@ int rsp_head_bwd(const float* dout1, const float* dout2, const float* pooled, co
                  float* dw1, float* db1, float* dw2, float* db2, void* dfeat, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * S3D-G (reference: models/s3dg.py). Self-gating of sep_conv (:54-72): gate = sigmoid(W * mean_S(x) + b), y = x*gate.
+ * x, y, dy, dx bf16 [N][S][C]; w fp32 [C_logical][C_logical] (the 1x1x1 excitation conv), b fp32 [C_logical];
+ * sums_ws / dgate_ws / dadd_ws fp32 [N][C] scratch; pooled fp32 [N][C_logical]; gate fp32 [N][C]; dw, db: +=.
+ * rsp_copy_channels moves a channel range between NDHWC tensors (inception concat :96 and its backward).
+ * ------------------------------------------------------------------------------------------------ */
+int rsp_gate_fwd(const void* x, int32_t N, int32_t S, int32_t C, int32_t C_logical, const float* w, const float* b,
+                 float* sums_ws, float* pooled, float* gate, void* y, void* stream);
+int rsp_gate_bwd(const void* dy, const void* x, int32_t N, int32_t S, int32_t C, int32_t C_logical, const float* w,
+                 const float* pooled, const float* gate, float* dgate_ws, float* dadd_ws, float* dw, float* db,
+                 void* dx, void* stream);
+int rsp_copy_channels(const void* src, int32_t c_src, int32_t src_off, void* dst, int32_t c_dst, int32_t dst_off,
+                      int32_t n_ch, int64_t M, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Layout: fp32 NCDHW [N][C][T][H][W] <-> bf16 NDHWC [N][T][H][W][Cs] (zero padded channels).
  * ------------------------------------------------------------------------------------------------ */
 int rsp_ncdhw_to_ndhwc_bf16(const float* x, void* y, int32_t N, int32_t C, int32_t Cs, int64_t THW, void* stream);
 int rsp_ndhwc_bf16_to_ncdhw(const void* x, float* y, int32_t N, int32_t C, int32_t Cs, int64_t THW, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * On-GPU clip pipeline (reference: datasets/transforms_video/transforms_tensor.py:214-233 per-clip loop applying
+ * ToTensorVideo, Resize (transforms_spatial.py:16-25, bilinear, align_corners=False), RandomGrayScale
+ * (transforms_tensor.py:13-31), RandomHorizontalFlipVideo, NormalizeVideo; crop boxes from RawVideoRandomCrop
+ * (transforms_spatial.py:42-83), frame indices from RandomStrideCrop (transforms_temporal.py:25-50)).
+ * frames: uint8 [F][Hs][Ws][3] decoded frame pool; frame_idx int32 [n_clips][T] rows of the pool;
+ * box int32 [n_clips][4] = (i, j, h, w); flags uint8 [n_clips]: bit0 = horizontal flip, bit1 = grayscale;
+ * mean3/std3: HOST pointers to 3 floats. layout 0: out fp32 [n_clips][3][T][S][S]; 1: bf16 [n_clips][T][S][S][4].
+ * ------------------------------------------------------------------------------------------------ */
+int rsp_clip_sample(const uint8_t* frames, const int32_t* frame_idx, const int32_t* box, const uint8_t* flags,
+                    const float* mean3, const float* std3, int32_t n_clips, int32_t T, int32_t Hs, int32_t Ws,
+                    int32_t S, int32_t layout, void* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * MoCo / RSP objective (reference: moco/builder_diffspeed_diffloss.py)

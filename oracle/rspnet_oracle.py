@@ -77,7 +77,71 @@ def c3d_feature(x, sd: State, p: str, train=True):
     return x
 
 
-FEATURES = {"resnet18": resnet18_feature, "c3d": c3d_feature}
+def r2plus1d_feature(x, sd: State, p: str, train=True):
+    """models/r2plus1d_vcop.py:218-224 (get_feature) with R2Plus1DNet((1,1,1,1)): SpatioTemporalConv (:13-72) =
+    (1,k,k) conv -> BN -> ReLU -> (k,1,1) conv; SpatioTemporalResBlock (:75-123)."""
+    def stconv(x, name, k, stride, pad):
+        x = _conv(x, sd, name + ".spatial_conv", (1, stride[1], stride[2]), (0, pad[1], pad[2]))
+        x = _r(F.relu(_bn(x, sd, name + ".bn", train)))
+        return _conv(x, sd, name + ".temporal_conv", (stride[0], 1, 1), (pad[0], 0, 0))
+
+    x = stconv(x, p + "conv1", (3, 7, 7), (1, 2, 2), (1, 3, 3))
+    x = _r(F.relu(_bn(x, sd, p + "bn1", train)))
+    for li, down in ((2, False), (3, True), (4, True), (5, True)):
+        b = f"{p}conv{li}.block1."
+        s = (2, 2, 2) if down else (1, 1, 1)
+        res = stconv(x, b + "conv1", (3, 3, 3), s, (1, 1, 1))
+        res = _r(F.relu(_bn(res, sd, b + "bn1", train)))
+        res = stconv(res, b + "conv2", (3, 3, 3), (1, 1, 1), (1, 1, 1))
+        res = _bn(res, sd, b + "bn2", train)
+        if down:
+            x = stconv(x, b + "downsampleconv", (1, 1, 1), (2, 2, 2), (0, 0, 0))
+            x = _r(_bn(x, sd, b + "downsamplebn", train))
+        x = _r(F.relu(x + res))
+    return x
+
+
+_S3DG_INC = ["sepInc_3b", "sepInc_3c", "sepInc_4b", "sepInc_4c", "sepInc_4d", "sepInc_4e", "sepInc_4f", "sepInc_5b",
+             "sepInc_5c"]
+
+
+def s3dg_feature(x, sd: State, p: str, train=True):
+    """models/s3dg.py:151-153 (get_feature): BasicConv3d (:6-33, BN eps 1e-3 momentum 0.001), sep_conv with
+    self-gating (:36-72), sep_inc (:74-99), feature stack (:105-121)."""
+    def basic(x, name, stride=(1, 1, 1), pad=(0, 0, 0)):
+        y = _conv(x, sd, name + ".conv3d", stride, pad)
+        return _r(F.relu(_bn(y, sd, name + ".bn", train, eps=1e-3, momentum=0.001)))
+
+    def sep(x, name, k, stride, pad):
+        x = basic(x, name + ".sep_conv.0", (stride, stride, stride), (0, pad, pad))
+        x = basic(x, name + ".sep_conv.1", (1, 1, 1), (pad, 0, 0))
+        w = x.mean(dim=(2, 3, 4), keepdim=True)
+        w = torch.sigmoid(F.conv3d(w, sd[name + ".excitation.weight"], sd[name + ".excitation.bias"]))
+        return _r(w * x)
+
+    def inc(x, name):
+        o0 = basic(x, name + ".branch0")
+        o1 = sep(basic(x, name + ".branch1.0"), name + ".branch1.1", 3, 1, 1)
+        o2 = sep(basic(x, name + ".branch2.0"), name + ".branch2.1", 3, 1, 1)
+        o3 = basic(F.max_pool3d(x, 3, 1, 1), name + ".branch3.1")
+        return torch.cat((o0, o1, o2, o3), 1)
+
+    f = p + "feature."
+    x = sep(x, f + "sepConv1", 7, 2, 3)
+    x = F.max_pool3d(x, (1, 3, 3), (1, 2, 2), (0, 1, 1))
+    x = basic(x, f + "basicConv3d")
+    x = sep(x, f + "sep_conv2", 3, 1, 1)
+    x = F.max_pool3d(x, (1, 3, 3), (1, 2, 2), (0, 1, 1))
+    x = inc(inc(x, f + "sepInc_3b"), f + "sepInc_3c")
+    x = F.max_pool3d(x, 3, 2, 1)
+    for n in _S3DG_INC[2:7]:
+        x = inc(x, f + n)
+    x = F.max_pool3d(x, 2, 2, 0)
+    return inc(inc(x, f + "sepInc_5b"), f + "sepInc_5c")
+
+
+FEATURES = {"resnet18": resnet18_feature, "c3d": c3d_feature, "r2plus1d-vcop": r2plus1d_feature,
+            "s3dg": s3dg_feature}
 
 
 def wrapper_forward(arch: str, x, sd: State, p: str, train=True):
@@ -213,7 +277,7 @@ def train_step(arch: str, sds: List[State], im_q: List[torch.Tensor], im_k: List
         la, lm = logits(q_a, q_m, kpos[r][0], kpos[r][1], kneg[r][0], kneg[r][1], sds[r]["queue"], T)
         total, ce, rank = loss(la, lm, margin, A, M)
         used = [n for n in names if not n.startswith("encoder_q.encoder.fc.") and
-                not n.startswith("encoder_q.encoder.linear.")]
+                not n.startswith("encoder_q.encoder.linear.")]  # classifier heads are never on the path
         gs = torch.autograd.grad(total, [leaves[n] for n in used], allow_unused=True)
         g = {n: (t if t is not None else torch.zeros_like(leaves[n])) for n, t in zip(used, gs)}
         grads = g if grads is None else {n: grads[n] + g[n] for n in g}

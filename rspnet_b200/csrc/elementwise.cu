@@ -598,3 +598,298 @@ int rsp_ndhwc_bf16_to_ncdhw(const void* x, float* y, int32_t N, int32_t C, int32
 }
 
 }  // extern "C"
+
+// =====================================================================================================================
+// On-GPU clip pipeline (reference: per-clip python loop of SequentialGPUCollateFn, datasets/transforms_video/
+// transforms_tensor.py:214-233, applying ToTensorVideo -> Resize(bilinear, align_corners=False) -> RandomGrayScale ->
+// RandomHorizontalFlip -> Normalize; crop boxes from RawVideoRandomCrop, frame indices from RandomStrideCrop).
+// One launch for the whole batch: every output pixel gathers its 4 bilinear taps straight from the decoded uint8 frame
+// pool through the per-clip descriptors.
+// =====================================================================================================================
+namespace rsp {
+
+struct ClipGeom {
+  int T, Hs, Ws, S;
+  float mean[3], inv_std_unused[3], stdv[3];
+};
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(256) clip_sample_kernel(const uint8_t* __restrict__ frames,
+                                                          const int32_t* __restrict__ frame_idx,
+                                                          const int32_t* __restrict__ box,
+                                                          const uint8_t* __restrict__ flags, ClipGeom g,
+                                                          void* __restrict__ outv, size_t total) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * 256) {
+    const int x = static_cast<int>(i % g.S);
+    size_t q = i / g.S;
+    const int y = static_cast<int>(q % g.S);
+    q /= g.S;
+    const int t = static_cast<int>(q % g.T);
+    const int clip = static_cast<int>(q / g.T);
+    const int bi = box[clip * 4 + 0], bj = box[clip * 4 + 1], bh = box[clip * 4 + 2], bw = box[clip * 4 + 3];
+    const uint8_t fl = flags[clip];
+    const int xs = (fl & 1) ? (g.S - 1 - x) : x;                 // horizontal flip acts on the resized clip
+    // torch upsample_bilinear2d, align_corners=False: src = scale*(dst+0.5)-0.5 clamped at 0
+    const float sh = static_cast<float>(bh) / g.S, sw = static_cast<float>(bw) / g.S;
+    float fy = sh * (y + 0.5f) - 0.5f, fx = sw * (xs + 0.5f) - 0.5f;
+    fy = fy < 0.f ? 0.f : fy;
+    fx = fx < 0.f ? 0.f : fx;
+    const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+    const int y1 = y0 + (y0 < bh - 1 ? 1 : 0), x1 = x0 + (x0 < bw - 1 ? 1 : 0);
+    const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
+    const uint8_t* f = frames + static_cast<size_t>(frame_idx[clip * g.T + t]) * g.Hs * g.Ws * 3;
+    const uint8_t* p00 = f + (static_cast<size_t>(bi + y0) * g.Ws + bj + x0) * 3;
+    const uint8_t* p01 = f + (static_cast<size_t>(bi + y0) * g.Ws + bj + x1) * 3;
+    const uint8_t* p10 = f + (static_cast<size_t>(bi + y1) * g.Ws + bj + x0) * 3;
+    const uint8_t* p11 = f + (static_cast<size_t>(bi + y1) * g.Ws + bj + x1) * 3;
+    float v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float a = p00[c] / 255.0f, b = p01[c] / 255.0f, cc = p10[c] / 255.0f, d = p11[c] / 255.0f;
+      v[c] = hy * (hx * a + lx * b) + ly * (hx * cc + lx * d);
+    }
+    if (fl & 2) {  // RandomGrayScale: ITU-R 601-2 luma, replicated on the three channels
+      const float gray = 0.2989f * v[0] + 0.5870f * v[1] + 0.1140f * v[2];
+      v[0] = v[1] = v[2] = gray;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = (v[c] - g.mean[c]) / g.stdv[c];
+    if (LAYOUT == 0) {
+      float* out = static_cast<float*>(outv);
+      const size_t plane = static_cast<size_t>(g.T) * g.S * g.S;
+      const size_t o = (static_cast<size_t>(clip) * 3 * g.T + t) * g.S * g.S + static_cast<size_t>(y) * g.S + x;
+      out[o] = v[0];
+      out[o + plane] = v[1];
+      out[o + 2 * plane] = v[2];
+    } else {
+      uint2 w;
+      w.x = pack_bf16x2(v[0], v[1]);
+      w.y = pack_bf16x2(v[2], 0.f);
+      static_cast<uint2*>(outv)[i] = w;
+    }
+  }
+}
+
+}  // namespace rsp
+
+extern "C" int rsp_clip_sample(const uint8_t* frames, const int32_t* frame_idx, const int32_t* box,
+                               const uint8_t* flags, const float* mean3, const float* std3, int32_t n_clips, int32_t T,
+                               int32_t Hs, int32_t Ws, int32_t S, int32_t layout, void* out, void* stream) {
+  RSP_REQUIRE(n_clips >= 0 && T > 0 && Hs > 0 && Ws > 0 && S > 0, "clip_sample: bad sizes");
+  RSP_REQUIRE(layout == 0 || layout == 1, "clip_sample: layout must be 0 (fp32 NCDHW) or 1 (bf16 NDHWC4)");
+  size_t total = static_cast<size_t>(n_clips) * T * S * S;
+  if (total == 0) return rsp::RSP_OK;
+  rsp::ClipGeom g{};
+  g.T = T; g.Hs = Hs; g.Ws = Ws; g.S = S;
+  for (int c = 0; c < 3; ++c) {
+    g.mean[c] = mean3[c];
+    g.stdv[c] = std3[c];
+  }
+  unsigned grid = rsp::ew_grid(total, 256);
+  if (layout == 0)
+    rsp::clip_sample_kernel<0><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(frames, frame_idx, box, flags, g,
+                                                                                     out, total);
+  else
+    rsp::clip_sample_kernel<1><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(frames, frame_idx, box, flags, g,
+                                                                                     out, total);
+  return rsp::check_launch("clip_sample");
+}
+
+// =====================================================================================================================
+// S3D-G pieces (reference: models/s3dg.py): self-gating of sep_conv (:54-72: AdaptiveAvgPool3d(1) -> 1x1x1 conv with
+// bias -> sigmoid -> broadcast multiply) and the inception channel concat (:96, torch.cat(dim=1)).
+// Activations bf16 [N][S][C] (S = T*H*W positions, C stored channels); gate statistics fp32 [N][C].
+// =====================================================================================================================
+namespace rsp {
+
+// MODE 0: out[n][c] = sum_s x[n][s][c];  MODE 1: out[n][c] = sum_s x[n][s][c] * y[n][s][c]
+// grid: (chunks over S, N); each thread owns one 8-channel group and strides over positions; fp32 atomics per block.
+template <int MODE>
+__global__ void __launch_bounds__(256) sample_channel_sum_kernel(const uint4* __restrict__ x,
+                                                                 const uint4* __restrict__ y, int S, int C,
+                                                                 float* __restrict__ out) {
+  const int G = C >> 3;
+  const int rows_per_iter = 256 / G;
+  const int g = threadIdx.x % G, rsub = threadIdx.x / G;
+  const int n = blockIdx.y;
+  const uint4* xb = x + static_cast<size_t>(n) * S * G;
+  const uint4* yb = MODE ? y + static_cast<size_t>(n) * S * G : nullptr;
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = 0.f;
+  for (int s = blockIdx.x * rows_per_iter + rsub; s < S; s += gridDim.x * rows_per_iter) {
+    float xv[8], yv[8];
+    unpack8(__ldg(xb + static_cast<size_t>(s) * G + g), xv);
+    if (MODE) unpack8(__ldg(yb + static_cast<size_t>(s) * G + g), yv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] += MODE ? xv[i] * yv[i] : xv[i];
+  }
+  __shared__ float sa[256 * 8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sa[threadIdx.x * 8 + i] = a[i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float s0 = 0.f;
+    for (int r = 0; r < rows_per_iter; ++r) s0 += sa[(r * G + (c >> 3)) * 8 + (c & 7)];
+    atomicAdd(out + static_cast<size_t>(n) * C + c, s0);
+  }
+}
+
+// gate[n][c] = sigmoid(b[c] + sum_k W[c][k] * mean[n][k]);  block per sample
+__global__ void __launch_bounds__(256) gate_linear_fwd_kernel(const float* __restrict__ sums, float inv_s,
+                                                              const float* __restrict__ w, const float* __restrict__ b,
+                                                              int C, int Cl, float* __restrict__ pooled,
+                                                              float* __restrict__ gate) {
+  extern __shared__ float sp[];
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < Cl; c += 256) {
+    float m = sums[static_cast<size_t>(n) * C + c] * inv_s;
+    sp[c] = m;
+    pooled[static_cast<size_t>(n) * Cl + c] = m;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float g = 0.f;
+    if (c < Cl) {
+      float z = b[c];
+      const float* wr = w + static_cast<size_t>(c) * Cl;
+      for (int k = 0; k < Cl; ++k) z = fmaf(wr[k], sp[k], z);
+      g = 1.f / (1.f + __expf(-z));
+    }
+    gate[static_cast<size_t>(n) * C + c] = g;
+  }
+}
+
+// y = x * gate[n][c]   (MODE 0)        dx = dy * gate[n][c] + add[n][c]   (MODE 1)
+template <int MODE>
+__global__ void __launch_bounds__(256) gate_scale_kernel(const uint4* __restrict__ x, const float* __restrict__ gate,
+                                                         const float* __restrict__ add, uint4* __restrict__ out,
+                                                         size_t nvec, int S, int C) {
+  const int G = C >> 3;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < nvec;
+       i += static_cast<size_t>(gridDim.x) * 256) {
+    const int g = static_cast<int>(i % G);
+    const size_t n = i / (static_cast<size_t>(S) * G);
+    const float* gr = gate + n * C + g * 8;
+    float v[8];
+    unpack8(__ldg(x + i), v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = MODE ? fmaf(v[e], gr[e], add[n * C + g * 8 + e]) : v[e] * gr[e];
+    out[i] = pack8(v);
+  }
+}
+
+// backward of the gate linear: dz = dgate * g * (1-g); dW += dz^T pooled; db += dz; dmean_over_S[n][k] = (dz W)[k] / S
+__global__ void __launch_bounds__(256) gate_linear_bwd_kernel(const float* __restrict__ dgate,
+                                                              const float* __restrict__ gate,
+                                                              const float* __restrict__ pooled,
+                                                              const float* __restrict__ w, int C, int Cl, float inv_s,
+                                                              float* __restrict__ dw, float* __restrict__ db,
+                                                              float* __restrict__ dadd) {
+  extern __shared__ float sm[];
+  float* dz = sm;        // [Cl]
+  float* sp = sm + Cl;   // [Cl]
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < Cl; c += 256) {
+    float g = gate[static_cast<size_t>(n) * C + c];
+    dz[c] = dgate[static_cast<size_t>(n) * C + c] * g * (1.f - g);
+    sp[c] = pooled[static_cast<size_t>(n) * Cl + c];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < Cl; c += 256) atomicAdd(db + c, dz[c]);
+  for (int i = threadIdx.x; i < Cl * Cl; i += 256) {
+    int c = i / Cl, k = i - c * Cl;
+    atomicAdd(dw + i, dz[c] * sp[k]);
+  }
+  for (int k = threadIdx.x; k < C; k += 256) {
+    float a = 0.f;
+    if (k < Cl)
+      for (int c = 0; c < Cl; ++c) a = fmaf(dz[c], w[static_cast<size_t>(c) * Cl + k], a);
+    dadd[static_cast<size_t>(n) * C + k] = a * inv_s;
+  }
+}
+
+// dst[m][dst_off + j] = src[m][src_off + j], j < n_ch, 8-channel (16 B) granularity
+__global__ void __launch_bounds__(256) copy_channels_kernel(const uint4* __restrict__ src, int src_g, int src_off_g,
+                                                            uint4* __restrict__ dst, int dst_g, int dst_off_g,
+                                                            int n_g, size_t total) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * 256) {
+    const size_t m = i / n_g;
+    const int j = static_cast<int>(i - m * n_g);
+    dst[m * dst_g + dst_off_g + j] = __ldg(src + m * src_g + src_off_g + j);
+  }
+}
+
+}  // namespace rsp
+
+extern "C" {
+
+int rsp_gate_fwd(const void* x, int32_t N, int32_t S, int32_t C, int32_t C_logical, const float* w, const float* b,
+                 float* sums_ws, float* pooled, float* gate, void* y, void* stream_) {
+  using namespace rsp;
+  int rc = check_c(C, "gate_fwd");
+  if (rc != RSP_OK) return rc;
+  RSP_REQUIRE(N > 0 && S > 0 && C_logical <= C && C_logical * sizeof(float) <= 48 * 1024, "gate_fwd: bad sizes");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  cudaError_t e = cudaMemsetAsync(sums_ws, 0, static_cast<size_t>(N) * C * sizeof(float), stream);
+  if (e != cudaSuccess) {
+    set_error("gate_fwd memset: %s", cudaGetErrorString(e));
+    return RSP_ERR_CUDA;
+  }
+  const int rows_per_iter = 256 / (C / 8);
+  int gx = (S + rows_per_iter * 8 - 1) / (rows_per_iter * 8);
+  if (gx < 1) gx = 1;
+  if (gx > 64) gx = 64;
+  sample_channel_sum_kernel<0><<<dim3(gx, N), 256, 0, stream>>>(static_cast<const uint4*>(x), nullptr, S, C, sums_ws);
+  gate_linear_fwd_kernel<<<N, 256, C_logical * sizeof(float), stream>>>(sums_ws, 1.f / S, w, b, C, C_logical, pooled,
+                                                                        gate);
+  size_t nvec = static_cast<size_t>(N) * S * (C / 8);
+  gate_scale_kernel<0><<<ew_grid(nvec, 256), 256, 0, stream>>>(static_cast<const uint4*>(x), gate, nullptr,
+                                                               static_cast<uint4*>(y), nvec, S, C);
+  return check_launch("gate_fwd");
+}
+
+int rsp_gate_bwd(const void* dy, const void* x, int32_t N, int32_t S, int32_t C, int32_t C_logical, const float* w,
+                 const float* pooled, const float* gate, float* dgate_ws, float* dadd_ws, float* dw, float* db,
+                 void* dx, void* stream_) {
+  using namespace rsp;
+  int rc = check_c(C, "gate_bwd");
+  if (rc != RSP_OK) return rc;
+  RSP_REQUIRE(N > 0 && S > 0 && C_logical <= C && 2 * C_logical * sizeof(float) <= 48 * 1024, "gate_bwd: bad sizes");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  cudaError_t e = cudaMemsetAsync(dgate_ws, 0, static_cast<size_t>(N) * C * sizeof(float), stream);
+  if (e != cudaSuccess) {
+    set_error("gate_bwd memset: %s", cudaGetErrorString(e));
+    return RSP_ERR_CUDA;
+  }
+  const int rows_per_iter = 256 / (C / 8);
+  int gx = (S + rows_per_iter * 8 - 1) / (rows_per_iter * 8);
+  if (gx < 1) gx = 1;
+  if (gx > 64) gx = 64;
+  sample_channel_sum_kernel<1><<<dim3(gx, N), 256, 0, stream>>>(static_cast<const uint4*>(dy),
+                                                                 static_cast<const uint4*>(x), S, C, dgate_ws);
+  gate_linear_bwd_kernel<<<N, 256, 2 * C_logical * sizeof(float), stream>>>(dgate_ws, gate, pooled, w, C, C_logical,
+                                                                            1.f / S, dw, db, dadd_ws);
+  size_t nvec = static_cast<size_t>(N) * S * (C / 8);
+  gate_scale_kernel<1><<<ew_grid(nvec, 256), 256, 0, stream>>>(static_cast<const uint4*>(dy), gate, dadd_ws,
+                                                               static_cast<uint4*>(dx), nvec, S, C);
+  return check_launch("gate_bwd");
+}
+
+int rsp_copy_channels(const void* src, int32_t c_src, int32_t src_off, void* dst, int32_t c_dst, int32_t dst_off,
+                      int32_t n_ch, int64_t M, void* stream) {
+  using namespace rsp;
+  RSP_REQUIRE(c_src % 8 == 0 && c_dst % 8 == 0 && src_off % 8 == 0 && dst_off % 8 == 0 && n_ch % 8 == 0 &&
+                  src_off + n_ch <= c_src && dst_off + n_ch <= c_dst,
+              "copy_channels: channel ranges must be multiples of 8 and in range");
+  size_t total = static_cast<size_t>(M) * (n_ch / 8);
+  if (total == 0) return RSP_OK;
+  copy_channels_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(src), c_src / 8, src_off / 8, static_cast<uint4*>(dst), c_dst / 8, dst_off / 8,
+      n_ch / 8, total);
+  return check_launch("copy_channels");
+}
+
+}  // extern "C"

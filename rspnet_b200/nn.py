@@ -178,3 +178,57 @@ def as_ndhwc(x: torch.Tensor) -> torch.Tensor:
     if not x.is_cuda:
         raise RuntimeError("rspnet_b200: forward needs CUDA tensors (there is no CPU path)")
     return ToNDHWC.apply(x, ops.pad_channels(x.shape[1]))
+
+
+class GateFn(torch.autograd.Function):
+    """S3D-G self-gating: y = x * sigmoid(excitation(mean_{T,H,W} x))  (models/s3dg.py:64-72)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, c_logical):
+        y, pooled, gate = ops.gate_fwd(x, c_logical, weight, bias)
+        ctx.c_logical = c_logical
+        ctx.wshape = tuple(weight.shape)
+        ctx.save_for_backward(x, weight, pooled, gate)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, pooled, gate = ctx.saved_tensors
+        dx, dw, db = ops.gate_bwd(dy.contiguous(), x, ctx.c_logical, weight, pooled, gate)
+        return dx, dw.view(ctx.wshape), db, None
+
+
+class ConcatChannelsFn(torch.autograd.Function):
+    """torch.cat(dim=1) of NDHWC tensors with zero-padded channels: logical channels are packed back to back."""
+
+    @staticmethod
+    def forward(ctx, logical, *xs):
+        total = sum(logical)
+        cs = ops.pad_channels(total)
+        out = torch.zeros(tuple(xs[0].shape[:-1]) + (cs,), dtype=torch.bfloat16, device=xs[0].device)
+        off = 0
+        for x, cl in zip(xs, logical):
+            ops.copy_channels(x, 0, out, off, cl)
+            off += cl
+        ctx.logical = logical
+        ctx.stored = [x.shape[-1] for x in xs]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = dout.contiguous()
+        grads, off = [], 0
+        for cl, cs in zip(ctx.logical, ctx.stored):
+            g = torch.zeros(tuple(dout.shape[:-1]) + (cs,), dtype=torch.bfloat16, device=dout.device) if cs != cl \
+                else torch.empty(tuple(dout.shape[:-1]) + (cs,), dtype=torch.bfloat16, device=dout.device)
+            ops.copy_channels(dout, off, g, 0, cl)
+            grads.append(g)
+            off += cl
+        return (None, *grads)
+
+
+def concat_channels(xs, logical):
+    for cl in logical:
+        if cl % 8:
+            raise NotImplementedError("rspnet_b200: channel concat needs multiples of 8 channels per branch")
+    return ConcatChannelsFn.apply(tuple(logical), *xs)

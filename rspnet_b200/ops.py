@@ -281,3 +281,38 @@ def ce0_bwd(logits, lse, g_scalar):
     out = torch.empty_like(logits)
     call("rsp_ce0_bwd", ptr(logits), ptr(lse), n, l, ptr(g_scalar), ptr(out), stream_ptr())
     return out
+
+
+# ------------------------------------------------------------------------------------------------ S3D-G
+def gate_fwd(x: torch.Tensor, c_logical: int, w: torch.Tensor, b: torch.Tensor):
+    """Self-gating (models/s3dg.py:64-72): y = x * sigmoid(W mean_S(x) + b). Returns y, pooled, gate."""
+    n, c = x.shape[0], x.shape[-1]
+    s = x.numel() // (n * c)
+    dev = x.device
+    sums = torch.empty((n, c), dtype=torch.float32, device=dev)
+    pooled = torch.empty((n, c_logical), dtype=torch.float32, device=dev)
+    gate = torch.empty((n, c), dtype=torch.float32, device=dev)
+    y = torch.empty_like(x)
+    w2 = w.detach().reshape(c_logical, c_logical).contiguous().float()
+    call("rsp_gate_fwd", ptr(x), n, s, c, c_logical, ptr(w2), ptr(b), ptr(sums), ptr(pooled), ptr(gate), ptr(y),
+         stream_ptr())
+    return y, pooled, gate
+
+
+def gate_bwd(dy, x, c_logical, w, pooled, gate):
+    n, c = x.shape[0], x.shape[-1]
+    s = x.numel() // (n * c)
+    dev = x.device
+    ws = torch.empty((2, n, c), dtype=torch.float32, device=dev)
+    dw = torch.zeros((c_logical, c_logical), dtype=torch.float32, device=dev)
+    db = torch.zeros((c_logical,), dtype=torch.float32, device=dev)
+    dx = torch.empty_like(x)
+    w2 = w.detach().reshape(c_logical, c_logical).contiguous().float()
+    call("rsp_gate_bwd", ptr(dy), ptr(x), n, s, c, c_logical, ptr(w2), ptr(pooled), ptr(gate), ptr(ws[0]), ptr(ws[1]),
+         ptr(dw), ptr(db), ptr(dx), stream_ptr())
+    return dx, dw, db
+
+
+def copy_channels(src, src_off, dst, dst_off, n_ch):
+    m = src.numel() // src.shape[-1]
+    call("rsp_copy_channels", ptr(src), src.shape[-1], src_off, ptr(dst), dst.shape[-1], dst_off, n_ch, m, stream_ptr())

@@ -1,0 +1,166 @@
+"""On-GPU clip sampling for the pretraining loader (subsystem 4 of the hot path).
+
+Host side: the reference's random decisions, drawn from python's ``random`` in the reference's order
+(SURVEY.md appendix B): per video ``RandomStrideCrop`` twice (two clips; datasets/transforms_video/
+transforms_temporal.py:25-50, fallback :16-22), then per clip ``RawVideoRandomCrop.get_params``
+(transforms_spatial.py:50-83), then per clip on the main process ``RandomGrayScale`` and
+``RandomHorizontalFlipVideo`` (transforms_tensor.py:13-31; torchvision).  Device side: ONE kernel
+(``rsp_clip_sample``) replaces the per-clip loop of ``SequentialGPUCollateFn`` (transforms_tensor.py:214-233):
+uint8 frame gather + crop + bilinear resize + gray + flip + normalise for the whole batch.
+
+ColorJitter (brightness/contrast/saturation/hue in random order) is the "next" row of SURVEY.md §8f and is not
+implemented: construct the sampler from a config patched with ``add.no_color_jitter``.
+"""
+import ctypes as C
+import math
+import random
+from bisect import bisect_left
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream_ptr
+
+
+def calc_needed_frames(size: int, stride: int) -> int:
+    return (size - 1) * stride + 1
+
+
+def fallback_select(size: int, stride: int, num_frames: int):
+    """Short videos: wrap around, or spread evenly (transforms_temporal.py:16-22)."""
+    assert num_frames > 0, 'No frames in video'
+    if num_frames <= size:
+        return np.arange(size) % num_frames
+    if num_frames < calc_needed_frames(size, stride):
+        return np.linspace(0, num_frames - 1, num=size).round().astype(int)
+    return None
+
+
+class RandomStrideCrop:
+    """``size`` frame indices at a stride drawn from a weighted list; draws: random.random() then random.randint()."""
+
+    def __init__(self, size: int, strides=({'stride': 1, 'weight': 1},)):
+        self.size = size
+        self.set_strides(strides)
+
+    def set_strides(self, strides=({'stride': 1, 'weight': 1},)):
+        self.strides = [dict(s) for s in strides]
+        total = sum(s['weight'] for s in self.strides)
+        acc, self.prefix_weight_sum = 0, []
+        for s in self.strides:
+            s['weight'] /= total
+            acc += s['weight']
+            self.prefix_weight_sum.append(acc)
+
+    def set_size(self, size: int):
+        self.size = size
+
+    def __call__(self, frame_indices: np.ndarray) -> np.ndarray:
+        num_frames = len(frame_indices)
+        stride = self.strides[bisect_left(self.prefix_weight_sum, random.random())]['stride']
+        selected = fallback_select(self.size, stride, num_frames)
+        if selected is None:
+            needed = calc_needed_frames(self.size, stride)
+            start = random.randint(0, num_frames - needed)
+            selected = np.arange(start, start + needed, stride)
+        return frame_indices[selected]
+
+
+class RawVideoRandomCrop:
+    """Random-resized-crop box on the raw frame (scale / log-uniform ratio, 10 tries, centre fallback)."""
+
+    def __init__(self, scale=(0.08, 1.0), ratio=(3. / 4., 4. / 3.)):
+        self.scale = scale
+        self.ratio = ratio
+
+    def get_params(self, height: int, width: int) -> Tuple[int, int, int, int]:
+        area = height * width
+        for _ in range(10):
+            target_area = random.uniform(*self.scale) * area
+            log_ratio = (math.log(self.ratio[0]), math.log(self.ratio[1]))
+            aspect_ratio = math.exp(random.uniform(*log_ratio))
+            w = int(round(math.sqrt(target_area * aspect_ratio)))
+            h = int(round(math.sqrt(target_area / aspect_ratio)))
+            if 0 < w <= width and 0 < h <= height:
+                i = random.randint(0, height - h)
+                j = random.randint(0, width - w)
+                return i, j, h, w
+        in_ratio = float(width) / float(height)
+        if in_ratio < min(self.ratio):
+            w = width
+            h = int(round(w / min(self.ratio)))
+        elif in_ratio > max(self.ratio):
+            h = height
+            w = int(round(h * max(self.ratio)))
+        else:
+            w, h = width, height
+        return (height - h) // 2, (width - w) // 2, h, w
+
+
+def clip_sample(frames: torch.Tensor, frame_idx: torch.Tensor, boxes: torch.Tensor, flags: torch.Tensor,
+                mean: Sequence[float], std: Sequence[float], size: int, layout: int = 0) -> torch.Tensor:
+    """frames uint8 [F,H,W,3] (device); frame_idx int32 [n,T]; boxes int32 [n,4]; flags uint8 [n]."""
+    assert frames.dtype == torch.uint8 and frames.is_contiguous() and frames.shape[-1] == 3
+    n, t = frame_idx.shape
+    _, hs, ws, _ = frames.shape
+    dev = frames.device
+    if layout == 0:
+        out = torch.empty((n, 3, t, size, size), dtype=torch.float32, device=dev)
+    else:
+        out = torch.empty((n, t, size, size, 4), dtype=torch.bfloat16, device=dev)
+    m3 = (C.c_float * 3)(*[float(v) for v in mean])
+    s3 = (C.c_float * 3)(*[float(v) for v in std])
+    call("rsp_clip_sample", ptr(frames), ptr(frame_idx), ptr(boxes), ptr(flags), m3, s3, n, t, hs, ws, size, layout,
+         ptr(out), stream_ptr())
+    return out
+
+
+class GPUClipSampler:
+    """Produces the loader contract ``((clip_q, clip_k), None)`` (datasets/classification/__init__.py:22-50) from a
+    device-resident pool of decoded uint8 frames: ``frames`` [F,H,W,3] with ``video_offsets``/``video_lengths``
+    describing where each video's frames live."""
+
+    def __init__(self, size: int = 112, temporal_size: int = 32, strides=({'stride': 1, 'weight': 1},),
+                 crop_scale=(0.4, 1.0), gray_p: float = 0.2, flip_p: float = 0.5,
+                 mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
+        self.size = size
+        self.temporal = RandomStrideCrop(temporal_size, strides)
+        self.crop = RawVideoRandomCrop(scale=crop_scale)
+        self.gray_p, self.flip_p = gray_p, flip_p
+        self.mean, self.std = list(mean), list(std)
+
+    def draw(self, video_lengths: Sequence[int], height: int, width: int):
+        """All random decisions for one batch, in the reference's order. Returns numpy arrays in clip-major layout
+        [2][B]: frame indices (video-relative), boxes, flags."""
+        b = len(video_lengths)
+        t = self.temporal.size
+        idx = np.zeros((2, b, t), dtype=np.int32)
+        box = np.zeros((2, b, 4), dtype=np.int32)
+        flags = np.zeros((2, b), dtype=np.uint8)
+        for v, n_frames in enumerate(video_lengths):          # worker side: per video
+            base = np.arange(n_frames)
+            for c in range(2):
+                idx[c, v] = self.temporal(base)
+            for c in range(2):
+                box[c, v] = self.crop.get_params(height, width)
+        for v in range(b):                                     # main process: per video, per clip GPU transforms
+            for c in range(2):
+                gray = random.random() < self.gray_p
+                flip = random.random() < self.flip_p
+                flags[c, v] = (1 if flip else 0) | (2 if gray else 0)
+        return idx, box, flags
+
+    def __call__(self, frames: torch.Tensor, video_offsets: Sequence[int], video_lengths: Sequence[int],
+                 layout: int = 0):
+        _, h, w, _ = frames.shape
+        idx, box, flags = self.draw(video_lengths, h, w)
+        b = len(video_lengths)
+        idx = idx + np.asarray(video_offsets, dtype=np.int32)[None, :, None]
+        dev = frames.device
+        t_idx = torch.from_numpy(idx.reshape(2 * b, -1)).to(dev, non_blocking=True)
+        t_box = torch.from_numpy(box.reshape(2 * b, 4)).to(dev, non_blocking=True)
+        t_flags = torch.from_numpy(flags.reshape(2 * b)).to(dev, non_blocking=True)
+        out = clip_sample(frames, t_idx, t_box, t_flags, self.mean, self.std, self.size, layout)
+        return (out[:b], out[b:]), None

@@ -290,3 +290,46 @@ def test_conv3d_fprop_dgrad_wgrad(n, ci, co, dims, k, s, p):
     if cis % 64 == 0:
         dx = ops.conv3d_dgrad(desc, dyn, ops.conv3d_pack_weight(desc, w, 1))
         close(ops.to_ncdhw_f32(dx, ci), xr.grad, 1e-2)
+
+
+# ------------------------------------------------------------------------------------------------ S3D-G pieces
+@pytest.mark.parametrize("c_l", [64, 208, 24])
+def test_gate_fwd_bwd(c_l):
+    ops = _ops()
+    n, t, h, w = 3, 2, 5, 4
+    x = rand(n, c_l, t, h, w, seed=1)
+    wt, b = rand(c_l, c_l, 1, 1, 1, seed=2, scale=c_l ** -0.5), rand(c_l, seed=3)
+    xr = x.bfloat16().float().requires_grad_(True)
+    wr, br = wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    g = torch.sigmoid(F.conv3d(xr.mean(dim=(2, 3, 4), keepdim=True), wr, br))
+    y = g * xr
+    dy = rand(n, c_l, t, h, w, seed=4)
+    y.backward(dy.bfloat16().float())
+    cs = ops.pad_channels(c_l)
+    xn = ops.to_ndhwc_bf16(x, cs)
+    yo, pooled, gate = ops.gate_fwd(xn, c_l, wt, b)
+    torch.testing.assert_close(ops.to_ncdhw_f32(yo, c_l), y.detach(), rtol=2e-2, atol=2e-2)
+    dx, dw, db = ops.gate_bwd(ops.to_ndhwc_bf16(dy, cs), xn, c_l, wt, pooled, gate)
+    torch.testing.assert_close(ops.to_ncdhw_f32(dx, c_l), xr.grad, rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(dw, wr.grad.view(c_l, c_l), rtol=2e-2, atol=2e-3)
+    torch.testing.assert_close(db, br.grad, rtol=2e-2, atol=2e-3)
+    if cs != c_l:
+        assert torch.count_nonzero(yo[..., c_l:]) == 0
+
+
+def test_concat_channels_fwd_bwd():
+    from rspnet_b200 import nn as rnn
+    ops = _ops()
+    widths = (64, 208, 48, 64)
+    xs = [rand(2, c, 2, 3, 3, seed=i) for i, c in enumerate(widths)]
+    xn = [ops.to_ndhwc_bf16(x).requires_grad_(True) for x in xs]
+    out = rnn.concat_channels(xn, widths)
+    ref = torch.cat([x.bfloat16().float() for x in xs], 1)
+    assert out.shape[-1] == 384
+    assert torch.equal(ops.to_ncdhw_f32(out, 384), ref)
+    gout = rand(2, 384, 2, 3, 3, seed=9)
+    out.backward(ops.to_ndhwc_bf16(gout, 384))
+    off = 0
+    for x, c in zip(xn, widths):
+        assert torch.equal(ops.to_ncdhw_f32(x.grad, c), gout[:, off:off + c].bfloat16().float())
+        off += c

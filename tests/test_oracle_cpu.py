@@ -9,7 +9,7 @@ import torch
 from helpers import build_product_moco, check_packed, load_golden, make_inputs, summarize
 from oracle import rspnet_oracle as oracle
 
-CASES = ["r3d18_w1", "r3d18_w2", "c3d_w1"]
+CASES = ["r3d18_w1", "r3d18_w2", "c3d_w1", "r2plus1d_w1", "s3dg_w1"]
 
 
 @pytest.mark.parametrize("name", CASES)

@@ -24,7 +24,7 @@ def _cos(a, b):
     return float((a @ b) / (a.norm() * b.norm() + 1e-30))
 
 
-@pytest.mark.parametrize("name", ["r3d18_w1", "c3d_w1"])
+@pytest.mark.parametrize("name", ["r3d18_w1", "c3d_w1", "r2plus1d_w1", "s3dg_w1"])
 def test_step_matches_reference_golden(name):
     from rspnet_b200.moco import Loss
     g = load_golden(name)
