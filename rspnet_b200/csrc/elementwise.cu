@@ -46,10 +46,11 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const uint4* __rest
                                                              const float* __restrict__ mean,
                                                              const float* __restrict__ invstd, int relu, size_t M,
                                                              int C, float* __restrict__ r0, float* __restrict__ r1) {
-  const int G = C >> 3;             // channel groups per row (divides 256)
+  const int G = C >> 3;             // channel groups per row (<= 256)
   const int rows_per_iter = 256 / G;
   const int g = threadIdx.x % G;
   const int rsub = threadIdx.x / G;
+  const bool active = rsub < rows_per_iter;   // threads beyond rows_per_iter*G idle (G need not divide 256)
   float a[8], b[8], mu[8], is[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const uint4* __rest
       is[i] = invstd[g * 8 + i];
     }
   }
-  for (size_t row = static_cast<size_t>(blockIdx.x) * rows_per_iter + rsub; row < M;
+  for (size_t row = static_cast<size_t>(blockIdx.x) * rows_per_iter + rsub; active && row < M;
        row += static_cast<size_t>(gridDim.x) * rows_per_iter) {
     size_t o = row * G + g;
     float xv[8];
@@ -454,7 +455,7 @@ __global__ void __launch_bounds__(256) ndhwc_to_ncdhw_kernel(const __nv_bfloat16
 }
 
 static int check_c(int C, const char* what) {
-  RSP_REQUIRE(C >= 8 && C % 8 == 0 && 256 % (C / 8) == 0, "%s: channel count %d unsupported (need C/8 to divide 256)",
+  RSP_REQUIRE(C >= 8 && C % 8 == 0 && C <= 2048, "%s: channel count %d unsupported (need a multiple of 8, <= 2048)",
               what, C);
   return RSP_OK;
 }
@@ -712,13 +713,14 @@ __global__ void __launch_bounds__(256) sample_channel_sum_kernel(const uint4* __
   const int G = C >> 3;
   const int rows_per_iter = 256 / G;
   const int g = threadIdx.x % G, rsub = threadIdx.x / G;
+  const bool active = rsub < rows_per_iter;
   const int n = blockIdx.y;
   const uint4* xb = x + static_cast<size_t>(n) * S * G;
   const uint4* yb = MODE ? y + static_cast<size_t>(n) * S * G : nullptr;
   float a[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) a[i] = 0.f;
-  for (int s = blockIdx.x * rows_per_iter + rsub; s < S; s += gridDim.x * rows_per_iter) {
+  for (int s = blockIdx.x * rows_per_iter + rsub; active && s < S; s += gridDim.x * rows_per_iter) {
     float xv[8], yv[8];
     unpack8(__ldg(xb + static_cast<size_t>(s) * G + g), xv);
     if (MODE) unpack8(__ldg(yb + static_cast<size_t>(s) * G + g), yv);

@@ -167,7 +167,8 @@ def test_moco_logits_loss_fwd_bwd(n, k):
 
 
 # ------------------------------------------------------------------------------------------------ BN / pool / head
-@pytest.mark.parametrize("c,relu,res", [(64, True, False), (128, True, True), (512, False, False), (256, True, True)])
+@pytest.mark.parametrize("c,relu,res", [(64, True, False), (128, True, True), (512, False, False), (256, True, True),
+                                        (192, True, False), (576, True, True)])
 def test_bn_act_fwd_bwd(c, relu, res):
     ops = _ops()
     n, t, h, w = 2, 3, 5, 7
