@@ -30,7 +30,7 @@ CONFIGS = {
     "r3d18_w2": dict(arch="resnet18", world=2, batch=2, frames=8, size=64, K=64, steps=2, seed=0),
     "c3d_w1": dict(arch="c3d", world=1, batch=2, frames=16, size=64, K=32, steps=2, seed=0),
     "r2plus1d_w1": dict(arch="r2plus1d-vcop", world=1, batch=2, frames=16, size=64, K=32, steps=1, seed=0),
-    "s3dg_w1": dict(arch="s3dg", world=1, batch=2, frames=16, size=64, K=32, steps=1, seed=0),
+    "s3dg_w1": dict(arch="s3dg", world=1, batch=4, frames=16, size=128, K=32, steps=1, seed=0),
 }
 HYPER = dict(dim=128, m=0.999, T=0.07, diff_speed=[2], margin=2.0, A=1.0, M=1.0, lr=0.1, momentum=0.9,
              weight_decay=1e-4)

@@ -72,7 +72,6 @@ def dbg_hb(d1, d2, pooled, raw, shape, w1, w2, want_dfeat=True):
     return r
 
 
-ops.moco_logits_bwd, ops.head_bwd = dbg_mlb, dbg_hb
 it = iter(draws)
 orig_rp = torch.randperm
 torch.randperm = lambda n, *a, **k: (lambda r: r.to(k["device"]) if "device" in k else r.clone())(next(it))
@@ -85,7 +84,6 @@ print("loss product", [float(loss), float(ce), float(rank)], "emu", [float(t) fo
 print("logits max diff vs emu", (out[0].detach().cpu() - emu["logits_a"][0][0]).abs().max().item(),
       "vs ref", (out[0].detach().cpu() - rec["logits1"]).abs().max().item())
 print("ORACLE q_a.k_a", (emu["q"][0][0] * emu["k"][0][0]).sum(1).tolist(), "logits_m", [t.flatten().tolist() for t in emu["logits_m"][0]])
-sys.exit(0)
 # forward: encoder_k pass 1 (k_neg), pass 2 (k), then encoder_q
 for nm in p_in:
     for i, (a, b) in enumerate(zip(p_in[nm], o_in.get(nm, []))):
