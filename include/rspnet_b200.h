@@ -54,9 +54,12 @@ int rsp_conv3d_pack_weight(const rsp_conv3d_desc* d, int Ci_logical, int Co_logi
 /* Bytes of the fp32 split-K accumulation buffer fprop (which = 0) / dgrad (which = 1) want for this geometry
  * (0: the K loop is not split). Passing NULL as workspace is always legal and disables split-K. */
 int64_t rsp_conv3d_workspace_bytes(const rsp_conv3d_desc* d, int which);
-/* y[N,To,Ho,Wo,Co] = conv(x[N,Ti,Hi,Wi,Ci], wp) (+ bias[Co] fp32, may be NULL). */
+/* y[N,To,Ho,Wo,Co] = conv(x[N,Ti,Hi,Wi,Ci], wp) (+ bias[Co] fp32, may be NULL).
+ * stats (may be NULL): fp32 [2][Co], the epilogue ADDS the per-channel sum and sum of squares of the stored bf16
+ * output (the BatchNorm batch statistics); ignored (left untouched) when split-K is active, i.e. when a non-NULL
+ * workspace is passed for a geometry with rsp_conv3d_workspace_bytes() > 0 — use rsp_bn_stats then. */
 int rsp_conv3d_fprop(const rsp_conv3d_desc* d, const void* x, const void* wp, const float* bias, void* y,
-                     void* workspace, void* stream);
+                     void* workspace, float* stats, void* stream);
 /* dx[N,Ti,Hi,Wi,Ci] = conv_transpose(dy[N,To,Ho,Wo,Co], wd). Strides must be powers of two. */
 int rsp_conv3d_dgrad(const rsp_conv3d_desc* d, const void* dy, const void* wd, void* dx, void* workspace,
                      void* stream);
@@ -73,10 +76,11 @@ int rsp_conv3d_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, c
 int rsp_bn_stats(const void* x, int64_t M, int32_t C, float* sum, float* sumsq, void* stream);
 /* mean/var from the sums; writes scale = gamma*invstd, shift = beta - mean*scale, mean, invstd, and updates
  * running_mean / running_var (unbiased) with `momentum` exactly like F.batch_norm(training=True).
- * running_* may be NULL. C_logical <= C: padded channels get scale = shift = 0. */
-int rsp_bn_finalize(const float* sum, const float* sumsq, int64_t count, const float* gamma, const float* beta,
-                    float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
-                    float* mean, float* invstd, int32_t C, int32_t C_logical, void* stream);
+ * running_* may be NULL. C_logical <= C: padded channels get scale = shift = 0.
+ * clear_sums != 0: sum / sumsq are reset to zero after being read (persistent accumulators, no memset needed). */
+int rsp_bn_finalize(float* sum, float* sumsq, int32_t clear_sums, int64_t count, const float* gamma,
+                    const float* beta, float eps, float momentum, float* running_mean, float* running_var, float* scale,
+                    float* shift, float* mean, float* invstd, int32_t C, int32_t C_logical, void* stream);
 /* out = act(x*scale + shift (+ residual)); relu != 0 applies max(0,.). residual may be NULL. */
 int rsp_bn_act_fwd(const void* x, const float* scale, const float* shift, const void* residual, int relu, void* out,
                    int64_t M, int32_t C, void* stream);

@@ -45,11 +45,11 @@ SIGNATURES = {
     "rsp_conv3d_packed_elems": (c_i64, [C.POINTER(ConvDesc), c_i32]),
     "rsp_conv3d_pack_weight": (c_i32, [C.POINTER(ConvDesc), c_i32, c_i32, _P, _P, c_i32, _P]),
     "rsp_conv3d_workspace_bytes": (c_i64, [C.POINTER(ConvDesc), c_i32]),
-    "rsp_conv3d_fprop": (c_i32, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
+    "rsp_conv3d_fprop": (c_i32, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P]),
     "rsp_conv3d_dgrad": (c_i32, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P]),
     "rsp_conv3d_wgrad": (c_i32, [C.POINTER(ConvDesc), c_i32, c_i32, _P, _P, _P, _P, c_i32, _P]),
     "rsp_bn_stats": (c_i32, [_P, c_i64, c_i32, _P, _P, _P]),
-    "rsp_bn_finalize": (c_i32, [_P, _P, c_i64, _P, _P, c_f32, c_f32, _P, _P, _P, _P, _P, _P, c_i32, c_i32, _P]),
+    "rsp_bn_finalize": (c_i32, [_P, _P, c_i32, c_i64, _P, _P, c_f32, c_f32, _P, _P, _P, _P, _P, _P, c_i32, c_i32, _P]),
     "rsp_bn_act_fwd": (c_i32, [_P, _P, _P, _P, c_i32, _P, c_i64, c_i32, _P]),
     "rsp_bn_act_bwd_reduce": (c_i32, [_P, _P, _P, _P, _P, c_i32, _P, _P, c_i64, c_i32, _P]),
     "rsp_bn_act_bwd_apply": (c_i32, [_P, _P, _P, _P, _P, _P, _P, _P, c_i32, _P, _P, c_i64, c_i32, c_i32, _P]),

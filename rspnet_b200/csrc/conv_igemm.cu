@@ -93,6 +93,7 @@ struct ConvParams {
   int wgtKb;                 // K blocks per filter row of `wgt` (== g.numKb unless a parity class uses a tap subset)
   float* acc;                // split-K: fp32 [M][Nout] accumulation buffer (zeroed by the host), else null
   int kbPerSplit;            // K blocks handled by one z-slice
+  float* stats;              // optional [2][Nout]: += per-channel sum / sum of squares of the stored (bf16) output
 };
 
 struct WgradParams {
@@ -243,6 +244,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvParams p
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* accum_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  float* red = reinterpret_cast<float*>(tmem_slot + 2);  // [2][NT] per-CTA channel sums (BN statistics)
 
   const int t = threadIdx.x;
   const int warp = t >> 5;
@@ -260,6 +262,9 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvParams p
     }
     mbar_init(accum_bar, 1);
     fence_mbar_init();
+  }
+  if (p.stats) {
+    for (int i = t; i < 2 * NT; i += kThreads) red[i] = 0.f;
   }
   if (warp == 4) tmem_alloc(tmem_slot, NT);
   tc_fence_before_sync();
@@ -365,7 +370,8 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvParams p
                        "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
                        : "memory");
         }
-      } else if (row_ok) {
+      } else {
+        float r[32];  // the values as stored (bias added, rounded to bf16); zero for rows beyond M
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           float f[8];
@@ -379,8 +385,32 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvParams p
           o.y = pack_bf16x2(f[2], f[3]);
           o.z = pack_bf16x2(f[4], f[5]);
           o.w = pack_bf16x2(f[6], f[7]);
-          *reinterpret_cast<uint4*>(orow + c0 + j) = o;
+          if (row_ok) *reinterpret_cast<uint4*>(orow + c0 + j) = o;
+          if (p.stats) {
+            const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              r[j + 2 * e] = row_ok ? __uint_as_float(w[e] << 16) : 0.f;
+              r[j + 2 * e + 1] = row_ok ? __uint_as_float(w[e] & 0xffff0000u) : 0.f;
+            }
+          }
         }
+        if (p.stats) {
+          float q[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) q[j] = r[j] * r[j];
+          warp_column_sums(r, t & 31);
+          warp_column_sums(q, t & 31);
+          atomicAdd(&red[c0 + (t & 31)], r[0]);
+          atomicAdd(&red[NT + c0 + (t & 31)], q[0]);
+        }
+      }
+    }
+    if (p.stats) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+      for (int i = t; i < NT; i += 128) {
+        atomicAdd(p.stats + n0 + i, red[i]);
+        atomicAdd(p.stats + p.Nout + n0 + i, red[NT + i]);
       }
     }
   } else {
@@ -749,6 +779,7 @@ static int launch_igemm(ConvParams& p, cudaStream_t stream) {
   if (p.acc && !p.g.cls) splits = choose_splits(p.g.M, p.Nout, NT, p.g.numKb, device_sm_count());
   float* acc = splits > 1 ? p.acc : nullptr;
   p.acc = acc;
+  if (acc) p.stats = nullptr;  // split-K partial tiles cannot produce statistics of the final values
   p.kbPerSplit = (p.g.numKb + splits - 1) / splits;
   splits = (p.g.numKb + p.kbPerSplit - 1) / p.kbPerSplit;
   if (acc) {
@@ -758,7 +789,7 @@ static int launch_igemm(ConvParams& p, cudaStream_t stream) {
       return RSP_ERR_CUDA;
     }
   }
-  constexpr int smem = STAGES * (128 * 128 + NT * 128) + 1024 + 256;
+  constexpr int smem = STAGES * (128 * 128 + NT * 128) + 1024 + 256 + 2 * NT * 4;
   auto kern = conv_igemm_kernel<NT, STAGES, MODE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) {
@@ -816,8 +847,8 @@ static int dispatch_wgrad(WgradParams& p, int sm_count, cudaStream_t stream) {
 
 int device_sm_count();
 bool stem_supported(const rsp_conv3d_desc* d);
-int launch_stem(const rsp_conv3d_desc* d, const void* x, const void* wst, const float* bias, void* y, int sm_count,
-                cudaStream_t stream);
+int launch_stem(const rsp_conv3d_desc* d, const void* x, const void* wst, const float* bias, void* y, float* stats,
+                int sm_count, cudaStream_t stream);
 int pack_stem(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const float* w, void* wst,
               cudaStream_t stream);
 int launch_stem_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const void* x, const void* dy,
@@ -890,7 +921,7 @@ int64_t rsp_conv3d_workspace_bytes(const rsp_conv3d_desc* d, int which) {
 }
 
 int rsp_conv3d_fprop(const rsp_conv3d_desc* d, const void* x, const void* wp, const float* bias, void* y,
-                     void* workspace, void* stream_) {
+                     void* workspace, float* stats, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int mode = conv_mode(d);
   ConvParams p{};
@@ -899,7 +930,7 @@ int rsp_conv3d_fprop(const rsp_conv3d_desc* d, const void* x, const void* wp, co
   RSP_REQUIRE(d->Co % 64 == 0, "conv3d fprop: Co=%d must be a multiple of 64", d->Co);
   if (stem_supported(d)) {
     const __nv_bfloat16* wst = static_cast<const __nv_bfloat16*>(wp) + static_cast<size_t>(d->Co) * p.g.numKb * 64;
-    return launch_stem(d, x, wst, bias, y, device_sm_count(), stream);
+    return launch_stem(d, x, wst, bias, y, stats, device_sm_count(), stream);
   }
   p.g.src = static_cast<const __nv_bfloat16*>(x);
   p.wgt = static_cast<const __nv_bfloat16*>(wp);
@@ -907,6 +938,7 @@ int rsp_conv3d_fprop(const rsp_conv3d_desc* d, const void* x, const void* wp, co
   p.bias = bias;
   p.Nout = d->Co;
   p.acc = mode == MODE_GENERIC ? static_cast<float*>(workspace) : nullptr;
+  p.stats = stats;
   return mode == MODE_GENERIC ? dispatch_igemm<MODE_GENERIC>(p, stream) : dispatch_igemm<MODE_SMALLC>(p, stream);
 }
 

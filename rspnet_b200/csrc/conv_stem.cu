@@ -25,6 +25,7 @@ struct StemParams {
   const __nv_bfloat16* wst;  // [kt][kh][4 kchunk][8 co-group][8 co][8 k] bf16
   __nv_bfloat16* y;          // [N][To][Ho][Wo][64]
   const float* bias;
+  float* stats;              // optional [2][64]: += per-channel sum / sum of squares of the stored output
   int N, Ti, Hi, Wi, To, Ho, Wo;
   int kt, kh, st, sh, pt, ph;
   int hq;        // ceil(Ho / 4)
@@ -129,6 +130,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
     // ------------------------------------------------------------------ epilogue
     const int ew = warp - 4;          // TMEM lane quarter
     const int lane = t & 31;
+    float ssum[2] = {0.f, 0.f}, ssq[2] = {0.f, 0.f};  // running channel sums: lane l <-> channels l and 32 + l
     uint32_t iter_ctr = 0;
     for (int it = blockIdx.x; it < p.numIters; it += gridDim.x, ++iter_ctr) {
       const int buf = iter_ctr & 1;
@@ -150,27 +152,50 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
           uint32_t v[32];
           tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * 128 + m * 64 + c0, v);
           tmem_ld_wait();
-          if (ok) {
+          float r[32];
 #pragma unroll
-            for (int jx = 0; jx < 32; jx += 8) {
-              float f[8];
+          for (int jx = 0; jx < 32; jx += 8) {
+            float f[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                f[e] = __uint_as_float(v[jx + e]);
-                if (p.bias) f[e] += __ldg(p.bias + c0 + jx + e);
-              }
-              uint4 o;
-              o.x = pack_bf16x2(f[0], f[1]);
-              o.y = pack_bf16x2(f[2], f[3]);
-              o.z = pack_bf16x2(f[4], f[5]);
-              o.w = pack_bf16x2(f[6], f[7]);
-              *reinterpret_cast<uint4*>(orow + c0 + jx) = o;
+            for (int e = 0; e < 8; ++e) {
+              f[e] = __uint_as_float(v[jx + e]);
+              if (p.bias) f[e] += __ldg(p.bias + c0 + jx + e);
             }
+            uint4 o;
+            o.x = pack_bf16x2(f[0], f[1]);
+            o.y = pack_bf16x2(f[2], f[3]);
+            o.z = pack_bf16x2(f[4], f[5]);
+            o.w = pack_bf16x2(f[6], f[7]);
+            if (ok) *reinterpret_cast<uint4*>(orow + c0 + jx) = o;
+            if (p.stats) {
+              const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                r[jx + 2 * e] = ok ? __uint_as_float(w[e] << 16) : 0.f;
+                r[jx + 2 * e + 1] = ok ? __uint_as_float(w[e] & 0xffff0000u) : 0.f;
+              }
+            }
+          }
+          if (p.stats) {
+            float q[32];
+#pragma unroll
+            for (int jx = 0; jx < 32; ++jx) q[jx] = r[jx] * r[jx];
+            warp_column_sums(r, lane);
+            warp_column_sums(q, lane);
+            ssum[c0 >> 5] += r[0];
+            ssq[c0 >> 5] += q[0];
           }
         }
       }
       tc_fence_before_sync();
       mbar_arrive(&acc_empty[buf]);
+    }
+    if (p.stats) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        atomicAdd(p.stats + h * 32 + lane, ssum[h]);
+        atomicAdd(p.stats + 64 + h * 32 + lane, ssq[h]);
+      }
     }
   } else {
     // ------------------------------------------------------------------ MMA issuer
@@ -245,13 +270,14 @@ bool stem_supported(const rsp_conv3d_desc* d) {
   return d->Ci == 4 && d->Co == 64 && d->kw == 7 && d->sw == 2 && d->pw == 3 && d->kh == 7 && d->sh == 2 && (d->Wi % 2) == 0 && d->Wi + 4 <= 124 && Wo <= 64 && (3 * d->sh + d->kh) <= kStemMaxRows;
 }
 
-int launch_stem(const rsp_conv3d_desc* d, const void* x, const void* wst, const float* bias, void* y, int sm_count,
-                cudaStream_t stream) {
+int launch_stem(const rsp_conv3d_desc* d, const void* x, const void* wst, const float* bias, void* y, float* stats,
+                int sm_count, cudaStream_t stream) {
   StemParams p{};
   p.x = static_cast<const __nv_bfloat16*>(x);
   p.wst = static_cast<const __nv_bfloat16*>(wst);
   p.y = static_cast<__nv_bfloat16*>(y);
   p.bias = bias;
+  p.stats = stats;
   p.N = d->N; p.Ti = d->Ti; p.Hi = d->Hi; p.Wi = d->Wi;
   p.To = (d->Ti + 2 * d->pt - d->kt) / d->st + 1;
   p.Ho = (d->Hi + 2 * d->ph - d->kh) / d->sh + 1;

@@ -104,13 +104,18 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const uint4* __rest
   }
 }
 
-__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, float count,
+__global__ void bn_finalize_kernel(float* __restrict__ sum, float* __restrict__ sumsq, int clear, float count,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, float* __restrict__ rmean, float* __restrict__ rvar,
                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean,
                                    float* __restrict__ invstd, int C, int Cl) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  const float s1 = sum[c], s2 = sumsq[c];
+  if (clear) {  // leave the accumulators zeroed for the next forward (persistent per-layer buffers, no memset launches)
+    sum[c] = 0.f;
+    sumsq[c] = 0.f;
+  }
   if (c >= Cl) {
     scale[c] = 0.f;
     shift[c] = 0.f;
@@ -118,8 +123,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
     invstd[c] = 0.f;
     return;
   }
-  float mu = sum[c] / count;
-  float var = fmaxf(sumsq[c] / count - mu * mu, 0.f);
+  float mu = s1 / count;
+  float var = fmaxf(s2 / count - mu * mu, 0.f);
   float is = rsqrtf(var + eps);
   float sc = gamma[c] * is;
   scale[c] = sc;
@@ -491,12 +496,12 @@ int rsp_bn_stats(const void* x, int64_t M, int32_t C, float* sum, float* sumsq, 
   return check_launch("bn_stats");
 }
 
-int rsp_bn_finalize(const float* sum, const float* sumsq, int64_t count, const float* gamma, const float* beta,
-                    float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
-                    float* mean, float* invstd, int32_t C, int32_t C_logical, void* stream) {
+int rsp_bn_finalize(float* sum, float* sumsq, int32_t clear_sums, int64_t count, const float* gamma,
+                    const float* beta, float eps, float momentum, float* running_mean, float* running_var, float* scale,
+                    float* shift, float* mean, float* invstd, int32_t C, int32_t C_logical, void* stream) {
   RSP_REQUIRE(count > 0 && C_logical <= C, "bn_finalize: bad count / channels");
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      sum, sumsq, static_cast<float>(count), gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean,
+      sum, sumsq, clear_sums, static_cast<float>(count), gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean,
       invstd, C, C_logical);
   return check_launch("bn_finalize");
 }

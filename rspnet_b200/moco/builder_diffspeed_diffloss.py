@@ -177,6 +177,8 @@ class _MoCoBase(nn.Module):
         if stale:
             self._flat_q = flatten_parameters(self.encoder_q)
             self._flat_k = flatten_parameters(self.encoder_k)
+            for enc in (self.encoder_q, self.encoder_k):
+                enc._rsp_bn_counters = rnn.batch_bn_counters(enc)
             rnn.bump_weight_epoch()
 
     def flat_parameters(self) -> Tuple[Tensor, Tensor]:

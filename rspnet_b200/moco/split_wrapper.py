@@ -51,6 +51,9 @@ class MultiTaskWrapper(nn.Module):
     def forward(self, x: Tensor):
         feat = self.encoder.feature_ndhwc(x)  # bf16 NDHWC
         self.feat = feat
+        counters = getattr(self, "_rsp_bn_counters", None)
+        if counters is not None:   # all BatchNorm num_batches_tracked of this encoder, one launch (see nn.batch_bn_counters)
+            counters += 1
         fused = (not self.finetune and self.fc_type == 'linear' and self.groups == 1)
         if fused:
             l1, l2 = self.fc1[2], self.fc2[2]

@@ -44,6 +44,7 @@ class _PackCache:
 
 
 _pack_cache = _PackCache()
+_stats_acc = {}
 
 
 def _pad_vec(v: Optional[torch.Tensor], n: int):
@@ -61,11 +62,17 @@ class ConvBNAct(torch.autograd.Function):
         co = ops.pad_channels(weight.shape[0])
         desc = ops.conv_desc(x.shape, co, kernel, stride, padding)
         wp = _pack_cache.get(weight, desc, 0)
-        y = ops.conv3d_fprop(desc, x, wp, _pad_vec(bias, co))
-        s, ss = ops.bn_stats(y)
+        # per-layer persistent statistics accumulator: zero at rest (bn_finalize clears it after reading)
+        key = (id(gamma), co, x.device)
+        acc = _stats_acc.get(key)
+        if acc is None:
+            acc = _stats_acc[key] = torch.zeros((2, co), dtype=torch.float32, device=x.device)
+        y = ops.conv3d_fprop(desc, x, wp, _pad_vec(bias, co), stats=acc)   # statistics fused into the conv epilogue
+        if not ops.conv3d_fprop.stats_done:
+            ops.bn_stats(y, out=acc)                                        # split-K layers: separate reduction
         count = y.numel() // co
-        scale, shift, mean, invstd = ops.bn_finalize(s, ss, count, gamma, beta, eps, momentum, running_mean,
-                                                     running_var, co)
+        scale, shift, mean, invstd = ops.bn_finalize(acc[0], acc[1], count, gamma, beta, eps, momentum, running_mean,
+                                                     running_var, co, clear_sums=True)
         out = ops.bn_act_fwd(y, scale, shift, residual, relu)
         ctx.desc = desc
         ctx.relu = relu
@@ -98,9 +105,24 @@ def conv_bn_act(x, conv: torch.nn.Conv3d, bn: torch.nn.BatchNorm3d, relu: bool =
     momentum = bn.momentum if bn.momentum is not None else 0.0
     out = ConvBNAct.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual,
                           tuple(conv.kernel_size), tuple(conv.stride), tuple(conv.padding), bn.eps, momentum, relu)
-    if bn.track_running_stats and bn.num_batches_tracked is not None:
+    if bn.track_running_stats and bn.num_batches_tracked is not None and not getattr(bn, "_rsp_counter_batched", False):
         bn.num_batches_tracked += 1
     return out
+
+
+def batch_bn_counters(module: torch.nn.Module):
+    """Re-homes every BatchNorm ``num_batches_tracked`` of ``module`` into one int64 buffer (the per-layer buffers become
+    views, names/values unchanged) so that one increment per forward replaces one tiny kernel per layer.
+    Returns the flat counter tensor (or None when there is no BatchNorm)."""
+    bns = [m for m in module.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm) and
+           m.track_running_stats and m.num_batches_tracked is not None]
+    if not bns:
+        return None
+    flat = torch.stack([m.num_batches_tracked.detach().reshape(()) for m in bns]).clone()
+    for i, m in enumerate(bns):
+        m._buffers["num_batches_tracked"] = flat[i]
+        m._rsp_counter_batched = True
+    return flat
 
 
 class MaxPool3dFn(torch.autograd.Function):

@@ -50,13 +50,22 @@ def _splitk_workspace(desc: ConvDesc, which: int, device):
     return torch.empty((n // 4,), dtype=torch.float32, device=device) if n > 0 else None
 
 
-def conv3d_fprop(desc: ConvDesc, x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor] = None):
+def conv3d_fprop(desc: ConvDesc, x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                 stats: Optional[torch.Tensor] = None):
+    """Returns y; when ``stats`` ([2, Co] fp32, zeroed) is given the epilogue accumulates the BN batch statistics into
+    it — unless the layer runs split-K, in which case ``conv3d_fprop.stats_done`` is False and the caller must run
+    ``bn_stats``."""
     assert x.dtype == torch.bfloat16 and x.is_contiguous()
     to, ho, wo = desc.out_dims()
     y = torch.empty((desc.N, to, ho, wo, desc.Co), dtype=torch.bfloat16, device=x.device)
     ws = _splitk_workspace(desc, 0, x.device)
-    call("rsp_conv3d_fprop", C.byref(desc), ptr(x), ptr(wp), ptr(bias), ptr(y), ptr(ws), stream_ptr())
+    conv3d_fprop.stats_done = stats is not None and ws is None
+    call("rsp_conv3d_fprop", C.byref(desc), ptr(x), ptr(wp), ptr(bias), ptr(y), ptr(ws),
+         ptr(stats) if conv3d_fprop.stats_done else None, stream_ptr())
     return y
+
+
+conv3d_fprop.stats_done = False
 
 
 def conv3d_dgrad(desc: ConvDesc, dy: torch.Tensor, wd: torch.Tensor):
@@ -82,19 +91,21 @@ def conv3d_wgrad(desc: ConvDesc, x: torch.Tensor, dy: torch.Tensor, weight_shape
 
 
 # ------------------------------------------------------------------------------------------------ batch norm
-def bn_stats(x: torch.Tensor):
+def bn_stats(x: torch.Tensor, out: Optional[torch.Tensor] = None):
+    """Per-channel sum and sum of squares; accumulates into ``out`` ([2, C], must be zero) when given."""
     c = x.shape[-1]
     m = x.numel() // c
-    s = torch.zeros((2, c), dtype=torch.float32, device=x.device)
+    s = out if out is not None else torch.zeros((2, c), dtype=torch.float32, device=x.device)
     call("rsp_bn_stats", ptr(x), m, c, ptr(s[0]), ptr(s[1]), stream_ptr())
     return s[0], s[1]
 
 
-def bn_finalize(s, ss, count, gamma, beta, eps, momentum, running_mean, running_var, c_stored):
+def bn_finalize(s, ss, count, gamma, beta, eps, momentum, running_mean, running_var, c_stored, clear_sums=False):
     dev = s.device
     out = torch.empty((4, c_stored), dtype=torch.float32, device=dev)
-    call("rsp_bn_finalize", ptr(s), ptr(ss), count, ptr(gamma), ptr(beta), eps, momentum, ptr(running_mean),
-         ptr(running_var), ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(out[3]), c_stored, gamma.numel(), stream_ptr())
+    call("rsp_bn_finalize", ptr(s), ptr(ss), int(clear_sums), count, ptr(gamma), ptr(beta), eps, momentum,
+         ptr(running_mean), ptr(running_var), ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(out[3]), c_stored,
+         gamma.numel(), stream_ptr())
     return out[0], out[1], out[2], out[3]  # scale, shift, mean, invstd
 
 

@@ -283,8 +283,15 @@ def test_conv3d_fprop_dgrad_wgrad(n, ci, co, dims, k, s, p):
     cis, cos = ops.pad_channels(ci), ops.pad_channels(co)
     xn = ops.to_ndhwc_bf16(x, cis)
     desc = ops.conv_desc(xn.shape, cos, k, s, p)
-    y = ops.conv3d_fprop(desc, xn, ops.conv3d_pack_weight(desc, w, 0), bias)
+    stats = torch.zeros(2, cos, device=DEV)
+    y = ops.conv3d_fprop(desc, xn, ops.conv3d_pack_weight(desc, w, 0), bias, stats=stats)
     close(ops.to_ncdhw_f32(y, co), yref.detach(), 1e-2)
+    if ops.conv3d_fprop.stats_done:   # BN statistics fused into the epilogue describe the stored bf16 tensor
+        yf = y.float().reshape(-1, cos)
+        torch.testing.assert_close(stats[0], yf.sum(0), rtol=1e-3, atol=1e-2)
+        torch.testing.assert_close(stats[1], (yf * yf).sum(0), rtol=1e-3, atol=1e-2)
+    else:
+        assert torch.count_nonzero(stats) == 0
     dyn = ops.to_ndhwc_bf16(dy, cos)
     dw = ops.conv3d_wgrad(desc, xn, dyn, w.shape)
     close(dw, wr.grad, 1e-2)
