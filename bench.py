@@ -323,9 +323,9 @@ def conv_roofline(args, B, ms_step):
     shapes = []
     orig = ops.conv3d_fprop
 
-    def spy(desc, x, wp, bias=None):
+    def spy(desc, x, wp, bias=None, **kw):
         shapes.append((desc, tuple(x.shape), x.requires_grad))
-        return orig(desc, x, wp, bias)
+        return orig(desc, x, wp, bias, **kw)
 
     ops.conv3d_fprop = spy
     net = get_model_class(arch=args.arch)(num_classes=1).cuda()

@@ -15,9 +15,9 @@ shapes = []
 orig = ops.conv3d_fprop
 
 
-def spy(desc, x, wp, bias=None):
+def spy(desc, x, wp, bias=None, **kw):
     shapes.append((desc, tuple(x.shape)))
-    return orig(desc, x, wp, bias)
+    return orig(desc, x, wp, bias, **kw)
 
 
 ops.conv3d_fprop = spy
