@@ -111,10 +111,10 @@ int rsp_maxpool3d_bwd(const rsp_pool3d_desc* d, const void* dy, const uint8_t* i
 int rsp_head_fwd(const void* feat, int32_t B, int32_t S, int32_t C, int32_t C_logical, int32_t D, const float* w1,
                  const float* b1, const float* w2, const float* b2, float* pooled, float* raw1, float* raw2,
                  float* out1, float* out2, void* stream);
-/* dw*, db*: += (caller owns zeroing); dfeat bf16 [B][S][C] overwritten (may be NULL). */
+/* dw*, db*: += (caller owns zeroing); dfeat bf16 [B][S][C] overwritten (may be NULL); dr_ws: fp32 [B][2][D] scratch. */
 int rsp_head_bwd(const float* dout1, const float* dout2, const float* pooled, const float* raw1, const float* raw2,
                  int32_t B, int32_t S, int32_t C, int32_t C_logical, int32_t D, const float* w1, const float* w2,
-                 float* dw1, float* db1, float* dw2, float* db2, void* dfeat, void* stream);
+                 float* dr_ws, float* dw1, float* db1, float* dw2, float* db2, void* dfeat, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * S3D-G (reference: models/s3dg.py). Self-gating of sep_conv (:54-72): gate = sigmoid(W * mean_S(x) + b), y = x*gate.

@@ -56,7 +56,7 @@ SIGNATURES = {
     "rsp_maxpool3d_fwd": (c_i32, [C.POINTER(PoolDesc), _P, _P, _P, _P]),
     "rsp_maxpool3d_bwd": (c_i32, [C.POINTER(PoolDesc), _P, _P, _P, _P]),
     "rsp_head_fwd": (c_i32, [_P, c_i32, c_i32, c_i32, c_i32, c_i32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "rsp_head_bwd": (c_i32, [_P, _P, _P, _P, _P, c_i32, c_i32, c_i32, c_i32, c_i32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "rsp_head_bwd": (c_i32, [_P, _P, _P, _P, _P, c_i32, c_i32, c_i32, c_i32, c_i32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "rsp_gate_fwd": (c_i32, [_P, c_i32, c_i32, c_i32, c_i32, _P, _P, _P, _P, _P, _P, _P]),
     "rsp_gate_bwd": (c_i32, [_P, _P, c_i32, c_i32, c_i32, c_i32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "rsp_copy_channels": (c_i32, [_P, c_i32, c_i32, _P, c_i32, c_i32, c_i32, c_i64, _P]),

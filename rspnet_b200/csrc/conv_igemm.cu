@@ -645,34 +645,53 @@ __device__ __forceinline__ bool k_to_filter(int mode, int k, int Cs, int Ci, int
   return ci < Ci && rr < kt * kh && px < kw;
 }
 
-// w fp32 [Co][Ci][kt][kh][kw] -> wp bf16 [CoPad][Kpad]  (fprop B operand)
-__global__ void pack_weight_fprop_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int mode, int Co,
-                                         int CoPad, int Ci, int Cs, int kt, int kh, int kw, int pxs, int Kpad) {
-  size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  size_t total = static_cast<size_t>(CoPad) * Kpad;
-  if (idx >= total) return;
-  int co = static_cast<int>(idx / Kpad), k = static_cast<int>(idx % Kpad);
-  int ci, a, b, c;
-  float v = 0.f;
-  if (co < Co && k_to_filter(mode, k, Cs, Ci, kt, kh, kw, pxs, ci, a, b, c))
-    v = w[(((static_cast<size_t>(co) * Ci + ci) * kt + a) * kh + b) * kw + c];
-  wp[idx] = __float2bfloat16(v);
+// w fp32 [Co][Ci][kt][kh][kw] -> wp bf16 [CoPad][Kpad]  (fprop B operand).  One block per output channel: the
+// filter of that channel (Ci*taps contiguous floats) is staged in smem with coalesced reads, then written in K order.
+__global__ void __launch_bounds__(256) pack_weight_fprop_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp,
+                                                                int mode, int Co, int Ci, int Cs, int kt, int kh, int kw,
+                                                                int pxs, int Kpad) {
+  extern __shared__ float sw[];
+  const int co = blockIdx.x;
+  const int per = Ci * kt * kh * kw;
+  if (co < Co)
+    for (int i = threadIdx.x; i < per; i += 256) sw[i] = w[static_cast<size_t>(co) * per + i];
+  __syncthreads();
+  const int taps = kt * kh * kw;
+  for (int k = threadIdx.x; k < Kpad; k += 256) {
+    int ci, a, b, c;
+    float v = 0.f;
+    if (co < Co && k_to_filter(mode, k, Cs, Ci, kt, kh, kw, pxs, ci, a, b, c))
+      v = sw[ci * taps + (a * kh + b) * kw + c];
+    wp[static_cast<size_t>(co) * Kpad + k] = __float2bfloat16(v);
+  }
 }
 
-// w fp32 [Co][Ci][kt][kh][kw] -> wd bf16 [CiPad][taps*CoPad]  (dgrad B operand: K index = tap*CoPad + co)
-__global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wd, int Co, int CoPad,
-                                         int Ci, int CiPad, int kt, int kh, int kw) {
-  size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  int taps = kt * kh * kw;
-  size_t K = static_cast<size_t>(taps) * CoPad;
-  size_t total = static_cast<size_t>(CiPad) * K;
-  if (idx >= total) return;
-  int ci = static_cast<int>(idx / K);
-  int k = static_cast<int>(idx % K);
-  int tap = k / CoPad, co = k - tap * CoPad;
-  float v = 0.f;
-  if (ci < Ci && co < Co) v = w[(static_cast<size_t>(co) * Ci + ci) * taps + tap];
-  wd[idx] = __float2bfloat16(v);
+// w fp32 [Co][Ci][kt][kh][kw] -> wd bf16 [CiPad][taps*CoPad]  (dgrad B operand: K index = tap*CoPad + co).
+// One block per (32 co x 32 ci) tile and tap-group: transposes through smem so that reads (along taps within one
+// (co,ci)) and writes (along co) are both contiguous enough.
+__global__ void __launch_bounds__(256) pack_weight_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wd,
+                                                                int Co, int CoPad, int Ci, int CiPad, int taps) {
+  extern __shared__ float sw[];  // [32 co][32 ci][taps] (+1 padding on the ci stride)
+  const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * 32;
+  const int stride_ci = taps, stride_co = 32 * taps + 1;
+  // coalesced read: for fixed co the 32 ci x taps floats are contiguous in w
+  for (int i = threadIdx.x; i < 32 * 32 * taps; i += 256) {
+    const int col = i / (32 * taps), rem = i - col * 32 * taps;  // rem = cil*taps + tap
+    const int co = co0 + col, cil = rem / taps;
+    float v = 0.f;
+    if (co < Co && ci0 + cil < Ci) v = w[(static_cast<size_t>(co) * Ci + ci0) * taps + rem];
+    sw[col * stride_co + rem] = v;
+  }
+  __syncthreads();
+  const size_t K = static_cast<size_t>(taps) * CoPad;
+  for (int i = threadIdx.x; i < 32 * 32 * taps; i += 256) {
+    const int col = i & 31;                 // co fastest: contiguous bf16 writes
+    const int rest = i >> 5;
+    const int tap = rest % taps, cil = rest / taps;
+    if (ci0 + cil < CiPad && co0 + col < CoPad)
+      wd[static_cast<size_t>(ci0 + cil) * K + static_cast<size_t>(tap) * CoPad + co0 + col] =
+          __float2bfloat16(sw[col * stride_co + cil * stride_ci + tap]);
+  }
 }
 
 // dwt fp32 [Kpad][CoPad] -> dw fp32 [Co][Ci][kt][kh][kw]   (accumulate != 0: +=)
@@ -889,9 +908,16 @@ int rsp_conv3d_pack_weight(const rsp_conv3d_desc* d, int Ci_logical, int Co_logi
     if (rc != RSP_OK) return rc;
     const int Kpad = g.numKb * 64;
     size_t total = static_cast<size_t>(d->Co) * Kpad;
-    pack_weight_fprop_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
-        w, static_cast<__nv_bfloat16*>(wp), mode, Co_logical, d->Co, Ci_logical, d->Ci, d->kt, d->kh, d->kw, g.pxs,
-        Kpad);
+    const size_t per = static_cast<size_t>(Ci_logical) * d->kt * d->kh * d->kw * sizeof(float);
+    RSP_REQUIRE(per <= 200 * 1024, "pack_weight: one filter (%zu bytes) does not fit in shared memory", per);
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(pack_weight_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(pack_weight_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr_done = true;
+    }
+    pack_weight_fprop_kernel<<<d->Co, 256, per, stream>>>(w, static_cast<__nv_bfloat16*>(wp), mode, Co_logical,
+                                                          Ci_logical, d->Ci, d->kt, d->kh, d->kw, g.pxs, Kpad);
     rc = check_launch("pack_weight_fprop");
     if (rc != RSP_OK) return rc;
     if (stem_supported(d))
@@ -899,9 +925,17 @@ int rsp_conv3d_pack_weight(const rsp_conv3d_desc* d, int Ci_logical, int Co_logi
     return RSP_OK;
   }
   RSP_REQUIRE(mode == MODE_GENERIC, "pack_weight(dgrad): small-channel convs have no dgrad");
-  size_t total = static_cast<size_t>(d->Ci) * d->kt * d->kh * d->kw * d->Co;
-  pack_weight_dgrad_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
-      w, static_cast<__nv_bfloat16*>(wp), Co_logical, d->Co, Ci_logical, d->Ci, d->kt, d->kh, d->kw);
+  const int taps = d->kt * d->kh * d->kw;
+  const size_t sm = (static_cast<size_t>(32) * (32 * taps + 1)) * sizeof(float);
+  RSP_REQUIRE(sm <= 200 * 1024, "pack_weight(dgrad): filter too large for the transpose tile");
+  static bool attr_done2 = false;
+  if (!attr_done2) {
+    cudaFuncSetAttribute(pack_weight_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done2 = true;
+  }
+  dim3 grid((d->Co + 31) / 32, (d->Ci + 31) / 32);
+  pack_weight_dgrad_kernel<<<grid, 256, sm, stream>>>(w, static_cast<__nv_bfloat16*>(wp), Co_logical, d->Co,
+                                                      Ci_logical, d->Ci, taps);
   return check_launch("pack_weight_dgrad");
 }
 

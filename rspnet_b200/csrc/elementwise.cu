@@ -333,18 +333,22 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return s;
 }
 
-__global__ void __launch_bounds__(128) head_fwd_kernel(const __nv_bfloat16* __restrict__ feat, int S, int C, int Cl,
+// forward: block per sample, 256 threads = 8 warps. Pooled features in smem; every output feature is a warp-level dot
+// product with coalesced reads of its weight row.
+__global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __restrict__ feat, int S, int C, int Cl,
                                                        int D, const float* __restrict__ w1,
                                                        const float* __restrict__ b1, const float* __restrict__ w2,
                                                        const float* __restrict__ b2, float* __restrict__ pooled,
                                                        float* __restrict__ raw1, float* __restrict__ raw2,
                                                        float* __restrict__ out1, float* __restrict__ out2) {
   extern __shared__ float sm[];
-  float* sp = sm;  // [Cl]
-  __shared__ float red[4];
+  float* sp = sm;             // [Cl]
+  float* sraw = sm + Cl;      // [2][D]
+  __shared__ float red[8];
   const int bidx = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const __nv_bfloat16* f = feat + static_cast<size_t>(bidx) * S * C;
-  for (int c = threadIdx.x; c < Cl; c += blockDim.x) {
+  for (int c = threadIdx.x; c < Cl; c += 256) {
     float s = 0.f;
     for (int i = 0; i < S; ++i) s += __bfloat162float(f[static_cast<size_t>(i) * C + c]);
     s /= S;
@@ -352,84 +356,96 @@ __global__ void __launch_bounds__(128) head_fwd_kernel(const __nv_bfloat16* __re
     pooled[static_cast<size_t>(bidx) * Cl + c] = s;
   }
   __syncthreads();
-  for (int head = 0; head < 2; ++head) {
-    const float* w = head ? w2 : w1;
-    const float* bb = head ? b2 : b1;
-    float* raw = (head ? raw2 : raw1) + static_cast<size_t>(bidx) * D;
-    float* out = (head ? out2 : out1) + static_cast<size_t>(bidx) * D;
-    float sq = 0.f;
-    for (int j = threadIdx.x; j < D; j += blockDim.x) {
-      float acc = bb ? bb[j] : 0.f;
-      const float* wr = w + static_cast<size_t>(j) * Cl;
-      for (int c = 0; c < Cl; ++c) acc = fmaf(wr[c], sp[c], acc);
-      raw[j] = acc;
-      sq += acc * acc;
-    }
-    float nrm = fmaxf(sqrtf(block_sum(sq, red)), 1e-12f);
-    for (int j = threadIdx.x; j < D; j += blockDim.x) out[j] = raw[j] / nrm;
-  }
-}
-
-__global__ void __launch_bounds__(128) head_bwd_kernel(const float* __restrict__ dout1, const float* __restrict__ dout2,
-                                                       const float* __restrict__ pooled, const float* __restrict__ raw1,
-                                                       const float* __restrict__ raw2, int S, int C, int Cl, int D,
-                                                       const float* __restrict__ w1, const float* __restrict__ w2,
-                                                       float* __restrict__ dw1, float* __restrict__ db1,
-                                                       float* __restrict__ dw2, float* __restrict__ db2,
-                                                       __nv_bfloat16* __restrict__ dfeat) {
-  extern __shared__ float sm[];
-  float* dr1 = sm;          // [D] grad wrt raw1
-  float* dr2 = sm + D;      // [D]
-  float* sp = sm + 2 * D;   // [Cl] pooled
-  __shared__ float red[4];
-  const int bidx = blockIdx.x;
-  for (int c = threadIdx.x; c < Cl; c += blockDim.x) sp[c] = pooled[static_cast<size_t>(bidx) * Cl + c];
-  for (int head = 0; head < 2; ++head) {
-    const float* raw = (head ? raw2 : raw1) + static_cast<size_t>(bidx) * D;
-    const float* dout = (head ? dout2 : dout1) + static_cast<size_t>(bidx) * D;
-    float* dr = head ? dr2 : dr1;
-    float sq = 0.f, dot = 0.f;
-    for (int j = threadIdx.x; j < D; j += blockDim.x) {
-      sq += raw[j] * raw[j];
-      dot += raw[j] * dout[j];
-    }
-    float ss = block_sum(sq, red);
-    float dd = block_sum(dot, red);
-    float nrm = sqrtf(ss);
-    for (int j = threadIdx.x; j < D; j += blockDim.x) {
-      float g;
-      if (nrm > 1e-12f) {
-        // y = x/n: dx = dy/n - x * (x.dy) / n^3
-        g = dout[j] / nrm - raw[j] * dd / (nrm * nrm * nrm);
-      } else {
-        g = dout[j] / 1e-12f;
-      }
-      dr[j] = g;
+  for (int o = warp; o < 2 * D; o += 8) {
+    const int head = o / D, j = o - head * D;
+    const float* wr = (head ? w2 : w1) + static_cast<size_t>(j) * Cl;
+    float acc = 0.f;
+    for (int c = lane; c < Cl; c += 32) acc = fmaf(wr[c], sp[c], acc);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) {
+      const float* bb = head ? b2 : b1;
+      sraw[o] = acc + (bb ? bb[j] : 0.f);
     }
   }
   __syncthreads();
-  // parameter gradients (accumulated over samples with atomics)
-  for (int j = threadIdx.x; j < D; j += blockDim.x) {
-    atomicAdd(db1 + j, dr1[j]);
-    atomicAdd(db2 + j, dr2[j]);
+  for (int head = 0; head < 2; ++head) {
+    float* raw = (head ? raw2 : raw1) + static_cast<size_t>(bidx) * D;
+    float* out = (head ? out2 : out1) + static_cast<size_t>(bidx) * D;
+    float sq = 0.f;
+    for (int j = threadIdx.x; j < D; j += 256) sq += sraw[head * D + j] * sraw[head * D + j];
+    float nrm = fmaxf(sqrtf(block_sum(sq, red)), 1e-12f);
+    for (int j = threadIdx.x; j < D; j += 256) {
+      raw[j] = sraw[head * D + j];
+      out[j] = sraw[head * D + j] / nrm;
+    }
   }
-  for (int i = threadIdx.x; i < D * Cl; i += blockDim.x) {
-    int j = i / Cl, c = i - j * Cl;
-    atomicAdd(dw1 + i, dr1[j] * sp[c]);
-    atomicAdd(dw2 + i, dr2[j] * sp[c]);
+}
+
+// backward, step 1 (block per sample): gradient w.r.t. the pre-normalisation outputs -> dr_ws [B][2][D];
+// dfeat = (dr1 W1 + dr2 W2) / S broadcast over the S positions.
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dout1, const float* __restrict__ dout2,
+                                                       const float* __restrict__ raw1, const float* __restrict__ raw2,
+                                                       int S, int C, int Cl, int D, const float* __restrict__ w1,
+                                                       const float* __restrict__ w2, float* __restrict__ dr_ws,
+                                                       __nv_bfloat16* __restrict__ dfeat) {
+  extern __shared__ float sm[];
+  float* dr = sm;  // [2][D]
+  __shared__ float red[8];
+  const int bidx = blockIdx.x;
+  for (int head = 0; head < 2; ++head) {
+    const float* raw = (head ? raw2 : raw1) + static_cast<size_t>(bidx) * D;
+    const float* dout = (head ? dout2 : dout1) + static_cast<size_t>(bidx) * D;
+    float sq = 0.f, dot = 0.f;
+    for (int j = threadIdx.x; j < D; j += 256) {
+      sq += raw[j] * raw[j];
+      dot += raw[j] * dout[j];
+    }
+    const float ss = block_sum(sq, red);
+    const float dd = block_sum(dot, red);
+    const float nrm = sqrtf(ss);
+    for (int j = threadIdx.x; j < D; j += 256) {
+      // y = x/n: dx = dy/n - x * (x.dy) / n^3   (n clamped at eps like F.normalize)
+      float g = nrm > 1e-12f ? dout[j] / nrm - raw[j] * dd / (nrm * nrm * nrm) : dout[j] / 1e-12f;
+      dr[head * D + j] = g;
+      dr_ws[(static_cast<size_t>(bidx) * 2 + head) * D + j] = g;
+    }
   }
+  __syncthreads();
   if (dfeat) {
     __nv_bfloat16* df = dfeat + static_cast<size_t>(bidx) * S * C;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    for (int c = threadIdx.x; c < C; c += 256) {   // coalesced over c: w[j][c]
       float acc = 0.f;
       if (c < Cl) {
         for (int j = 0; j < D; ++j)
-          acc += dr1[j] * w1[static_cast<size_t>(j) * Cl + c] + dr2[j] * w2[static_cast<size_t>(j) * Cl + c];
+          acc += dr[j] * w1[static_cast<size_t>(j) * Cl + c] + dr[D + j] * w2[static_cast<size_t>(j) * Cl + c];
         acc /= S;
       }
-      __nv_bfloat16 v = __float2bfloat16(acc);
+      const __nv_bfloat16 v = __float2bfloat16(acc);
       for (int i = 0; i < S; ++i) df[static_cast<size_t>(i) * C + c] = v;
     }
+  }
+}
+
+// backward, step 2: dW_h[j][c] += sum_b dr[b][h][j] * pooled[b][c]; db_h[j] += sum_b dr[b][h][j].  No atomics.
+__global__ void __launch_bounds__(256) head_wgrad_kernel(const float* __restrict__ dr_ws, const float* __restrict__ pooled,
+                                                         int B, int Cl, int D, float* __restrict__ dw1,
+                                                         float* __restrict__ db1, float* __restrict__ dw2,
+                                                         float* __restrict__ db2) {
+  const int head = blockIdx.z;
+  const int j = blockIdx.y;
+  float* dw = head ? dw2 : dw1;
+  float* db = head ? db2 : db1;
+  for (int c = blockIdx.x * 256 + threadIdx.x; c < Cl; c += gridDim.x * 256) {
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b)
+      acc = fmaf(dr_ws[(static_cast<size_t>(b) * 2 + head) * D + j], pooled[static_cast<size_t>(b) * Cl + c], acc);
+    dw[static_cast<size_t>(j) * Cl + c] += acc;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc += dr_ws[(static_cast<size_t>(b) * 2 + head) * D + j];
+    db[j] += acc;
   }
 }
 
@@ -568,20 +584,22 @@ int rsp_maxpool3d_bwd(const rsp_pool3d_desc* d, const void* dy, const uint8_t* i
 int rsp_head_fwd(const void* feat, int32_t B, int32_t S, int32_t C, int32_t C_logical, int32_t D, const float* w1,
                  const float* b1, const float* w2, const float* b2, float* pooled, float* raw1, float* raw2,
                  float* out1, float* out2, void* stream) {
-  RSP_REQUIRE(B > 0 && S > 0 && C_logical <= C && C_logical <= 8192, "head_fwd: bad sizes");
-  head_fwd_kernel<<<B, 128, C_logical * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+  RSP_REQUIRE(B > 0 && S > 0 && C_logical <= C && (C_logical + 2 * D) * sizeof(float) <= 48 * 1024,
+              "head_fwd: bad sizes");
+  head_fwd_kernel<<<B, 256, (C_logical + 2 * D) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(feat), S, C, C_logical, D, w1, b1, w2, b2, pooled, raw1, raw2, out1, out2);
   return check_launch("head_fwd");
 }
 
 int rsp_head_bwd(const float* dout1, const float* dout2, const float* pooled, const float* raw1, const float* raw2,
                  int32_t B, int32_t S, int32_t C, int32_t C_logical, int32_t D, const float* w1, const float* w2,
-                 float* dw1, float* db1, float* dw2, float* db2, void* dfeat, void* stream) {
-  RSP_REQUIRE(B > 0 && S > 0 && C_logical <= C && (2 * D + C_logical) * sizeof(float) <= 48 * 1024,
-              "head_bwd: bad sizes");
-  head_bwd_kernel<<<B, 128, (2 * D + C_logical) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      dout1, dout2, pooled, raw1, raw2, S, C, C_logical, D, w1, w2, dw1, db1, dw2, db2,
-      static_cast<__nv_bfloat16*>(dfeat));
+                 float* dr_ws, float* dw1, float* db1, float* dw2, float* db2, void* dfeat, void* stream) {
+  RSP_REQUIRE(B > 0 && S > 0 && C_logical <= C && 2 * D * sizeof(float) <= 48 * 1024, "head_bwd: bad sizes");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  head_bwd_kernel<<<B, 256, 2 * D * sizeof(float), st>>>(dout1, dout2, raw1, raw2, S, C, C_logical, D, w1, w2, dr_ws,
+                                                         static_cast<__nv_bfloat16*>(dfeat));
+  dim3 grid((C_logical + 255) / 256, D, 2);
+  head_wgrad_kernel<<<grid, 256, 0, st>>>(dr_ws, pooled, B, C_logical, D, dw1, db1, dw2, db2);
   return check_launch("head_bwd");
 }
 

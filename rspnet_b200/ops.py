@@ -178,8 +178,10 @@ def head_bwd(dout1, dout2, pooled, raw, feat_shape, w1, w2, want_dfeat=True):
     dw = torch.zeros((2, d, cl), dtype=torch.float32, device=dev)
     db = torch.zeros((2, d), dtype=torch.float32, device=dev)
     dfeat = torch.empty(tuple(feat_shape), dtype=torch.bfloat16, device=dev) if want_dfeat else None
+    dr_ws = torch.empty((b, 2, d), dtype=torch.float32, device=dev)
     call("rsp_head_bwd", ptr(dout1.contiguous()), ptr(dout2.contiguous()), ptr(pooled), ptr(raw[0]), ptr(raw[1]), b, s,
-         c, cl, d, ptr(w1), ptr(w2), ptr(dw[0]), ptr(db[0]), ptr(dw[1]), ptr(db[1]), ptr(dfeat), stream_ptr())
+         c, cl, d, ptr(w1), ptr(w2), ptr(dr_ws), ptr(dw[0]), ptr(db[0]), ptr(dw[1]), ptr(db[1]), ptr(dfeat),
+         stream_ptr())
     return dw[0], db[0], dw[1], db[1], dfeat
 
 
