@@ -105,7 +105,7 @@ _S3DG_INC = ["sepInc_3b", "sepInc_3c", "sepInc_4b", "sepInc_4c", "sepInc_4d", "s
              "sepInc_5c"]
 
 
-def s3dg_feature(x, sd: State, p: str, train=True):
+def s3dg_feature(x, sd: State, p: str, train=True, upto: Optional[str] = None):
     """models/s3dg.py:151-153 (get_feature): BasicConv3d (:6-33, BN eps 1e-3 momentum 0.001), sep_conv with
     self-gating (:36-72), sep_inc (:74-99), feature stack (:105-121)."""
     def basic(x, name, stride=(1, 1, 1), pad=(0, 0, 0)):
@@ -133,6 +133,8 @@ def s3dg_feature(x, sd: State, p: str, train=True):
     x = sep(x, f + "sep_conv2", 3, 1, 1)
     x = F.max_pool3d(x, (1, 3, 3), (1, 2, 2), (0, 1, 1))
     x = inc(inc(x, f + "sepInc_3b"), f + "sepInc_3c")
+    if upto == "sepInc_3c":
+        return x
     x = F.max_pool3d(x, 3, 2, 1)
     for n in _S3DG_INC[2:7]:
         x = inc(x, f + n)

@@ -1,0 +1,374 @@
+// Direct (im2col-free) tcgen05 convolution for unit-stride filters on 64-channel-multiple tensors
+// (reference: the 3x3x3 stride-1 nn.Conv3d of models/resnet.py:21-27 (BasicBlock), models/c3d.py:26-50, and their dgrad).
+//
+// Idea: flatten one padded (h, w) plane of the source with pitch Wp = Wi + 2*pw.  Output position q = ho*Wp + wo then
+// reads source position q + b*Wp + c for filter tap (b, c): a pure OFFSET.  So a contiguous run of padded source pixels
+// (one 128-byte row per pixel per 64-channel chunk, 128B-swizzled by address) sitting in shared memory is the K-major A
+// operand of EVERY tap — the UMMA descriptor just starts b*Wp + c rows later (the swizzle is a function of the smem
+// address, verified by tools/umma_shift_probe.cu).  A plane is therefore loaded once per (frame tap, channel chunk)
+// instead of once per filter tap, and one filter tile feeds G=2..4 accumulators of 128 positions, which takes the kernel
+// off the L2-bandwidth roofline that bounds the gather kernel for Co = 64.
+//
+// CTA (persistent, 1/SM): warps 0-3 producers (zero-filling cp.async), warps 4-7 epilogue, warp 8 MMA issuer.
+// Rings: 2 plane buffers, 6 filter tiles, 2 TMEM accumulator sets (G * NT columns each).
+#include "common.cuh"
+#include "rspnet_b200.h"
+
+namespace rsp {
+
+int device_sm_count();
+
+struct DirectParams {
+  const __nv_bfloat16* x;    // source [N][Ti][Hi][Wi][Cs]
+  const __nv_bfloat16* wgt;  // [Nout][taps*Cs]  (K index = tap*Cs + c)
+  __nv_bfloat16* y;          // [N][To][Ho][Wo][Nout]
+  const float* bias;
+  float* stats;              // optional [2][Nout]
+  int N, Ti, Hi, Wi, Cs;
+  int To, Ho, Wo, Nout;
+  int kt, kh, kw, pt, ph, pw;  // source = out - p + tap
+  int flip;                    // 1: filter tap index is mirrored (dgrad)
+  int Wp, Hp, P;               // padded pitch, padded rows, positions per plane (Ho*Wp)
+  int G;                       // accumulators (128-position chunks) per work item
+  int groups;                  // work items per plane
+  int len;                     // plane-buffer pixels (multiple of 8)
+  int numItems;                // ntiles * N * To * groups
+  unsigned long long mulWp;    // reciprocal of Wp (shift 32 + shWp)
+  int shWp;
+};
+
+constexpr int kDirThreads = 288;
+constexpr int kDirWStages = 6;
+
+__device__ __forceinline__ uint32_t fdiv64(uint32_t n, unsigned long long mul, int sh) {
+  return static_cast<uint32_t>((static_cast<unsigned long long>(n) * mul) >> sh);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(kDirThreads, 1) conv_direct_kernel(const DirectParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int planeBytes = p.len * 128;
+  uint8_t* wring = smem + 2 * planeBytes;
+  constexpr int W_BYTES = NT * 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wring + kDirWStages * W_BYTES);
+  uint64_t* plane_full = bars;             // [2]
+  uint64_t* plane_empty = bars + 2;        // [2]
+  uint64_t* w_full = bars + 4;             // [6]
+  uint64_t* w_empty = bars + 4 + kDirWStages;
+  uint64_t* acc_full = bars + 4 + 2 * kDirWStages;   // [2]
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int t = threadIdx.x;
+  const int warp = t >> 5;
+  const int cch = p.Cs >> 6;
+  const int ntiles = p.Nout / NT;
+  const int accCols = p.G * NT;            // columns of one accumulator set
+
+  if (t == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&plane_full[i], 128);
+      mbar_init(&plane_empty[i], 1);
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 128);
+    }
+    for (int i = 0; i < kDirWStages; ++i) {
+      mbar_init(&w_full[i], 128);
+      mbar_init(&w_empty[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work item -> (ntile, n, to, group); group fastest so that neighbouring CTAs share planes and filters in L2
+  auto decode_item = [&](int it, int& nt, int& n, int& to, int& grp) {
+    grp = it % p.groups;
+    int q = it / p.groups;
+    to = q % p.To;
+    q /= p.To;
+    n = q % p.N;
+    nt = q / p.N;
+  };
+
+  if (warp < 4) {
+    // ============================================================ producers
+    uint32_t pctr = 0, wctr = 0;
+    const int chunk = t & 7;
+    const size_t ldw = static_cast<size_t>(p.kt) * p.kh * p.kw * p.Cs;
+    for (int it = blockIdx.x; it < p.numItems; it += gridDim.x) {
+      int nt, n, to, grp;
+      decode_item(it, nt, n, to, grp);
+      const int q0 = grp * p.G * 128;
+      const __nv_bfloat16* wrow = p.wgt + static_cast<size_t>(nt * NT + (t >> 3)) * ldw + chunk * 8;
+      for (int a = 0; a < p.kt; ++a) {
+        const int ts = to - p.pt + a;
+        if (ts < 0 || ts >= p.Ti) continue;  // temporal padding: the whole plane is zero, skip it (MMA warp agrees)
+        const __nv_bfloat16* frame = p.x + (static_cast<size_t>(n) * p.Ti + ts) * p.Hi * p.Wi * p.Cs;
+        for (int cc = 0; cc < cch; ++cc, ++pctr) {
+          const int ps = pctr & 1;
+          mbar_wait(&plane_empty[ps], ((pctr >> 1) & 1) ^ 1);
+          const uint32_t buf = smem_u32(smem + ps * planeBytes);
+          const __nv_bfloat16* src0 = frame + cc * 64 + chunk * 8;
+          for (int i = t >> 3; i < p.len; i += 16) {
+            const uint32_t pp = static_cast<uint32_t>(q0 + i);          // padded-flattened source position
+            const uint32_t r = fdiv64(pp, p.mulWp, p.shWp);
+            const int hs = static_cast<int>(r) - p.ph;
+            const int ws = static_cast<int>(pp - r * p.Wp) - p.pw;
+            const bool ok = static_cast<unsigned>(hs) < static_cast<unsigned>(p.Hi) &&
+                            static_cast<unsigned>(ws) < static_cast<unsigned>(p.Wi);
+            const __nv_bfloat16* src = src0 + (ok ? (static_cast<size_t>(hs) * p.Wi + ws) * p.Cs : 0);
+            cp_async16(buf + i * 128 + ((chunk ^ (i & 7)) << 4), src, ok ? 16u : 0u);
+          }
+          cp_async_mbar_arrive(&plane_full[ps]);
+          mbar_arrive(&plane_full[ps]);
+          // the kh*kw filter tiles of this (frame tap, channel chunk)
+          for (int b = 0; b < p.kh; ++b) {
+            for (int c = 0; c < p.kw; ++c, ++wctr) {
+              const int ws_ = wctr % kDirWStages;
+              mbar_wait(&w_empty[ws_], ((wctr / kDirWStages) & 1) ^ 1);
+              const int ta = p.flip ? p.kt - 1 - a : a, tb = p.flip ? p.kh - 1 - b : b, tc = p.flip ? p.kw - 1 - c : c;
+              const size_t koff = (static_cast<size_t>((ta * p.kh + tb) * p.kw + tc)) * p.Cs + cc * 64;
+              const uint32_t wt = smem_u32(wring + ws_ * W_BYTES) + (t >> 3) * 128 + ((chunk ^ ((t >> 3) & 7)) << 4);
+#pragma unroll
+              for (int j = 0; j < NT / 16; ++j) cp_async16(wt + j * 2048, wrow + koff + static_cast<size_t>(j) * 16 * ldw, 16u);
+              cp_async_mbar_arrive(&w_full[ws_]);
+              mbar_arrive(&w_full[ws_]);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ============================================================ epilogue
+    const int ew = warp - 4, lane = t & 31;
+    float ssum[NT / 32], ssq[NT / 32];
+#pragma unroll
+    for (int i = 0; i < NT / 32; ++i) ssum[i] = ssq[i] = 0.f;
+    int cur_nt = -1;
+    auto flush = [&]() {
+      if (p.stats && cur_nt >= 0) {
+#pragma unroll
+        for (int i = 0; i < NT / 32; ++i) {
+          atomicAdd(p.stats + cur_nt * NT + i * 32 + lane, ssum[i]);
+          atomicAdd(p.stats + p.Nout + cur_nt * NT + i * 32 + lane, ssq[i]);
+          ssum[i] = ssq[i] = 0.f;
+        }
+      }
+    };
+    uint32_t ictr = 0;
+    for (int it = blockIdx.x; it < p.numItems; it += gridDim.x, ++ictr) {
+      int nt, n, to, grp;
+      decode_item(it, nt, n, to, grp);
+      if (nt != cur_nt) {
+        flush();
+        cur_nt = nt;
+      }
+      const int buf = ictr & 1;
+      const int q0 = grp * p.G * 128;
+      int chunks = (p.P - q0 + 127) / 128;
+      if (chunks > p.G) chunks = p.G;
+      mbar_wait(&acc_full[buf], (ictr >> 1) & 1);
+      tc_fence_after_sync();
+      for (int m = 0; m < chunks; ++m) {
+        const uint32_t q = static_cast<uint32_t>(q0 + m * 128 + ew * 32 + lane);
+        const uint32_t ho = fdiv64(q, p.mulWp, p.shWp);
+        const int wo = static_cast<int>(q - ho * p.Wp);
+        const bool ok = q < static_cast<uint32_t>(p.P) && wo < p.Wo;
+        __nv_bfloat16* orow = p.y + ((((static_cast<size_t>(n) * p.To + to) * p.Ho + (ok ? ho : 0)) * p.Wo) +
+                                     (ok ? wo : 0)) * p.Nout + nt * NT;
+#pragma unroll 1
+        for (int c0 = 0; c0 < NT; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * accCols + m * NT + c0, v);
+          tmem_ld_wait();
+          float r[32];
+#pragma unroll
+          for (int jx = 0; jx < 32; jx += 8) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              f[e] = __uint_as_float(v[jx + e]);
+              if (p.bias) f[e] += __ldg(p.bias + nt * NT + c0 + jx + e);
+            }
+            uint4 o;
+            o.x = pack_bf16x2(f[0], f[1]);
+            o.y = pack_bf16x2(f[2], f[3]);
+            o.z = pack_bf16x2(f[4], f[5]);
+            o.w = pack_bf16x2(f[6], f[7]);
+            if (ok) *reinterpret_cast<uint4*>(orow + c0 + jx) = o;
+            if (p.stats) {
+              const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                r[jx + 2 * e] = ok ? __uint_as_float(w[e] << 16) : 0.f;
+                r[jx + 2 * e + 1] = ok ? __uint_as_float(w[e] & 0xffff0000u) : 0.f;
+              }
+            }
+          }
+          if (p.stats) {
+            float qq[32];
+#pragma unroll
+            for (int jx = 0; jx < 32; ++jx) qq[jx] = r[jx] * r[jx];
+            warp_column_sums(r, lane);
+            warp_column_sums(qq, lane);
+            // c0/32 is a runtime index into a tiny register array: resolve with a predicated unrolled loop
+#pragma unroll
+            for (int i = 0; i < NT / 32; ++i) {
+              if (i == (c0 >> 5)) {
+                ssum[i] += r[0];
+                ssq[i] += qq[0];
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&acc_empty[buf]);
+    }
+    flush();
+  } else {
+    // ============================================================ MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(128, NT, 0, 0);
+    uint32_t pctr = 0, wctr = 0, ictr = 0;
+    for (int it = blockIdx.x; it < p.numItems; it += gridDim.x, ++ictr) {
+      int nt, n, to, grp;
+      decode_item(it, nt, n, to, grp);
+      const int buf = ictr & 1;
+      const int q0 = grp * p.G * 128;
+      int chunks = (p.P - q0 + 127) / 128;
+      if (chunks > p.G) chunks = p.G;
+      mbar_wait(&acc_empty[buf], ((ictr >> 1) & 1) ^ 1);
+      tc_fence_after_sync();
+      bool first = true;
+      for (int a = 0; a < p.kt; ++a) {
+        const int ts = to - p.pt + a;
+        if (ts < 0 || ts >= p.Ti) continue;
+        for (int cc = 0; cc < cch; ++cc, ++pctr) {
+          const int ps = pctr & 1;
+          mbar_wait(&plane_full[ps], (pctr >> 1) & 1);
+          const uint32_t abase = smem_u32(smem + ps * planeBytes);
+          for (int b = 0; b < p.kh; ++b) {
+            for (int c = 0; c < p.kw; ++c, ++wctr) {
+              const int ws_ = wctr % kDirWStages;
+              mbar_wait(&w_full[ws_], (wctr / kDirWStages) & 1);
+              fence_proxy_async_smem();
+              tc_fence_after_sync();
+              if ((t & 31) == 0) {
+                const uint64_t bdesc = make_smem_desc_sw128(smem_u32(wring + ws_ * W_BYTES), 16, 1024);
+                const uint64_t adesc0 = make_smem_desc_sw128(abase + (b * p.Wp + c) * 128, 16, 1024);
+                for (int m = 0; m < chunks; ++m) {
+                  const uint64_t adesc = adesc0 + static_cast<uint64_t>(m * 1024);  // 128 rows * 128 B / 16
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem_base + buf * accCols + m * NT, adesc + 2 * k, bdesc + 2 * k, idesc,
+                              (first && k == 0) ? 0u : 1u);
+                }
+                umma_commit(&w_empty[ws_]);
+              }
+              __syncwarp();
+              first = false;
+            }
+          }
+          if ((t & 31) == 0) umma_commit(&plane_empty[ps]);
+          __syncwarp();
+        }
+      }
+      if ((t & 31) == 0) umma_commit(&acc_full[buf]);
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+static bool direct_geometry(const rsp_conv3d_desc* d, int transposed, DirectParams& p, int& NT, size_t& smem) {
+  if (d->st != 1 || d->sh != 1 || d->sw != 1) return false;
+  const int Cs = transposed ? d->Co : d->Ci, Nout = transposed ? d->Ci : d->Co;
+  if (Cs % 64 != 0 || Nout % 64 != 0) return false;
+  const int To = d->Ti + 2 * d->pt - d->kt + 1, Ho = d->Hi + 2 * d->ph - d->kh + 1, Wo = d->Wi + 2 * d->pw - d->kw + 1;
+  if (To <= 0 || Ho <= 0 || Wo <= 0) return false;
+  p.N = d->N;
+  p.Cs = Cs;
+  p.Nout = Nout;
+  p.kt = d->kt; p.kh = d->kh; p.kw = d->kw;
+  if (!transposed) {
+    p.Ti = d->Ti; p.Hi = d->Hi; p.Wi = d->Wi;
+    p.To = To; p.Ho = Ho; p.Wo = Wo;
+    p.pt = d->pt; p.ph = d->ph; p.pw = d->pw;
+    p.flip = 0;
+  } else {  // dX[i] = sum_tap dY[i + p - tap] W[tap]: a unit-stride conv over dY with padding k-1-p and mirrored taps
+    p.Ti = To; p.Hi = Ho; p.Wi = Wo;
+    p.To = d->Ti; p.Ho = d->Hi; p.Wo = d->Wi;
+    p.pt = d->kt - 1 - d->pt; p.ph = d->kh - 1 - d->ph; p.pw = d->kw - 1 - d->pw;
+    p.flip = 1;
+    if (p.pt < 0 || p.ph < 0 || p.pw < 0) return false;
+  }
+  p.Wp = p.Wi + 2 * p.pw;
+  p.Hp = p.Hi + 2 * p.ph;
+  if (p.Wo != p.Wp - p.kw + 1 || p.Ho != p.Hp - p.kh + 1) return false;
+  p.P = p.Ho * p.Wp;
+  NT = (Nout % 128 == 0) ? 128 : 64;
+  p.G = NT == 64 ? 4 : 2;
+  if (p.P < 128 * p.G) return false;                 // small planes: the gather kernel wastes less
+  if (p.kh * p.kw < 2) return false;                 // 1x1 filters have nothing to reuse
+  p.groups = (p.P + 128 * p.G - 1) / (128 * p.G);
+  p.len = (128 * p.G + (p.kh - 1) * p.Wp + p.kw - 1 + 7) / 8 * 8;
+  smem = 2 * static_cast<size_t>(p.len) * 128 + static_cast<size_t>(kDirWStages) * NT * 128 + 1024 + 512;
+  if (smem > 225 * 1024) return false;
+  const long long items = static_cast<long long>(Nout / NT) * p.N * p.To * p.groups;
+  if (items > (1ll << 30)) return false;
+  p.numItems = static_cast<int>(items);
+  int l = 0;
+  while ((1 << l) < p.Wp) ++l;
+  p.shWp = 32 + l;
+  p.mulWp = ((1ull << p.shWp) + p.Wp - 1) / p.Wp;
+  return true;
+}
+
+bool direct_supported(const rsp_conv3d_desc* d, int transposed) {
+  DirectParams p{};
+  int NT;
+  size_t smem;
+  return direct_geometry(d, transposed, p, NT, smem);
+}
+
+int launch_direct(const rsp_conv3d_desc* d, int transposed, const void* x, const void* wgt, const float* bias, void* y,
+                  float* stats, cudaStream_t stream) {
+  DirectParams p{};
+  int NT;
+  size_t smem;
+  if (!direct_geometry(d, transposed, p, NT, smem)) {
+    set_error("conv_direct: unsupported geometry");
+    return RSP_ERR_INVALID;
+  }
+  p.x = static_cast<const __nv_bfloat16*>(x);
+  p.wgt = static_cast<const __nv_bfloat16*>(wgt);
+  p.y = static_cast<__nv_bfloat16*>(y);
+  p.bias = bias;
+  p.stats = stats;
+  const int sms = device_sm_count();
+  const int grid = p.numItems < sms ? p.numItems : sms;
+  cudaError_t e;
+  if (NT == 64) {
+    e = cudaFuncSetAttribute(conv_direct_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess) conv_direct_kernel<64><<<grid, kDirThreads, smem, stream>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(conv_direct_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess) conv_direct_kernel<128><<<grid, kDirThreads, smem, stream>>>(p);
+  }
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(conv_direct): %s", cudaGetErrorString(e));
+    return RSP_ERR_CUDA;
+  }
+  return check_launch("conv_direct");
+}
+
+}  // namespace rsp

@@ -872,6 +872,9 @@ int pack_stem(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const fl
               cudaStream_t stream);
 int launch_stem_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const void* x, const void* dy,
                       float* dw, int accumulate, int sm_count, cudaStream_t stream);
+bool direct_supported(const rsp_conv3d_desc* d, int transposed);
+int launch_direct(const rsp_conv3d_desc* d, int transposed, const void* x, const void* wgt, const float* bias, void* y,
+                  float* stats, cudaStream_t stream);
 
 }  // namespace rsp
 
@@ -948,6 +951,7 @@ int64_t rsp_conv3d_workspace_bytes(const rsp_conv3d_desc* d, int which) {
   const int Cs = which == 0 ? d->Ci : d->Co;
   if (Cs % 64 != 0 || Nout % 64 != 0) return 0;
   if (which == 1 && (d->st > 1 || d->sh > 1 || d->sw > 1)) return 0;
+  if (direct_supported(d, which)) return 0;
   const int NT = Nout % 128 == 0 ? 128 : 64;
   const int numKb = d->kt * d->kh * d->kw * (Cs / 64);
   if (choose_splits(M, Nout, NT, numKb, device_sm_count()) <= 1) return 0;
@@ -966,6 +970,7 @@ int rsp_conv3d_fprop(const rsp_conv3d_desc* d, const void* x, const void* wp, co
     const __nv_bfloat16* wst = static_cast<const __nv_bfloat16*>(wp) + static_cast<size_t>(d->Co) * p.g.numKb * 64;
     return launch_stem(d, x, wst, bias, y, stats, device_sm_count(), stream);
   }
+  if (mode == MODE_GENERIC && direct_supported(d, 0)) return launch_direct(d, 0, x, wp, bias, y, stats, stream);
   p.g.src = static_cast<const __nv_bfloat16*>(x);
   p.wgt = static_cast<const __nv_bfloat16*>(wp);
   p.out = static_cast<__nv_bfloat16*>(y);
@@ -1058,6 +1063,7 @@ int rsp_conv3d_dgrad(const rsp_conv3d_desc* d, const void* dy, const void* wd, v
         }
     return RSP_OK;
   }
+  if (direct_supported(d, 1)) return launch_direct(d, 1, dy, wd, nullptr, dx, nullptr, stream);
   int rc = fill_geom(p.g, d, MODE_GENERIC, 1);
   if (rc != RSP_OK) return rc;
   p.g.src = static_cast<const __nv_bfloat16*>(dy);
