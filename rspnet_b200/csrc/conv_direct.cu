@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(kDirThreads, 1) conv_direct_kernel(const Direc
               mbar_wait(&w_full[ws_], (wctr / kDirWStages) & 1);
               fence_proxy_async_smem();
               tc_fence_after_sync();
-              if ((t & 31) == 0) {
+              if (elect_one()) {
                 const uint64_t bdesc = make_smem_desc_sw128(smem_u32(wring + ws_ * W_BYTES), 16, 1024);
                 const uint64_t adesc0 = make_smem_desc_sw128(abase + (b * p.Wp + c) * 128, 16, 1024);
                 for (int m = 0; m < chunks; ++m) {
@@ -274,11 +274,11 @@ __global__ void __launch_bounds__(kDirThreads, 1) conv_direct_kernel(const Direc
               first = false;
             }
           }
-          if ((t & 31) == 0) umma_commit(&plane_empty[ps]);
+          if (elect_one()) umma_commit(&plane_empty[ps]);
           __syncwarp();
         }
       }
-      if ((t & 31) == 0) umma_commit(&acc_full[buf]);
+      if (elect_one()) umma_commit(&acc_full[buf]);
       __syncwarp();
     }
   }

@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvParams p
       mbar_wait(&full_bar[s], ph);
       fence_proxy_async_smem();
       tc_fence_after_sync();
-      if ((t & 31) == 0) {
+      if (elect_one()) {
         const uint32_t a_panel = smem_u32(smem + s * STAGE_BYTES);
         const uint32_t b_panel = a_panel + A_BYTES;
         const uint64_t adesc = make_smem_desc_sw128(a_panel, 16, 1024);
@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const WgradParams 
         mbar_wait(&full_bar[s], ph);
         fence_proxy_async_smem();
         tc_fence_after_sync();
-        if ((t & 31) == 0) {
+        if (elect_one()) {
           const uint32_t stage = smem_u32(smem + s * STAGE_BYTES);
           // MN-major: 64-wide panels PANEL bytes apart (LBO), 8-pixel groups 1024 B apart (SBO)
           const uint64_t adesc = make_smem_desc_sw128(stage, PANEL, 1024);
@@ -667,30 +667,28 @@ __global__ void __launch_bounds__(256) pack_weight_fprop_kernel(const float* __r
 }
 
 // w fp32 [Co][Ci][kt][kh][kw] -> wd bf16 [CiPad][taps*CoPad]  (dgrad B operand: K index = tap*CoPad + co).
-// One block per (32 co x 32 ci) tile and tap-group: transposes through smem so that reads (along taps within one
-// (co,ci)) and writes (along co) are both contiguous enough.
+// Seen as matrices this is a plain transpose: w is [Co] x [R = Ci*taps] (r = ci*taps + tap) and wd is
+// [CiPad*taps] x [CoPad] with the same r on its rows, so a 64 x 64 smem tile gives coalesced reads (along r) and
+// coalesced bf16 writes (along co); rows / columns beyond the logical extents are zero.
 __global__ void __launch_bounds__(256) pack_weight_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wd,
-                                                                int Co, int CoPad, int Ci, int CiPad, int taps) {
-  extern __shared__ float sw[];  // [32 co][32 ci][taps] (+1 padding on the ci stride)
-  const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * 32;
-  const int stride_ci = taps, stride_co = 32 * taps + 1;
-  // coalesced read: for fixed co the 32 ci x taps floats are contiguous in w
-  for (int i = threadIdx.x; i < 32 * 32 * taps; i += 256) {
-    const int col = i / (32 * taps), rem = i - col * 32 * taps;  // rem = cil*taps + tap
-    const int co = co0 + col, cil = rem / taps;
-    float v = 0.f;
-    if (co < Co && ci0 + cil < Ci) v = w[(static_cast<size_t>(co) * Ci + ci0) * taps + rem];
-    sw[col * stride_co + rem] = v;
+                                                                int Co, int CoPad, int R, int Rpad) {
+  __shared__ float tile[64][65];
+  const int r0 = blockIdx.x * 64, co0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int co = co0 + ty + 4 * i, r = r0 + tx;
+    tile[ty + 4 * i][tx] = (co < Co && r < R) ? w[static_cast<size_t>(co) * R + r] : 0.f;
   }
   __syncthreads();
-  const size_t K = static_cast<size_t>(taps) * CoPad;
-  for (int i = threadIdx.x; i < 32 * 32 * taps; i += 256) {
-    const int col = i & 31;                 // co fastest: contiguous bf16 writes
-    const int rest = i >> 5;
-    const int tap = rest % taps, cil = rest / taps;
-    if (ci0 + cil < CiPad && co0 + col < CoPad)
-      wd[static_cast<size_t>(ci0 + cil) * K + static_cast<size_t>(tap) * CoPad + co0 + col] =
-          __float2bfloat16(sw[col * stride_co + cil * stride_ci + tap]);
+  // each thread writes two adjacent output channels (one 32-bit store); a warp covers one 128 B row segment
+  const int cx = (threadIdx.x & 31) * 2, ry = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = r0 + ry + 8 * i;
+    if (r < Rpad && co0 + cx < CoPad)
+      *reinterpret_cast<uint32_t*>(wd + static_cast<size_t>(r) * CoPad + co0 + cx) =
+          pack_bf16x2(tile[cx][ry + 8 * i], tile[cx + 1][ry + 8 * i]);
   }
 }
 
@@ -916,7 +914,6 @@ int rsp_conv3d_pack_weight(const rsp_conv3d_desc* d, int Ci_logical, int Co_logi
     static bool attr_done = false;
     if (!attr_done) {
       cudaFuncSetAttribute(pack_weight_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      cudaFuncSetAttribute(pack_weight_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       attr_done = true;
     }
     pack_weight_fprop_kernel<<<d->Co, 256, per, stream>>>(w, static_cast<__nv_bfloat16*>(wp), mode, Co_logical,
@@ -929,16 +926,10 @@ int rsp_conv3d_pack_weight(const rsp_conv3d_desc* d, int Ci_logical, int Co_logi
   }
   RSP_REQUIRE(mode == MODE_GENERIC, "pack_weight(dgrad): small-channel convs have no dgrad");
   const int taps = d->kt * d->kh * d->kw;
-  const size_t sm = (static_cast<size_t>(32) * (32 * taps + 1)) * sizeof(float);
-  RSP_REQUIRE(sm <= 200 * 1024, "pack_weight(dgrad): filter too large for the transpose tile");
-  static bool attr_done2 = false;
-  if (!attr_done2) {
-    cudaFuncSetAttribute(pack_weight_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done2 = true;
-  }
-  dim3 grid((d->Co + 31) / 32, (d->Ci + 31) / 32);
-  pack_weight_dgrad_kernel<<<grid, 256, sm, stream>>>(w, static_cast<__nv_bfloat16*>(wp), Co_logical, d->Co,
-                                                      Ci_logical, d->Ci, taps);
+  RSP_REQUIRE(d->Co % 64 == 0 && d->Ci % 64 == 0, "pack_weight(dgrad): stored channel counts must be multiples of 64");
+  const int R = Ci_logical * taps, Rpad = d->Ci * taps;
+  dim3 grid((Rpad + 63) / 64, d->Co / 64);
+  pack_weight_dgrad_kernel<<<grid, 256, 0, stream>>>(w, static_cast<__nv_bfloat16*>(wp), Co_logical, d->Co, R, Rpad);
   return check_launch("pack_weight_dgrad");
 }
 

@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
         mbar_wait(&full_bar[s], ph);
         fence_proxy_async_smem();
         tc_fence_after_sync();
-        if ((t & 31) == 0) {
+        if (elect_one()) {
           // kh == 7 and sh == 2 (stem_supported): every descriptor is a compile-time offset from two bases, so the
           // issuing thread spends ~3 instructions per MMA instead of rebuilding 64-bit descriptors
           const uint32_t aslab = smem_u32(smem + s * kStemStageBytes);
@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(160, 1) conv_stem_wgrad_kernel(const StemWgrad
         mbar_wait(&full_bar[s], ph);
         fence_proxy_async_smem();
         tc_fence_after_sync();
-        if ((t & 31) == 0) {
+        if (elect_one()) {
           const uint32_t stage = smem_u32(smem + s * kSWStageBytes);
           // A: 16 pixels = two 8-row groups of the swizzled dY panel.
           // B: N chunk = the same 2-pixel window (16 B) of every filter row (rows are 1 KB apart -> SBO = 1024), so one
