@@ -43,10 +43,11 @@ class C3D(nn.Module):
     def feature_ndhwc(self, x):
         x = rnn.as_ndhwc(x)
         for tag, _, _ in self._PLAN:
-            x = rnn.conv_bn_act(x, getattr(self, "conv" + tag), getattr(self, "bn" + tag), relu=True)
             pool = self._POOL_AFTER.get(tag)
             if pool:
-                x = rnn.max_pool3d(x, getattr(self, pool))
+                x = rnn.conv_bn_relu_pool(x, getattr(self, "conv" + tag), getattr(self, "bn" + tag), getattr(self, pool))
+            else:
+                x = rnn.conv_bn_act(x, getattr(self, "conv" + tag), getattr(self, "bn" + tag), relu=True)
         if self.return_conv:
             x = rnn.max_pool3d(x, self.feature_pool)
         return x

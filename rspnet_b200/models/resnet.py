@@ -106,8 +106,7 @@ class ResNet(nn.Module):
     def feature_ndhwc(self, x):
         """get_feature on channels-last bf16 activations; returns bf16 [N, t, h, w, 512*expansion]."""
         x = rnn.as_ndhwc(x)
-        x = rnn.conv_bn_act(x, self.conv1, self.bn1, relu=True)
-        x = rnn.max_pool3d(x, self.maxpool)
+        x = rnn.conv_bn_relu_pool(x, self.conv1, self.bn1, self.maxpool)
         x = self.layer1(x)
         x = self.layer2(x)
         x = self.layer3(x)

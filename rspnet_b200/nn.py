@@ -96,6 +96,70 @@ class ConvBNAct(torch.autograd.Function):
         return dx, dw, dbias, dgamma, dbeta, None, None, dres, None, None, None, None, None, None
 
 
+class ConvBNReLUPool(torch.autograd.Function):
+    """Conv3d (+bias) -> train-mode BatchNorm3d -> ReLU -> MaxPool3d with the BN/ReLU/pool part fused into one kernel
+    each way (reference: models/resnet.py:203-206, models/c3d.py:111-139)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, kernel, stride, padding, eps, momentum,
+                pool_k, pool_s, pool_p):
+        co = ops.pad_channels(weight.shape[0])
+        desc = ops.conv_desc(x.shape, co, kernel, stride, padding)
+        wp = _pack_cache.get(weight, desc, 0)
+        key = (id(gamma), co, x.device)
+        acc = _stats_acc.get(key)
+        if acc is None:
+            acc = _stats_acc[key] = torch.zeros((2, co), dtype=torch.float32, device=x.device)
+        y = ops.conv3d_fprop(desc, x, wp, _pad_vec(bias, co), stats=acc)
+        if not ops.conv3d_fprop.stats_done:
+            ops.bn_stats(y, out=acc)
+        count = y.numel() // co
+        scale, shift, mean, invstd = ops.bn_finalize(acc[0], acc[1], count, gamma, beta, eps, momentum, running_mean,
+                                                     running_var, co, clear_sums=True)
+        pdesc = ops.pool_desc(y.shape, pool_k, pool_s, pool_p)
+        out, idx = ops.bn_relu_maxpool_fwd(pdesc, y, scale, shift)
+        ctx.desc, ctx.pdesc = desc, pdesc
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, weight, y, idx, scale, shift, mean, invstd, gamma)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight, y, idx, scale, shift, mean, invstd, gamma = ctx.saved_tensors
+        desc = ctx.desc
+        dy, dgamma, dbeta = ops.bn_relu_maxpool_bwd(ctx.pdesc, dout.contiguous(), idx, y, scale, shift, mean, invstd,
+                                                    gamma)
+        dw = ops.conv3d_wgrad(desc, x, dy, weight.shape)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.conv3d_dgrad(desc, dy, _pack_cache.get(weight, desc, 1))
+        dbias = torch.zeros(weight.shape[0], dtype=torch.float32, device=weight.device) if ctx.has_bias else None
+        return (dx, dw, dbias, dgamma, dbeta) + (None,) * 10
+
+
+def conv_bn_relu_pool(x, conv: torch.nn.Conv3d, bn: torch.nn.BatchNorm3d, pool: torch.nn.MaxPool3d):
+    """pool(relu(bn(conv(x)))) — fused when the pool geometry fits the kernel, else the two-step path."""
+    if pool.ceil_mode or pool.dilation not in (1, (1, 1, 1)):
+        raise NotImplementedError("rspnet_b200: ceil_mode / dilated MaxPool3d is not on the pretraining path")
+    pk = ops._triple(pool.kernel_size)
+    ps = ops._triple(pool.stride if pool.stride is not None else pool.kernel_size)
+    pp = ops._triple(pool.padding)
+    k, s, p = tuple(conv.kernel_size), tuple(conv.stride), tuple(conv.padding)
+    co = ops.pad_channels(conv.weight.shape[0])
+    cd = ops.conv_desc(x.shape, co, k, s, p)
+    to, ho, wo = cd.out_dims()
+    if not bn.training or not ops.bn_relu_maxpool_supported(ops.pool_desc((x.shape[0], to, ho, wo, co), pk, ps, pp)):
+        return max_pool3d(conv_bn_act(x, conv, bn, relu=True), pool)
+    if conv.groups != 1 or tuple(conv.dilation) != (1, 1, 1):
+        raise NotImplementedError("rspnet_b200: grouped / dilated Conv3d is not on the pretraining path")
+    momentum = bn.momentum if bn.momentum is not None else 0.0
+    out = ConvBNReLUPool.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, k, s, p,
+                               bn.eps, momentum, pk, ps, pp)
+    if bn.track_running_stats and bn.num_batches_tracked is not None and not getattr(bn, "_rsp_counter_batched", False):
+        bn.num_batches_tracked += 1
+    return out
+
+
 def conv_bn_act(x, conv: torch.nn.Conv3d, bn: torch.nn.BatchNorm3d, relu: bool = True, residual=None):
     """Fused Conv3d -> BatchNorm3d(train) -> (+residual) -> (ReLU) on NDHWC bf16 activations."""
     if not bn.training:

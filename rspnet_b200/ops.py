@@ -152,6 +152,32 @@ def maxpool3d_bwd(desc: PoolDesc, dy, idx):
     return dx
 
 
+def bn_relu_maxpool_supported(desc: PoolDesc) -> bool:
+    return bool(_lib.load().rsp_bn_relu_maxpool_supported(C.byref(desc)))
+
+
+def bn_relu_maxpool_fwd(desc: PoolDesc, x, scale, shift):
+    """maxpool(relu(x*scale + shift)) without materialising the activation; returns (y, argmax)."""
+    to, ho, wo = desc.out_dims()
+    y = torch.empty((desc.N, to, ho, wo, desc.C), dtype=torch.bfloat16, device=x.device)
+    idx = torch.empty((desc.N, to, ho, wo, desc.C), dtype=torch.uint8, device=x.device)
+    call("rsp_bn_relu_maxpool_fwd", C.byref(desc), ptr(x), ptr(scale), ptr(shift), ptr(y), ptr(idx), stream_ptr())
+    return y, idx
+
+
+def bn_relu_maxpool_bwd(desc: PoolDesc, dy, idx, x, scale, shift, mean, invstd, gamma):
+    """Gradient w.r.t. the conv output x plus (dgamma, dbeta) of the fused BN -> ReLU -> MaxPool block."""
+    c = x.shape[-1]
+    sums = torch.zeros((2, c), dtype=torch.float32, device=x.device)
+    call("rsp_bn_relu_maxpool_bwd_reduce", C.byref(desc), ptr(dy), ptr(idx), ptr(x), ptr(scale), ptr(shift), ptr(mean),
+         ptr(invstd), ptr(sums[0]), ptr(sums[1]), stream_ptr())
+    dx = torch.empty_like(x)
+    call("rsp_bn_relu_maxpool_bwd_apply", C.byref(desc), ptr(dy), ptr(idx), ptr(x), ptr(scale), ptr(shift), ptr(mean),
+         ptr(invstd), ptr(gamma), ptr(sums[0]), ptr(sums[1]), ptr(dx), gamma.numel(), stream_ptr())
+    cl = gamma.numel()
+    return dx, sums[1][:cl], sums[0][:cl]
+
+
 # ------------------------------------------------------------------------------------------------ heads
 def head_fwd(feat, c_logical, w1, b1, w2, b2):
     b = feat.shape[0]

@@ -227,6 +227,50 @@ def test_maxpool_fwd_bwd(k, s, p, shape):
     torch.testing.assert_close(ops.to_ncdhw_f32(dx, c), xb.grad, rtol=1e-2, atol=1e-2)
 
 
+@pytest.mark.parametrize("k,s,p,shape", [((3, 3, 3), (2, 2, 2), (1, 1, 1), (2, 64, 6, 12, 10)),
+                                          ((3, 3, 3), (2, 2, 2), (1, 1, 1), (1, 64, 5, 23, 56)),
+                                          ((1, 2, 2), (1, 2, 2), (0, 0, 0), (2, 64, 3, 8, 8)),
+                                          ((2, 2, 2), (2, 2, 2), (0, 0, 0), (1, 128, 4, 6, 6)),
+                                          ((2, 2, 2), (2, 2, 2), (0, 0, 0), (2, 512, 4, 7, 7)),
+                                          ((3, 3, 3), (1, 1, 1), (1, 1, 1), (1, 256, 3, 5, 5))])
+def test_bn_relu_maxpool_fused(k, s, p, shape):
+    """The fused BN -> ReLU -> MaxPool kernels against (a) the two-step kernels (bit-identical forward: same bf16 rounding of
+    the activation, same first-maximum rule) and (b) torch autograd in fp32."""
+    ops = _ops()
+    n, c = shape[0], shape[1]
+    x = rand(*shape, seed=1) * 1.5 + 0.3
+    gamma, beta = rand(c, seed=2).abs() + 0.5, rand(c, seed=3) * 0.5
+    xn = ops.to_ndhwc_bf16(x, c)
+    ssum, ssq = ops.bn_stats(xn)
+    scale, shift, mean, invstd = ops.bn_finalize(ssum, ssq, xn.numel() // c, gamma, beta, 1e-5, 0.1, None, None, c)
+    desc = ops.pool_desc(xn.shape, k, s, p)
+    assert ops.bn_relu_maxpool_supported(desc)
+    act = ops.bn_act_fwd(xn, scale, shift, None, True)
+    y2, idx2 = ops.maxpool3d_fwd(desc, act)
+    y1, idx1 = ops.bn_relu_maxpool_fwd(desc, xn, scale, shift)
+    assert torch.equal(y1, y2) and torch.equal(idx1, idx2)
+    dy = ops.to_ndhwc_bf16(rand(n, c, *y1.shape[1:4], seed=4), c)
+    dx1, dgamma1, dbeta1 = ops.bn_relu_maxpool_bwd(desc, dy, idx1, xn, scale, shift, mean, invstd, gamma)
+    dpool = ops.maxpool3d_bwd(desc, dy, idx2)               # rounds the routed gradient to bf16 (the fused path does not)
+    dx2, _, dgamma2, dbeta2 = ops.bn_act_bwd(dpool, act, xn, mean, invstd, gamma, True, False)
+    scale_dx = dx2.float().abs().max().item()
+    assert (dx1.float() - dx2.float()).abs().max().item() <= 2e-2 * scale_dx
+    torch.testing.assert_close(dgamma1, dgamma2, rtol=2e-2, atol=5e-2)
+    torch.testing.assert_close(dbeta1, dbeta2, rtol=2e-2, atol=5e-2)
+    # torch fp32 statement of the same block
+    xb = xn.float().permute(0, 4, 1, 2, 3).contiguous().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yt = F.max_pool3d(F.relu(F.batch_norm(xb, None, None, gr, br, True, 0.1, 1e-5)), k, s, p)
+    yt.backward(dy.float().permute(0, 4, 1, 2, 3))
+    torch.testing.assert_close(ops.to_ncdhw_f32(y1, c), yt.detach(), rtol=2e-2, atol=2e-2)
+    # argmax decisions are taken on bf16-rounded activations: a few windows may route differently -> robust statistic
+    err = (ops.to_ncdhw_f32(dx1, c) - xb.grad).abs()
+    assert err.median().item() < 1e-2 * xb.grad.abs().max().item()
+    assert (err > 5e-2 * xb.grad.abs().max().item()).float().mean().item() < 0.02
+    torch.testing.assert_close(dgamma1, gr.grad, rtol=5e-2, atol=0.5)
+    torch.testing.assert_close(dbeta1, br.grad, rtol=5e-2, atol=0.5)
+
+
 def test_head_fwd_bwd():
     ops = _ops()
     b, c, d = 5, 512, 128
