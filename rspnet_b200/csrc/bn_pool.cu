@@ -4,7 +4,8 @@
 // (conv -> bn -> relu -> pool1..4).  Unfused, the post-activation tensor is written and read back once in the forward
 // (bn_act_fwd + maxpool_fwd) and the pool gradient is materialised at full resolution in the backward (maxpool_bwd ->
 // bn reduce -> bn apply).  Here:
-//   forward : conv output x (bf16) --(scale, shift, relu, round to bf16)--> smem window rows --> pooled y + uint8 argmax
+//   forward : raw conv-output rows (bf16) --bulk copy--> smem; window scan on sign(scale)*x; affine + ReLU once per output
+//             --> pooled y + uint8 argmax
 //   backward: dz(input position) = [bn(x) > 0] * sum of dy over the windows whose argmax is this position, rebuilt on the
 //             fly from (dy, argmax) staged in smem; one pass reduces (sum dz, sum dz*xhat), one pass writes dx.
 // HBM traffic per input element: forward 2 B read (+ pooled output), backward 2 x 2 B read + 2 B write.
@@ -47,48 +48,72 @@ struct FPGeom {
 __host__ __device__ __forceinline__ int floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
 __host__ __device__ __forceinline__ int ceil_div(int a, int b) { return floor_div(a + b - 1, b); }
 
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
-// forward: one tile = HB output rows of one (n, to); smem holds the kt x rowsIn activated input rows it needs
+// forward: one tile = HB output rows of one (n, to).  The kt x rowsIn raw input rows it needs are contiguous per frame in
+// NDHWC, so one elected thread fetches them with bulk copies (UBLKCP) that complete on an mbarrier; 2-3 CTAs per SM keep
+// the copy of one tile under the compute of another.  max/relu/affine commute per channel:
+//   max_w relu(scale*x + shift) = relu(scale * max_w(sign(scale)*x) * sign(scale) + shift)
+// so the window scan compares sign-flipped raw values and the affine + ReLU runs once per output.
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bn_relu_maxpool_fwd_kernel(const uint4* __restrict__ x,
                                                                   const float* __restrict__ scale,
                                                                   const float* __restrict__ shift,
                                                                   uint4* __restrict__ y, uint2* __restrict__ idx,
                                                                   const FPGeom p) {
-  extern __shared__ uint4 tile[];  // [kt][rowsIn][Wi][G]
+  extern __shared__ __align__(128) uint4 tile[];  // [kt][rowsIn][Wi][G] raw bf16
+  __shared__ __align__(8) uint64_t bar;
   const int G = p.C >> 3;
   const int g = threadIdx.x % G;   // 256 % G == 0: a thread keeps its channel group across strided loops
   float sc[8], sf[8];
+  uint32_t flip[4];                // sign-bit masks per bf16 pair: compare sign(scale)*x
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     sc[e] = scale[g * 8 + e];
     sf[e] = shift[g * 8 + e];
   }
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+    flip[e] = (sc[2 * e] < 0.f ? 0x00008000u : 0u) | (sc[2 * e + 1] < 0.f ? 0x80000000u : 0u);
   const int rowVecs = p.Wi * G;
   const int frameVecs = p.rowsIn * rowVecs;
-  for (int tIdx = blockIdx.x; tIdx < p.numTiles; tIdx += gridDim.x) {
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+  for (int tIdx = blockIdx.x; tIdx < p.numTiles; tIdx += gridDim.x, phase ^= 1) {
     const int band = tIdx % p.bands;
     const int q = tIdx / p.bands;
     const int to = q % p.To, n = q / p.To;
     const int ho0 = band * p.HB;
     const int hi0 = ho0 * p.sh - p.ph, ti0 = to * p.st - p.pt;
+    const int h_lo = max(hi0, 0), h_hi = min(hi0 + p.rowsIn, p.Hi);   // valid input rows [h_lo, h_hi)
     __syncthreads();  // previous tile fully consumed
-    for (int a = 0; a < p.kt; ++a) {
-      const int ti = ti0 + a;
-      if (ti < 0 || ti >= p.Ti) continue;
-      const uint4* frame = x + (static_cast<size_t>(n) * p.Ti + ti) * p.Hi * rowVecs;
-      for (int v = threadIdx.x; v < frameVecs; v += 256) {
-        const int r = v / rowVecs;
-        const int hi = hi0 + r;
-        if (hi < 0 || hi >= p.Hi) continue;
-        float f[8];
-        unpack8(__ldg(frame + static_cast<size_t>(hi) * rowVecs + (v - r * rowVecs)), f);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = fmaxf(fmaf(f[e], sc[e], sf[e]), 0.f);
-        tile[a * frameVecs + v] = pack8(f);
+    if (threadIdx.x == 0) {
+      fence_proxy_async_smem();
+      uint32_t bytes = 0;
+      const uint32_t chunk = static_cast<uint32_t>(h_hi - h_lo) * rowVecs * 16u;
+      for (int a = 0; a < p.kt; ++a) {
+        const int ti = ti0 + a;
+        if (ti >= 0 && ti < p.Ti) bytes += chunk;
+      }
+      mbar_arrive_expect_tx(&bar, bytes);
+      for (int a = 0; a < p.kt; ++a) {
+        const int ti = ti0 + a;
+        if (ti < 0 || ti >= p.Ti) continue;
+        const uint4* src = x + ((static_cast<size_t>(n) * p.Ti + ti) * p.Hi + h_lo) * rowVecs;
+        bulk_g2s(tile + a * frameVecs + (h_lo - hi0) * rowVecs, src, chunk, &bar);
       }
     }
-    __syncthreads();
+    mbar_wait(&bar, phase);
     const int hbEff = min(p.HB, p.Ho - ho0);
     const int items = hbEff * p.Wo * G;
     for (int it = threadIdx.x; it < items; it += 256) {
@@ -101,7 +126,8 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_fwd_kernel(const uint4* _
         best[e] = -INFINITY;
         bi[e] = 0;
       }
-      bool any = false;
+      const int w0 = wo * p.sw - p.pw;
+      const int c_lo = max(0, -w0), c_hi = min(p.kw, p.Wi - w0);
       for (int a = 0; a < p.kt; ++a) {
         const int ti = ti0 + a;
         if (ti < 0 || ti >= p.Ti) continue;
@@ -109,24 +135,28 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_fwd_kernel(const uint4* _
           const int r = hb * p.sh + b;
           const int hi = hi0 + r;
           if (hi < 0 || hi >= p.Hi) continue;
-          const uint4* row = tile + a * frameVecs + r * rowVecs + g;
-          for (int c = 0; c < p.kw; ++c) {
-            const int wi = wo * p.sw - p.pw + c;
-            if (wi < 0 || wi >= p.Wi) continue;
+          const uint4* row = tile + a * frameVecs + r * rowVecs + w0 * G + g;
+          unsigned lin = (a * p.kh + b) * p.kw + c_lo;
+          for (int c = c_lo; c < c_hi; ++c, ++lin) {
+            uint4 raw = row[c * G];
+            raw.x ^= flip[0];
+            raw.y ^= flip[1];
+            raw.z ^= flip[2];
+            raw.w ^= flip[3];
             float v[8];
-            unpack8(row[wi * G], v);
-            const unsigned lin = (a * p.kh + b) * p.kw + c;
+            unpack8(raw, v);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              if (!any || v[e] > best[e]) {
+              if (v[e] > best[e]) {   // strict: the first maximum in (kt, kh, kw) order wins, as in nn.MaxPool3d
                 best[e] = v[e];
                 bi[e] = lin;
               }
             }
-            any = true;
           }
         }
       }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) best[e] = fmaxf(fmaf(best[e], fabsf(sc[e]), sf[e]), 0.f);  // |s| * (sign*x) = s*x
       const size_t o = (((static_cast<size_t>(n) * p.To + to) * p.Ho + ho0 + hb) * p.Wo + wo) * G + g;
       y[o] = pack8(best);
       uint2 iv;
@@ -138,37 +168,55 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_fwd_kernel(const uint4* _
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// backward: one tile = HB input rows of one (n, ti); smem holds dy / argmax of every window that can select them
+// backward: one tile = HB input rows of one (n, ti); bulk copies stage dy / argmax of every window that can select them
+// plus the x rows themselves.
 // MODE 0: per-channel sums (sum dz, sum dz*xhat) -> atomics.  MODE 1: dx = gamma*invstd*(dz - s1/M - xhat*s2/M).
 // ---------------------------------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(256) bn_relu_maxpool_bwd_kernel(
+__global__ void __launch_bounds__(256, 2) bn_relu_maxpool_bwd_kernel(
     const uint4* __restrict__ dy, const uint2* __restrict__ idx, const uint4* __restrict__ x,
     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ gamma, float* __restrict__ sum_dz,
     float* __restrict__ sum_dz_xhat, uint4* __restrict__ dx, const FPGeom p, int Cl, float inv_m, int maxWin) {
-  extern __shared__ uint4 stage[];                       // dy vectors, then argmax vectors
-  uint2* sidx = reinterpret_cast<uint2*>(stage + maxWin);
-  __shared__ float red[MODE == 0 ? 2 * 256 * 8 : 1];
+  extern __shared__ __align__(128) uint4 stage[];        // dy vectors | x rows | argmax vectors | tables
   const int G = p.C >> 3;
+  const int rowVecs = p.Wi * G, orowVecs = p.Wo * G;
+  uint4* xs = stage + maxWin;
+  uint2* sidx = reinterpret_cast<uint2*>(xs + p.HB * rowVecs);
+  int* wtab = reinterpret_cast<int*>(sidx + maxWin);     // [Wi]  w_lo | w_hi << 16
+  int* htab = wtab + p.Wi;                               // [HB]  h_lo | h_hi << 16
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ float red[MODE == 0 ? 2 * 256 * 8 : 1];
   const int g = threadIdx.x % G;
-  float sc[8], sf[8], mu[8], is[8], k[8], s1[8], s2[8], a0[8], a1[8];
+  // MODE 0: A = mean;                    a0 = sum dz, a1 = sum dz*(x - mean)   (invstd applied at the end)
+  // MODE 1: dx = K*dz + A + B*x with K = gamma*invstd, B = -K*s2*invstd, A = -K*s1 - B*mean
+  float sc[8], sf[8], A[8], B[8], K[8], a0[8], a1[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int c = g * 8 + e;
     sc[e] = scale[c];
     sf[e] = shift[c];
-    mu[e] = mean[c];
-    is[e] = invstd[c];
     a0[e] = a1[e] = 0.f;
-    if (MODE == 1) {
-      k[e] = c < Cl ? gamma[c] * is[e] : 0.f;
-      s1[e] = sum_dz[c] * inv_m;
-      s2[e] = sum_dz_xhat[c] * inv_m;
+    if (MODE == 0) {
+      A[e] = mean[c];
+    } else {
+      const float is = invstd[c];
+      K[e] = c < Cl ? gamma[c] * is : 0.f;
+      B[e] = -K[e] * (sum_dz_xhat[c] * inv_m) * is;
+      A[e] = -K[e] * (sum_dz[c] * inv_m) - B[e] * mean[c];
     }
   }
-  const int rowVecs = p.Wi * G, orowVecs = p.Wo * G;
-  for (int tIdx = blockIdx.x; tIdx < p.numTiles; tIdx += gridDim.x) {
+  for (int wi = threadIdx.x; wi < p.Wi; wi += 256) {
+    const int lo = max(0, ceil_div(wi + p.pw - p.kw + 1, p.sw)), hi = min(p.Wo - 1, floor_div(wi + p.pw, p.sw));
+    wtab[wi] = lo | (hi << 16);
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+  for (int tIdx = blockIdx.x; tIdx < p.numTiles; tIdx += gridDim.x, phase ^= 1) {
     const int band = tIdx % p.bands;
     const int q = tIdx / p.bands;
     const int ti = q % p.Ti, n = q / p.Ti;
@@ -179,15 +227,26 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_bwd_kernel(
     const int ho_hi = min(p.Ho - 1, floor_div(hi0 + hbEff - 1 + p.ph, p.sh));
     const int nto = max(0, to_hi - to_lo + 1), nho = max(0, ho_hi - ho_lo + 1);
     __syncthreads();
-    const int win = nto * nho * orowVecs;
-    for (int v = threadIdx.x; v < win; v += 256) {
-      const int r = v / orowVecs;                 // (to - to_lo) * nho + (ho - ho_lo)
-      const int tt = r / nho, hh = r - tt * nho;
-      const size_t o = ((static_cast<size_t>(n) * p.To + to_lo + tt) * p.Ho + ho_lo + hh) * orowVecs + (v - r * orowVecs);
-      stage[v] = __ldg(dy + o);
-      sidx[v] = __ldg(idx + o);
+    if (threadIdx.x == 0) {
+      fence_proxy_async_smem();
+      const uint32_t rows = static_cast<uint32_t>(nho) * orowVecs;       // vectors per candidate frame
+      const uint32_t xbytes = static_cast<uint32_t>(hbEff) * rowVecs * 16u;
+      mbar_arrive_expect_tx(&bar, xbytes + static_cast<uint32_t>(nto) * rows * 24u);
+      bulk_g2s(xs, x + ((static_cast<size_t>(n) * p.Ti + ti) * p.Hi + hi0) * rowVecs, xbytes, &bar);
+      if (rows)
+        for (int tt = 0; tt < nto; ++tt) {
+          const size_t o = ((static_cast<size_t>(n) * p.To + to_lo + tt) * p.Ho + ho_lo) * orowVecs;
+          bulk_g2s(stage + tt * rows, dy + o, rows * 16u, &bar);
+          bulk_g2s(sidx + tt * rows, idx + o, rows * 8u, &bar);
+        }
+    }
+    if (threadIdx.x < hbEff) {
+      const int hi = hi0 + threadIdx.x;
+      const int lo = max(ho_lo, ceil_div(hi + p.ph - p.kh + 1, p.sh)), hh = min(ho_hi, floor_div(hi + p.ph, p.sh));
+      htab[threadIdx.x] = lo | (hh << 16);
     }
     __syncthreads();
+    mbar_wait(&bar, phase);
     const int items = hbEff * rowVecs;
     for (int it = threadIdx.x; it < items; it += 256) {
       const int pix = it / G;
@@ -196,8 +255,8 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_bwd_kernel(
       float acc[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-      const int h_lo = max(ho_lo, ceil_div(hi + p.ph - p.kh + 1, p.sh)), h_hi = min(ho_hi, floor_div(hi + p.ph, p.sh));
-      const int w_lo = max(0, ceil_div(wi + p.pw - p.kw + 1, p.sw)), w_hi = min(p.Wo - 1, floor_div(wi + p.pw, p.sw));
+      const int ht = htab[hb], wt = wtab[wi];
+      const int h_lo = ht & 0xffff, h_hi = ht >> 16, w_lo = wt & 0xffff, w_hi = wt >> 16;
       for (int to = to_lo; to <= to_hi; ++to) {
         const int a = ti + p.pt - to * p.st;
         for (int ho = h_lo; ho <= h_hi; ++ho) {
@@ -217,21 +276,19 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_bwd_kernel(
           }
         }
       }
-      const size_t o = ((static_cast<size_t>(n) * p.Ti + ti) * p.Hi + hi) * rowVecs + wi * G + g;
       float xv[8], out[8];
-      unpack8(__ldg(x + o), xv);
+      unpack8(xs[it], xv);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float dz = fmaf(xv[e], sc[e], sf[e]) > 0.f ? acc[e] : 0.f;
-        const float xh = (xv[e] - mu[e]) * is[e];
         if (MODE == 0) {
           a0[e] += dz;
-          a1[e] = fmaf(dz, xh, a1[e]);
+          a1[e] = fmaf(dz, xv[e] - A[e], a1[e]);
         } else {
-          out[e] = k[e] * (dz - s1[e] - xh * s2[e]);
+          out[e] = fmaf(K[e], dz, fmaf(B[e], xv[e], A[e]));
         }
       }
-      if (MODE == 1) dx[o] = pack8(out);
+      if (MODE == 1) dx[((static_cast<size_t>(n) * p.Ti + ti) * p.Hi + hi0) * rowVecs + it] = pack8(out);
     }
   }
   if (MODE == 0) {
@@ -251,7 +308,7 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_bwd_kernel(
         t1 += red[2048 + (r * G + gg) * 8 + e];
       }
       atomicAdd(sum_dz + c, t0);
-      atomicAdd(sum_dz_xhat + c, t1);
+      atomicAdd(sum_dz_xhat + c, t1 * invstd[c]);
     }
   }
 }
@@ -280,10 +337,22 @@ using namespace rsp;
 
 extern "C" {
 
+static int bwd_smem_bytes(const FPGeom& g, int& maxWin) {
+  const int nto = (g.kt + g.st - 1) / g.st, nho = (g.HB + g.kh - 2) / g.sh + 1;
+  maxWin = nto * nho * g.Wo * (g.C / 8);
+  return maxWin * 24 + g.HB * g.Wi * (g.C / 8) * 16 + (g.Wi + g.HB) * 4 + 16;
+}
+
 int rsp_bn_relu_maxpool_supported(const rsp_pool3d_desc* d) {
-  if (d->C % 8 != 0 || d->C < 8 || 256 % (d->C / 8) != 0 || d->kt * d->kh * d->kw > 255) return 0;
+  // C % 16: the argmax rows move with 16-byte-granular bulk copies
+  if (d->C % 16 != 0 || 256 % (d->C / 8) != 0 || d->kt * d->kh * d->kw > 255) return 0;
   const size_t row = static_cast<size_t>(d->Wi) * d->C * 2;
-  return static_cast<size_t>(d->kt) * d->kh * row <= static_cast<size_t>(kFusedSmemBudget) ? 1 : 0;
+  if (static_cast<size_t>(d->kt) * d->kh * row > static_cast<size_t>(kFusedSmemBudget)) return 0;
+  FPGeom g;
+  if (fill_fp(g, d) != RSP_OK) return 0;
+  g.HB = g.Hi < 4 ? g.Hi : 4;
+  int maxWin;
+  return bwd_smem_bytes(g, maxWin) <= 200 * 1024 ? 1 : 0;
 }
 
 int rsp_bn_relu_maxpool_fwd(const rsp_pool3d_desc* d, const void* x, const float* scale, const float* shift, void* y,
@@ -332,13 +401,13 @@ static int launch_bwd(int mode, const rsp_pool3d_desc* d, const void* dy, const 
   if (tiles == 0) return RSP_OK;
   RSP_REQUIRE(tiles < (1ll << 31), "bn_relu_maxpool_bwd: too many tiles");
   g.numTiles = static_cast<int>(tiles);
-  const int nto = (g.kt + g.st - 1) / g.st, nho = (g.HB + g.kh - 2) / g.sh + 1;
-  const int maxWin = nto * nho * g.Wo * (g.C / 8);
-  const int smem = maxWin * 24;
-  RSP_REQUIRE(smem <= 160 * 1024, "bn_relu_maxpool_bwd: window staging (%d bytes) does not fit in shared memory", smem);
+  int maxWin;
+  const int smem = bwd_smem_bytes(g, maxWin);
+  RSP_REQUIRE(smem <= 200 * 1024, "bn_relu_maxpool_bwd: window staging (%d bytes) does not fit in shared memory", smem);
   const long long M = static_cast<long long>(g.N) * g.Ti * g.Hi * g.Wi;
   const float inv_m = 1.f / static_cast<float>(M);
-  long long grid = static_cast<long long>(device_sm_count()) * 4;
+  const int per_sm = (210 * 1024) / (smem + 17 * 1024) < 1 ? 1 : ((210 * 1024) / (smem + 17 * 1024) > 2 ? 2 : (210 * 1024) / (smem + 17 * 1024));
+  long long grid = static_cast<long long>(device_sm_count()) * per_sm;
   if (grid > tiles) grid = tiles;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaError_t e;

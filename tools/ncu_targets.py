@@ -1,7 +1,9 @@
 """One launch of each distinct tcgen05 conv kernel on its R3D-18 (batch 64) shape, for `ncu --set full` captures.
-usage (GPU box):  ncu --set full --clock-control none --import-source on -k regex:^conv_ -o gpurun_out/conv_full \
+usage (GPU box):  ncu --set full --clock-control none --import-source on --profile-from-start off \
+                      -k regex:"^conv_|bn_relu_maxpool" -o gpurun_out/conv_full \
                       python tools/ncu_targets.py [arch] [batch] [layer,layer,...]
-Launch order per selected layer: fprop, wgrad, dgrad (dgrad skipped for layer 0)."""
+Only the launches between cudaProfilerStart/Stop are captured.  Order per selected layer: fprop, wgrad, dgrad (dgrad
+skipped for layer 0); then the fused BN+ReLU+MaxPool forward / backward-reduce / backward-apply on the stem output."""
 import sys
 from pathlib import Path
 
@@ -29,6 +31,8 @@ with torch.no_grad():
     net.feature_ndhwc(torch.zeros(B, 3, 16, 112, 112, device="cuda"))
 ops.conv3d_fprop = orig
 del net
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
 for li in layers:
     d, xs = shapes[li]
     x = torch.randn(xs, device="cuda").bfloat16()
@@ -43,3 +47,13 @@ for li in layers:
         ops.conv3d_dgrad(d, dy, ops.conv3d_pack_weight(d, w, 1))
     torch.cuda.synchronize()
     print("layer", li, xs, d.Co, flush=True)
+if arch == "resnet18":
+    c = 64
+    y = torch.randn(B, 16, 56, 56, c, device="cuda").bfloat16()
+    pd = ops.pool_desc(y.shape, (3, 3, 3), (2, 2, 2), (1, 1, 1))
+    scale, shift = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda") * 0.1
+    mean, invstd, gamma = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda"), torch.ones(c, device="cuda")
+    out, idx = ops.bn_relu_maxpool_fwd(pd, y, scale, shift)
+    ops.bn_relu_maxpool_bwd(pd, torch.randn_like(out), idx, y, scale, shift, mean, invstd, gamma)
+    torch.cuda.synchronize()
+torch.cuda.profiler.stop()
