@@ -200,12 +200,16 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host = {}
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t0 = time.perf_counter()
         for i in range(steps):
             fn(i)
+        host["ms"] = (time.perf_counter() - t0) * 1e3 / steps   # CPU time to enqueue one step (no device sync inside)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -228,6 +232,7 @@ def run_b200(args):
         sampler.start()
     counter["on"], counter["n"] = True, 0
     ms_total = timed(resident_step, args.steps)
+    host_ms_step = host["ms"]
     counter["on"] = False
     clocks = sampler.stop() if rank == 0 else None
     loss_val = float(last["loss"][0])
@@ -296,7 +301,7 @@ def run_b200(args):
                                    f"2x{args.frames // 2}x{args.size}x{args.size} clips, K={HYPER['K']}, dim 128",
                        "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "inputs alternate between two 617 MB device batches (> 126 MB L2)"},
-            "loss": loss_val, "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roofline,
+            "loss": loss_val, "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms_step, "clocks": clocks, "e2e": e2e, "roofline": roofline,
             "cpu_baseline": cpu,
         }))
     if world > 1:

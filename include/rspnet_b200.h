@@ -107,19 +107,16 @@ int rsp_maxpool3d_bwd(const rsp_pool3d_desc* d, const void* dy, const uint8_t* i
  * models/c3d.py:111-139 bn/relu/pool1..4).  x is the conv output (bf16 NDHWC, the pool's input geometry); scale/shift/
  * mean/invstd come from rsp_bn_finalize.  The post-activation tensor is never materialised.
  *   fwd        : y bf16 [N][To][Ho][Wo][C], idx uint8 argmax inside the window (first maximum in (kt,kh,kw) order)
- *   bwd_reduce : sum_dz[c] += sum dz, sum_dz_xhat[c] += sum dz*xhat, dz = [bn(x) > 0] * (pool gradient routed by idx)
- *   bwd_apply  : dx = gamma*invstd*(dz - sum_dz/M - xhat*sum_dz_xhat/M)  (the gradient w.r.t. the conv output)
+ *   bwd_dz     : dz = [bn(x) > 0] * (pool gradient routed by idx), written as bf16 in x's layout, and
+ *                sum_dz[c] += sum dz, sum_dz_xhat[c] += sum dz*xhat (both must be zero on entry);
+ *                rsp_bn_act_bwd_apply(dout = dz, relu = 0) then yields the gradient w.r.t. the conv output.
  * rsp_bn_relu_maxpool_supported: 1 when the geometry fits the kernels' shared-memory tiles (else use the unfused calls). */
 int rsp_bn_relu_maxpool_supported(const rsp_pool3d_desc* d);
 int rsp_bn_relu_maxpool_fwd(const rsp_pool3d_desc* d, const void* x, const float* scale, const float* shift, void* y,
                             uint8_t* idx, void* stream);
-int rsp_bn_relu_maxpool_bwd_reduce(const rsp_pool3d_desc* d, const void* dy, const uint8_t* idx, const void* x,
-                                   const float* scale, const float* shift, const float* mean, const float* invstd,
-                                   float* sum_dz, float* sum_dz_xhat, void* stream);
-int rsp_bn_relu_maxpool_bwd_apply(const rsp_pool3d_desc* d, const void* dy, const uint8_t* idx, const void* x,
-                                  const float* scale, const float* shift, const float* mean, const float* invstd,
-                                  const float* gamma, const float* sum_dz, const float* sum_dz_xhat, void* dx,
-                                  int32_t C_logical, void* stream);
+int rsp_bn_relu_maxpool_bwd_dz(const rsp_pool3d_desc* d, const void* dy, const uint8_t* idx, const void* x,
+                               const float* scale, const float* shift, const float* mean, const float* invstd,
+                               float* sum_dz, float* sum_dz_xhat, void* dz, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Projection heads (reference: moco/split_wrapper.py:128-152,164-169): global average pool over the

@@ -57,9 +57,7 @@ SIGNATURES = {
     "rsp_maxpool3d_bwd": (c_i32, [C.POINTER(PoolDesc), _P, _P, _P, _P]),
     "rsp_bn_relu_maxpool_supported": (c_i32, [C.POINTER(PoolDesc)]),
     "rsp_bn_relu_maxpool_fwd": (c_i32, [C.POINTER(PoolDesc), _P, _P, _P, _P, _P, _P]),
-    "rsp_bn_relu_maxpool_bwd_reduce": (c_i32, [C.POINTER(PoolDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "rsp_bn_relu_maxpool_bwd_apply": (c_i32, [C.POINTER(PoolDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_i32,
-                                              _P]),
+    "rsp_bn_relu_maxpool_bwd_dz": (c_i32, [C.POINTER(PoolDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "rsp_head_fwd": (c_i32, [_P, c_i32, c_i32, c_i32, c_i32, c_i32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "rsp_head_bwd": (c_i32, [_P, _P, _P, _P, _P, c_i32, c_i32, c_i32, c_i32, c_i32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "rsp_gate_fwd": (c_i32, [_P, c_i32, c_i32, c_i32, c_i32, _P, _P, _P, _P, _P, _P, _P]),

@@ -6,9 +6,10 @@
 // bn reduce -> bn apply).  Here:
 //   forward : raw conv-output rows (bf16) --bulk copy--> smem; window scan on sign(scale)*x; affine + ReLU once per output
 //             --> pooled y + uint8 argmax
-//   backward: dz(input position) = [bn(x) > 0] * sum of dy over the windows whose argmax is this position, rebuilt on the
-//             fly from (dy, argmax) staged in smem; one pass reduces (sum dz, sum dz*xhat), one pass writes dx.
-// HBM traffic per input element: forward 2 B read (+ pooled output), backward 2 x 2 B read + 2 B write.
+//   backward: dz(input position) = [bn(x) > 0] * sum of dy over the windows whose argmax is this position, rebuilt from
+//             (dy, argmax) staged in smem, written once as bf16 and reduced to (sum dz, sum dz*xhat); the plain BN-apply
+//             kernel then turns dz into dx.
+// HBM traffic per input element: forward 2 B read (+ pooled output); backward 2 B read + 2 B write, then 4 B read + 2 B write.
 #include "common.cuh"
 #include "rspnet_b200.h"
 
@@ -59,9 +60,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // forward: one tile = HB output rows of one (n, to).  The kt x rowsIn raw input rows it needs are contiguous per frame in
 // NDHWC, so one elected thread fetches them with bulk copies (UBLKCP) that complete on an mbarrier; 2-3 CTAs per SM keep
 // the copy of one tile under the compute of another.  max/relu/affine commute per channel:
-//   max_w relu(scale*x + shift) = relu(scale * max_w(sign(scale)*x) * sign(scale) + shift)
-// so the window scan compares sign-flipped raw values and the affine + ReLU runs once per output.
+//   max_w relu(scale*x + shift) = relu(|scale| * max_w(sign(scale)*x) + shift)
+// so the window scan works on sign-flipped raw bf16 pairs (HSETP2 / LOP3: ~5 instructions per pair and tap) and the
+// affine + ReLU runs once per output.  KT/KH/KW > 0: compile-time window (fully unrolled scan); 0: runtime window.
 // ---------------------------------------------------------------------------------------------------------------------
+template <int KT, int KH, int KW>
 __global__ void __launch_bounds__(256) bn_relu_maxpool_fwd_kernel(const uint4* __restrict__ x,
                                                                   const float* __restrict__ scale,
                                                                   const float* __restrict__ shift,
@@ -69,6 +72,7 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_fwd_kernel(const uint4* _
                                                                   const FPGeom p) {
   extern __shared__ __align__(128) uint4 tile[];  // [kt][rowsIn][Wi][G] raw bf16
   __shared__ __align__(8) uint64_t bar;
+  const int kt = KT ? KT : p.kt, kh = KH ? KH : p.kh, kw = KW ? KW : p.kw;
   const int G = p.C >> 3;
   const int g = threadIdx.x % G;   // 256 % G == 0: a thread keeps its channel group across strided loops
   float sc[8], sf[8];
@@ -101,12 +105,12 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_fwd_kernel(const uint4* _
       fence_proxy_async_smem();
       uint32_t bytes = 0;
       const uint32_t chunk = static_cast<uint32_t>(h_hi - h_lo) * rowVecs * 16u;
-      for (int a = 0; a < p.kt; ++a) {
+      for (int a = 0; a < kt; ++a) {
         const int ti = ti0 + a;
         if (ti >= 0 && ti < p.Ti) bytes += chunk;
       }
       mbar_arrive_expect_tx(&bar, bytes);
-      for (int a = 0; a < p.kt; ++a) {
+      for (int a = 0; a < kt; ++a) {
         const int ti = ti0 + a;
         if (ti < 0 || ti >= p.Ti) continue;
         const uint4* src = x + ((static_cast<size_t>(n) * p.Ti + ti) * p.Hi + h_lo) * rowVecs;
@@ -119,65 +123,70 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_fwd_kernel(const uint4* _
     for (int it = threadIdx.x; it < items; it += 256) {
       const int pix = it / G;
       const int hb = pix / p.Wo, wo = pix - hb * p.Wo;
-      float best[8];
-      unsigned bi[8];
+      uint32_t best[4], bi[4];     // packed bf16 pairs / packed 16-bit tap indices
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        best[e] = -INFINITY;
+      for (int e = 0; e < 4; ++e) {
+        best[e] = 0xff80ff80u;     // (-inf, -inf)
         bi[e] = 0;
       }
       const int w0 = wo * p.sw - p.pw;
-      const int c_lo = max(0, -w0), c_hi = min(p.kw, p.Wi - w0);
-      for (int a = 0; a < p.kt; ++a) {
+#pragma unroll(KT ? KT : 1)
+      for (int a = 0; a < (KT ? KT : 8); ++a) {
+        if (a >= kt) break;
         const int ti = ti0 + a;
         if (ti < 0 || ti >= p.Ti) continue;
-        for (int b = 0; b < p.kh; ++b) {
+#pragma unroll(KH ? KH : 1)
+        for (int b = 0; b < (KH ? KH : 8); ++b) {
+          if (b >= kh) break;
           const int r = hb * p.sh + b;
           const int hi = hi0 + r;
           if (hi < 0 || hi >= p.Hi) continue;
           const uint4* row = tile + a * frameVecs + r * rowVecs + w0 * G + g;
-          unsigned lin = (a * p.kh + b) * p.kw + c_lo;
-          for (int c = c_lo; c < c_hi; ++c, ++lin) {
+#pragma unroll(KW ? KW : 1)
+          for (int c = 0; c < (KW ? KW : 8); ++c) {
+            if (c >= kw) break;
+            if (w0 + c < 0 || w0 + c >= p.Wi) continue;
             uint4 raw = row[c * G];
-            raw.x ^= flip[0];
-            raw.y ^= flip[1];
-            raw.z ^= flip[2];
-            raw.w ^= flip[3];
-            float v[8];
-            unpack8(raw, v);
+            const uint32_t lin = static_cast<uint32_t>((a * kh + b) * kw + c) * 0x00010001u;
+            const uint32_t v[4] = {raw.x ^ flip[0], raw.y ^ flip[1], raw.z ^ flip[2], raw.w ^ flip[3]};
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              if (v[e] > best[e]) {   // strict: the first maximum in (kt, kh, kw) order wins, as in nn.MaxPool3d
-                best[e] = v[e];
-                bi[e] = lin;
-              }
+            for (int e = 0; e < 4; ++e) {
+              // strict >: the first maximum in (kt, kh, kw) order wins, as in nn.MaxPool3d
+              const uint32_t m = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&v[e]),
+                                             *reinterpret_cast<const __nv_bfloat162*>(&best[e]));
+              best[e] = (v[e] & m) | (best[e] & ~m);
+              bi[e] = (lin & m) | (bi[e] & ~m);
             }
           }
         }
       }
+      float f[8];
+      uint4 bv;
+      bv.x = best[0]; bv.y = best[1]; bv.z = best[2]; bv.w = best[3];
+      unpack8(bv, f);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) best[e] = fmaxf(fmaf(best[e], fabsf(sc[e]), sf[e]), 0.f);  // |s| * (sign*x) = s*x
+      for (int e = 0; e < 8; ++e) f[e] = fmaxf(fmaf(f[e], fabsf(sc[e]), sf[e]), 0.f);  // |s| * (sign*x) = s*x
       const size_t o = (((static_cast<size_t>(n) * p.To + to) * p.Ho + ho0 + hb) * p.Wo + wo) * G + g;
-      y[o] = pack8(best);
+      y[o] = pack8(f);
       uint2 iv;
-      iv.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
-      iv.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+      iv.x = __byte_perm(bi[0], bi[1], 0x6420);
+      iv.y = __byte_perm(bi[2], bi[3], 0x6420);
       idx[o] = iv;
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// backward: one tile = HB input rows of one (n, ti); bulk copies stage dy / argmax of every window that can select them
-// plus the x rows themselves.
-// MODE 0: per-channel sums (sum dz, sum dz*xhat) -> atomics.  MODE 1: dx = gamma*invstd*(dz - s1/M - xhat*s2/M).
+// backward, pass 1: one tile = HB input rows of one (n, ti); bulk copies stage dy / argmax of every window that can select
+// them plus the x rows themselves.  dz = [bn(x) > 0] * (sum of dy over the windows whose argmax is this position) is written
+// as bf16 and reduced to per-channel (sum dz, sum dz*xhat); pass 2 is the plain BN-backward apply kernel on dz.
+// Input pixels are visited class by class (wi mod sw) so that the lanes of a warp share the same candidate windows.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int MODE>
 __global__ void __launch_bounds__(256, 2) bn_relu_maxpool_bwd_kernel(
     const uint4* __restrict__ dy, const uint2* __restrict__ idx, const uint4* __restrict__ x,
     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
-    const float* __restrict__ invstd, const float* __restrict__ gamma, float* __restrict__ sum_dz,
-    float* __restrict__ sum_dz_xhat, uint4* __restrict__ dx, const FPGeom p, int Cl, float inv_m, int maxWin) {
+    const float* __restrict__ invstd, float* __restrict__ sum_dz, float* __restrict__ sum_dz_xhat,
+    uint4* __restrict__ dz_out, const FPGeom p, int maxWin) {
   extern __shared__ __align__(128) uint4 stage[];        // dy vectors | x rows | argmax vectors | tables
   const int G = p.C >> 3;
   const int rowVecs = p.Wi * G, orowVecs = p.Wo * G;
@@ -186,25 +195,16 @@ __global__ void __launch_bounds__(256, 2) bn_relu_maxpool_bwd_kernel(
   int* wtab = reinterpret_cast<int*>(sidx + maxWin);     // [Wi]  w_lo | w_hi << 16
   int* htab = wtab + p.Wi;                               // [HB]  h_lo | h_hi << 16
   __shared__ __align__(8) uint64_t bar;
-  __shared__ float red[MODE == 0 ? 2 * 256 * 8 : 1];
+  __shared__ float red[2 * 256 * 8];
   const int g = threadIdx.x % G;
-  // MODE 0: A = mean;                    a0 = sum dz, a1 = sum dz*(x - mean)   (invstd applied at the end)
-  // MODE 1: dx = K*dz + A + B*x with K = gamma*invstd, B = -K*s2*invstd, A = -K*s1 - B*mean
-  float sc[8], sf[8], A[8], B[8], K[8], a0[8], a1[8];
+  float sc[8], sf[8], mu[8], a0[8], a1[8];   // a0 = sum dz, a1 = sum dz*(x - mean)  (invstd applied at the end)
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int c = g * 8 + e;
     sc[e] = scale[c];
     sf[e] = shift[c];
+    mu[e] = mean[c];
     a0[e] = a1[e] = 0.f;
-    if (MODE == 0) {
-      A[e] = mean[c];
-    } else {
-      const float is = invstd[c];
-      K[e] = c < Cl ? gamma[c] * is : 0.f;
-      B[e] = -K[e] * (sum_dz_xhat[c] * inv_m) * is;
-      A[e] = -K[e] * (sum_dz[c] * inv_m) - B[e] * mean[c];
-    }
   }
   for (int wi = threadIdx.x; wi < p.Wi; wi += 256) {
     const int lo = max(0, ceil_div(wi + p.pw - p.kw + 1, p.sw)), hi = min(p.Wo - 1, floor_div(wi + p.pw, p.sw));
@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(256, 2) bn_relu_maxpool_bwd_kernel(
     fence_mbar_init();
   }
   __syncthreads();
+  const int perClass = (p.Wi + p.sw - 1) / p.sw;   // pixels of one w-class per row
   uint32_t phase = 0;
   for (int tIdx = blockIdx.x; tIdx < p.numTiles; tIdx += gridDim.x, phase ^= 1) {
     const int band = tIdx % p.bands;
@@ -247,10 +248,14 @@ __global__ void __launch_bounds__(256, 2) bn_relu_maxpool_bwd_kernel(
     }
     __syncthreads();
     mbar_wait(&bar, phase);
-    const int items = hbEff * rowVecs;
+    const int items = hbEff * p.sw * perClass * G;
     for (int it = threadIdx.x; it < items; it += 256) {
-      const int pix = it / G;
-      const int hb = pix / p.Wi, wi = pix - hb * p.Wi;
+      const int r = it / G;
+      const int r2 = r / perClass;
+      const int kk = r - r2 * perClass;
+      const int hb = r2 / p.sw, cls = r2 - hb * p.sw;
+      const int wi = kk * p.sw + cls;
+      if (wi >= p.Wi) continue;
       const int hi = hi0 + hb;
       float acc[8];
 #pragma unroll
@@ -264,52 +269,52 @@ __global__ void __launch_bounds__(256, 2) bn_relu_maxpool_bwd_kernel(
           const int base = ((to - to_lo) * nho + (ho - ho_lo)) * orowVecs + g;
           for (int wo = w_lo; wo <= w_hi; ++wo) {
             const int c = wi + p.pw - wo * p.sw;
-            const unsigned lin = (a * p.kh + b) * p.kw + c;
+            const uint32_t lin4 = static_cast<uint32_t>((a * p.kh + b) * p.kw + c) * 0x01010101u;
             const uint2 iv = sidx[base + wo * G];
-            float d[8];
-            unpack8(stage[base + wo * G], d);
+            uint4 d = stage[base + wo * G];
+            const uint32_t m0 = __vcmpeq4(iv.x, lin4), m1 = __vcmpeq4(iv.y, lin4);
+            if ((m0 | m1) == 0) continue;
+            d.x &= __byte_perm(m0, 0, 0x1100);
+            d.y &= __byte_perm(m0, 0, 0x3322);
+            d.z &= __byte_perm(m1, 0, 0x1100);
+            d.w &= __byte_perm(m1, 0, 0x3322);
+            float f[8];
+            unpack8(d, f);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const unsigned sel = ((e < 4 ? iv.x : iv.y) >> (8 * (e & 3))) & 0xffu;
-              if (sel == lin) acc[e] += d[e];
-            }
+            for (int e = 0; e < 8; ++e) acc[e] += f[e];
           }
         }
       }
-      float xv[8], out[8];
-      unpack8(xs[it], xv);
+      const int xi = (hb * p.Wi + wi) * G + g;
+      float xv[8];
+      unpack8(xs[xi], xv);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float dz = fmaf(xv[e], sc[e], sf[e]) > 0.f ? acc[e] : 0.f;
-        if (MODE == 0) {
-          a0[e] += dz;
-          a1[e] = fmaf(dz, xv[e] - A[e], a1[e]);
-        } else {
-          out[e] = fmaf(K[e], dz, fmaf(B[e], xv[e], A[e]));
-        }
+        acc[e] = dz;
+        a0[e] += dz;
+        a1[e] = fmaf(dz, xv[e] - mu[e], a1[e]);
       }
-      if (MODE == 1) dx[((static_cast<size_t>(n) * p.Ti + ti) * p.Hi + hi0) * rowVecs + it] = pack8(out);
+      dz_out[((static_cast<size_t>(n) * p.Ti + ti) * p.Hi + hi0) * rowVecs + xi] = pack8(acc);
     }
   }
-  if (MODE == 0) {
-    __syncthreads();
+  __syncthreads();
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      red[threadIdx.x * 8 + e] = a0[e];
-      red[2048 + threadIdx.x * 8 + e] = a1[e];
+  for (int e = 0; e < 8; ++e) {
+    red[threadIdx.x * 8 + e] = a0[e];
+    red[2048 + threadIdx.x * 8 + e] = a1[e];
+  }
+  __syncthreads();
+  const int reps = 256 / G;
+  for (int c = threadIdx.x; c < p.C; c += 256) {
+    const int gg = c >> 3, e = c & 7;
+    float t0 = 0.f, t1 = 0.f;
+    for (int r = 0; r < reps; ++r) {
+      t0 += red[(r * G + gg) * 8 + e];
+      t1 += red[2048 + (r * G + gg) * 8 + e];
     }
-    __syncthreads();
-    const int reps = 256 / G;
-    for (int c = threadIdx.x; c < p.C; c += 256) {
-      const int gg = c >> 3, e = c & 7;
-      float t0 = 0.f, t1 = 0.f;
-      for (int r = 0; r < reps; ++r) {
-        t0 += red[(r * G + gg) * 8 + e];
-        t1 += red[2048 + (r * G + gg) * 8 + e];
-      }
-      atomicAdd(sum_dz + c, t0);
-      atomicAdd(sum_dz_xhat + c, t1 * invstd[c]);
-    }
+    atomicAdd(sum_dz + c, t0);
+    atomicAdd(sum_dz_xhat + c, t1 * invstd[c]);
   }
 }
 
@@ -345,7 +350,7 @@ static int bwd_smem_bytes(const FPGeom& g, int& maxWin) {
 
 int rsp_bn_relu_maxpool_supported(const rsp_pool3d_desc* d) {
   // C % 16: the argmax rows move with 16-byte-granular bulk copies
-  if (d->C % 16 != 0 || 256 % (d->C / 8) != 0 || d->kt * d->kh * d->kw > 255) return 0;
+  if (d->C % 16 != 0 || 256 % (d->C / 8) != 0 || d->kt > 8 || d->kh > 8 || d->kw > 8) return 0;
   const size_t row = static_cast<size_t>(d->Wi) * d->C * 2;
   if (static_cast<size_t>(d->kt) * d->kh * row > static_cast<size_t>(kFusedSmemBudget)) return 0;
   FPGeom g;
@@ -375,22 +380,37 @@ int rsp_bn_relu_maxpool_fwd(const rsp_pool3d_desc* d, const void* x, const float
   RSP_REQUIRE(tiles < (1ll << 31), "bn_relu_maxpool_fwd: too many tiles");
   g.numTiles = static_cast<int>(tiles);
   const int smem = static_cast<int>(g.kt * g.rowsIn * row);
-  cudaError_t e = cudaFuncSetAttribute(bn_relu_maxpool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int per_sm = smem > 0 ? (200 * 1024) / (smem + 1024) : 8;
+  long long grid = static_cast<long long>(device_sm_count()) * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
+  if (grid > tiles) grid = tiles;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaSuccess;
+#define RSP_LAUNCH_POOL_FWD(KT, KH, KW)                                                                                \
+  do {                                                                                                                 \
+    e = cudaFuncSetAttribute(bn_relu_maxpool_fwd_kernel<KT, KH, KW>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                             smem);                                                                                    \
+    if (e == cudaSuccess)                                                                                              \
+      bn_relu_maxpool_fwd_kernel<KT, KH, KW><<<static_cast<unsigned>(grid), 256, smem, s>>>(                           \
+          static_cast<const uint4*>(x), scale, shift, static_cast<uint4*>(y), reinterpret_cast<uint2*>(idx), g);      \
+  } while (0)
+  if (g.kt == 3 && g.kh == 3 && g.kw == 3) RSP_LAUNCH_POOL_FWD(3, 3, 3);
+  else if (g.kt == 2 && g.kh == 2 && g.kw == 2) RSP_LAUNCH_POOL_FWD(2, 2, 2);
+  else if (g.kt == 1 && g.kh == 2 && g.kw == 2) RSP_LAUNCH_POOL_FWD(1, 2, 2);
+  else {
+    RSP_REQUIRE(g.kt <= 8 && g.kh <= 8 && g.kw <= 8, "bn_relu_maxpool_fwd: window extents above 8 are not supported");
+    RSP_LAUNCH_POOL_FWD(0, 0, 0);
+  }
+#undef RSP_LAUNCH_POOL_FWD
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(bn_relu_maxpool_fwd): %s", cudaGetErrorString(e));
     return RSP_ERR_CUDA;
   }
-  const int per_sm = smem > 0 ? (200 * 1024) / (smem + 1024) : 8;
-  long long grid = static_cast<long long>(device_sm_count()) * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
-  if (grid > tiles) grid = tiles;
-  bn_relu_maxpool_fwd_kernel<<<static_cast<unsigned>(grid), 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint4*>(x), scale, shift, static_cast<uint4*>(y), reinterpret_cast<uint2*>(idx), g);
   return check_launch("bn_relu_maxpool_fwd");
 }
 
-static int launch_bwd(int mode, const rsp_pool3d_desc* d, const void* dy, const uint8_t* idx, const void* x,
-                      const float* scale, const float* shift, const float* mean, const float* invstd,
-                      const float* gamma, float* sum_dz, float* sum_dz_xhat, void* dx, int C_logical, void* stream) {
+int rsp_bn_relu_maxpool_bwd_dz(const rsp_pool3d_desc* d, const void* dy, const uint8_t* idx, const void* x,
+                               const float* scale, const float* shift, const float* mean, const float* invstd,
+                               float* sum_dz, float* sum_dz_xhat, void* dz, void* stream) {
   FPGeom g;
   int rc = fill_fp(g, d);
   if (rc != RSP_OK) return rc;
@@ -403,46 +423,21 @@ static int launch_bwd(int mode, const rsp_pool3d_desc* d, const void* dy, const 
   g.numTiles = static_cast<int>(tiles);
   int maxWin;
   const int smem = bwd_smem_bytes(g, maxWin);
-  RSP_REQUIRE(smem <= 200 * 1024, "bn_relu_maxpool_bwd: window staging (%d bytes) does not fit in shared memory", smem);
-  const long long M = static_cast<long long>(g.N) * g.Ti * g.Hi * g.Wi;
-  const float inv_m = 1.f / static_cast<float>(M);
-  const int per_sm = (210 * 1024) / (smem + 17 * 1024) < 1 ? 1 : ((210 * 1024) / (smem + 17 * 1024) > 2 ? 2 : (210 * 1024) / (smem + 17 * 1024));
+  RSP_REQUIRE(d->C % 16 == 0 && smem <= 200 * 1024,
+              "bn_relu_maxpool_bwd: window staging (%d bytes) does not fit in shared memory", smem);
+  const int fit = (210 * 1024) / (smem + 17 * 1024);
+  const int per_sm = fit < 1 ? 1 : (fit > 2 ? 2 : fit);
   long long grid = static_cast<long long>(device_sm_count()) * per_sm;
   if (grid > tiles) grid = tiles;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  cudaError_t e;
-  if (mode == 0) {
-    e = cudaFuncSetAttribute(bn_relu_maxpool_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess)
-      bn_relu_maxpool_bwd_kernel<0><<<static_cast<unsigned>(grid), 256, smem, s>>>(
-          static_cast<const uint4*>(dy), reinterpret_cast<const uint2*>(idx), static_cast<const uint4*>(x), scale, shift,
-          mean, invstd, gamma, sum_dz, sum_dz_xhat, nullptr, g, C_logical, inv_m, maxWin);
-  } else {
-    e = cudaFuncSetAttribute(bn_relu_maxpool_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess)
-      bn_relu_maxpool_bwd_kernel<1><<<static_cast<unsigned>(grid), 256, smem, s>>>(
-          static_cast<const uint4*>(dy), reinterpret_cast<const uint2*>(idx), static_cast<const uint4*>(x), scale, shift,
-          mean, invstd, gamma, sum_dz, sum_dz_xhat, static_cast<uint4*>(dx), g, C_logical, inv_m, maxWin);
-  }
+  cudaError_t e = cudaFuncSetAttribute(bn_relu_maxpool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(bn_relu_maxpool_bwd): %s", cudaGetErrorString(e));
     return RSP_ERR_CUDA;
   }
+  bn_relu_maxpool_bwd_kernel<<<static_cast<unsigned>(grid), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(dy), reinterpret_cast<const uint2*>(idx), static_cast<const uint4*>(x), scale, shift, mean,
+      invstd, sum_dz, sum_dz_xhat, static_cast<uint4*>(dz), g, maxWin);
   return check_launch("bn_relu_maxpool_bwd");
-}
-
-int rsp_bn_relu_maxpool_bwd_reduce(const rsp_pool3d_desc* d, const void* dy, const uint8_t* idx, const void* x,
-                                   const float* scale, const float* shift, const float* mean, const float* invstd,
-                                   float* sum_dz, float* sum_dz_xhat, void* stream) {
-  return launch_bwd(0, d, dy, idx, x, scale, shift, mean, invstd, nullptr, sum_dz, sum_dz_xhat, nullptr, 0, stream);
-}
-
-int rsp_bn_relu_maxpool_bwd_apply(const rsp_pool3d_desc* d, const void* dy, const uint8_t* idx, const void* x,
-                                  const float* scale, const float* shift, const float* mean, const float* invstd,
-                                  const float* gamma, const float* sum_dz, const float* sum_dz_xhat, void* dx,
-                                  int32_t C_logical, void* stream) {
-  return launch_bwd(1, d, dy, idx, x, scale, shift, mean, invstd, gamma, const_cast<float*>(sum_dz),
-                    const_cast<float*>(sum_dz_xhat), dx, C_logical, stream);
 }
 
 }  // extern "C"

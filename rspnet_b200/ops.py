@@ -168,12 +168,14 @@ def bn_relu_maxpool_fwd(desc: PoolDesc, x, scale, shift):
 def bn_relu_maxpool_bwd(desc: PoolDesc, dy, idx, x, scale, shift, mean, invstd, gamma):
     """Gradient w.r.t. the conv output x plus (dgamma, dbeta) of the fused BN -> ReLU -> MaxPool block."""
     c = x.shape[-1]
+    m = x.numel() // c
     sums = torch.zeros((2, c), dtype=torch.float32, device=x.device)
-    call("rsp_bn_relu_maxpool_bwd_reduce", C.byref(desc), ptr(dy), ptr(idx), ptr(x), ptr(scale), ptr(shift), ptr(mean),
-         ptr(invstd), ptr(sums[0]), ptr(sums[1]), stream_ptr())
+    dz = torch.empty_like(x)
+    call("rsp_bn_relu_maxpool_bwd_dz", C.byref(desc), ptr(dy), ptr(idx), ptr(x), ptr(scale), ptr(shift), ptr(mean),
+         ptr(invstd), ptr(sums[0]), ptr(sums[1]), ptr(dz), stream_ptr())
     dx = torch.empty_like(x)
-    call("rsp_bn_relu_maxpool_bwd_apply", C.byref(desc), ptr(dy), ptr(idx), ptr(x), ptr(scale), ptr(shift), ptr(mean),
-         ptr(invstd), ptr(gamma), ptr(sums[0]), ptr(sums[1]), ptr(dx), gamma.numel(), stream_ptr())
+    call("rsp_bn_act_bwd_apply", ptr(dz), None, ptr(x), ptr(mean), ptr(invstd), ptr(gamma), ptr(sums[0]), ptr(sums[1]),
+         0, ptr(dx), None, m, c, gamma.numel(), stream_ptr())
     cl = gamma.numel()
     return dx, sums[1][:cl], sums[0][:cl]
 
