@@ -200,7 +200,7 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    host = {}
+    host_t = {}
 
     def timed(fn, steps):
         barrier()
@@ -209,7 +209,7 @@ def run_b200(args):
         t0 = time.perf_counter()
         for i in range(steps):
             fn(i)
-        host["ms"] = (time.perf_counter() - t0) * 1e3 / steps   # CPU time to enqueue one step (no device sync inside)
+        host_t["ms"] = (time.perf_counter() - t0) * 1e3 / steps   # CPU time to enqueue one step (no device sync inside)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -232,7 +232,7 @@ def run_b200(args):
         sampler.start()
     counter["on"], counter["n"] = True, 0
     ms_total = timed(resident_step, args.steps)
-    host_ms_step = host["ms"]
+    host_ms_step = host_t["ms"]
     counter["on"] = False
     clocks = sampler.stop() if rank == 0 else None
     loss_val = float(last["loss"][0])

@@ -26,6 +26,48 @@ int check_launch(const char* what) {
   return RSP_OK;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const unsigned long long* dims,
+                   const unsigned long long* strides_bytes, const unsigned* box) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      set_error("cuTensorMapEncodeTiled is not available from this driver (%s)", cudaGetErrorString(e));
+      return RSP_ERR_CUDA;
+    }
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  RSP_REQUIRE(rank >= 1 && rank <= 5, "tensor map: rank %d", rank);
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    RSP_REQUIRE(box[i] >= 1 && box[i] <= 256, "tensor map: box[%d] = %u out of range", i, box[i]);
+    if (i > 0) {
+      gstr[i - 1] = strides_bytes[i - 1];
+      RSP_REQUIRE(strides_bytes[i - 1] % 16 == 0, "tensor map: stride %d not a multiple of 16 bytes", i);
+    }
+  }
+  RSP_REQUIRE(reinterpret_cast<uintptr_t>(base) % 16 == 0, "tensor map: base address not 16-byte aligned");
+  RSP_REQUIRE(box[0] * 2 <= 128, "tensor map: inner box exceeds the 128-byte swizzle span");
+  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
+                      gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+    return RSP_ERR_CUDA;
+  }
+  return RSP_OK;
+}
+
 int device_sm_count() {
   if (g_sm_count == 0) {
     int dev = 0;

@@ -5,6 +5,7 @@
 // No CUTLASS/CuTe dependency; bit layouts follow the PTX ISA descriptor tables.
 #pragma once
 
+#include <cuda.h>        // CUtensorMap (types only: the encoder is resolved at run time, libcuda is not linked)
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -24,6 +25,11 @@ enum : int {
 
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
+
+// Tiled bf16 tensor map with 128-byte swizzle and zero fill outside the tensor (cuTensorMapEncodeTiled).
+// dims / box: extents per dimension, innermost first; strides_bytes: rank-1 entries for dimensions 1..rank-1.
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const unsigned long long* dims,
+                   const unsigned long long* strides_bytes, const unsigned* box);
 
 #define RSP_REQUIRE(cond, ...)                    \
   do {                                            \
@@ -113,6 +119,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(tmap), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
+      "[%2];" ::"r"(dst),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {

@@ -9,8 +9,13 @@
 // instead of once per filter tap, and one filter tile feeds G=2..4 accumulators of 128 positions, which takes the kernel
 // off the L2-bandwidth roofline that bounds the gather kernel for Co = 64.
 //
-// CTA (persistent, 1/SM): warps 0-3 producers (zero-filling cp.async), warps 4-7 epilogue, warp 8 MMA issuer.
-// Rings: 2 plane buffers, 6 filter tiles, 2 TMEM accumulator sets (G * NT columns each).
+// The plane run is one TMA box: the source is a 5-D tensor {C, W, H, T, N}; a box {64, Wp, rows, 1, 1} starting at
+// (cc*64, -pw, row0 - ph, ts, n) lands as rows x Wp pixels of 128 B, 128B-swizzled, with the padding columns / rows
+// zero-filled by the TMA unit (out-of-bounds coordinates) — exactly the padded-flattened layout above.  Filter tiles are
+// 2-D TMA boxes {64, NT} of the packed filter.  No thread computes an address per element any more.
+//
+// CTA (persistent, 1/SM): warps 0-3 epilogue, warp 4 TMA producer (one elected lane), warp 5 MMA issuer.
+// Rings: 2 plane buffers, 3-6 filter tiles, 2 TMEM accumulator sets (G * NT columns each).
 #include "common.cuh"
 #include "rspnet_b200.h"
 
@@ -19,6 +24,8 @@ namespace rsp {
 int device_sm_count();
 
 struct DirectParams {
+  CUtensorMap tmapX;         // source as {Cs, Wi, Hi, Ti, N}, box {64, Wp, rowsBuf, 1, 1}
+  CUtensorMap tmapW;         // filter as {taps*Cs, Nout}, box {64, NT}
   const __nv_bfloat16* x;    // source [N][Ti][Hi][Wi][Cs]
   const __nv_bfloat16* wgt;  // [Nout][taps*Cs]  (K index = tap*Cs + c)
   __nv_bfloat16* y;          // [N][To][Ho][Wo][Nout]
@@ -31,55 +38,57 @@ struct DirectParams {
   int Wp, Hp, P;               // padded pitch, padded rows, positions per plane (Ho*Wp)
   int G;                       // accumulators (128-position chunks) per work item
   int groups;                  // work items per plane
-  int len;                     // plane-buffer pixels (multiple of 8)
+  int rowsBuf;                 // padded rows per plane buffer (TMA box height)
+  int planeBytes;              // bytes reserved per plane buffer (multiple of 1024)
+  int wStages;                 // filter-tile ring depth
   int numItems;                // ntiles * N * To * groups
   unsigned long long mulWp;    // reciprocal of Wp (shift 32 + shWp)
   int shWp;
 };
 
-constexpr int kDirThreads = 288;
-constexpr int kDirWStages = 6;
+constexpr int kDirThreads = 192;
+constexpr int kDirMaxWStages = 6;
 
 __device__ __forceinline__ uint32_t fdiv64(uint32_t n, unsigned long long mul, int sh) {
   return static_cast<uint32_t>((static_cast<unsigned long long>(n) * mul) >> sh);
 }
 
 template <int NT>
-__global__ void __launch_bounds__(kDirThreads, 1) conv_direct_kernel(const DirectParams p) {
+__global__ void __launch_bounds__(kDirThreads, 1) conv_direct_kernel(const __grid_constant__ DirectParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int planeBytes = p.len * 128;
+  const int planeBytes = p.planeBytes;
   uint8_t* wring = smem + 2 * planeBytes;
   constexpr int W_BYTES = NT * 128;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wring + kDirWStages * W_BYTES);
+  const int wStages = p.wStages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wring + wStages * W_BYTES);
   uint64_t* plane_full = bars;             // [2]
   uint64_t* plane_empty = bars + 2;        // [2]
-  uint64_t* w_full = bars + 4;             // [6]
-  uint64_t* w_empty = bars + 4 + kDirWStages;
-  uint64_t* acc_full = bars + 4 + 2 * kDirWStages;   // [2]
+  uint64_t* w_full = bars + 4;             // [wStages]
+  uint64_t* w_empty = bars + 4 + kDirMaxWStages;
+  uint64_t* acc_full = bars + 4 + 2 * kDirMaxWStages;   // [2]
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int t = threadIdx.x;
   const int warp = t >> 5;
   const int cch = p.Cs >> 6;
-  const int ntiles = p.Nout / NT;
   const int accCols = p.G * NT;            // columns of one accumulator set
 
   if (t == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&plane_full[i], 128);
+      mbar_init(&plane_full[i], 1);
       mbar_init(&plane_empty[i], 1);
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], 128);
     }
-    for (int i = 0; i < kDirWStages; ++i) {
-      mbar_init(&w_full[i], 128);
+    for (int i = 0; i < wStages; ++i) {
+      mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
     }
     fence_mbar_init();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  if (warp == 5) tmem_alloc(tmem_slot, 512);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -95,57 +104,50 @@ __global__ void __launch_bounds__(kDirThreads, 1) conv_direct_kernel(const Direc
     nt = q / p.N;
   };
 
-  if (warp < 4) {
-    // ============================================================ producers
+  if (warp == 4) {
+    // ============================================================ TMA producer
     uint32_t pctr = 0, wctr = 0;
-    const int chunk = t & 7;
-    const size_t ldw = static_cast<size_t>(p.kt) * p.kh * p.kw * p.Cs;
+    const uint32_t planeTx = static_cast<uint32_t>(p.rowsBuf) * p.Wp * 128u;
+    if (elect_one()) {
+      tma_prefetch_desc(&p.tmapX);
+      tma_prefetch_desc(&p.tmapW);
+    }
     for (int it = blockIdx.x; it < p.numItems; it += gridDim.x) {
       int nt, n, to, grp;
       decode_item(it, nt, n, to, grp);
       const int q0 = grp * p.G * 128;
-      const __nv_bfloat16* wrow = p.wgt + static_cast<size_t>(nt * NT + (t >> 3)) * ldw + chunk * 8;
+      const int row0 = static_cast<int>(fdiv64(static_cast<uint32_t>(q0), p.mulWp, p.shWp));  // first padded row
       for (int a = 0; a < p.kt; ++a) {
         const int ts = to - p.pt + a;
         if (ts < 0 || ts >= p.Ti) continue;  // temporal padding: the whole plane is zero, skip it (MMA warp agrees)
-        const __nv_bfloat16* frame = p.x + (static_cast<size_t>(n) * p.Ti + ts) * p.Hi * p.Wi * p.Cs;
         for (int cc = 0; cc < cch; ++cc, ++pctr) {
           const int ps = pctr & 1;
           mbar_wait(&plane_empty[ps], ((pctr >> 1) & 1) ^ 1);
-          const uint32_t buf = smem_u32(smem + ps * planeBytes);
-          const __nv_bfloat16* src0 = frame + cc * 64 + chunk * 8;
-          for (int i = t >> 3; i < p.len; i += 16) {
-            const uint32_t pp = static_cast<uint32_t>(q0 + i);          // padded-flattened source position
-            const uint32_t r = fdiv64(pp, p.mulWp, p.shWp);
-            const int hs = static_cast<int>(r) - p.ph;
-            const int ws = static_cast<int>(pp - r * p.Wp) - p.pw;
-            const bool ok = static_cast<unsigned>(hs) < static_cast<unsigned>(p.Hi) &&
-                            static_cast<unsigned>(ws) < static_cast<unsigned>(p.Wi);
-            const __nv_bfloat16* src = src0 + (ok ? (static_cast<size_t>(hs) * p.Wi + ws) * p.Cs : 0);
-            cp_async16(buf + i * 128 + ((chunk ^ (i & 7)) << 4), src, ok ? 16u : 0u);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&plane_full[ps], planeTx);
+            tma_load_5d(smem_u32(smem + ps * planeBytes), &p.tmapX, &plane_full[ps], cc * 64, -p.pw, row0 - p.ph, ts, n);
           }
-          cp_async_mbar_arrive(&plane_full[ps]);
-          mbar_arrive(&plane_full[ps]);
+          __syncwarp();
           // the kh*kw filter tiles of this (frame tap, channel chunk)
           for (int b = 0; b < p.kh; ++b) {
             for (int c = 0; c < p.kw; ++c, ++wctr) {
-              const int ws_ = wctr % kDirWStages;
-              mbar_wait(&w_empty[ws_], ((wctr / kDirWStages) & 1) ^ 1);
-              const int ta = p.flip ? p.kt - 1 - a : a, tb = p.flip ? p.kh - 1 - b : b, tc = p.flip ? p.kw - 1 - c : c;
-              const size_t koff = (static_cast<size_t>((ta * p.kh + tb) * p.kw + tc)) * p.Cs + cc * 64;
-              const uint32_t wt = smem_u32(wring + ws_ * W_BYTES) + (t >> 3) * 128 + ((chunk ^ ((t >> 3) & 7)) << 4);
-#pragma unroll
-              for (int j = 0; j < NT / 16; ++j) cp_async16(wt + j * 2048, wrow + koff + static_cast<size_t>(j) * 16 * ldw, 16u);
-              cp_async_mbar_arrive(&w_full[ws_]);
-              mbar_arrive(&w_full[ws_]);
+              const int ws_ = wctr % wStages;
+              mbar_wait(&w_empty[ws_], ((wctr / wStages) & 1) ^ 1);
+              if (elect_one()) {
+                const int ta = p.flip ? p.kt - 1 - a : a, tb = p.flip ? p.kh - 1 - b : b, tc = p.flip ? p.kw - 1 - c : c;
+                const int koff = ((ta * p.kh + tb) * p.kw + tc) * p.Cs + cc * 64;
+                mbar_arrive_expect_tx(&w_full[ws_], W_BYTES);
+                tma_load_2d(smem_u32(wring + ws_ * W_BYTES), &p.tmapW, &w_full[ws_], koff, nt * NT);
+              }
+              __syncwarp();
             }
           }
         }
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < 4) {
     // ============================================================ epilogue
-    const int ew = warp - 4, lane = t & 31;
+    const int ew = warp, lane = t & 31;
     float ssum[NT / 32], ssq[NT / 32];
 #pragma unroll
     for (int i = 0; i < NT / 32; ++i) ssum[i] = ssq[i] = 0.f;
@@ -240,6 +242,8 @@ __global__ void __launch_bounds__(kDirThreads, 1) conv_direct_kernel(const Direc
       decode_item(it, nt, n, to, grp);
       const int buf = ictr & 1;
       const int q0 = grp * p.G * 128;
+      const int row0 = static_cast<int>(fdiv64(static_cast<uint32_t>(q0), p.mulWp, p.shWp));
+      const int shift = q0 - row0 * p.Wp;   // the work item's first position inside the plane buffer
       int chunks = (p.P - q0 + 127) / 128;
       if (chunks > p.G) chunks = p.G;
       mbar_wait(&acc_empty[buf], ((ictr >> 1) & 1) ^ 1);
@@ -251,12 +255,12 @@ __global__ void __launch_bounds__(kDirThreads, 1) conv_direct_kernel(const Direc
         for (int cc = 0; cc < cch; ++cc, ++pctr) {
           const int ps = pctr & 1;
           mbar_wait(&plane_full[ps], (pctr >> 1) & 1);
-          const uint32_t abase = smem_u32(smem + ps * planeBytes);
+          tc_fence_after_sync();
+          const uint32_t abase = smem_u32(smem + ps * planeBytes) + shift * 128;
           for (int b = 0; b < p.kh; ++b) {
             for (int c = 0; c < p.kw; ++c, ++wctr) {
-              const int ws_ = wctr % kDirWStages;
-              mbar_wait(&w_full[ws_], (wctr / kDirWStages) & 1);
-              fence_proxy_async_smem();
+              const int ws_ = wctr % wStages;
+              mbar_wait(&w_full[ws_], (wctr / wStages) & 1);
               tc_fence_after_sync();
               if (elect_one()) {
                 const uint64_t bdesc = make_smem_desc_sw128(smem_u32(wring + ws_ * W_BYTES), 16, 1024);
@@ -285,7 +289,7 @@ __global__ void __launch_bounds__(kDirThreads, 1) conv_direct_kernel(const Direc
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, 512);
+  if (warp == 5) tmem_dealloc(tmem_base, 512);
 }
 
 // --------------------------------------------------------------------------------------------------------------------
@@ -320,9 +324,19 @@ static bool direct_geometry(const rsp_conv3d_desc* d, int transposed, DirectPara
   if (p.P < 128 * p.G) return false;                 // small planes: the gather kernel wastes less
   if (p.kh * p.kw < 2) return false;                 // 1x1 filters have nothing to reuse
   p.groups = (p.P + 128 * p.G - 1) / (128 * p.G);
-  p.len = (128 * p.G + (p.kh - 1) * p.Wp + p.kw - 1 + 7) / 8 * 8;
-  smem = 2 * static_cast<size_t>(p.len) * 128 + static_cast<size_t>(kDirWStages) * NT * 128 + 1024 + 512;
-  if (smem > 225 * 1024) return false;
+  if (p.Wp > 256) return false;                                          // TMA box extent
+  p.rowsBuf = (128 * p.G + p.kh * p.Wp + p.kw - 3) / p.Wp + 1;           // see the header: run + halo, row aligned
+  if (p.rowsBuf > 256) return false;
+  p.planeBytes = (p.rowsBuf * p.Wp * 128 + 1023) / 1024 * 1024;
+  p.wStages = 0;
+  for (int ws = kDirMaxWStages; ws >= 3; --ws) {
+    smem = 2 * static_cast<size_t>(p.planeBytes) + static_cast<size_t>(ws) * NT * 128 + 1024 + 512;
+    if (smem <= 227 * 1024) {
+      p.wStages = ws;
+      break;
+    }
+  }
+  if (p.wStages == 0) return false;
   const long long items = static_cast<long long>(Nout / NT) * p.N * p.To * p.groups;
   if (items > (1ll << 30)) return false;
   p.numItems = static_cast<int>(items);
@@ -354,6 +368,20 @@ int launch_direct(const rsp_conv3d_desc* d, int transposed, const void* x, const
   p.y = static_cast<__nv_bfloat16*>(y);
   p.bias = bias;
   p.stats = stats;
+  {
+    const unsigned long long C = p.Cs, W = p.Wi, H = p.Hi, T = p.Ti, N = p.N;
+    const unsigned long long dims[5] = {C, W, H, T, N};
+    const unsigned long long strides[4] = {C * 2, W * C * 2, H * W * C * 2, T * H * W * C * 2};
+    const unsigned box[5] = {64, static_cast<unsigned>(p.Wp), static_cast<unsigned>(p.rowsBuf), 1, 1};
+    int rc = make_tmap_bf16(&p.tmapX, x, 5, dims, strides, box);
+    if (rc != RSP_OK) return rc;
+    const unsigned long long K = static_cast<unsigned long long>(p.kt) * p.kh * p.kw * p.Cs;
+    const unsigned long long wdims[2] = {K, static_cast<unsigned long long>(p.Nout)};
+    const unsigned long long wstrides[1] = {K * 2};
+    const unsigned wbox[2] = {64, static_cast<unsigned>(NT)};
+    rc = make_tmap_bf16(&p.tmapW, wgt, 2, wdims, wstrides, wbox);
+    if (rc != RSP_OK) return rc;
+  }
   const int sms = device_sm_count();
   const int grid = p.numItems < sms ? p.numItems : sms;
   cudaError_t e;

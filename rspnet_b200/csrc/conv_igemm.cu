@@ -85,6 +85,7 @@ __device__ __forceinline__ void row_state(const GatherGeom& g, long long m, int 
 }
 
 struct ConvParams {
+  CUtensorMap tmapW;         // wgt as a 2-D tensor {K, Nout}, box {64, NT}, 128 B swizzle: one TMA per K block
   GatherGeom g;
   const __nv_bfloat16* wgt;  // [Nout][numKb*64]
   __nv_bfloat16* out;        // [M][Nout]
@@ -231,7 +232,7 @@ __device__ __forceinline__ void load_rows(uint32_t panel, const __nv_bfloat16* b
 // fprop / dgrad kernel:  out[M][Nout] = gather(src)[M][K] * wgt[Nout][K]^T (+ bias)
 // ---------------------------------------------------------------------------------------------
 template <int NT, int STAGES, int MODE>
-__global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvParams p) {
+__global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int A_BYTES = 128 * 128;
   constexpr int B_BYTES = NT * 128;
@@ -274,7 +275,6 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvParams p
 
   if (warp < 4) {
     // ---------------- producers ----------------
-    const size_t ldw = static_cast<size_t>(p.wgtKb) * 64;
     if (MODE == MODE_GENERIC && g.fast) {
       // fast path: ~10 instructions per 16 B copy (row state precomputed, taps advanced incrementally)
       const int chunk = t & 7;
@@ -283,8 +283,6 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvParams p
 #pragma unroll
       for (int i = 0; i < 8; ++i) row_state(g, m0 + (t >> 3) + 16 * i, chunk, rbase[i], rmask[i]);
       const uint32_t dst0 = swz(t >> 3, chunk * 16);  // rows (t>>3)+16i share the swizzle phase: + i*2048
-      const __nv_bfloat16* wrow = p.wgt + static_cast<size_t>(n0 + (t >> 3)) * ldw + chunk * 8;
-      const size_t wstep = 16 * ldw;
       const int dirCs = g.transposed ? -g.Cs : g.Cs;
       const int cchunks = g.Cs >> 6;
       int cc = kbBegin % cchunks;
@@ -309,11 +307,13 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvParams p
         const int kbw = g.cls ? (((g.wa0 + g.was * a) * g.wkh + (g.wb0 + g.wbs * b)) * g.wkw + (g.wc0 + g.wcs * c)) *
                                         cchunks + cc
                               : kbBegin + kb;
-        const __nv_bfloat16* wsrc = wrow + static_cast<size_t>(kbw) * 64;
-#pragma unroll
-        for (int i = 0; i < NT / 16; ++i) cp_async16(a_panel + A_BYTES + i * 2048, wsrc + i * wstep, 16u);
         cp_async_mbar_arrive(&full_bar[s]);
-        mbar_arrive(&full_bar[s]);
+        if (t == 0) {   // the filter tile of this K block: one bulk tensor copy, counted in bytes on the same barrier
+          mbar_arrive_expect_tx(&full_bar[s], B_BYTES);
+          tma_load_2d(smem_u32(smem + s * STAGE_BYTES) + A_BYTES, &p.tmapW, &full_bar[s], kbw * 64, n0);
+        } else {
+          mbar_arrive(&full_bar[s]);
+        }
         if (++cc == cchunks) {
           cc = 0;
           if (++c == g.kw) {
@@ -339,9 +339,13 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvParams p
         const uint32_t a_panel = smem_u32(smem + s * STAGE_BYTES);
         const uint32_t b_panel = a_panel + A_BYTES;
         gather_panel<MODE, 128>(g, a_panel, kbBegin + kb, t, rows);
-        load_rows<NT>(b_panel, p.wgt + static_cast<size_t>(kbBegin + kb) * 64, n0, p.Nout, ldw, t);
         cp_async_mbar_arrive(&full_bar[s]);
-        mbar_arrive(&full_bar[s]);
+        if (t == 0) {
+          mbar_arrive_expect_tx(&full_bar[s], B_BYTES);
+          tma_load_2d(b_panel, &p.tmapW, &full_bar[s], (kbBegin + kb) * 64, n0);
+        } else {
+          mbar_arrive(&full_bar[s]);
+        }
       }
     }
     // ---------------- epilogue ----------------
@@ -805,6 +809,13 @@ static int launch_igemm(ConvParams& p, cudaStream_t stream) {
       set_error("split-K memset: %s", cudaGetErrorString(e));
       return RSP_ERR_CUDA;
     }
+  }
+  {
+    const unsigned long long dims[2] = {static_cast<unsigned long long>(p.wgtKb) * 64, static_cast<unsigned long long>(p.Nout)};
+    const unsigned long long strides[1] = {static_cast<unsigned long long>(p.wgtKb) * 64 * 2};
+    const unsigned box[2] = {64, NT};
+    int rc = make_tmap_bf16(&p.tmapW, p.wgt, 2, dims, strides, box);
+    if (rc != RSP_OK) return rc;
   }
   constexpr int smem = STAGES * (128 * 128 + NT * 128) + 1024 + 256 + 2 * NT * 4;
   auto kern = conv_igemm_kernel<NT, STAGES, MODE>;

@@ -9,10 +9,10 @@
 // (rows overlap, which a descriptor does not mind): descriptor start = row address, LBO = 16 B (next 2 pixels),
 // SBO = 128 B (next 8 output pixels).  Rows are stored 1024 B apart per h-stride phase so that output row ho+1
 // (input row + sh) is the second half of an M=128 tile.  No gather, no index math, no im2col traffic: each input
-// row is read once per (tile, frame tap) with plain 16 B cp.async, the filter slab of one frame tap (kh*4 KB) arrives
-// with one bulk-TMA copy.
+// row is read once per (tile, frame tap) with ONE bulk copy (cp.async.bulk, 8*Wi bytes) issued by a lane of the producer
+// warp, the filter slab of one frame tap (kh*4 KB) with another; rows outside the image are zeroed in place.
 //
-// CTA (persistent, 1/SM): 4 producer warps, 4 epilogue warps, 1 MMA warp.  One iteration = 4 output rows of one
+// CTA (persistent, 1/SM): 4 epilogue warps, 1 producer warp, 1 MMA warp.  One iteration = 4 output rows of one
 // (n, to) = two 128x64 accumulators in TMEM, double buffered (256 columns) so the epilogue of iteration i overlaps the
 // MMAs of i+1.  Pipeline stage = one frame tap a: {13 input rows, kh*4 KB filter slab}, 4 stages.
 #include "common.cuh"
@@ -32,7 +32,7 @@ struct StemParams {
   int numIters;  // N * To * hq
 };
 
-constexpr int kStemThreads = 288;
+constexpr int kStemThreads = 192;
 constexpr int kStemStages = 4;
 constexpr int kStemRowBytes = 1024;   // 128 pixel slots of 8 B; slot s holds input pixel s - 4
 constexpr int kStemMaxRows = 14;      // rows per A slab (two h-phases x 7)
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
     reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (t == 0) {
     for (int s = 0; s < kStemStages; ++s) {
-      mbar_init(&full_bar[s], 128 + 1);
+      mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -84,18 +84,18 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
     }
     fence_mbar_init();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, 256);
+  if (warp == 5) tmem_alloc(tmem_slot, 256);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    // ------------------------------------------------------------------ producers
+  if (warp == 4) {
+    // ------------------------------------------------------------------ producer (bulk copies, one lane per input row)
     uint32_t stage_ctr = 0;
-    const int chunksPerRow = p.Wi >> 1;           // 16 B = 2 pixels
-    const int totalChunks = rowsA * chunksPerRow;
+    const int lane = t & 31;
+    const uint32_t rowBytes = static_cast<uint32_t>(p.Wi) * 8u;
     for (int it = blockIdx.x; it < p.numIters; it += gridDim.x) {
       const int hq = it % p.hq;
       const int q = it / p.hq;
@@ -106,29 +106,37 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
         const uint32_t ph = (stage_ctr / kStemStages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* aslab = smem + s * kStemStageBytes;
-        if (t == 0) {
-          mbar_arrive_expect_tx(&full_bar[s], bslab_bytes);
+        const int ti = to * p.st - p.pt + a;
+        const bool tok = ti >= 0 && ti < p.Ti;
+        const int hi = hi0 + lane;                         // lane j owns input row j of the slab
+        const bool mine = lane < rowsA;
+        const bool ok = mine && tok && hi >= 0 && hi < p.Hi;
+        const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+        const unsigned zmask = __ballot_sync(0xffffffffu, mine && !ok);
+        // rows outside the image: plain zero stores (the slot may hold a previous row), made visible to the async proxy
+        for (unsigned m = zmask; m; m &= m - 1) {
+          const int j = __ffs(m) - 1;
+          uint4* dst = reinterpret_cast<uint4*>(aslab + ((j % p.sh) * perPhase + j / p.sh) * kStemRowBytes + 32);
+          for (int c = lane; c < (p.Wi >> 1); c += 32) dst[c] = make_uint4(0, 0, 0, 0);
+        }
+        if (zmask) fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&full_bar[s], bslab_bytes + static_cast<uint32_t>(__popc(okmask)) * rowBytes);
           bulk_copy_g2s(smem_u32(aslab + kStemASlab), p.wst + static_cast<size_t>(a) * p.kh * 2048, bslab_bytes,
                         &full_bar[s]);
         }
-        const int ti = to * p.st - p.pt + a;
-        const bool tok = ti >= 0 && ti < p.Ti;
-        const __nv_bfloat16* frame = p.x + (static_cast<size_t>(n) * p.Ti + (tok ? ti : 0)) * p.Hi * p.Wi * 4;
-        for (int idx = t; idx < totalChunks; idx += 128) {
-          const int j = idx / chunksPerRow, c = idx - j * chunksPerRow;
-          const int hi = hi0 + j;
-          const bool ok = tok && hi >= 0 && hi < p.Hi;
-          const uint32_t dst = smem_u32(aslab) + ((j % p.sh) * perPhase + j / p.sh) * kStemRowBytes + 32 + c * 16;
-          const __nv_bfloat16* src = frame + (static_cast<size_t>(ok ? hi : 0) * p.Wi) * 4 + c * 8;
-          cp_async16(dst, src, ok ? 16u : 0u);
+        if (ok) {
+          const __nv_bfloat16* src = p.x + ((static_cast<size_t>(n) * p.Ti + ti) * p.Hi + hi) * p.Wi * 4;
+          bulk_copy_g2s(smem_u32(aslab) + ((lane % p.sh) * perPhase + lane / p.sh) * kStemRowBytes + 32, src, rowBytes,
+                        &full_bar[s]);
         }
-        cp_async_mbar_arrive(&full_bar[s]);
-        mbar_arrive(&full_bar[s]);
+        __syncwarp();
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < 4) {
     // ------------------------------------------------------------------ epilogue
-    const int ew = warp - 4;          // TMEM lane quarter
+    const int ew = warp;              // TMEM lane quarter
     const int lane = t & 31;
     float ssum[2] = {0.f, 0.f}, ssq[2] = {0.f, 0.f};  // running channel sums: lane l <-> channels l and 32 + l
     uint32_t iter_ctr = 0;
@@ -243,7 +251,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, 256);
+  if (warp == 5) tmem_dealloc(tmem_base, 256);
 }
 
 // w fp32 [64][Ci<=4][kt][kh][7] -> wst bf16 [kt][kh][4][8][8][8]; K slot q = kchunk*8 + e: pixel slot q/4 (kw = slot-1), ch q%4
@@ -315,6 +323,7 @@ int pack_stem(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const fl
 // grid: x = workers over output rows, y = pairs of frame taps.
 // =====================================================================================================================
 struct StemWgradParams {
+  CUtensorMap tmapDy;       // dy as {64, Wo, N*To*Ho}, box {64, 64, 1}: one output row per copy, pixels >= Wo zero-filled
   const __nv_bfloat16* x;   // [N][Ti][Hi][Wi][4]
   const __nv_bfloat16* dy;  // [N][To][Ho][Wo][64]
   float* dw;                // [Co][Ci][kt][kh][kw] fp32, accumulated atomically
@@ -329,7 +338,7 @@ constexpr int kSWDyBytes = 64 * 128;
 constexpr int kSWRowsMax = 14;
 constexpr int kSWStageBytes = kSWDyBytes + kSWRowsMax * kStemRowBytes;
 
-__global__ void __launch_bounds__(160, 1) conv_stem_wgrad_kernel(const StemWgradParams p) {
+__global__ void __launch_bounds__(192, 1) conv_stem_wgrad_kernel(const __grid_constant__ StemWgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // 1 KB of zeros follows the stages: pixels ow >= Wo of the last raw row are read (and multiplied by zero dY rows),
@@ -347,17 +356,17 @@ __global__ void __launch_bounds__(160, 1) conv_stem_wgrad_kernel(const StemWgrad
   int iters = 0;
   for (int r = blockIdx.x; r < p.numRows; r += gridDim.x) ++iters;
 
-  for (int i = t; i < (kSWStages * kSWStageBytes + 1024) / 16; i += 160)
+  for (int i = t; i < (kSWStages * kSWStageBytes + 1024) / 16; i += 192)
     reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (t == 0) {
     for (int s = 0; s < kSWStages; ++s) {
-      mbar_init(&full_bar[s], 128);
+      mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(accum_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, 512);
+  if (warp == 5) tmem_alloc(tmem_slot, 512);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
@@ -365,9 +374,13 @@ __global__ void __launch_bounds__(160, 1) conv_stem_wgrad_kernel(const StemWgrad
   const uint32_t tmem_base = *tmem_slot;
 
   if (iters > 0) {
-    if (warp < 4) {
-      const int chunksPerRow = p.Wi >> 1;
+    if (warp == 4) {
+      // ---------------- producer: one TMA box for the dY row, one bulk copy per raw input row (lane fr owns filter row fr)
+      const int lane = t & 31;
+      const uint32_t rowBytes = static_cast<uint32_t>(p.Wi) * 8u;
+      const int al = lane / p.kh, b = lane - al * p.kh;
       int it = 0;
+      if (lane == 0) tma_prefetch_desc(&p.tmapDy);
       for (int r = blockIdx.x; r < p.numRows; r += gridDim.x, ++it) {
         const int s = it % kSWStages;
         const uint32_t ph = (it / kSWStages) & 1;
@@ -376,28 +389,33 @@ __global__ void __launch_bounds__(160, 1) conv_stem_wgrad_kernel(const StemWgrad
         const int to = q % p.To, n = q / p.To;
         mbar_wait(&empty_bar[s], ph ^ 1);
         const uint32_t stage = smem_u32(smem + s * kSWStageBytes);
-        // dY row -> 128B-swizzled panel (pixel rows beyond Wo are zero so that garbage B rows contribute nothing)
-        const __nv_bfloat16* dyrow = p.dy + static_cast<size_t>(r) * p.Wo * 64;
-        for (int idx = t; idx < 64 * 8; idx += 128) {
-          const int row = idx >> 3, ch = idx & 7;
-          const bool ok = row < p.Wo;
-          cp_async16(stage + row * 128 + ((ch ^ (row & 7)) << 4), dyrow + (ok ? row * 64 + ch * 8 : 0), ok ? 16u : 0u);
+        const int ti = to * p.st - p.pt + a0 + al;
+        const int hi = ho * p.sh - p.ph + b;
+        const bool mine = lane < nrows;
+        const bool ok = mine && ti >= 0 && ti < p.Ti && hi >= 0 && hi < p.Hi;
+        const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+        const unsigned zmask = __ballot_sync(0xffffffffu, mine && !ok);
+        for (unsigned m = zmask; m; m &= m - 1) {
+          const int j = __ffs(m) - 1;
+          uint4* dst = reinterpret_cast<uint4*>(smem + s * kSWStageBytes + kSWDyBytes + j * kStemRowBytes + 32);
+          for (int c = lane; c < (p.Wi >> 1); c += 32) dst[c] = make_uint4(0, 0, 0, 0);
         }
-        // raw input rows of the filter rows (a, b)
-        const int total = nrows * chunksPerRow;
-        for (int idx = t; idx < total; idx += 128) {
-          const int fr = idx / chunksPerRow, c = idx - fr * chunksPerRow;
-          const int al = fr / p.kh, b = fr - al * p.kh;
-          const int ti = to * p.st - p.pt + a0 + al;
-          const int hi = ho * p.sh - p.ph + b;
-          const bool ok = ti >= 0 && ti < p.Ti && hi >= 0 && hi < p.Hi;
-          const __nv_bfloat16* src =
-              p.x + (((static_cast<size_t>(n) * p.Ti + (ok ? ti : 0)) * p.Hi + (ok ? hi : 0)) * p.Wi) * 4 + c * 8;
-          cp_async16(stage + kSWDyBytes + fr * kStemRowBytes + 32 + c * 16, src, ok ? 16u : 0u);
+        if (zmask) fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&full_bar[s], kSWDyBytes + static_cast<uint32_t>(__popc(okmask)) * rowBytes);
+          asm volatile(
+              "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+              ::"r"(stage), "l"(&p.tmapDy), "r"(smem_u32(&full_bar[s])), "r"(0), "r"(0), "r"(r)
+              : "memory");
         }
-        cp_async_mbar_arrive(&full_bar[s]);
-        mbar_arrive(&full_bar[s]);
+        if (ok) {
+          const __nv_bfloat16* src = p.x + ((static_cast<size_t>(n) * p.Ti + ti) * p.Hi + hi) * p.Wi * 4;
+          bulk_copy_g2s(stage + kSWDyBytes + lane * kStemRowBytes + 32, src, rowBytes, &full_bar[s]);
+        }
+        __syncwarp();
       }
+    } else if (warp < 4) {
       // ---------------- epilogue: TMEM lanes of an M=64 accumulator: co = 16*warp + lane, lanes 16..31 unused
       mbar_wait(accum_bar, 0);
       tc_fence_after_sync();
@@ -458,7 +476,7 @@ __global__ void __launch_bounds__(160, 1) conv_stem_wgrad_kernel(const StemWgrad
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 512);
+  if (warp == 5) tmem_dealloc(tmem_base, 512);
 }
 
 int launch_stem_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const void* x, const void* dy,
@@ -492,8 +510,15 @@ int launch_stem_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, 
   int workers = sm_count / groups;
   if (workers < 1) workers = 1;
   if (workers > p.numRows) workers = p.numRows;
+  {
+    const unsigned long long dims[3] = {64, static_cast<unsigned long long>(p.Wo), static_cast<unsigned long long>(p.numRows)};
+    const unsigned long long strides[2] = {128, static_cast<unsigned long long>(p.Wo) * 128};
+    const unsigned box[3] = {64, 64, 1};
+    int rc = make_tmap_bf16(&p.tmapDy, dy, 3, dims, strides, box);
+    if (rc != RSP_OK) return rc;
+  }
   dim3 grid(workers, groups);
-  conv_stem_wgrad_kernel<<<grid, 160, smem, stream>>>(p);
+  conv_stem_wgrad_kernel<<<grid, 192, smem, stream>>>(p);
   return check_launch("conv_stem_wgrad");
 }
 
