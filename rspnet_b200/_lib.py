@@ -119,8 +119,16 @@ def _ensure_device():
         _initialised = True
 
 
+_device_index = None
+
+
 def stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    """Raw cudaStream_t of torch's current stream (one process drives one GPU: the device index is read once).
+    torch.cuda.current_stream() builds a Stream object through several Python layers (~15 us); this is ~0.3 us."""
+    global _device_index
+    if _device_index is None:
+        _device_index = torch.cuda.current_device()
+    return torch._C._cuda_getCurrentRawStream(_device_index)
 
 
 def ptr(t):
@@ -131,10 +139,15 @@ def ptr(t):
     return t.data_ptr()
 
 
+_fn_cache = {}
+
+
 def call(name: str, *args):
     """Invoke a C-ABI entry point on the current stream; raises RuntimeError on a non-zero return."""
-    _ensure_device()
-    lib = load()
-    rc = getattr(lib, name)(*args)
+    fn = _fn_cache.get(name)
+    if fn is None:
+        _ensure_device()
+        fn = _fn_cache[name] = getattr(load(), name)
+    rc = fn(*args)
     if rc != 0:
-        raise RuntimeError(f"{name} failed ({rc}): {lib.rsp_last_error().decode()}")
+        raise RuntimeError(f"{name} failed ({rc}): {load().rsp_last_error().decode()}")

@@ -55,24 +55,31 @@ def _pad_vec(v: Optional[torch.Tensor], n: int):
     return out
 
 
+def _conv_bn_stats(x, weight, bias, gamma, beta, running_mean, running_var, kernel, stride, padding, eps, momentum):
+    """Conv fprop with the BN batch statistics taken in its epilogue, then bn_finalize. Returns desc, y, co and the
+    (scale, shift, mean, invstd) rows."""
+    co = ops.pad_channels(weight.shape[0])
+    desc = ops.conv_desc(x.shape, co, kernel, stride, padding)
+    wp = _pack_cache.get(weight, desc, 0)
+    # per-layer persistent statistics accumulator: zero at rest (bn_finalize clears it after reading)
+    key = (id(gamma), co)
+    acc = _stats_acc.get(key)
+    if acc is None or acc.device != x.device:
+        acc = _stats_acc[key] = torch.zeros((2, co), dtype=torch.float32, device=x.device)
+    y = ops.conv3d_fprop(desc, x, wp, _pad_vec(bias, co), stats=acc)   # statistics fused into the conv epilogue
+    if not ops.conv3d_fprop.stats_done:
+        ops.bn_stats(y, out=acc)                                        # split-K layers: separate reduction
+    rows = ops.bn_finalize(acc[0], acc[1], y.numel() // co, gamma, beta, eps, momentum, running_mean, running_var, co,
+                           clear_sums=True)
+    return desc, y, rows
+
+
 class ConvBNAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, residual, kernel, stride, padding, eps,
                 momentum, relu):
-        co = ops.pad_channels(weight.shape[0])
-        desc = ops.conv_desc(x.shape, co, kernel, stride, padding)
-        wp = _pack_cache.get(weight, desc, 0)
-        # per-layer persistent statistics accumulator: zero at rest (bn_finalize clears it after reading)
-        key = (id(gamma), co, x.device)
-        acc = _stats_acc.get(key)
-        if acc is None:
-            acc = _stats_acc[key] = torch.zeros((2, co), dtype=torch.float32, device=x.device)
-        y = ops.conv3d_fprop(desc, x, wp, _pad_vec(bias, co), stats=acc)   # statistics fused into the conv epilogue
-        if not ops.conv3d_fprop.stats_done:
-            ops.bn_stats(y, out=acc)                                        # split-K layers: separate reduction
-        count = y.numel() // co
-        scale, shift, mean, invstd = ops.bn_finalize(acc[0], acc[1], count, gamma, beta, eps, momentum, running_mean,
-                                                     running_var, co, clear_sums=True)
+        desc, y, (scale, shift, mean, invstd) = _conv_bn_stats(x, weight, bias, gamma, beta, running_mean, running_var,
+                                                               kernel, stride, padding, eps, momentum)
         out = ops.bn_act_fwd(y, scale, shift, residual, relu)
         ctx.desc = desc
         ctx.relu = relu
@@ -103,19 +110,8 @@ class ConvBNReLUPool(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, kernel, stride, padding, eps, momentum,
                 pool_k, pool_s, pool_p):
-        co = ops.pad_channels(weight.shape[0])
-        desc = ops.conv_desc(x.shape, co, kernel, stride, padding)
-        wp = _pack_cache.get(weight, desc, 0)
-        key = (id(gamma), co, x.device)
-        acc = _stats_acc.get(key)
-        if acc is None:
-            acc = _stats_acc[key] = torch.zeros((2, co), dtype=torch.float32, device=x.device)
-        y = ops.conv3d_fprop(desc, x, wp, _pad_vec(bias, co), stats=acc)
-        if not ops.conv3d_fprop.stats_done:
-            ops.bn_stats(y, out=acc)
-        count = y.numel() // co
-        scale, shift, mean, invstd = ops.bn_finalize(acc[0], acc[1], count, gamma, beta, eps, momentum, running_mean,
-                                                     running_var, co, clear_sums=True)
+        desc, y, (scale, shift, mean, invstd) = _conv_bn_stats(x, weight, bias, gamma, beta, running_mean, running_var,
+                                                               kernel, stride, padding, eps, momentum)
         pdesc = ops.pool_desc(y.shape, pool_k, pool_s, pool_p)
         out, idx = ops.bn_relu_maxpool_fwd(pdesc, y, scale, shift)
         ctx.desc, ctx.pdesc = desc, pdesc
@@ -153,8 +149,13 @@ def conv_bn_relu_pool(x, conv: torch.nn.Conv3d, bn: torch.nn.BatchNorm3d, pool: 
     if conv.groups != 1 or tuple(conv.dilation) != (1, 1, 1):
         raise NotImplementedError("rspnet_b200: grouped / dilated Conv3d is not on the pretraining path")
     momentum = bn.momentum if bn.momentum is not None else 0.0
-    out = ConvBNReLUPool.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, k, s, p,
-                               bn.eps, momentum, pk, ps, pp)
+    if not torch.is_grad_enabled():
+        _, y, (scale, shift, _, _) = _conv_bn_stats(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean,
+                                                    bn.running_var, k, s, p, bn.eps, momentum)
+        out = ops.bn_relu_maxpool_fwd(ops.pool_desc(y.shape, pk, ps, pp), y, scale, shift)[0]
+    else:
+        out = ConvBNReLUPool.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, k, s,
+                                   p, bn.eps, momentum, pk, ps, pp)
     if bn.track_running_stats and bn.num_batches_tracked is not None and not getattr(bn, "_rsp_counter_batched", False):
         bn.num_batches_tracked += 1
     return out
@@ -167,8 +168,15 @@ def conv_bn_act(x, conv: torch.nn.Conv3d, bn: torch.nn.BatchNorm3d, relu: bool =
     if conv.groups != 1 or tuple(conv.dilation) != (1, 1, 1):
         raise NotImplementedError("rspnet_b200: grouped / dilated Conv3d is not on the pretraining path")
     momentum = bn.momentum if bn.momentum is not None else 0.0
-    out = ConvBNAct.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual,
-                          tuple(conv.kernel_size), tuple(conv.stride), tuple(conv.padding), bn.eps, momentum, relu)
+    if not torch.is_grad_enabled():
+        # key-encoder passes: same kernels without the autograd.Function round trip
+        _, y, (scale, shift, _, _) = _conv_bn_stats(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean,
+                                                    bn.running_var, conv.kernel_size, conv.stride, conv.padding, bn.eps,
+                                                    momentum)
+        out = ops.bn_act_fwd(y, scale, shift, residual, relu)
+    else:
+        out = ConvBNAct.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual,
+                              tuple(conv.kernel_size), tuple(conv.stride), tuple(conv.padding), bn.eps, momentum, relu)
     if bn.track_running_stats and bn.num_batches_tracked is not None and not getattr(bn, "_rsp_counter_batched", False):
         bn.num_batches_tracked += 1
     return out

@@ -101,12 +101,12 @@ def bn_stats(x: torch.Tensor, out: Optional[torch.Tensor] = None):
 
 
 def bn_finalize(s, ss, count, gamma, beta, eps, momentum, running_mean, running_var, c_stored, clear_sums=False):
-    dev = s.device
-    out = torch.empty((4, c_stored), dtype=torch.float32, device=dev)
+    out = torch.empty((4, c_stored), dtype=torch.float32, device=s.device)
+    base, row = out.data_ptr(), 4 * c_stored
     call("rsp_bn_finalize", ptr(s), ptr(ss), int(clear_sums), count, ptr(gamma), ptr(beta), eps, momentum,
-         ptr(running_mean), ptr(running_var), ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(out[3]), c_stored,
+         ptr(running_mean), ptr(running_var), base, base + row, base + 2 * row, base + 3 * row, c_stored,
          gamma.numel(), stream_ptr())
-    return out[0], out[1], out[2], out[3]  # scale, shift, mean, invstd
+    return out.unbind(0)  # scale, shift, mean, invstd
 
 
 def bn_act_fwd(x, scale, shift, residual, relu: bool):
