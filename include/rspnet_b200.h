@@ -51,6 +51,10 @@ int64_t rsp_conv3d_packed_elems(const rsp_conv3d_desc* d, int which);
  * (dgrad).  wp must hold rsp_conv3d_packed_elems(d, which) elements. */
 int rsp_conv3d_pack_weight(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const float* w, void* wp,
                            int which, void* stream);
+/* The which = 0 packing of n filters in one launch per 24 filters (host arrays of descriptors / pointers): what the
+ * training loop calls after every optimizer and momentum-encoder update. */
+int rsp_conv3d_pack_weights(int32_t n, const rsp_conv3d_desc* descs, const int32_t* ci_logical,
+                            const int32_t* co_logical, const float* const* w, void* const* wp, void* stream);
 /* Bytes of the fp32 split-K accumulation buffer fprop (which = 0) / dgrad (which = 1) want for this geometry
  * (0: the K loop is not split). Passing NULL as workspace is always legal and disables split-K. */
 int64_t rsp_conv3d_workspace_bytes(const rsp_conv3d_desc* d, int which);

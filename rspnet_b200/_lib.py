@@ -44,6 +44,8 @@ SIGNATURES = {
     "rsp_conv3d_kpad": (c_i32, [C.POINTER(ConvDesc), c_i32]),
     "rsp_conv3d_packed_elems": (c_i64, [C.POINTER(ConvDesc), c_i32]),
     "rsp_conv3d_pack_weight": (c_i32, [C.POINTER(ConvDesc), c_i32, c_i32, _P, _P, c_i32, _P]),
+    "rsp_conv3d_pack_weights": (c_i32, [c_i32, C.POINTER(ConvDesc), C.POINTER(c_i32), C.POINTER(c_i32),
+                                        C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _P]),
     "rsp_conv3d_workspace_bytes": (c_i64, [C.POINTER(ConvDesc), c_i32]),
     "rsp_conv3d_fprop": (c_i32, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P]),
     "rsp_conv3d_dgrad": (c_i32, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P]),

@@ -670,6 +670,39 @@ __global__ void __launch_bounds__(256) pack_weight_fprop_kernel(const float* __r
   }
 }
 
+// The same for up to kPackBatch filters in one launch (a whole encoder is re-packed after every optimizer / EMA step):
+// blockIdx.x walks the output channels of all jobs back to back.
+constexpr int kPackBatch = 24;
+struct PackJob {
+  const float* w;
+  __nv_bfloat16* wp;
+  int mode, Co, CoPad, Ci, Cs, kt, kh, kw, pxs, Kpad, blk0;
+};
+struct PackBatch {
+  PackJob j[kPackBatch];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) pack_weight_fprop_batch_kernel(const __grid_constant__ PackBatch b) {
+  extern __shared__ float sw[];
+  int ji = 0;
+  while (ji + 1 < b.n && static_cast<int>(blockIdx.x) >= b.j[ji + 1].blk0) ++ji;
+  const PackJob& J = b.j[ji];
+  const int co = blockIdx.x - J.blk0;
+  const int taps = J.kt * J.kh * J.kw;
+  const int per = J.Ci * taps;
+  if (co < J.Co)
+    for (int i = threadIdx.x; i < per; i += 256) sw[i] = J.w[static_cast<size_t>(co) * per + i];
+  __syncthreads();
+  for (int k = threadIdx.x; k < J.Kpad; k += 256) {
+    int ci, a, bb, c;
+    float v = 0.f;
+    if (co < J.Co && k_to_filter(J.mode, k, J.Cs, J.Ci, J.kt, J.kh, J.kw, J.pxs, ci, a, bb, c))
+      v = sw[ci * taps + (a * J.kh + bb) * J.kw + c];
+    J.wp[static_cast<size_t>(co) * J.Kpad + k] = __float2bfloat16(v);
+  }
+}
+
 // w fp32 [Co][Ci][kt][kh][kw] -> wd bf16 [CiPad][taps*CoPad]  (dgrad B operand: K index = tap*CoPad + co).
 // Seen as matrices this is a plain transpose: w is [Co] x [R = Ci*taps] (r = ci*taps + tap) and wd is
 // [CiPad*taps] x [CoPad] with the same r on its rows, so a 64 x 64 smem tile gives coalesced reads (along r) and
@@ -942,6 +975,56 @@ int rsp_conv3d_pack_weight(const rsp_conv3d_desc* d, int Ci_logical, int Co_logi
   dim3 grid((Rpad + 63) / 64, d->Co / 64);
   pack_weight_dgrad_kernel<<<grid, 256, 0, stream>>>(w, static_cast<__nv_bfloat16*>(wp), Co_logical, d->Co, R, Rpad);
   return check_launch("pack_weight_dgrad");
+}
+
+int rsp_conv3d_pack_weights(int32_t n, const rsp_conv3d_desc* descs, const int32_t* ci_logical,
+                            const int32_t* co_logical, const float* const* w, void* const* wp, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(pack_weight_fprop_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = true;
+  }
+  for (int base = 0; base < n; base += kPackBatch) {
+    PackBatch b{};
+    b.n = (n - base) < kPackBatch ? (n - base) : kPackBatch;
+    int blocks = 0;
+    size_t smem = 0;
+    for (int i = 0; i < b.n; ++i) {
+      const rsp_conv3d_desc* d = descs + base + i;
+      const int mode = conv_mode(d);
+      GatherGeom g{};
+      int rc = fill_geom(g, d, mode, 0);
+      if (rc != RSP_OK) return rc;
+      PackJob& J = b.j[i];
+      J.w = w[base + i];
+      J.wp = static_cast<__nv_bfloat16*>(wp[base + i]);
+      J.mode = mode;
+      J.Co = co_logical[base + i];
+      J.CoPad = d->Co;
+      J.Ci = ci_logical[base + i];
+      J.Cs = d->Ci;
+      J.kt = d->kt; J.kh = d->kh; J.kw = d->kw;
+      J.pxs = g.pxs;
+      J.Kpad = g.numKb * 64;
+      J.blk0 = blocks;
+      blocks += d->Co;
+      const size_t per = static_cast<size_t>(J.Ci) * d->kt * d->kh * d->kw * sizeof(float);
+      RSP_REQUIRE(per <= 200 * 1024, "pack_weights: one filter (%zu bytes) does not fit in shared memory", per);
+      if (per > smem) smem = per;
+    }
+    pack_weight_fprop_batch_kernel<<<blocks, 256, smem, stream>>>(b);
+    int rc = check_launch("pack_weight_fprop_batch");
+    if (rc != RSP_OK) return rc;
+    for (int i = 0; i < b.n; ++i) {
+      const rsp_conv3d_desc* d = descs + base + i;
+      if (stem_supported(d)) {
+        rc = pack_stem(d, b.j[i].Ci, b.j[i].Co, b.j[i].w, b.j[i].wp + static_cast<size_t>(d->Co) * b.j[i].Kpad, stream);
+        if (rc != RSP_OK) return rc;
+      }
+    }
+  }
+  return RSP_OK;
 }
 
 int64_t rsp_conv3d_workspace_bytes(const rsp_conv3d_desc* d, int which) {

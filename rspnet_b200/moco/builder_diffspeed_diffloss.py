@@ -191,6 +191,7 @@ class _MoCoBase(nn.Module):
         self._ensure_flat()
         ops.ema_update_(self._flat_k, self._flat_q, self.m)
         rnn.bump_weight_epoch()
+        rnn.refresh_packed_weights()   # both encoders are final for this step: one batched re-pack
 
     @torch.no_grad()
     def _dequeue_and_enqueue(self, keys, gathered: bool = False):

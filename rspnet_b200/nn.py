@@ -26,21 +26,41 @@ def bump_weight_epoch():
     _weight_epoch += 1
 
 
+def refresh_packed_weights():
+    """Batch re-pack of all stale filter operands (see _PackCache.refresh)."""
+    _pack_cache.refresh()
+
+
 class _PackCache:
     """Per-parameter cache of packed filter operands, keyed by (which, geometry, weight version)."""
 
     def __init__(self):
         self._store = {}
 
+    @staticmethod
+    def _tag(weight):
+        return (_weight_epoch, weight._version, weight.data_ptr())
+
     def get(self, weight: torch.Tensor, desc, which: int):
         key = (id(weight), which, desc.Ci, desc.Co, desc.kt, desc.kh, desc.kw)
-        tag = (_weight_epoch, weight._version, weight.data_ptr())
         hit = self._store.get(key)
+        tag = self._tag(weight)
         if hit is not None and hit[0] == tag:
             return hit[1]
         packed = ops.conv3d_pack_weight(desc, weight, which)
-        self._store[key] = (tag, packed)
+        self._store[key] = (tag, packed, weight, desc)
         return packed
+
+    def refresh(self):
+        """Re-pack every fprop/wgrad operand seen so far whose parameter changed, in place, a whole encoder per launch
+        (called once per step after the SGD / EMA updates instead of one small launch per layer)."""
+        stale = [(k, e) for k, e in self._store.items() if k[1] == 0 and e[0] != self._tag(e[2]) and
+                 e[2].dtype == torch.float32 and e[2].is_contiguous()]
+        if not stale:
+            return
+        ops.conv3d_pack_weights([e[3] for _, e in stale], [e[2] for _, e in stale], [e[1] for _, e in stale])
+        for k, e in stale:
+            self._store[k] = (self._tag(e[2]), e[1], e[2], e[3])
 
 
 _pack_cache = _PackCache()

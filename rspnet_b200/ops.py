@@ -43,6 +43,17 @@ def conv3d_pack_weight(desc: ConvDesc, weight: torch.Tensor, which: int = 0) -> 
     return out
 
 
+def conv3d_pack_weights(descs, weights, outs):
+    """Batched ``conv3d_pack_weight(which=0)`` into existing packed buffers."""
+    n = len(descs)
+    d_arr = (ConvDesc * n)(*descs)
+    ci = (C.c_int32 * n)(*[w.shape[1] for w in weights])
+    co = (C.c_int32 * n)(*[w.shape[0] for w in weights])
+    w_arr = (C.c_void_p * n)(*[w.data_ptr() for w in weights])
+    o_arr = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+    call("rsp_conv3d_pack_weights", n, d_arr, ci, co, w_arr, o_arr, stream_ptr())
+
+
 def _splitk_workspace(desc: ConvDesc, which: int, device):
     """fp32 accumulation buffer for split-K on small-M layers (None when the library does not want one)."""
     _lib._ensure_device()

@@ -76,15 +76,15 @@ __global__ void layout_probe(const __nv_bfloat16* A, const __nv_bfloat16* B, flo
 }
 
 template <int N, int TS>
-__global__ void rate_probe(long long* out, int iters) {
+__global__ void rate_probe(long long* out, int iters, int shift_rows) {
   extern __shared__ __align__(1024) uint8_t raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sa = smem;            // 128 rows * 128 B
-  uint8_t* sb = smem + 16384;    // N rows * 128 B
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 16384 + 256 * 128);
+  uint8_t* sa = smem;            // (128 + 16) rows * 128 B
+  uint8_t* sb = smem + 20480;    // N rows * 128 B
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 20480 + 256 * 128);
   uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
   int t = threadIdx.x;
-  for (int i = t; i < (16384 + 256 * 128) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = t; i < (20480 + 256 * 128) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (t == 0) { mbar_init(bar, 1); fence_mbar_init(); }
   if (t < 32) tmem_alloc(slot, 512);
   fence_proxy_async_smem();
@@ -95,7 +95,7 @@ __global__ void rate_probe(long long* out, int iters) {
   long long t0 = 0, t1 = 0;
   if (t < 32) {
     if (elect_one()) {
-      const uint64_t adesc = make_smem_desc_sw128(smem_u32(sa), 16, 1024);
+      const uint64_t adesc = make_smem_desc_sw128(smem_u32(sa) + shift_rows * 128, 16, 1024);
       const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sb), 16, 1024);
       constexpr uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
       t0 = clock64();
@@ -121,10 +121,10 @@ namespace rsp { void set_error(const char*, ...) {} int check_launch(const char*
 int make_tmap_bf16(CUtensorMap*, const void*, int, const unsigned long long*, const unsigned long long*, const unsigned*) { return 0; } }
 
 template <int N, int TS>
-void run_rate(long long* d, int grid) {
+void run_rate(long long* d, int grid, int shift_rows = 0) {
   const int iters = 512;
   cudaFuncSetAttribute(rate_probe<N, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  rate_probe<N, TS><<<grid, 128, 52 * 1024>>>(d, iters);
+  rate_probe<N, TS><<<grid, 128, 56 * 1024>>>(d, iters, shift_rows);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("rate N=%d TS=%d: CUDA error %s\n", N, TS, cudaGetErrorString(e)); exit(1); }
   std::vector<long long> h(grid);
@@ -132,8 +132,8 @@ void run_rate(long long* d, int grid) {
   long long mx = 0;
   for (auto v : h) mx = v > mx ? v : mx;
   double per = double(mx) / (iters * 4);
-  printf("%s  M=128 N=%3d K=16 grid %3d: %.1f clk per MMA (floor %d) -> %.0f%% of the tensor pipe\n", TS ? "TS (A in TMEM)" : "SS (A in smem)",
-         N, grid, per, N / 2, 100.0 * (N / 2) / per);
+  printf("%s  M=128 N=%3d K=16 grid %3d A start row %d: %.1f clk per MMA (floor %d) -> %.0f%% of the tensor pipe\n",
+         TS ? "TS (A in TMEM)" : "SS (A in smem)", N, grid, shift_rows, per, N / 2, 100.0 * (N / 2) / per);
 }
 
 int main() {
@@ -157,6 +157,11 @@ int main() {
     run_rate<64, 0>(dT, grid); run_rate<64, 1>(dT, grid);
     run_rate<128, 0>(dT, grid); run_rate<128, 1>(dT, grid);
     run_rate<256, 0>(dT, grid); run_rate<256, 1>(dT, grid);
+  }
+  // does an A tile that starts in the middle of a 1024-byte swizzle atom (direct conv: arbitrary pixel-row offsets) cost more?
+  for (int shift : {1, 3, 4, 8, 9}) {
+    run_rate<64, 0>(dT, 148, shift);
+    run_rate<128, 0>(dT, 148, shift);
   }
   return 0;
 }
