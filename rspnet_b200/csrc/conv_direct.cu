@@ -106,13 +106,15 @@ __global__ void __launch_bounds__(kDirThreads, 1) conv_direct_kernel(const __gri
 
   if (warp == 4) {
     // ============================================================ TMA producer
+    // one elected lane runs the whole loop: a single instruction stream without per-step warp re-convergence
     uint32_t pctr = 0, wctr = 0;
     const uint32_t planeTx = static_cast<uint32_t>(p.rowsBuf) * p.Wp * 128u;
-    if (elect_one()) {
+    const bool leader = elect_one();
+    if (leader) {
       tma_prefetch_desc(&p.tmapX);
       tma_prefetch_desc(&p.tmapW);
     }
-    for (int it = blockIdx.x; it < p.numItems; it += gridDim.x) {
+    for (int it = blockIdx.x; leader && it < p.numItems; it += gridDim.x) {
       int nt, n, to, grp;
       decode_item(it, nt, n, to, grp);
       const int q0 = grp * p.G * 128;
@@ -123,23 +125,17 @@ __global__ void __launch_bounds__(kDirThreads, 1) conv_direct_kernel(const __gri
         for (int cc = 0; cc < cch; ++cc, ++pctr) {
           const int ps = pctr & 1;
           mbar_wait(&plane_empty[ps], ((pctr >> 1) & 1) ^ 1);
-          if (elect_one()) {
-            mbar_arrive_expect_tx(&plane_full[ps], planeTx);
-            tma_load_5d(smem_u32(smem + ps * planeBytes), &p.tmapX, &plane_full[ps], cc * 64, -p.pw, row0 - p.ph, ts, n);
-          }
-          __syncwarp();
+          mbar_arrive_expect_tx(&plane_full[ps], planeTx);
+          tma_load_5d(smem_u32(smem + ps * planeBytes), &p.tmapX, &plane_full[ps], cc * 64, -p.pw, row0 - p.ph, ts, n);
           // the kh*kw filter tiles of this (frame tap, channel chunk)
           for (int b = 0; b < p.kh; ++b) {
             for (int c = 0; c < p.kw; ++c, ++wctr) {
               const int ws_ = wctr % wStages;
               mbar_wait(&w_empty[ws_], ((wctr / wStages) & 1) ^ 1);
-              if (elect_one()) {
-                const int ta = p.flip ? p.kt - 1 - a : a, tb = p.flip ? p.kh - 1 - b : b, tc = p.flip ? p.kw - 1 - c : c;
-                const int koff = ((ta * p.kh + tb) * p.kw + tc) * p.Cs + cc * 64;
-                mbar_arrive_expect_tx(&w_full[ws_], W_BYTES);
-                tma_load_2d(smem_u32(wring + ws_ * W_BYTES), &p.tmapW, &w_full[ws_], koff, nt * NT);
-              }
-              __syncwarp();
+              const int ta = p.flip ? p.kt - 1 - a : a, tb = p.flip ? p.kh - 1 - b : b, tc = p.flip ? p.kw - 1 - c : c;
+              const int koff = ((ta * p.kh + tb) * p.kw + tc) * p.Cs + cc * 64;
+              mbar_arrive_expect_tx(&w_full[ws_], W_BYTES);
+              tma_load_2d(smem_u32(wring + ws_ * W_BYTES), &p.tmapW, &w_full[ws_], koff, nt * NT);
             }
           }
         }
@@ -235,9 +231,12 @@ __global__ void __launch_bounds__(kDirThreads, 1) conv_direct_kernel(const __gri
     flush();
   } else {
     // ============================================================ MMA issuer
+    // one elected lane waits, issues and commits: the issue stream is ~2 instructions per MMA with no warp-level
+    // re-convergence in between (measured with tools/umma_ts_probe: an elect/syncwarp per 4 MMAs costs ~25 clk per MMA)
     constexpr uint32_t idesc = make_idesc_bf16(128, NT, 0, 0);
     uint32_t pctr = 0, wctr = 0, ictr = 0;
-    for (int it = blockIdx.x; it < p.numItems; it += gridDim.x, ++ictr) {
+    const bool leader = elect_one();
+    for (int it = blockIdx.x; leader && it < p.numItems; it += gridDim.x, ++ictr) {
       int nt, n, to, grp;
       decode_item(it, nt, n, to, grp);
       const int buf = ictr & 1;
@@ -262,28 +261,23 @@ __global__ void __launch_bounds__(kDirThreads, 1) conv_direct_kernel(const __gri
               const int ws_ = wctr % wStages;
               mbar_wait(&w_full[ws_], (wctr / wStages) & 1);
               tc_fence_after_sync();
-              if (elect_one()) {
-                const uint64_t bdesc = make_smem_desc_sw128(smem_u32(wring + ws_ * W_BYTES), 16, 1024);
-                const uint64_t adesc0 = make_smem_desc_sw128(abase + (b * p.Wp + c) * 128, 16, 1024);
-                for (int m = 0; m < chunks; ++m) {
-                  const uint64_t adesc = adesc0 + static_cast<uint64_t>(m * 1024);  // 128 rows * 128 B / 16
+              const uint64_t bdesc = make_smem_desc_sw128(smem_u32(wring + ws_ * W_BYTES), 16, 1024);
+              const uint64_t adesc0 = make_smem_desc_sw128(abase + (b * p.Wp + c) * 128, 16, 1024);
+              for (int m = 0; m < chunks; ++m) {
+                const uint64_t adesc = adesc0 + static_cast<uint64_t>(m * 1024);  // 128 rows * 128 B / 16
 #pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    umma_bf16(tmem_base + buf * accCols + m * NT, adesc + 2 * k, bdesc + 2 * k, idesc,
-                              (first && k == 0) ? 0u : 1u);
-                }
-                umma_commit(&w_empty[ws_]);
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(tmem_base + buf * accCols + m * NT, adesc + 2 * k, bdesc + 2 * k, idesc,
+                            (first && k == 0) ? 0u : 1u);
               }
-              __syncwarp();
+              umma_commit(&w_empty[ws_]);
               first = false;
             }
           }
-          if (elect_one()) umma_commit(&plane_empty[ps]);
-          __syncwarp();
+          umma_commit(&plane_empty[ps]);
         }
       }
-      if (elect_one()) umma_commit(&acc_full[buf]);
-      __syncwarp();
+      umma_commit(&acc_full[buf]);
     }
   }
 

@@ -419,28 +419,29 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
     }
   } else {
     // ---------------- MMA issuer ----------------
+    // one elected lane waits, issues and commits (no warp-level re-convergence between K blocks)
     constexpr uint32_t idesc = make_idesc_bf16(128, NT, 0, 0);
-    for (int kb = 0; kb < numKb; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (kb / STAGES) & 1;
-      mbar_wait(&full_bar[s], ph);
-      fence_proxy_async_smem();
-      tc_fence_after_sync();
-      if (elect_one()) {
-        const uint32_t a_panel = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t b_panel = a_panel + A_BYTES;
-        const uint64_t adesc = make_smem_desc_sw128(a_panel, 16, 1024);
-        const uint64_t bdesc = make_smem_desc_sw128(b_panel, 16, 1024);
+    if (elect_one()) {
+      const uint64_t adesc0 = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
+      const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(smem) + A_BYTES, 16, 1024);
+      for (int kb = 0; kb < numKb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        fence_proxy_async_smem();
+        tc_fence_after_sync();
+        const uint64_t adesc = adesc0 + static_cast<uint64_t>(s * (STAGE_BYTES >> 4));
+        const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(s * (STAGE_BYTES >> 4));
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           // +32 B per K=16 step inside the 128 B swizzle row (descriptor address is in 16 B units)
           umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
         }
         umma_commit(&empty_bar[s]);
-        if (kb == numKb - 1) umma_commit(accum_bar);
       }
-      __syncwarp();
+      umma_commit(accum_bar);
     }
+    __syncwarp();
   }
 
   tc_fence_before_sync();
@@ -594,27 +595,28 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const WgradParams 
       }
     } else {
       constexpr uint32_t idesc = make_idesc_bf16(128, NT, 1, 1);
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
-        fence_proxy_async_smem();
-        tc_fence_after_sync();
-        if (elect_one()) {
-          const uint32_t stage = smem_u32(smem + s * STAGE_BYTES);
-          // MN-major: 64-wide panels PANEL bytes apart (LBO), 8-pixel groups 1024 B apart (SBO)
-          const uint64_t adesc = make_smem_desc_sw128(stage, PANEL, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(stage + 2 * PANEL, PANEL, 1024);
+      if (elect_one()) {
+        // MN-major: 64-wide panels PANEL bytes apart (LBO), 8-pixel groups 1024 B apart (SBO)
+        const uint64_t adesc0 = make_smem_desc_sw128(smem_u32(smem), PANEL, 1024);
+        const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(smem) + 2 * PANEL, PANEL, 1024);
+        for (int it = 0; it < iters; ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          fence_proxy_async_smem();
+          tc_fence_after_sync();
+          const uint64_t adesc = adesc0 + static_cast<uint64_t>(s * (STAGE_BYTES >> 4));
+          const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(s * (STAGE_BYTES >> 4));
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             // K=16 pixels = two 8-pixel groups = 2048 B
             umma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, idesc, (it | k) != 0);
           }
           umma_commit(&empty_bar[s]);
-          if (it == iters - 1) umma_commit(accum_bar);
         }
-        __syncwarp();
+        umma_commit(accum_bar);
       }
+      __syncwarp();
     }
   }
 

@@ -207,9 +207,11 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
     }
   } else {
     // ------------------------------------------------------------------ MMA issuer
+    // one elected lane waits, issues and commits (no warp-level re-convergence between stages)
     constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
     uint32_t stage_ctr = 0, iter_ctr = 0;
-    for (int it = blockIdx.x; it < p.numIters; it += gridDim.x, ++iter_ctr) {
+    const bool leader = elect_one();
+    for (int it = blockIdx.x; leader && it < p.numIters; it += gridDim.x, ++iter_ctr) {
       const int buf = iter_ctr & 1;
       const uint32_t aph = (iter_ctr >> 1) & 1;
       mbar_wait(&acc_empty[buf], aph ^ 1);
@@ -220,31 +222,28 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
         mbar_wait(&full_bar[s], ph);
         fence_proxy_async_smem();
         tc_fence_after_sync();
-        if (elect_one()) {
-          // kh == 7 and sh == 2 (stem_supported): every descriptor is a compile-time offset from two bases, so the
-          // issuing thread spends ~3 instructions per MMA instead of rebuilding 64-bit descriptors
-          const uint32_t aslab = smem_u32(smem + s * kStemStageBytes);
-          const uint64_t abase = make_smem_desc_nosw(aslab, 16, 128);
-          const uint64_t bbase = make_smem_desc_nosw(aslab + kStemASlab, 1024, 128);
-          const uint32_t dcol = tmem_base + buf * 128;
+        // kh == 7 and sh == 2 (stem_supported): every descriptor is a compile-time offset from two bases, so the
+        // issuing thread spends ~2 instructions per MMA instead of rebuilding 64-bit descriptors
+        const uint32_t aslab = smem_u32(smem + s * kStemStageBytes);
+        const uint64_t abase = make_smem_desc_nosw(aslab, 16, 128);
+        const uint64_t bbase = make_smem_desc_nosw(aslab + kStemASlab, 1024, 128);
+        const uint32_t dcol = tmem_base + buf * 128;
 #pragma unroll
-          for (int b = 0; b < 7; ++b) {
+        for (int b = 0; b < 7; ++b) {
 #pragma unroll
-            for (int m = 0; m < 2; ++m) {
-              constexpr int kPerPhase = 7;                       // (3*2 + 7 + 1) / 2
-              const int j = 4 * m + b;                           // 2*m*sh + b
-              const int arow = ((j & 1) * kPerPhase + (j >> 1)) * kStemRowBytes;
+          for (int m = 0; m < 2; ++m) {
+            constexpr int kPerPhase = 7;                       // (3*2 + 7 + 1) / 2
+            const int j = 4 * m + b;                           // 2*m*sh + b
+            const int arow = ((j & 1) * kPerPhase + (j >> 1)) * kStemRowBytes;
 #pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                umma_bf16(dcol + m * 64, abase + static_cast<uint64_t>((arow + ks * 32) >> 4),
-                          bbase + static_cast<uint64_t>((b * 4096 + ks * 2048) >> 4), idesc, (a | b | ks) != 0);
-              }
+            for (int ks = 0; ks < 2; ++ks) {
+              umma_bf16(dcol + m * 64, abase + static_cast<uint64_t>((arow + ks * 32) >> 4),
+                        bbase + static_cast<uint64_t>((b * 4096 + ks * 2048) >> 4), idesc, (a | b | ks) != 0);
             }
           }
-          umma_commit(&empty_bar[s]);
-          if (a == p.kt - 1) umma_commit(&acc_full[buf]);
         }
-        __syncwarp();
+        umma_commit(&empty_bar[s]);
+        if (a == p.kt - 1) umma_commit(&acc_full[buf]);
       }
     }
   }
@@ -446,31 +445,29 @@ __global__ void __launch_bounds__(192, 1) conv_stem_wgrad_kernel(const __grid_co
     } else {
       const int ncol = nrows * 8;                                    // accumulator columns per pixel-pair window
       const uint32_t idesc = make_idesc_bf16(64, ncol, 1, 1);
-      for (int it = 0; it < iters; ++it) {
+      const bool leader = elect_one();
+      for (int it = 0; leader && it < iters; ++it) {
         const int s = it % kSWStages;
         const uint32_t ph = (it / kSWStages) & 1;
         mbar_wait(&full_bar[s], ph);
         fence_proxy_async_smem();
         tc_fence_after_sync();
-        if (elect_one()) {
-          const uint32_t stage = smem_u32(smem + s * kSWStageBytes);
-          // A: 16 pixels = two 8-row groups of the swizzled dY panel.
-          // B: N chunk = the same 2-pixel window (16 B) of every filter row (rows are 1 KB apart -> SBO = 1024), so one
-          //    instruction covers all nrows filter rows (N = 8*nrows <= 112); K: 8-pixel groups 128 B apart (LBO).
-          const uint64_t abase = make_smem_desc_sw128(stage, 8192, 1024);
-          const uint64_t bbase = make_smem_desc_nosw(stage + kSWDyBytes, 128, kStemRowBytes);
+        const uint32_t stage = smem_u32(smem + s * kSWStageBytes);
+        // A: 16 pixels = two 8-row groups of the swizzled dY panel.
+        // B: N chunk = the same 2-pixel window (16 B) of every filter row (rows are 1 KB apart -> SBO = 1024), so one
+        //    instruction covers all nrows filter rows (N = 8*nrows <= 112); K: 8-pixel groups 128 B apart (LBO).
+        const uint64_t abase = make_smem_desc_sw128(stage, 8192, 1024);
+        const uint64_t bbase = make_smem_desc_nosw(stage + kSWDyBytes, 128, kStemRowBytes);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 4; ++j) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              umma_bf16(tmem_base + j * ncol, abase + static_cast<uint64_t>((ks * 2048) >> 4),
-                        bbase + static_cast<uint64_t>((j * 16 + ks * 256) >> 4), idesc, (it | ks) != 0);
-            }
+          for (int ks = 0; ks < 4; ++ks) {
+            umma_bf16(tmem_base + j * ncol, abase + static_cast<uint64_t>((ks * 2048) >> 4),
+                      bbase + static_cast<uint64_t>((j * 16 + ks * 256) >> 4), idesc, (it | ks) != 0);
           }
-          umma_commit(&empty_bar[s]);
-          if (it == iters - 1) umma_commit(accum_bar);
         }
-        __syncwarp();
+        umma_commit(&empty_bar[s]);
+        if (it == iters - 1) umma_commit(accum_bar);
       }
     }
   }

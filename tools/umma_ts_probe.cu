@@ -75,16 +75,20 @@ __global__ void layout_probe(const __nv_bfloat16* A, const __nv_bfloat16* B, flo
   if (t < 32) tmem_dealloc(tm, 128);
 }
 
-template <int N, int TS>
+// TILES distinct A tiles (128 rows x 128 B: four K=16 steps each) and B tiles (N rows x 128 B) are cycled so that no operand
+// is fetched twice in a row; TILES = 1 repeats the same operands (what an operand cache would hide).
+template <int N, int TS, int TILES>
 __global__ void rate_probe(long long* out, int iters, int shift_rows) {
   extern __shared__ __align__(1024) uint8_t raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sa = smem;            // (128 + 16) rows * 128 B
-  uint8_t* sb = smem + 20480;    // N rows * 128 B
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 20480 + 256 * 128);
+  constexpr int A_TILE = 16384, B_TILE = N * 128;
+  uint8_t* sa = smem;                              // TILES A tiles (+ 2 KB slack for the row shift)
+  uint8_t* sb = smem + TILES * A_TILE + 2048;      // TILES B tiles
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sb + TILES * B_TILE);
   uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
   int t = threadIdx.x;
-  for (int i = t; i < (20480 + 256 * 128) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = t; i < (TILES * (A_TILE + B_TILE) + 2048) / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (t == 0) { mbar_init(bar, 1); fence_mbar_init(); }
   if (t < 32) tmem_alloc(slot, 512);
   fence_proxy_async_smem();
@@ -95,14 +99,17 @@ __global__ void rate_probe(long long* out, int iters, int shift_rows) {
   long long t0 = 0, t1 = 0;
   if (t < 32) {
     if (elect_one()) {
-      const uint64_t adesc = make_smem_desc_sw128(smem_u32(sa) + shift_rows * 128, 16, 1024);
-      const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sb), 16, 1024);
+      const uint64_t adesc0 = make_smem_desc_sw128(smem_u32(sa) + shift_rows * 128, 16, 1024);
+      const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(sb), 16, 1024);
       constexpr uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
       t0 = clock64();
       for (int i = 0; i < iters; ++i) {
+        const int tile = i % TILES;
+        const uint64_t adesc = adesc0 + static_cast<uint64_t>(tile * (A_TILE >> 4));
+        const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(tile * (B_TILE >> 4));
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          if (TS) umma_bf16_ts(tm, tm + 256 + 8 * k, bdesc + 2 * k, idesc, 1);
+          if (TS) umma_bf16_ts(tm, tm + 256 + 32 * (tile & 3) + 8 * k, bdesc + 2 * k, idesc, 1);
           else umma_bf16(tm, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
         }
       }
@@ -117,14 +124,116 @@ __global__ void rate_probe(long long* out, int iters, int shift_rows) {
   __syncthreads();
   if (t < 32) tmem_dealloc(tm, 512);
 }
+// Interference probe: SS-form MMAs (N = 64, 4 distinct tiles) with parts of a real mainloop switched on one at a time:
+//  flags & 1 : tcgen05.commit to an mbarrier after every 16 MMAs            flags & 2 : rotate over 4 accumulators
+//  flags & 4 : warps 1-3 keep reading TMEM (tcgen05.ld, what an epilogue does)
+//  flags & 8 : warps 1-3 keep writing shared memory (st.shared.v4 into a scratch ring, what the producers' traffic does)
+//  flags & 16: mbarrier try_wait + tcgen05.fence::after_thread_sync before every 16 MMAs
+//  flags & 32: warps 1-3 keep issuing warp shuffles (epilogue statistics)
+template <int N>
+__global__ void interference_probe(long long* out, int iters, int flags, float* sink) {
+  extern __shared__ __align__(1024) uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  constexpr int TILES = 4, A_TILE = 16384, B_TILE = N * 128;
+  uint8_t* sa = smem;
+  uint8_t* sb = smem + TILES * A_TILE;
+  uint8_t* scratch = sb + TILES * B_TILE;            // 32 KB written by the interfering warps
+  uint64_t* bar = reinterpret_cast<uint64_t*>(scratch + 32768);
+  uint64_t* dummy = bar + 1;
+  uint64_t* ready = bar + 2;
+  volatile int* stop = reinterpret_cast<volatile int*>(bar + 3);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 4);
+  int t = threadIdx.x;
+  for (int i = t; i < (TILES * (A_TILE + B_TILE) + 32768) / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (t == 0) { mbar_init(bar, 1); mbar_init(dummy, 1 << 20); mbar_init(ready, 1); mbar_arrive(ready); *stop = 0; fence_mbar_init(); }
+  if (t < 32) tmem_alloc(slot, 512);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  uint32_t tm = *slot;
+  if (t < 32) {
+    long long t0 = 0, t1 = 0;
+    const uint64_t adesc0 = make_smem_desc_sw128(smem_u32(sa), 16, 1024);
+    const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(sb), 16, 1024);
+    constexpr uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+    t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      if ((flags & 16) && (i & 3) == 0) {
+        mbar_wait(ready, 0);
+        tc_fence_after_sync();
+      }
+      if (elect_one()) {
+        const int tile = i % TILES;
+        const uint64_t adesc = adesc0 + static_cast<uint64_t>(tile * (A_TILE >> 4));
+        const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(tile * (B_TILE >> 4));
+        const uint32_t d = tm + ((flags & 2) ? (i & 3) * N : 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
+        if ((flags & 1) && (i & 3) == 3) umma_commit(dummy);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(bar);
+    __syncwarp();
+    mbar_wait(bar, 0);
+    t1 = clock64();
+    *stop = 1;
+    if (t == 0) out[blockIdx.x] = t1 - t0;
+  } else {
+    float acc = 0.f;
+    const int w = t >> 5;
+    uint32_t it = 0;
+    while (!*stop) {
+      if (flags & 4) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tm + (static_cast<uint32_t>(w * 32) << 16) + 256 + (it & 3) * 32, v);
+        tmem_ld_wait();
+        acc += __uint_as_float(v[it & 31]);
+      }
+      if (flags & 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(scratch + ((it * 8 + j) & 63) * 512 + (t & 31) * 16) = make_uint4(it, j, t, 0);
+      }
+      if (flags & 32) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc += __shfl_xor_sync(0xffffffffu, acc + j, 1 + (j & 15));
+      }
+      ++it;
+    }
+    if (acc == 123.456f) sink[t] = acc;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (t < 32) tmem_dealloc(tm, 512);
+}
+
+template <int N>
+void run_interference(long long* d, float* sink, int flags, const char* what) {
+  const int iters = 512, grid = 148;
+  const int smem = 4 * (16384 + N * 128) + 32768 + 1024 + 128;
+  cudaFuncSetAttribute(interference_probe<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  interference_probe<N><<<grid, 128, smem>>>(d, iters, flags, sink);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("interference flags %d: CUDA error %s\n", flags, cudaGetErrorString(e)); exit(1); }
+  std::vector<long long> h(grid);
+  cudaMemcpy(h.data(), d, grid * 8, cudaMemcpyDeviceToHost);
+  long long mx = 0;
+  for (auto v : h) mx = v > mx ? v : mx;
+  printf("SS N=%3d + %-58s: %.1f clk per MMA\n", N, what, double(mx) / (iters * 4));
+}
+
 namespace rsp { void set_error(const char*, ...) {} int check_launch(const char*) { return 0; }
 int make_tmap_bf16(CUtensorMap*, const void*, int, const unsigned long long*, const unsigned long long*, const unsigned*) { return 0; } }
 
-template <int N, int TS>
+template <int N, int TS, int TILES>
 void run_rate(long long* d, int grid, int shift_rows = 0) {
   const int iters = 512;
-  cudaFuncSetAttribute(rate_probe<N, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  rate_probe<N, TS><<<grid, 128, 56 * 1024>>>(d, iters, shift_rows);
+  const int smem = TILES * (16384 + N * 128) + 2048 + 1024 + 64;
+  cudaFuncSetAttribute(rate_probe<N, TS, TILES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  rate_probe<N, TS, TILES><<<grid, 128, smem>>>(d, iters, shift_rows);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("rate N=%d TS=%d: CUDA error %s\n", N, TS, cudaGetErrorString(e)); exit(1); }
   std::vector<long long> h(grid);
@@ -132,8 +241,8 @@ void run_rate(long long* d, int grid, int shift_rows = 0) {
   long long mx = 0;
   for (auto v : h) mx = v > mx ? v : mx;
   double per = double(mx) / (iters * 4);
-  printf("%s  M=128 N=%3d K=16 grid %3d A start row %d: %.1f clk per MMA (floor %d) -> %.0f%% of the tensor pipe\n",
-         TS ? "TS (A in TMEM)" : "SS (A in smem)", N, grid, shift_rows, per, N / 2, 100.0 * (N / 2) / per);
+  printf("%s  M=128 N=%3d K=16 grid %3d, %d distinct operand tiles, A start row %d: %.1f clk per MMA (floor %d) -> %.0f%% of the tensor pipe\n",
+         TS ? "TS (A in TMEM)" : "SS (A in smem)", N, grid, TILES, shift_rows, per, N / 2, 100.0 * (N / 2) / per);
 }
 
 int main() {
@@ -154,14 +263,29 @@ int main() {
   printf("TS layout (lane = row, column j = elements 2j, 2j+1): %s (%d mismatches)\n", bad ? "WRONG" : "ok", bad);
   if (bad) for (int n = 0; n < 16; ++n) printf("  D[1][%d] = %g, A[1][%d] = %g\n", n, hD[64 + n], n, __bfloat162float(hA[16 + n]));
   for (int grid : {1, 148}) {
-    run_rate<64, 0>(dT, grid); run_rate<64, 1>(dT, grid);
-    run_rate<128, 0>(dT, grid); run_rate<128, 1>(dT, grid);
-    run_rate<256, 0>(dT, grid); run_rate<256, 1>(dT, grid);
+    run_rate<64, 0, 1>(dT, grid); run_rate<64, 1, 1>(dT, grid);
+    run_rate<128, 0, 1>(dT, grid); run_rate<128, 1, 1>(dT, grid);
+    run_rate<256, 0, 1>(dT, grid); run_rate<256, 1, 1>(dT, grid);
   }
+  run_rate<64, 0, 4>(dT, 148); run_rate<64, 1, 4>(dT, 148);
+  run_rate<128, 0, 4>(dT, 148); run_rate<128, 1, 4>(dT, 148);
+  run_rate<256, 0, 4>(dT, 148); run_rate<256, 1, 4>(dT, 148);
   // does an A tile that starts in the middle of a 1024-byte swizzle atom (direct conv: arbitrary pixel-row offsets) cost more?
-  for (int shift : {1, 3, 4, 8, 9}) {
-    run_rate<64, 0>(dT, 148, shift);
-    run_rate<128, 0>(dT, 148, shift);
+  for (int shift : {1, 9}) {
+    run_rate<64, 0, 4>(dT, 148, shift);
+    run_rate<128, 0, 4>(dT, 148, shift);
   }
+  float* sink; cudaMalloc(&sink, 4096);
+  run_interference<64>(dT, sink, 0, "nothing");
+  run_interference<64>(dT, sink, 1, "commit every 16 MMAs");
+  run_interference<64>(dT, sink, 2, "4 accumulators in rotation");
+  run_interference<64>(dT, sink, 4, "3 warps reading TMEM");
+  run_interference<64>(dT, sink, 8, "3 warps writing shared memory");
+  run_interference<64>(dT, sink, 16, "mbarrier wait + tcgen05.fence every 16 MMAs");
+  run_interference<64>(dT, sink, 32, "3 warps shuffling");
+  run_interference<64>(dT, sink, 1 | 2 | 4 | 16, "commit + accumulators + TMEM reads + waits");
+  run_interference<128>(dT, sink, 0, "nothing");
+  run_interference<128>(dT, sink, 8, "3 warps writing shared memory");
+  run_interference<128>(dT, sink, 1 | 2 | 4 | 16, "commit + accumulators + TMEM reads + waits");
   return 0;
 }
