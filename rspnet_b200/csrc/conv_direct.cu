@@ -46,6 +46,11 @@ struct DirectParams {
   int shWp;
 };
 
+// Diagnostic switches for timing experiments (tools/direct_probe.py); 0 in production.
+//   1: the MMA lane does not wait for operands   2: the epilogue does not store   4: the producer loads nothing after
+//   the first two planes / filter ring fill (barriers are still signalled)
+__device__ int g_direct_debug = 0;
+
 constexpr int kDirThreads = 192;
 constexpr int kDirMaxWStages = 6;
 
@@ -74,6 +79,7 @@ __global__ void __launch_bounds__(kDirThreads, 1) conv_direct_kernel(const __gri
   const int warp = t >> 5;
   const int cch = p.Cs >> 6;
   const int accCols = p.G * NT;            // columns of one accumulator set
+  const int dbg = g_direct_debug;
 
   if (t == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -125,8 +131,12 @@ __global__ void __launch_bounds__(kDirThreads, 1) conv_direct_kernel(const __gri
         for (int cc = 0; cc < cch; ++cc, ++pctr) {
           const int ps = pctr & 1;
           mbar_wait(&plane_empty[ps], ((pctr >> 1) & 1) ^ 1);
-          mbar_arrive_expect_tx(&plane_full[ps], planeTx);
-          tma_load_5d(smem_u32(smem + ps * planeBytes), &p.tmapX, &plane_full[ps], cc * 64, -p.pw, row0 - p.ph, ts, n);
+          if ((dbg & 4) && pctr >= 2) {
+            mbar_arrive(&plane_full[ps]);
+          } else {
+            mbar_arrive_expect_tx(&plane_full[ps], planeTx);
+            tma_load_5d(smem_u32(smem + ps * planeBytes), &p.tmapX, &plane_full[ps], cc * 64, -p.pw, row0 - p.ph, ts, n);
+          }
           // the kh*kw filter tiles of this (frame tap, channel chunk)
           for (int b = 0; b < p.kh; ++b) {
             for (int c = 0; c < p.kw; ++c, ++wctr) {
@@ -134,8 +144,12 @@ __global__ void __launch_bounds__(kDirThreads, 1) conv_direct_kernel(const __gri
               mbar_wait(&w_empty[ws_], ((wctr / wStages) & 1) ^ 1);
               const int ta = p.flip ? p.kt - 1 - a : a, tb = p.flip ? p.kh - 1 - b : b, tc = p.flip ? p.kw - 1 - c : c;
               const int koff = ((ta * p.kh + tb) * p.kw + tc) * p.Cs + cc * 64;
-              mbar_arrive_expect_tx(&w_full[ws_], W_BYTES);
-              tma_load_2d(smem_u32(wring + ws_ * W_BYTES), &p.tmapW, &w_full[ws_], koff, nt * NT);
+              if ((dbg & 4) && wctr >= static_cast<uint32_t>(wStages)) {
+                mbar_arrive(&w_full[ws_]);
+              } else {
+                mbar_arrive_expect_tx(&w_full[ws_], W_BYTES);
+                tma_load_2d(smem_u32(wring + ws_ * W_BYTES), &p.tmapW, &w_full[ws_], koff, nt * NT);
+              }
             }
           }
         }
@@ -170,7 +184,7 @@ __global__ void __launch_bounds__(kDirThreads, 1) conv_direct_kernel(const __gri
       const int q0 = grp * p.G * 128;
       int chunks = (p.P - q0 + 127) / 128;
       if (chunks > p.G) chunks = p.G;
-      mbar_wait(&acc_full[buf], (ictr >> 1) & 1);
+      mbar_wait_warp(&acc_full[buf], (ictr >> 1) & 1);
       tc_fence_after_sync();
       for (int m = 0; m < chunks; ++m) {
         const uint32_t q = static_cast<uint32_t>(q0 + m * 128 + ew * 32 + lane);
@@ -198,7 +212,7 @@ __global__ void __launch_bounds__(kDirThreads, 1) conv_direct_kernel(const __gri
             o.y = pack_bf16x2(f[2], f[3]);
             o.z = pack_bf16x2(f[4], f[5]);
             o.w = pack_bf16x2(f[6], f[7]);
-            if (ok) *reinterpret_cast<uint4*>(orow + c0 + jx) = o;
+            if (ok && !(dbg & 2)) *reinterpret_cast<uint4*>(orow + c0 + jx) = o;
             if (p.stats) {
               const uint32_t w[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
@@ -253,13 +267,13 @@ __global__ void __launch_bounds__(kDirThreads, 1) conv_direct_kernel(const __gri
         if (ts < 0 || ts >= p.Ti) continue;
         for (int cc = 0; cc < cch; ++cc, ++pctr) {
           const int ps = pctr & 1;
-          mbar_wait(&plane_full[ps], (pctr >> 1) & 1);
+          if (!(dbg & 1)) mbar_wait(&plane_full[ps], (pctr >> 1) & 1);
           tc_fence_after_sync();
           const uint32_t abase = smem_u32(smem + ps * planeBytes) + shift * 128;
           for (int b = 0; b < p.kh; ++b) {
             for (int c = 0; c < p.kw; ++c, ++wctr) {
               const int ws_ = wctr % wStages;
-              mbar_wait(&w_full[ws_], (wctr / wStages) & 1);
+              if (!(dbg & 1)) mbar_wait(&w_full[ws_], (wctr / wStages) & 1);
               tc_fence_after_sync();
               const uint64_t bdesc = make_smem_desc_sw128(smem_u32(wring + ws_ * W_BYTES), 16, 1024);
               const uint64_t adesc0 = make_smem_desc_sw128(abase + (b * p.Wp + c) * 128, 16, 1024);
@@ -340,6 +354,14 @@ static bool direct_geometry(const rsp_conv3d_desc* d, int transposed, DirectPara
   p.mulWp = ((1ull << p.shWp) + p.Wp - 1) / p.Wp;
   return true;
 }
+
+}  // namespace rsp
+
+extern "C" int rsp_debug_direct(int flags) {   // timing experiments only (not part of the public header)
+  return cudaMemcpyToSymbol(rsp::g_direct_debug, &flags, sizeof(int)) == cudaSuccess ? 0 : -2;
+}
+
+namespace rsp {
 
 bool direct_supported(const rsp_conv3d_desc* d, int transposed) {
   DirectParams p{};

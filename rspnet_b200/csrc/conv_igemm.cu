@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
         const uint32_t ph = (kb / STAGES) & 1;
         const int koff = ((a * g.Hs + b) * g.Ws + c) * dirCs + cc * 64;
         const int sb = 8 + b, sc = 16 + c;
-        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_wait_warp(&empty_bar[s], ph ^ 1);
         const uint32_t a_panel = smem_u32(smem + s * STAGE_BYTES) + dst0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
       for (int kb = 0; kb < numKb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_wait_warp(&empty_bar[s], ph ^ 1);
         const uint32_t a_panel = smem_u32(smem + s * STAGE_BYTES);
         const uint32_t b_panel = a_panel + A_BYTES;
         gather_panel<MODE, 128>(g, a_panel, kbBegin + kb, t, rows);
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
       }
     }
     // ---------------- epilogue ----------------
-    mbar_wait(accum_bar, 0);
+    mbar_wait_warp(accum_bar, 0);
     tc_fence_after_sync();
     const long long row = m0 + warp * 32 + (t & 31);
     const bool row_ok = row < g.M;
@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const WgradParams 
             w0[i] = wd * g.sw - g.pw;
             base[i] = (((n * g.Ts + t0[i]) * g.Hs + h0[i]) * g.Ws + w0[i]) * g.Cs + chunk * 8;
           }
-          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_wait_warp(&empty_bar[s], ph ^ 1);
           const uint32_t stage = smem_u32(smem + s * STAGE_BYTES) + dst0;
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const WgradParams 
           int row = (MODE == MODE_GENERIC) ? (t >> 3) + 16 * i : (t >> 4) + 8 * i;
           rows[i] = decode_row(g, prow0 + row);
         }
-        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_wait_warp(&empty_bar[s], ph ^ 1);
         const uint32_t stage = smem_u32(smem + s * STAGE_BYTES);
         gather_panel<MODE, 64>(g, stage, kb0, t, rows);
         gather_panel<MODE, 64>(g, stage + PANEL, kb0 + 1, t, rows);
@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const WgradParams 
         mbar_arrive(&full_bar[s]);
       }
       // epilogue: D row = K index inside the pair of K blocks, columns = cout
-      mbar_wait(accum_bar, 0);
+      mbar_wait_warp(accum_bar, 0);
       tc_fence_after_sync();
       const int krow = kb0 * 64 + warp * 32 + (t & 31);
       const bool row_ok = krow < g.numKb * 64;
