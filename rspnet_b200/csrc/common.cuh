@@ -95,32 +95,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-// Whole-warp wait that does not hammer the barrier: ONE lane polls, with a hardware suspend hint, and the warp
-// re-converges.  A warp that spins on try_wait with all 32 lanes keeps the SM's MIO / shared-memory pipe busy, which is
-// the same pipe the tensor core fetches its operands through: tools/umma_ts_probe measures 74 instead of 48 clocks per
-// N=64 MMA when three idle warps poll shared memory next to the issuing warp.
-__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
-  if ((threadIdx.x & 31) == 0) {
-    uint32_t spins = 0;
-    uint32_t ok = 0;
-    while (!ok) {
-      asm volatile(
-          "{\n\t.reg .pred P;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
-          "selp.u32 %0, 1, 0, P;\n\t}"
-          : "=r"(ok)
-          : "r"(smem_u32(bar)), "r"(parity), "r"(2000u)
-          : "memory");
-      if (!ok && ++spins > (1u << 22)) {
-        printf("rspnet_b200: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
-               threadIdx.x);
-        __trap();
-      }
-    }
-  }
-  __syncwarp();
-}
-
 // ---------------------------------------------------------------------------
 // cp.async (LDGSTS) with zero-fill, completion tracked on an mbarrier
 // ---------------------------------------------------------------------------

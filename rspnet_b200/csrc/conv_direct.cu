@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(kDirThreads, 1) conv_direct_kernel(const __gri
     // ============================================================ TMA producer
     // one elected lane runs the whole loop: a single instruction stream without per-step warp re-convergence
     uint32_t pctr = 0, wctr = 0;
+    uint32_t ws_ = 0, wph = 1;   // filter ring slot and the parity its "empty" barrier must have passed
     const uint32_t planeTx = static_cast<uint32_t>(p.rowsBuf) * p.Wp * 128u;
     const bool leader = elect_one();
     if (leader) {
@@ -140,8 +141,7 @@ __global__ void __launch_bounds__(kDirThreads, 1) conv_direct_kernel(const __gri
           // the kh*kw filter tiles of this (frame tap, channel chunk)
           for (int b = 0; b < p.kh; ++b) {
             for (int c = 0; c < p.kw; ++c, ++wctr) {
-              const int ws_ = wctr % wStages;
-              mbar_wait(&w_empty[ws_], ((wctr / wStages) & 1) ^ 1);
+              mbar_wait(&w_empty[ws_], wph);
               const int ta = p.flip ? p.kt - 1 - a : a, tb = p.flip ? p.kh - 1 - b : b, tc = p.flip ? p.kw - 1 - c : c;
               const int koff = ((ta * p.kh + tb) * p.kw + tc) * p.Cs + cc * 64;
               if ((dbg & 4) && wctr >= static_cast<uint32_t>(wStages)) {
@@ -149,6 +149,10 @@ __global__ void __launch_bounds__(kDirThreads, 1) conv_direct_kernel(const __gri
               } else {
                 mbar_arrive_expect_tx(&w_full[ws_], W_BYTES);
                 tma_load_2d(smem_u32(wring + ws_ * W_BYTES), &p.tmapW, &w_full[ws_], koff, nt * NT);
+              }
+              if (++ws_ == static_cast<uint32_t>(wStages)) {
+                ws_ = 0;
+                wph ^= 1;
               }
             }
           }
@@ -184,7 +188,7 @@ __global__ void __launch_bounds__(kDirThreads, 1) conv_direct_kernel(const __gri
       const int q0 = grp * p.G * 128;
       int chunks = (p.P - q0 + 127) / 128;
       if (chunks > p.G) chunks = p.G;
-      mbar_wait_warp(&acc_full[buf], (ictr >> 1) & 1);
+      mbar_wait(&acc_full[buf], (ictr >> 1) & 1);
       tc_fence_after_sync();
       for (int m = 0; m < chunks; ++m) {
         const uint32_t q = static_cast<uint32_t>(q0 + m * 128 + ew * 32 + lane);
@@ -247,46 +251,66 @@ __global__ void __launch_bounds__(kDirThreads, 1) conv_direct_kernel(const __gri
     // ============================================================ MMA issuer
     // one elected lane waits, issues and commits: the issue stream is ~2 instructions per MMA with no warp-level
     // re-convergence in between (measured with tools/umma_ts_probe: an elect/syncwarp per 4 MMAs costs ~25 clk per MMA)
+    // The issue stream is kept to a few instructions per MMA: ring slots, parities and descriptors advance incrementally
+    // (a single lane retires roughly one dependent instruction per 5-8 clocks, and an N=64 MMA lasts 48).
     constexpr uint32_t idesc = make_idesc_bf16(128, NT, 0, 0);
-    uint32_t pctr = 0, wctr = 0, ictr = 0;
+    constexpr int G = NT == 64 ? 4 : 2;                     // == p.G
+    constexpr uint64_t kWStep = W_BYTES >> 4;
+    uint32_t pctr = 0, ictr = 0;
+    uint32_t ws_ = 0, wph = 0;
+    const uint64_t bdesc_base = make_smem_desc_sw128(smem_u32(wring), 16, 1024);
+    uint64_t bdesc = bdesc_base;
+    const uint64_t rowStep = static_cast<uint64_t>((p.Wp - p.kw) * 8);   // descriptor units (16 B) from tap (b, kw) to (b+1, 0)
     const bool leader = elect_one();
     for (int it = blockIdx.x; leader && it < p.numItems; it += gridDim.x, ++ictr) {
       int nt, n, to, grp;
       decode_item(it, nt, n, to, grp);
       const int buf = ictr & 1;
-      const int q0 = grp * p.G * 128;
+      const int q0 = grp * G * 128;
       const int row0 = static_cast<int>(fdiv64(static_cast<uint32_t>(q0), p.mulWp, p.shWp));
       const int shift = q0 - row0 * p.Wp;   // the work item's first position inside the plane buffer
       int chunks = (p.P - q0 + 127) / 128;
-      if (chunks > p.G) chunks = p.G;
+      if (chunks > G) chunks = G;
+      const uint32_t dacc = tmem_base + buf * accCols;
       mbar_wait(&acc_empty[buf], ((ictr >> 1) & 1) ^ 1);
       tc_fence_after_sync();
-      bool first = true;
+      uint32_t accflag = 0;
       for (int a = 0; a < p.kt; ++a) {
         const int ts = to - p.pt + a;
         if (ts < 0 || ts >= p.Ti) continue;
         for (int cc = 0; cc < cch; ++cc, ++pctr) {
           const int ps = pctr & 1;
           if (!(dbg & 1)) mbar_wait(&plane_full[ps], (pctr >> 1) & 1);
-          tc_fence_after_sync();
-          const uint32_t abase = smem_u32(smem + ps * planeBytes) + shift * 128;
+          uint64_t adesc0 = make_smem_desc_sw128(smem_u32(smem + ps * planeBytes) + shift * 128, 16, 1024);
           for (int b = 0; b < p.kh; ++b) {
-            for (int c = 0; c < p.kw; ++c, ++wctr) {
-              const int ws_ = wctr % wStages;
-              if (!(dbg & 1)) mbar_wait(&w_full[ws_], (wctr / wStages) & 1);
+            for (int c = 0; c < p.kw; ++c) {
+              if (!(dbg & 1)) mbar_wait(&w_full[ws_], wph);
               tc_fence_after_sync();
-              const uint64_t bdesc = make_smem_desc_sw128(smem_u32(wring + ws_ * W_BYTES), 16, 1024);
-              const uint64_t adesc0 = make_smem_desc_sw128(abase + (b * p.Wp + c) * 128, 16, 1024);
-              for (int m = 0; m < chunks; ++m) {
-                const uint64_t adesc = adesc0 + static_cast<uint64_t>(m * 1024);  // 128 rows * 128 B / 16
+              if (chunks == G) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16(tmem_base + buf * accCols + m * NT, adesc + 2 * k, bdesc + 2 * k, idesc,
-                            (first && k == 0) ? 0u : 1u);
+                for (int m = 0; m < G; ++m)
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16(dacc + m * NT, adesc0 + static_cast<uint64_t>(m * 1024 + 2 * k), bdesc + 2 * k, idesc,
+                              k == 0 ? accflag : 1u);
+              } else {
+                for (int m = 0; m < chunks; ++m)
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16(dacc + m * NT, adesc0 + static_cast<uint64_t>(m * 1024 + 2 * k), bdesc + 2 * k, idesc,
+                              k == 0 ? accflag : 1u);
               }
               umma_commit(&w_empty[ws_]);
-              first = false;
+              accflag = 1;
+              adesc0 += 8;                                   // next tap along w: one pixel row = 128 B
+              bdesc += kWStep;
+              if (++ws_ == static_cast<uint32_t>(wStages)) {
+                ws_ = 0;
+                wph ^= 1;
+                bdesc = bdesc_base;
+              }
             }
+            adesc0 += rowStep;
           }
           umma_commit(&plane_empty[ps]);
         }

@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
         const uint32_t ph = (kb / STAGES) & 1;
         const int koff = ((a * g.Hs + b) * g.Ws + c) * dirCs + cc * 64;
         const int sb = 8 + b, sc = 16 + c;
-        mbar_wait_warp(&empty_bar[s], ph ^ 1);
+        mbar_wait(&empty_bar[s], ph ^ 1);
         const uint32_t a_panel = smem_u32(smem + s * STAGE_BYTES) + dst0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
       for (int kb = 0; kb < numKb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait_warp(&empty_bar[s], ph ^ 1);
+        mbar_wait(&empty_bar[s], ph ^ 1);
         const uint32_t a_panel = smem_u32(smem + s * STAGE_BYTES);
         const uint32_t b_panel = a_panel + A_BYTES;
         gather_panel<MODE, 128>(g, a_panel, kbBegin + kb, t, rows);
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
       }
     }
     // ---------------- epilogue ----------------
-    mbar_wait_warp(accum_bar, 0);
+    mbar_wait(accum_bar, 0);
     tc_fence_after_sync();
     const long long row = m0 + warp * 32 + (t & 31);
     const bool row_ok = row < g.M;
@@ -424,20 +424,28 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
     if (elect_one()) {
       const uint64_t adesc0 = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
       const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(smem) + A_BYTES, 16, 1024);
+      int s = 0;
+      uint32_t ph = 0, acc = 0;
+      uint64_t adesc = adesc0, bdesc = bdesc0;
       for (int kb = 0; kb < numKb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         fence_proxy_async_smem();
         tc_fence_after_sync();
-        const uint64_t adesc = adesc0 + static_cast<uint64_t>(s * (STAGE_BYTES >> 4));
-        const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(s * (STAGE_BYTES >> 4));
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           // +32 B per K=16 step inside the 128 B swizzle row (descriptor address is in 16 B units)
-          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, k == 0 ? acc : 1u);
         }
         umma_commit(&empty_bar[s]);
+        acc = 1;
+        adesc += STAGE_BYTES >> 4;
+        bdesc += STAGE_BYTES >> 4;
+        if (++s == STAGES) {
+          s = 0;
+          ph ^= 1;
+          adesc = adesc0;
+          bdesc = bdesc0;
+        }
       }
       umma_commit(accum_bar);
     }
@@ -529,7 +537,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const WgradParams 
             w0[i] = wd * g.sw - g.pw;
             base[i] = (((n * g.Ts + t0[i]) * g.Hs + h0[i]) * g.Ws + w0[i]) * g.Cs + chunk * 8;
           }
-          mbar_wait_warp(&empty_bar[s], ph ^ 1);
+          mbar_wait(&empty_bar[s], ph ^ 1);
           const uint32_t stage = smem_u32(smem + s * STAGE_BYTES) + dst0;
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
@@ -562,7 +570,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const WgradParams 
           int row = (MODE == MODE_GENERIC) ? (t >> 3) + 16 * i : (t >> 4) + 8 * i;
           rows[i] = decode_row(g, prow0 + row);
         }
-        mbar_wait_warp(&empty_bar[s], ph ^ 1);
+        mbar_wait(&empty_bar[s], ph ^ 1);
         const uint32_t stage = smem_u32(smem + s * STAGE_BYTES);
         gather_panel<MODE, 64>(g, stage, kb0, t, rows);
         gather_panel<MODE, 64>(g, stage + PANEL, kb0 + 1, t, rows);
@@ -573,7 +581,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const WgradParams 
         mbar_arrive(&full_bar[s]);
       }
       // epilogue: D row = K index inside the pair of K blocks, columns = cout
-      mbar_wait_warp(accum_bar, 0);
+      mbar_wait(accum_bar, 0);
       tc_fence_after_sync();
       const int krow = kb0 * 64 + warp * 32 + (t & 31);
       const bool row_ok = krow < g.numKb * 64;
@@ -599,20 +607,28 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const WgradParams 
         // MN-major: 64-wide panels PANEL bytes apart (LBO), 8-pixel groups 1024 B apart (SBO)
         const uint64_t adesc0 = make_smem_desc_sw128(smem_u32(smem), PANEL, 1024);
         const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(smem) + 2 * PANEL, PANEL, 1024);
+        int s = 0;
+        uint32_t ph = 0, acc = 0;
+        uint64_t adesc = adesc0, bdesc = bdesc0;
         for (int it = 0; it < iters; ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           fence_proxy_async_smem();
           tc_fence_after_sync();
-          const uint64_t adesc = adesc0 + static_cast<uint64_t>(s * (STAGE_BYTES >> 4));
-          const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(s * (STAGE_BYTES >> 4));
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             // K=16 pixels = two 8-pixel groups = 2048 B
-            umma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, idesc, (it | k) != 0);
+            umma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, idesc, k == 0 ? acc : 1u);
           }
           umma_commit(&empty_bar[s]);
+          acc = 1;
+          adesc += STAGE_BYTES >> 4;
+          bdesc += STAGE_BYTES >> 4;
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+            adesc = adesc0;
+            bdesc = bdesc0;
+          }
         }
         umma_commit(accum_bar);
       }

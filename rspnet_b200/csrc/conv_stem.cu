@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
       for (int a = 0; a < p.kt; ++a, ++stage_ctr) {
         const int s = stage_ctr % kStemStages;
         const uint32_t ph = (stage_ctr / kStemStages) & 1;
-        mbar_wait_warp(&empty_bar[s], ph ^ 1);
+        mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* aslab = smem + s * kStemStageBytes;
         const int ti = to * p.st - p.pt + a;
         const bool tok = ti >= 0 && ti < p.Ti;
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
       const int hq = it % p.hq;
       const int q = it / p.hq;
       const int to = q % p.To, n = q / p.To;
-      mbar_wait_warp(&acc_full[buf], ph);
+      mbar_wait(&acc_full[buf], ph);
       tc_fence_after_sync();
 #pragma unroll 1
       for (int m = 0; m < 2; ++m) {
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(192, 1) conv_stem_wgrad_kernel(const __grid_co
         const int ho = r % p.Ho;
         const int q = r / p.Ho;
         const int to = q % p.To, n = q / p.To;
-        mbar_wait_warp(&empty_bar[s], ph ^ 1);
+        mbar_wait(&empty_bar[s], ph ^ 1);
         const uint32_t stage = smem_u32(smem + s * kSWStageBytes);
         const int ti = to * p.st - p.pt + a0 + al;
         const int hi = ho * p.sh - p.ph + b;
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(192, 1) conv_stem_wgrad_kernel(const __grid_co
       }
     } else if (warp < 4) {
       // ---------------- epilogue: TMEM lanes of an M=64 accumulator: co = 16*warp + lane, lanes 16..31 unused
-      mbar_wait_warp(accum_bar, 0);
+      mbar_wait(accum_bar, 0);
       tc_fence_after_sync();
       const int lane = t & 31;
       const int co = warp * 16 + lane;
