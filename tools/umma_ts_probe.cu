@@ -225,6 +225,64 @@ void run_interference(long long* d, float* sink, int flags, const char* what) {
   printf("SS N=%3d + %-58s: %.1f clk per MMA\n", N, what, double(mx) / (iters * 4));
 }
 
+// The RGB-stem operand layout: A = raw input rows, K-major WITHOUT swizzle, rows 16 B apart (LBO 16, SBO 128: overlapping
+// windows); B = filter slab, K-major without swizzle (LBO 1024, SBO 128).  Same MMA shape (128 x 64 x 16).
+__global__ void stem_layout_rate_probe(long long* out, int iters, int swizzled_b) {
+  extern __shared__ __align__(1024) uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sa = smem;               // 14 rows * 1024 B
+  uint8_t* sb = smem + 14336;       // 7 * 4096 B
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 14336 + 28672);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  int t = threadIdx.x;
+  for (int i = t; i < (14336 + 28672) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (t == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  if (t < 32) tmem_alloc(slot, 256);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  uint32_t tm = *slot;
+  if (t < 32) {
+    long long t0 = 0, t1 = 0;
+    if (elect_one()) {
+      auto nosw = [](uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+        uint64_t d = 0;
+        d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
+        d |= static_cast<uint64_t>((lbo >> 4) & 0x3FFF) << 16;
+        d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFF) << 32;
+        d |= 1ull << 46;
+        return d;
+      };
+      const uint64_t abase = nosw(smem_u32(sa), 16, 128);
+      const uint64_t bbase = swizzled_b ? make_smem_desc_sw128(smem_u32(sb), 16, 1024) : nosw(smem_u32(sb), 1024, 128);
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+      t0 = clock64();
+      for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int b = 0; b < 7; ++b)
+#pragma unroll
+          for (int m = 0; m < 2; ++m) {
+            const int j = 4 * m + b;
+            const int arow = ((j & 1) * 7 + (j >> 1)) * 1024;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+              umma_bf16(tm + m * 64, abase + static_cast<uint64_t>((arow + ks * 32) >> 4),
+                        bbase + static_cast<uint64_t>(swizzled_b ? (b * 512 + ks * 2) : ((b * 4096 + ks * 2048) >> 4)), idesc, 1);
+          }
+      }
+      umma_commit(bar);
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+    t1 = clock64();
+    if (t == 0) out[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (t < 32) tmem_dealloc(tm, 256);
+}
+
 namespace rsp { void set_error(const char*, ...) {} int check_launch(const char*) { return 0; }
 int make_tmap_bf16(CUtensorMap*, const void*, int, const unsigned long long*, const unsigned long long*, const unsigned*) { return 0; } }
 
@@ -274,6 +332,18 @@ int main() {
   for (int shift : {1, 9}) {
     run_rate<64, 0, 4>(dT, 148, shift);
     run_rate<128, 0, 4>(dT, 148, shift);
+  }
+  for (int sw = 0; sw < 2; ++sw) {
+    cudaFuncSetAttribute(stem_layout_rate_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024);
+    stem_layout_rate_probe<<<148, 128, 45 * 1024>>>(dT, 64, sw);
+    cudaError_t e2 = cudaDeviceSynchronize();
+    if (e2 != cudaSuccess) { printf("stem layout probe: CUDA error %s\n", cudaGetErrorString(e2)); return 1; }
+    std::vector<long long> h(148);
+    cudaMemcpy(h.data(), dT, 148 * 8, cudaMemcpyDeviceToHost);
+    long long mx = 0;
+    for (auto v : h) mx = v > mx ? v : mx;
+    printf("stem operand layout (A: no swizzle, 16-byte row pitch; B: %s): %.1f clk per MMA (M=128 N=64 K=16)\n",
+           sw ? "128B swizzle" : "no swizzle, LBO 1024", double(mx) / (64 * 28));
   }
   float* sink; cudaMalloc(&sink, 4096);
   run_interference<64>(dT, sink, 0, "nothing");
