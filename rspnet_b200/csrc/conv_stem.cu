@@ -12,9 +12,10 @@
 // row is read once per (tile, frame tap) with ONE bulk copy (cp.async.bulk, 8*Wi bytes) issued by a lane of the producer
 // warp, the filter slab of one frame tap (kh*4 KB) with another; rows outside the image are zeroed in place.
 //
-// CTA (persistent, 1/SM): 4 epilogue warps, 1 producer warp, 1 MMA warp.  One iteration = 4 output rows of one
-// (n, to) = two 128x64 accumulators in TMEM, double buffered (256 columns) so the epilogue of iteration i overlaps the
-// MMAs of i+1.  Pipeline stage = one frame tap a: {13 input rows, kh*4 KB filter slab}, 4 stages.
+// CTA (persistent, 1/SM): 4 epilogue warps, 1 producer warp, 1 MMA warp.  One iteration = 8 output rows of one
+// (n, to) = four 128x64 accumulators in TMEM, double buffered (512 columns) so the epilogue of iteration i overlaps the
+// MMAs of i+1.  Pipeline stage = one frame tap a: {21 input rows, kh*4 KB filter slab}, 4 stages.  (All 148 SMs stream
+// the same 196 KB filter from L2 over and over: eight rows per slab fetch instead of four halves that traffic.)
 #include "common.cuh"
 #include "rspnet_b200.h"
 
@@ -28,14 +29,15 @@ struct StemParams {
   float* stats;              // optional [2][64]: += per-channel sum / sum of squares of the stored output
   int N, Ti, Hi, Wi, To, Ho, Wo;
   int kt, kh, st, sh, pt, ph;
-  int hq;        // ceil(Ho / 4)
+  int hq;        // ceil(Ho / kStemOutRows)
   int numIters;  // N * To * hq
 };
 
 constexpr int kStemThreads = 192;
 constexpr int kStemStages = 4;
 constexpr int kStemRowBytes = 1024;   // 128 pixel slots of 8 B; slot s holds input pixel s - 4
-constexpr int kStemMaxRows = 14;      // rows per A slab (two h-phases x 7)
+constexpr int kStemOutRows = 8;       // output rows per iteration: four M=128 tiles (two rows each) share one filter slab
+constexpr int kStemMaxRows = 22;      // rows per A slab (two h-phases x 11)
 constexpr int kStemASlab = kStemMaxRows * kStemRowBytes;
 constexpr int kStemBSlabMax = 7 * 4096;
 constexpr int kStemStageBytes = kStemASlab + kStemBSlabMax;
@@ -66,7 +68,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
 
   const int t = threadIdx.x;
   const int warp = t >> 5;
-  const int rowsA = 3 * p.sh + p.kh;              // input rows feeding 4 output rows
+  const int rowsA = (kStemOutRows - 1) * p.sh + p.kh;   // input rows feeding the output rows of one iteration
   const int perPhase = (rowsA + p.sh - 1) / p.sh; // rows of one h-phase, stored 1024 B apart
   const uint32_t bslab_bytes = static_cast<uint32_t>(p.kh) * 4096u;
 
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
     }
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc(tmem_slot, 256);
+  if (warp == 5) tmem_alloc(tmem_slot, 512);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
       const int hq = it % p.hq;
       const int q = it / p.hq;
       const int to = q % p.To, n = q / p.To;
-      const int hi0 = hq * 4 * p.sh - p.ph;
+      const int hi0 = hq * kStemOutRows * p.sh - p.ph;
       for (int a = 0; a < p.kt; ++a, ++stage_ctr) {
         const int s = stage_ctr % kStemStages;
         const uint32_t ph = (stage_ctr / kStemStages) & 1;
@@ -149,8 +151,8 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
       mbar_wait(&acc_full[buf], ph);
       tc_fence_after_sync();
 #pragma unroll 1
-      for (int m = 0; m < 2; ++m) {
-        const int ho = hq * 4 + 2 * m + (ew >> 1);
+      for (int m = 0; m < kStemOutRows / 2; ++m) {
+        const int ho = hq * kStemOutRows + 2 * m + (ew >> 1);
         const int ow = (ew & 1) * 32 + lane;
         const bool ok = ho < p.Ho && ow < p.Wo;
         __nv_bfloat16* orow =
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
 #pragma unroll 1
         for (int c0 = 0; c0 < 64; c0 += 32) {
           uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * 128 + m * 64 + c0, v);
+          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * 256 + m * 64 + c0, v);
           tmem_ld_wait();
           float r[32];
 #pragma unroll
@@ -227,12 +229,12 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
         const uint32_t aslab = smem_u32(smem + s * kStemStageBytes);
         const uint64_t abase = make_smem_desc_nosw(aslab, 16, 128);
         const uint64_t bbase = make_smem_desc_nosw(aslab + kStemASlab, 1024, 128);
-        const uint32_t dcol = tmem_base + buf * 128;
+        const uint32_t dcol = tmem_base + buf * 256;
 #pragma unroll
         for (int b = 0; b < 7; ++b) {
 #pragma unroll
-          for (int m = 0; m < 2; ++m) {
-            constexpr int kPerPhase = 7;                       // (3*2 + 7 + 1) / 2
+          for (int m = 0; m < kStemOutRows / 2; ++m) {
+            constexpr int kPerPhase = 11;                      // ((kStemOutRows - 1) * 2 + 7 + 1) / 2
             const int j = 4 * m + b;                           // 2*m*sh + b
             const int arow = ((j & 1) * kPerPhase + (j >> 1)) * kStemRowBytes;
 #pragma unroll
@@ -250,7 +252,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, 256);
+  if (warp == 5) tmem_dealloc(tmem_base, 512);
 }
 
 // w fp32 [64][Ci<=4][kt][kh][7] -> wst bf16 [kt][kh][4][8][8][8]; K slot q = kchunk*8 + e: pixel slot q/4 (kw = slot-1), ch q%4
@@ -274,7 +276,7 @@ __global__ void pack_weight_stem_kernel(const float* __restrict__ w, __nv_bfloat
 
 bool stem_supported(const rsp_conv3d_desc* d) {
   const int Wo = (d->Wi + 2 * d->pw - d->kw) / d->sw + 1;
-  return d->Ci == 4 && d->Co == 64 && d->kw == 7 && d->sw == 2 && d->pw == 3 && d->kh == 7 && d->sh == 2 && (d->Wi % 2) == 0 && d->Wi + 4 <= 124 && Wo <= 64 && (3 * d->sh + d->kh) <= kStemMaxRows;
+  return d->Ci == 4 && d->Co == 64 && d->kw == 7 && d->sw == 2 && d->pw == 3 && d->kh == 7 && d->sh == 2 && (d->Wi % 2) == 0 && d->Wi + 4 <= 124 && Wo <= 64 && ((kStemOutRows - 1) * d->sh + d->kh) <= kStemMaxRows;
 }
 
 int launch_stem(const rsp_conv3d_desc* d, const void* x, const void* wst, const float* bias, void* y, float* stats,
@@ -290,7 +292,7 @@ int launch_stem(const rsp_conv3d_desc* d, const void* x, const void* wst, const 
   p.Ho = (d->Hi + 2 * d->ph - d->kh) / d->sh + 1;
   p.Wo = (d->Wi + 2 * d->pw - d->kw) / d->sw + 1;
   p.kt = d->kt; p.kh = d->kh; p.st = d->st; p.sh = d->sh; p.pt = d->pt; p.ph = d->ph;
-  p.hq = (p.Ho + 3) / 4;
+  p.hq = (p.Ho + kStemOutRows - 1) / kStemOutRows;
   p.numIters = p.N * p.To * p.hq;
   constexpr int smem = kStemStages * kStemStageBytes + 1024 + 256;
   cudaError_t e = cudaFuncSetAttribute(conv_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
