@@ -30,8 +30,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const unsigned long long* dims,
-                   const unsigned long long* strides_bytes, const unsigned* box) {
+static EncodeTiledFn tmap_encoder() {
   static EncodeTiledFn encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -39,10 +38,17 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const unsigned 
     cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
     if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
       set_error("cuTensorMapEncodeTiled is not available from this driver (%s)", cudaGetErrorString(e));
-      return RSP_ERR_CUDA;
+      return nullptr;
     }
     encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
+  return encode;
+}
+
+static int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, CUtensorMapSwizzle swz, const void* base, int rank,
+                       const unsigned long long* dims, const unsigned long long* strides_bytes, const unsigned* box) {
+  EncodeTiledFn encode = tmap_encoder();
+  if (!encode) return RSP_ERR_CUDA;
   RSP_REQUIRE(rank >= 1 && rank <= 5, "tensor map: rank %d", rank);
   cuuint64_t gdim[5], gstr[4];
   cuuint32_t bdim[5], estr[5];
@@ -57,15 +63,26 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const unsigned 
     }
   }
   RSP_REQUIRE(reinterpret_cast<uintptr_t>(base) % 16 == 0, "tensor map: base address not 16-byte aligned");
-  RSP_REQUIRE(box[0] * 2 <= 128, "tensor map: inner box exceeds the 128-byte swizzle span");
-  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
-                      gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = encode(out, dtype, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstr, bdim, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
     return RSP_ERR_CUDA;
   }
   return RSP_OK;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const unsigned long long* dims,
+                   const unsigned long long* strides_bytes, const unsigned* box) {
+  RSP_REQUIRE(box[0] * 2 <= 128, "tensor map: inner box exceeds the 128-byte swizzle span");
+  return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_128B, base, rank, dims, strides_bytes, box);
+}
+
+// 8-byte elements (one RGBx pixel of four bf16), no swizzle: box rows land back to back, out-of-range elements are zero.
+int make_tmap_u64_rows(CUtensorMap* out, const void* base, int rank, const unsigned long long* dims,
+                       const unsigned long long* strides_bytes, const unsigned* box) {
+  return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_UINT64, CU_TENSOR_MAP_SWIZZLE_NONE, base, rank, dims, strides_bytes, box);
 }
 
 int device_sm_count() {

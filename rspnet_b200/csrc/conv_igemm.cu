@@ -932,6 +932,10 @@ int pack_stem(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const fl
               cudaStream_t stream);
 int launch_stem_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const void* x, const void* dy,
                       float* dw, int accumulate, int sm_count, cudaStream_t stream);
+bool stem3_supported(const rsp_conv3d_desc* d);
+int pack_stem3(int Ci_logical, int Co_logical, const float* w, void* wst, cudaStream_t stream);
+int launch_stem3(const rsp_conv3d_desc* d, const void* x, const void* wst, const float* bias, void* y, float* stats,
+                 int sm_count, cudaStream_t stream);
 bool direct_supported(const rsp_conv3d_desc* d, int transposed);
 int launch_direct(const rsp_conv3d_desc* d, int transposed, const void* x, const void* wgt, const float* bias, void* y,
                   float* stats, cudaStream_t stream);
@@ -958,6 +962,7 @@ int64_t rsp_conv3d_packed_elems(const rsp_conv3d_desc* d, int which) {
   if (which == 1) return static_cast<int64_t>(d->Ci) * kpad;
   int64_t n = static_cast<int64_t>(d->Co) * kpad;
   if (stem_supported(d)) n += static_cast<int64_t>(d->kt) * d->kh * 2048;  // direct-conv filter slabs appended
+  if (stem3_supported(d)) n += 9 * 1024;
   return n;
 }
 
@@ -984,6 +989,7 @@ int rsp_conv3d_pack_weight(const rsp_conv3d_desc* d, int Ci_logical, int Co_logi
     if (rc != RSP_OK) return rc;
     if (stem_supported(d))
       return pack_stem(d, Ci_logical, Co_logical, w, static_cast<__nv_bfloat16*>(wp) + total, stream);
+    if (stem3_supported(d)) return pack_stem3(Ci_logical, Co_logical, w, static_cast<__nv_bfloat16*>(wp) + total, stream);
     return RSP_OK;
   }
   RSP_REQUIRE(mode == MODE_GENERIC, "pack_weight(dgrad): small-channel convs have no dgrad");
@@ -1040,6 +1046,10 @@ int rsp_conv3d_pack_weights(int32_t n, const rsp_conv3d_desc* descs, const int32
         rc = pack_stem(d, b.j[i].Ci, b.j[i].Co, b.j[i].w, b.j[i].wp + static_cast<size_t>(d->Co) * b.j[i].Kpad, stream);
         if (rc != RSP_OK) return rc;
       }
+      if (stem3_supported(d)) {
+        rc = pack_stem3(b.j[i].Ci, b.j[i].Co, b.j[i].w, b.j[i].wp + static_cast<size_t>(d->Co) * b.j[i].Kpad, stream);
+        if (rc != RSP_OK) return rc;
+      }
     }
   }
   return RSP_OK;
@@ -1072,6 +1082,10 @@ int rsp_conv3d_fprop(const rsp_conv3d_desc* d, const void* x, const void* wp, co
   if (stem_supported(d)) {
     const __nv_bfloat16* wst = static_cast<const __nv_bfloat16*>(wp) + static_cast<size_t>(d->Co) * p.g.numKb * 64;
     return launch_stem(d, x, wst, bias, y, stats, device_sm_count(), stream);
+  }
+  if (stem3_supported(d)) {
+    const __nv_bfloat16* wst = static_cast<const __nv_bfloat16*>(wp) + static_cast<size_t>(d->Co) * p.g.numKb * 64;
+    return launch_stem3(d, x, wst, bias, y, stats, device_sm_count(), stream);
   }
   if (mode == MODE_GENERIC && direct_supported(d, 0)) return launch_direct(d, 0, x, wp, bias, y, stats, stream);
   p.g.src = static_cast<const __nv_bfloat16*>(x);

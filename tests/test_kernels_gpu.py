@@ -312,6 +312,9 @@ CONV_CASES = [
     (1, 3, 64, (6, 20, 20), (7, 7, 7), (1, 2, 2), (3, 3, 3)),
     (2, 3, 64, (4, 12, 12), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
     (3, 256, 512, (2, 7, 7), (3, 3, 3), (2, 2, 2), (1, 1, 1)),
+    # 3x3x3 unit-stride RGB stem (C3D conv1): the even/odd raw-row kernel, ragged H and odd T
+    (1, 3, 64, (3, 10, 14), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (2, 3, 64, (5, 33, 112), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
     # shapes that take the direct (im2col-free) kernel: unit stride, >= 512 (Co=64) / 256 (Co%128==0) padded positions
     (2, 64, 64, (3, 28, 28), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
     (1, 128, 128, (3, 20, 22), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
