@@ -962,7 +962,7 @@ int64_t rsp_conv3d_packed_elems(const rsp_conv3d_desc* d, int which) {
   if (which == 1) return static_cast<int64_t>(d->Ci) * kpad;
   int64_t n = static_cast<int64_t>(d->Co) * kpad;
   if (stem_supported(d)) n += static_cast<int64_t>(d->kt) * d->kh * 2048;  // direct-conv filter slabs appended
-  if (stem3_supported(d)) n += 9 * 1024;
+  if (stem3_supported(d)) n += 2 * 9 * 1024 + 512;   // two filter sets + a zero row
   return n;
 }
 

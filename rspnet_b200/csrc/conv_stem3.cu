@@ -3,18 +3,17 @@
 //
 // The layer is HBM-bound (2 x 64 bytes written per 8 bytes read); the generic gather kernel spends ~40 instructions per
 // 8-byte pixel and runs 10x slower than the output write.  Here the raw-row trick of conv_stem.cu is applied to a
-// w-stride of 1: in the K-major no-swizzle UMMA layout consecutive A rows are 16 bytes = TWO pixels apart, so one raw input
-// row in shared memory is the A operand of every second output pixel.  Each input row is therefore staged twice:
-//   copy E (pixel x at byte 8 + 8x, i.e. the row starts at pixel -1): A row j = pixels 2j-1 .. 2j+2 -> output pixel 2j
-//   copy O (pixel x at byte 8x):                                      A row j = pixels 2j .. 2j+3   -> output pixel 2j+1
-// Both copies come from the same 4-D tensor map over {W, H, T, N} with 8-byte elements (one pixel = one element): the box
-// starts at x = -1 or x = 0, is 128 pixels wide (the 1 KB smem row pitch) and R+2 rows high; everything outside the image
-// (left/right halo, rows above/below, frames before/after the clip) is zero-filled by the TMA unit.
-//   K = 16 = 4 pixel slots x 4 channels: slots 0..2 are the kw taps, slot 3 multiplies a zero filter entry.
-//   M = 128 = 64 pixel pairs of output row h and 64 of row h+1 (input rows are 1 KB apart, SBO 128 B, 56 of 64 used).
-// The whole filter (27 taps x 64 x 4, packed 18 KB) stays resident in shared memory.
+// w-stride of 1: in the K-major no-swizzle UMMA layout consecutive A rows are 16 bytes = TWO pixels apart, so A row j of
+// a raw input row in shared memory is the 4-pixel window (2j .. 2j+3), K = 16 = 4 pixel slots x 4 channels.  That window
+// serves TWO output pixels with two differently packed copies of the filter:
+//   odd  pixel 2j+1: taps (w-1, w, w+1) = window slots 0, 1, 2   (filter set O, slot 3 zero)
+//   even pixel 2j  : row j-1, i.e. the window (2j-2 .. 2j+1): slots 1, 2, 3 (filter set E, slot 0 zero)
+// Rows sit 1 KB apart with the pixels at byte 16 (the 16 bytes in front and everything behind the row stay zero: the
+// left / right padding), so M = 128 = 64 windows of output row h and 64 of row h+1 (56 of 64 used).  Each input row is one
+// bulk copy (cp.async.bulk); rows outside the clip are copied from a zero row stored behind the packed filter.
+// Both filter sets (2 x 9 x 2 KB) stay resident in shared memory.
 //
-// CTA (persistent, 1/SM): warps 0-3 epilogue, warp 4 producer lane, warp 5 MMA lane.  One iteration = 4 output rows of one
+// CTA (persistent, 1/SM): warps 0-3 epilogue, warp 4 producer, warp 5 MMA lane.  One iteration = 4 output rows of one
 // (n, to) = 4 accumulators (row pair x parity) of 128 x 64, double buffered in TMEM (512 columns); stage = one frame tap.
 #include "common.cuh"
 #include "rspnet_b200.h"
@@ -24,8 +23,8 @@ namespace rsp {
 int device_sm_count();
 
 struct Stem3Params {
-  CUtensorMap tmapX;         // {Wi, Hi, Ti, N} of 8-byte pixels, box {128, kS3Rows, 1, 1}, no swizzle
-  const __nv_bfloat16* wst;  // [kt][kh][2 kchunk][8 co-group][8 co][8 k]
+  const __nv_bfloat16* x;    // [N][Ti][Hi][Wi][4]
+  const __nv_bfloat16* wst;  // [2 sets][kt][kh][2 kchunk][8 co-group][8 co][8 k], then 512 zeros
   __nv_bfloat16* y;          // [N][To][Ho][Wo][64]
   const float* bias;
   float* stats;
@@ -38,9 +37,9 @@ constexpr int kS3Threads = 192;
 constexpr int kS3Stages = 4;
 constexpr int kS3OutRows = 4;
 constexpr int kS3Rows = kS3OutRows + 2;             // input rows per stage
-constexpr int kS3CopyBytes = kS3Rows * 1024;        // one copy (E or O) of the rows
-constexpr int kS3StageBytes = 2 * kS3CopyBytes;
-constexpr int kS3FilterBytes = 9 * 2048;            // (frame tap, filter row) x [64 co x 16 k] bf16
+constexpr int kS3StageBytes = kS3Rows * 1024;
+constexpr int kS3SetBytes = 9 * 2048;               // (frame tap, filter row) x [64 co x 16 k] bf16
+constexpr int kS3FilterBytes = 2 * kS3SetBytes;     // set O, set E
 
 __device__ __forceinline__ uint64_t s3_desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   uint64_t d = 0;
@@ -51,20 +50,13 @@ __device__ __forceinline__ uint64_t s3_desc_nosw(uint32_t saddr, uint32_t lbo, u
   return d;
 }
 
-__device__ __forceinline__ void s3_tma_load_4d(uint32_t dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-
 __device__ __forceinline__ void s3_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
 
-__global__ void __launch_bounds__(kS3Threads, 1) conv_stem3_kernel(const __grid_constant__ Stem3Params p) {
+__global__ void __launch_bounds__(kS3Threads, 1) conv_stem3_kernel(const Stem3Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* filt = smem + kS3Stages * kS3StageBytes;
@@ -77,6 +69,8 @@ __global__ void __launch_bounds__(kS3Threads, 1) conv_stem3_kernel(const __grid_
 
   const int t = threadIdx.x;
   const int warp = t >> 5;
+  // zero the row slots once: the 16 bytes in front of a row and everything behind it are never written afterwards
+  for (int i = t; i < kS3Stages * kS3StageBytes / 16; i += kS3Threads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (t == 0) {
     for (int s = 0; s < kS3Stages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -90,38 +84,44 @@ __global__ void __launch_bounds__(kS3Threads, 1) conv_stem3_kernel(const __grid_
     fence_mbar_init();
   }
   if (warp == 5) tmem_alloc(tmem_slot, 512);
+  fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 4) {
-    // ------------------------------------------------------------------ producer lane
-    if (elect_one()) {
-      tma_prefetch_desc(&p.tmapX);
+    // ------------------------------------------------------------------ producer: lane r copies input row r of the stage
+    const int lane = t & 31;
+    const uint32_t rowBytes = static_cast<uint32_t>(p.Wi) * 8u;
+    const __nv_bfloat16* zero_row = p.wst + kS3FilterBytes / 2;
+    if (lane == 0) {
       mbar_arrive_expect_tx(filt_bar, kS3FilterBytes);
       s3_bulk_g2s(smem_u32(filt), p.wst, kS3FilterBytes, filt_bar);
-      int s = 0;
-      uint32_t ph = 1;
-      for (int it = blockIdx.x; it < p.numIters; it += gridDim.x) {
-        const int hq = it % p.hq;
-        const int q = it / p.hq;
-        const int to = q % p.To, n = q / p.To;
-        const int hi0 = hq * kS3OutRows - 1;
-        for (int a = 0; a < 3; ++a) {
-          mbar_wait(&empty_bar[s], ph);
-          const uint32_t dst = smem_u32(smem + s * kS3StageBytes);
-          mbar_arrive_expect_tx(&full_bar[s], kS3StageBytes);
-          s3_tma_load_4d(dst, &p.tmapX, &full_bar[s], -1, hi0, to - 1 + a, n);                 // copy E
-          s3_tma_load_4d(dst + kS3CopyBytes, &p.tmapX, &full_bar[s], 0, hi0, to - 1 + a, n);   // copy O
-          if (++s == kS3Stages) {
-            s = 0;
-            ph ^= 1;
-          }
+    }
+    int s = 0;
+    uint32_t ph = 1;
+    for (int it = blockIdx.x; it < p.numIters; it += gridDim.x) {
+      const int hq = it % p.hq;
+      const int q = it / p.hq;
+      const int to = q % p.To, n = q / p.To;
+      const int hi = hq * kS3OutRows - 1 + lane;
+      for (int a = 0; a < 3; ++a) {
+        mbar_wait(&empty_bar[s], ph);
+        const int ti = to - 1 + a;
+        if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], kS3Rows * rowBytes);
+        __syncwarp();
+        if (lane < kS3Rows) {
+          const bool ok = ti >= 0 && ti < p.Ti && hi >= 0 && hi < p.Hi;
+          const __nv_bfloat16* src = ok ? p.x + ((static_cast<size_t>(n) * p.Ti + ti) * p.Hi + hi) * p.Wi * 4 : zero_row;
+          s3_bulk_g2s(smem_u32(smem + s * kS3StageBytes) + lane * 1024 + 16, src, rowBytes, &full_bar[s]);
+        }
+        if (++s == kS3Stages) {
+          s = 0;
+          ph ^= 1;
         }
       }
     }
-    __syncwarp();
   } else if (warp < 4) {
     // ------------------------------------------------------------------ epilogue
     const int ew = warp, lane = t & 31;
@@ -216,9 +216,11 @@ __global__ void __launch_bounds__(kS3Threads, 1) conv_stem3_kernel(const __grid_
 #pragma unroll
             for (int tile = 0; tile < 4; ++tile) {
               const int rp = tile >> 1, par = tile & 1;
-              // A: copy `par`, input slab rows (2*rp + b) and (2*rp + b + 1) = output rows 2*rp, 2*rp + 1 for filter row b
-              umma_bf16(dcol + tile * 64, abase + static_cast<uint64_t>((par * kS3CopyBytes + (2 * rp + b) * 1024) >> 4),
-                        bbase + static_cast<uint64_t>(((a * 3 + b) * 2048) >> 4), idesc, (a | b) != 0);
+              // A: stage rows (2*rp + b) and (2*rp + b + 1) = output rows 2*rp, 2*rp + 1 for filter row b; odd pixels start at
+              // the row's pixel 0 (byte 16) with filter set O, even pixels one window earlier (byte 0) with filter set E
+              umma_bf16(dcol + tile * 64, abase + static_cast<uint64_t>(((2 * rp + b) * 1024 + par * 16) >> 4),
+                        bbase + static_cast<uint64_t>(((1 - par) * kS3SetBytes + (a * 3 + b) * 2048) >> 4), idesc,
+                        (a | b) != 0);
             }
           }
           umma_commit(&empty_bar[s]);
@@ -238,39 +240,40 @@ __global__ void __launch_bounds__(kS3Threads, 1) conv_stem3_kernel(const __grid_
   if (warp == 5) tmem_dealloc(tmem_base, 512);
 }
 
-// w fp32 [64][Ci<=4][3][3][3] -> wst bf16 [a][b][2][8][8][8]; K slot q = kchunk*8 + e: pixel slot q/4 (= kw tap, slot 3 is
-// always zero), channel q%4
+// w fp32 [64][Ci<=4][3][3][3] -> wst bf16 [set][a][b][2][8][8][8] + 512 zeros; K slot q = kchunk*8 + e: window pixel q/4,
+// channel q%4; set 0 (odd pixels): kw tap = slot (slot 3 zero); set 1 (even pixels): kw tap = slot - 1 (slot 0 zero)
 __global__ void pack_weight_stem3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wst, int Co, int Ci) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 9 * 1024) return;
-  const int e = idx & 7, r = (idx >> 3) & 7, g = (idx >> 6) & 7, j = (idx >> 9) & 1;
-  const int ab = idx >> 10;
-  const int a = ab / 3, b = ab - a * 3;
-  const int co = g * 8 + r;
-  const int qk = j * 8 + e;
-  const int c = qk >> 2, ch = qk & 3;
+  if (idx >= 2 * 9 * 1024 + 512) return;
   float v = 0.f;
-  if (co < Co && ch < Ci && c < 3) v = w[(((static_cast<size_t>(co) * Ci + ch) * 3 + a) * 3 + b) * 3 + c];
+  if (idx < 2 * 9 * 1024) {
+    const int set = idx / (9 * 1024), rem = idx - set * 9 * 1024;
+    const int e = rem & 7, r = (rem >> 3) & 7, g = (rem >> 6) & 7, j = (rem >> 9) & 1;
+    const int ab = rem >> 10;
+    const int a = ab / 3, b = ab - a * 3;
+    const int co = g * 8 + r;
+    const int qk = j * 8 + e;
+    const int c = (qk >> 2) - set, ch = qk & 3;
+    if (co < Co && ch < Ci && c >= 0 && c < 3) v = w[(((static_cast<size_t>(co) * Ci + ch) * 3 + a) * 3 + b) * 3 + c];
+  }
   wst[idx] = __float2bfloat16(v);
 }
 
 bool stem3_supported(const rsp_conv3d_desc* d) {
   return d->Ci == 4 && d->Co == 64 && d->kt == 3 && d->kh == 3 && d->kw == 3 && d->st == 1 && d->sh == 1 && d->sw == 1 &&
-         d->pt == 1 && d->ph == 1 && d->pw == 1 && (d->Wi % 2) == 0 && d->Wi <= 126;
+         d->pt == 1 && d->ph == 1 && d->pw == 1 && (d->Wi % 2) == 0 && d->Wi <= 124;
 }
 
 int pack_stem3(int Ci_logical, int Co_logical, const float* w, void* wst, cudaStream_t stream) {
-  pack_weight_stem3_kernel<<<(9 * 1024 + 255) / 256, 256, 0, stream>>>(w, static_cast<__nv_bfloat16*>(wst), Co_logical,
+  pack_weight_stem3_kernel<<<(2 * 9 * 1024 + 512 + 255) / 256, 256, 0, stream>>>(w, static_cast<__nv_bfloat16*>(wst), Co_logical,
                                                                        Ci_logical);
   return check_launch("pack_weight_stem3");
 }
 
-int make_tmap_u64_rows(CUtensorMap* out, const void* base, int rank, const unsigned long long* dims,
-                       const unsigned long long* strides_bytes, const unsigned* box);
-
 int launch_stem3(const rsp_conv3d_desc* d, const void* x, const void* wst, const float* bias, void* y, float* stats,
                  int sm_count, cudaStream_t stream) {
   Stem3Params p{};
+  p.x = static_cast<const __nv_bfloat16*>(x);
   p.wst = static_cast<const __nv_bfloat16*>(wst);
   p.y = static_cast<__nv_bfloat16*>(y);
   p.bias = bias;
@@ -279,14 +282,6 @@ int launch_stem3(const rsp_conv3d_desc* d, const void* x, const void* wst, const
   p.To = d->Ti; p.Ho = d->Hi; p.Wo = d->Wi;
   p.hq = (p.Ho + kS3OutRows - 1) / kS3OutRows;
   p.numIters = p.N * p.To * p.hq;
-  {
-    const unsigned long long W = p.Wi, H = p.Hi, T = p.Ti, N = p.N;
-    const unsigned long long dims[4] = {W, H, T, N};
-    const unsigned long long strides[3] = {W * 8, H * W * 8, T * H * W * 8};
-    const unsigned box[4] = {128, kS3Rows, 1, 1};
-    int rc = make_tmap_u64_rows(&p.tmapX, x, 4, dims, strides, box);
-    if (rc != RSP_OK) return rc;
-  }
   constexpr int smem = kS3Stages * kS3StageBytes + kS3FilterBytes + 1024 + 256;
   cudaError_t e = cudaFuncSetAttribute(conv_stem3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) {
