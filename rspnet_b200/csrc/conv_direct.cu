@@ -190,19 +190,23 @@ __global__ void __launch_bounds__(kDirThreads, 1) conv_direct_kernel(const __gri
       if (chunks > p.G) chunks = p.G;
       mbar_wait(&acc_full[buf], (ictr >> 1) & 1);
       tc_fence_after_sync();
-      for (int m = 0; m < chunks; ++m) {
-        const uint32_t q = static_cast<uint32_t>(q0 + m * 128 + ew * 32 + lane);
-        const uint32_t ho = fdiv64(q, p.mulWp, p.shWp);
-        const int wo = static_cast<int>(q - ho * p.Wp);
-        const bool ok = q < static_cast<uint32_t>(p.P) && wo < p.Wo;
-        __nv_bfloat16* orow = p.y + ((((static_cast<size_t>(n) * p.To + to) * p.Ho + (ok ? ho : 0)) * p.Wo) +
-                                     (ok ? wo : 0)) * p.Nout + nt * NT;
+      // columns outer, position chunks inner: BN statistics are reduced across lanes once per 32 columns and work item
 #pragma unroll 1
-        for (int c0 = 0; c0 < NT; c0 += 32) {
+      for (int c0 = 0; c0 < NT; c0 += 32) {
+        float ra[32], qa[32];
+#pragma unroll
+        for (int jx = 0; jx < 32; ++jx) ra[jx] = qa[jx] = 0.f;
+#pragma unroll 1
+        for (int m = 0; m < chunks; ++m) {
+          const uint32_t q = static_cast<uint32_t>(q0 + m * 128 + ew * 32 + lane);
+          const uint32_t ho = fdiv64(q, p.mulWp, p.shWp);
+          const int wo = static_cast<int>(q - ho * p.Wp);
+          const bool ok = q < static_cast<uint32_t>(p.P) && wo < p.Wo;
+          __nv_bfloat16* orow = p.y + ((((static_cast<size_t>(n) * p.To + to) * p.Ho + (ok ? ho : 0)) * p.Wo) +
+                                       (ok ? wo : 0)) * p.Nout + nt * NT;
           uint32_t v[32];
           tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * accCols + m * NT + c0, v);
           tmem_ld_wait();
-          float r[32];
 #pragma unroll
           for (int jx = 0; jx < 32; jx += 8) {
             float f[8];
@@ -217,28 +221,28 @@ __global__ void __launch_bounds__(kDirThreads, 1) conv_direct_kernel(const __gri
             o.z = pack_bf16x2(f[4], f[5]);
             o.w = pack_bf16x2(f[6], f[7]);
             if (ok && !(dbg & 2)) *reinterpret_cast<uint4*>(orow + c0 + jx) = o;
-            if (p.stats) {
+            if (p.stats && ok) {
               const uint32_t w[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                r[jx + 2 * e] = ok ? __uint_as_float(w[e] << 16) : 0.f;
-                r[jx + 2 * e + 1] = ok ? __uint_as_float(w[e] & 0xffff0000u) : 0.f;
+                const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
+                ra[jx + 2 * e] += lo;
+                ra[jx + 2 * e + 1] += hi;
+                qa[jx + 2 * e] = fmaf(lo, lo, qa[jx + 2 * e]);
+                qa[jx + 2 * e + 1] = fmaf(hi, hi, qa[jx + 2 * e + 1]);
               }
             }
           }
-          if (p.stats) {
-            float qq[32];
+        }
+        if (p.stats) {
+          warp_column_sums(ra, lane);
+          warp_column_sums(qa, lane);
+          // c0/32 is a runtime index into a tiny register array: resolve with a predicated unrolled loop
 #pragma unroll
-            for (int jx = 0; jx < 32; ++jx) qq[jx] = r[jx] * r[jx];
-            warp_column_sums(r, lane);
-            warp_column_sums(qq, lane);
-            // c0/32 is a runtime index into a tiny register array: resolve with a predicated unrolled loop
-#pragma unroll
-            for (int i = 0; i < NT / 32; ++i) {
-              if (i == (c0 >> 5)) {
-                ssum[i] += r[0];
-                ssq[i] += qq[0];
-              }
+          for (int i = 0; i < NT / 32; ++i) {
+            if (i == (c0 >> 5)) {
+              ssum[i] += ra[0];
+              ssq[i] += qa[0];
             }
           }
         }

@@ -135,20 +135,23 @@ __global__ void __launch_bounds__(kS3Threads, 1) conv_stem3_kernel(const Stem3Pa
       const int to = q % p.To, n = q / p.To;
       mbar_wait(&acc_full[buf], ph);
       tc_fence_after_sync();
+      // columns outer, tiles inner: BN statistics are reduced across lanes once per 32 columns and iteration
 #pragma unroll 1
-      for (int tile = 0; tile < 4; ++tile) {   // tile = row pair * 2 + parity
-        const int rp = tile >> 1, par = tile & 1;
-        const int ho = hq * kS3OutRows + 2 * rp + (ew >> 1);
-        const int ow = 2 * ((ew & 1) * 32 + lane) + par;
-        const bool ok = ho < p.Ho && ow < p.Wo;
-        __nv_bfloat16* orow =
-            p.y + ((((static_cast<size_t>(n) * p.To + to) * p.Ho + (ok ? ho : 0)) * p.Wo) + (ok ? ow : 0)) * 64;
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        float ra[32], qa[32];
+#pragma unroll
+        for (int jx = 0; jx < 32; ++jx) ra[jx] = qa[jx] = 0.f;
 #pragma unroll 1
-        for (int c0 = 0; c0 < 64; c0 += 32) {
+        for (int tile = 0; tile < 4; ++tile) {   // tile = row pair * 2 + parity
+          const int rp = tile >> 1, par = tile & 1;
+          const int ho = hq * kS3OutRows + 2 * rp + (ew >> 1);
+          const int ow = 2 * ((ew & 1) * 32 + lane) + par;
+          const bool ok = ho < p.Ho && ow < p.Wo;
+          __nv_bfloat16* orow =
+              p.y + ((((static_cast<size_t>(n) * p.To + to) * p.Ho + (ok ? ho : 0)) * p.Wo) + (ok ? ow : 0)) * 64;
           uint32_t v[32];
           tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * 256 + tile * 64 + c0, v);
           tmem_ld_wait();
-          float r[32];
 #pragma unroll
           for (int jx = 0; jx < 32; jx += 8) {
             float f[8];
@@ -163,24 +166,24 @@ __global__ void __launch_bounds__(kS3Threads, 1) conv_stem3_kernel(const Stem3Pa
             o.z = pack_bf16x2(f[4], f[5]);
             o.w = pack_bf16x2(f[6], f[7]);
             if (ok) *reinterpret_cast<uint4*>(orow + c0 + jx) = o;
-            if (p.stats) {
+            if (p.stats && ok) {
               const uint32_t w[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                r[jx + 2 * e] = ok ? __uint_as_float(w[e] << 16) : 0.f;
-                r[jx + 2 * e + 1] = ok ? __uint_as_float(w[e] & 0xffff0000u) : 0.f;
+                const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
+                ra[jx + 2 * e] += lo;
+                ra[jx + 2 * e + 1] += hi;
+                qa[jx + 2 * e] = fmaf(lo, lo, qa[jx + 2 * e]);
+                qa[jx + 2 * e + 1] = fmaf(hi, hi, qa[jx + 2 * e + 1]);
               }
             }
           }
-          if (p.stats) {
-            float qq[32];
-#pragma unroll
-            for (int jx = 0; jx < 32; ++jx) qq[jx] = r[jx] * r[jx];
-            warp_column_sums(r, lane);
-            warp_column_sums(qq, lane);
-            ssum[c0 >> 5] += r[0];
-            ssq[c0 >> 5] += qq[0];
-          }
+        }
+        if (p.stats) {
+          warp_column_sums(ra, lane);
+          warp_column_sums(qa, lane);
+          ssum[c0 >> 5] += ra[0];
+          ssq[c0 >> 5] += qa[0];
         }
       }
       tc_fence_before_sync();
