@@ -95,17 +95,17 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
 
   if (warp == 4) {
     // ------------------------------------------------------------------ producer (bulk copies, one lane per input row)
-    uint32_t stage_ctr = 0;
+    int s = 0;
+    uint32_t ph = 0;
     const int lane = t & 31;
     const uint32_t rowBytes = static_cast<uint32_t>(p.Wi) * 8u;
+    const int rowSlot = ((lane % p.sh) * perPhase + lane / p.sh) * kStemRowBytes + 32;
     for (int it = blockIdx.x; it < p.numIters; it += gridDim.x) {
       const int hq = it % p.hq;
       const int q = it / p.hq;
       const int to = q % p.To, n = q / p.To;
       const int hi0 = hq * kStemOutRows * p.sh - p.ph;
-      for (int a = 0; a < p.kt; ++a, ++stage_ctr) {
-        const int s = stage_ctr % kStemStages;
-        const uint32_t ph = (stage_ctr / kStemStages) & 1;
+      for (int a = 0; a < p.kt; ++a) {
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* aslab = smem + s * kStemStageBytes;
         const int ti = to * p.st - p.pt + a;
@@ -130,10 +130,13 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
         }
         if (ok) {
           const __nv_bfloat16* src = p.x + ((static_cast<size_t>(n) * p.Ti + ti) * p.Hi + hi) * p.Wi * 4;
-          bulk_copy_g2s(smem_u32(aslab) + ((lane % p.sh) * perPhase + lane / p.sh) * kStemRowBytes + 32, src, rowBytes,
-                        &full_bar[s]);
+          bulk_copy_g2s(smem_u32(aslab) + rowSlot, src, rowBytes, &full_bar[s]);
         }
         __syncwarp();
+        if (++s == kStemStages) {
+          s = 0;
+          ph ^= 1;
+        }
       }
     }
   } else if (warp < 4) {
@@ -215,16 +218,16 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
     // ------------------------------------------------------------------ MMA issuer
     // one elected lane waits, issues and commits (no warp-level re-convergence between stages)
     constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
-    uint32_t stage_ctr = 0, iter_ctr = 0;
+    uint32_t iter_ctr = 0;
+    int s = 0;
+    uint32_t ph = 0;
     const bool leader = elect_one();
     for (int it = blockIdx.x; leader && it < p.numIters; it += gridDim.x, ++iter_ctr) {
       const int buf = iter_ctr & 1;
       const uint32_t aph = (iter_ctr >> 1) & 1;
       mbar_wait(&acc_empty[buf], aph ^ 1);
       tc_fence_after_sync();
-      for (int a = 0; a < p.kt; ++a, ++stage_ctr) {
-        const int s = stage_ctr % kStemStages;
-        const uint32_t ph = (stage_ctr / kStemStages) & 1;
+      for (int a = 0; a < p.kt; ++a) {
         mbar_wait(&full_bar[s], ph);
         fence_proxy_async_smem();
         tc_fence_after_sync();
@@ -250,6 +253,10 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
         }
         umma_commit(&empty_bar[s]);
         if (a == p.kt - 1) umma_commit(&acc_full[buf]);
+        if (++s == kStemStages) {
+          s = 0;
+          ph ^= 1;
+        }
       }
     }
   }
@@ -384,14 +391,14 @@ __global__ void __launch_bounds__(192, 1) conv_stem_wgrad_kernel(const __grid_co
       const int lane = t & 31;
       const uint32_t rowBytes = static_cast<uint32_t>(p.Wi) * 8u;
       const int al = lane / p.kh, b = lane - al * p.kh;
-      int it = 0;
       if (lane == 0) tma_prefetch_desc(&p.tmapDy);
-      for (int r = blockIdx.x; r < p.numRows; r += gridDim.x, ++it) {
-        const int s = it % kSWStages;
-        const uint32_t ph = (it / kSWStages) & 1;
-        const int ho = r % p.Ho;
-        const int q = r / p.Ho;
-        const int to = q % p.To, n = q / p.To;
+      // (n, to, ho) of output row r advance incrementally: the producer is a single serial instruction stream and four
+      // integer divisions per stage were most of it
+      int s = 0;
+      uint32_t ph = 0;
+      int ho = blockIdx.x % p.Ho, to = (blockIdx.x / p.Ho) % p.To, n = blockIdx.x / (p.Ho * p.To);
+      const int dho = gridDim.x % p.Ho, dto = (gridDim.x / p.Ho) % p.To, dn = gridDim.x / (p.Ho * p.To);
+      for (int r = blockIdx.x; r < p.numRows; r += gridDim.x) {
         mbar_wait(&empty_bar[s], ph ^ 1);
         const uint32_t stage = smem_u32(smem + s * kSWStageBytes);
         const int ti = to * p.st - p.pt + a0 + al;
@@ -419,6 +426,21 @@ __global__ void __launch_bounds__(192, 1) conv_stem_wgrad_kernel(const __grid_co
           bulk_copy_g2s(stage + kSWDyBytes + lane * kStemRowBytes + 32, src, rowBytes, &full_bar[s]);
         }
         __syncwarp();
+        if (++s == kSWStages) {
+          s = 0;
+          ph ^= 1;
+        }
+        ho += dho;
+        to += dto;
+        n += dn;
+        if (ho >= p.Ho) {
+          ho -= p.Ho;
+          ++to;
+        }
+        if (to >= p.To) {
+          to -= p.To;
+          ++n;
+        }
       }
     } else if (warp < 4) {
       // ---------------- epilogue: TMEM lanes of an M=64 accumulator: co = 16*warp + lane, lanes 16..31 unused
@@ -452,9 +474,9 @@ __global__ void __launch_bounds__(192, 1) conv_stem_wgrad_kernel(const __grid_co
       const int ncol = nrows * 8;                                    // accumulator columns per pixel-pair window
       const uint32_t idesc = make_idesc_bf16(64, ncol, 1, 1);
       const bool leader = elect_one();
+      int s = 0;
+      uint32_t ph = 0;
       for (int it = 0; leader && it < iters; ++it) {
-        const int s = it % kSWStages;
-        const uint32_t ph = (it / kSWStages) & 1;
         mbar_wait(&full_bar[s], ph);
         fence_proxy_async_smem();
         tc_fence_after_sync();
@@ -474,6 +496,10 @@ __global__ void __launch_bounds__(192, 1) conv_stem_wgrad_kernel(const __grid_co
         }
         umma_commit(&empty_bar[s]);
         if (it == iters - 1) umma_commit(accum_bar);
+        if (++s == kSWStages) {
+          s = 0;
+          ph ^= 1;
+        }
       }
     }
   }
