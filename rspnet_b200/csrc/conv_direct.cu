@@ -357,7 +357,15 @@ static bool direct_geometry(const rsp_conv3d_desc* d, int transposed, DirectPara
   p.P = p.Ho * p.Wp;
   NT = (Nout % 128 == 0) ? 128 : 64;
   p.G = NT == 64 ? 4 : 2;
-  if (p.P < 128 * p.G) return false;                 // small planes: the gather kernel wastes less
+  // small planes: the last 128-position chunk of a plane is partly empty; below 3/4 useful rows the gather kernel wastes less
+  {
+    const int chunksTotal = (p.P + 127) / 128;
+    if (p.P < 128 || p.P * 4 < chunksTotal * 128 * 3) return false;
+    // planes that do not fill whole groups (14 x 14: 224 of 256 rows): worth it only when the gather kernel's 128-row
+    // tiles would not even fill three waves (R3D-18 layer2: 392 tiles) — measured both ways on R3D-18 / C3D shapes
+    const long long gatherTiles = ((static_cast<long long>(p.N) * p.To * p.Ho * p.Wo + 127) / 128) * (Nout / NT);
+    if (p.P < 128 * p.G && gatherTiles >= 6ll * device_sm_count()) return false;
+  }
   if (p.kh * p.kw < 2) return false;                 // 1x1 filters have nothing to reuse
   p.groups = (p.P + 128 * p.G - 1) / (128 * p.G);
   if (p.Wp > 256) return false;                                          // TMA box extent
