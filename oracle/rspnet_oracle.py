@@ -241,6 +241,36 @@ def enqueue(sd: State, keys_all):
     sd["queue_ptr"][0] = (ptr + n) % K
 
 
+def single_head_encoder(x, sd: State, p: str, train=True):
+    """models/resnet.py:215-223 (get_output_and_feature / forward) for resnet18: AvgPool3d over the (1, 4, 4) feature map of
+    a 16 x 112 x 112 clip, then ``fc``; L2-normalised as builder:177,207 do."""
+    feat = resnet18_feature(_r(x), sd, p, train)
+    pooled = F.avg_pool3d(feat, (1, 4, 4), stride=1).flatten(1)
+    return F.normalize(F.linear(pooled, sd[p + "fc.weight"], sd[p + "fc.bias"]), dim=1)
+
+
+def single_head_forward(sd: State, im_q, im_k, perm, idx_shuffles, *, d=2, m=0.999, T=0.07):
+    """MoCoDiffLoss.forward (builder:184-245), one process (the shuffles permute within the batch): returns
+    (logits1, logits2), (l_pos, l_neg_speed), q (with grad) and enqueues ``k``.  ``sd`` holds leaves for encoder_q."""
+    momentum_update(sd, m)
+    q_in, k_in, kneg_in = diff_speed(im_q, im_k, perm, d)
+
+    def enc_k(x, idx):                                       # builder:171-183
+        with torch.no_grad():
+            k = single_head_encoder(x[idx], sd, "encoder_k.", True)
+        return k[torch.argsort(idx)]
+
+    speed_k = enc_k(kneg_in, idx_shuffles[0])
+    k = enc_k(k_in, idx_shuffles[1])
+    q = single_head_encoder(q_in, sd, "encoder_q.", True)
+    l_pos = torch.einsum('nc,nc->n', [q, k]).unsqueeze(-1) / T
+    l_neg = torch.einsum('nc,ck->nk', [q, sd["queue"].clone().detach()]) / T
+    l_neg_speed = torch.einsum('nc,nc->n', [q, speed_k]).unsqueeze(-1) / T
+    out = (torch.cat([l_pos, l_neg], 1), torch.cat([l_neg_speed, l_neg], 1)), (l_pos, l_neg_speed)
+    enqueue(sd, k)
+    return out
+
+
 # --------------------------------------------------------------------------------------------------------------
 # one full training step over W simulated ranks
 # --------------------------------------------------------------------------------------------------------------

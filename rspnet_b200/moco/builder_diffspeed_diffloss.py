@@ -319,7 +319,34 @@ class MoCoDiffLoss(_MoCoBase):
             raise NotImplementedError("mlp=True is not part of any shipped pretrain config")
         self._init_common(base_encoder, dim, K, m, T, diff_speed)
 
+    @torch.no_grad()
+    def _forward_encoder_k(self, im_k, return_all: bool = False):
+        """ref :171-183: shuffle, encoder_k, L2 normalise, unshuffle (one embedding per clip)."""
+        im_k, idx_unshuffle = self._batch_shuffle_ddp(rnn.as_ndhwc(im_k))
+        k = nn.functional.normalize(self.encoder_k(im_k).float(), dim=1)
+        return self._batch_unshuffle_ddp(k, idx_unshuffle, return_all)
+
+    @torch.no_grad()
+    def _diff_speed(self, im_q: Tensor, im_k: Tensor):
+        """ref :136-162: re-sampled q / k clips and the embedding of the speed-swapped key clip."""
+        q, k, k_neg = self._speed_views(im_q, im_k)
+        return q, k, self._forward_encoder_k(k_neg)
+
     def forward(self, im_q, im_k):
-        raise NotImplementedError(
-            "MoCoDiffLoss (single projection head) is dead code w.r.t. every reference entry point "
-            "(moco/__init__.py builds MoCoDiffLossTwoFc); only its constructor/state_dict surface is provided")
+        """
+        Input: im_q, im_k: [B, 3, T, H, W] clips (T = diff_speed * clip length).
+        Output (ref :184-245): (logits1, logits2), labels (zeros), (l_pos, l_neg_speed), ranking_target (ones) with
+        logits1 = [q.k | q.queue] / T, logits2 = [q.speed_k | q.queue] / T; the key ``k`` is enqueued.
+        """
+        with torch.no_grad():
+            self._momentum_update_key_encoder()
+            im_q, im_k, speed_k = self._diff_speed(im_q, im_k)
+            k, k_all = self._forward_encoder_k(im_k, return_all=True)
+        q = nn.functional.normalize(self.encoder_q(im_q).float(), dim=1)
+        # the two-head kernel with both heads fed by the same embedding: logits1 = [q.k | q.queue], logits2 =
+        # [q.speed_k | q.queue], ranking pair (q.k, q.speed_k); autograd sums the two gradient paths into q
+        logits, ranking_logits = self._logits(q, q, k, k, speed_k, speed_k)
+        labels = torch.zeros(q.shape[0], dtype=torch.long, device=q.device)
+        ranking_target = torch.ones_like(labels)
+        self._dequeue_and_enqueue(k_all, gathered=True)
+        return logits, labels, ranking_logits, ranking_target

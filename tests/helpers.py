@@ -41,6 +41,15 @@ def build_product_moco(cfg, hyper, rank=0):
                              diff_speed=list(hyper["diff_speed"]))
 
 
+def build_product_single_head(cfg, hyper, rank=0):
+    """The product's MoCoDiffLoss (single head: the backbone's own fc is the projection) under the reference's seeding."""
+    from rspnet_b200.models import get_model_class
+    from rspnet_b200.moco import MoCoDiffLoss
+    initialize_seed(cfg["seed"] + rank)
+    return MoCoDiffLoss(get_model_class(arch=cfg["arch"]), dim=hyper["dim"], K=cfg["K"], m=hyper["m"], T=hyper["T"],
+                        diff_speed=list(hyper["diff_speed"]))
+
+
 def summarize(t):
     t = t.detach().double().flatten()
     return dict(sum=float(t.sum()), abssum=float(t.abs().sum()), n=t.numel(), head=t[:32].float().clone())

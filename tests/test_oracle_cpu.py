@@ -6,7 +6,8 @@ import copy
 import pytest
 import torch
 
-from helpers import build_product_moco, check_packed, load_golden, make_inputs, summarize
+from helpers import (build_product_moco, build_product_single_head, check_packed, load_golden, make_inputs,
+                     summarize)
 from oracle import rspnet_oracle as oracle
 
 CASES = ["r3d18_w1", "r3d18_w2", "c3d_w1", "r2plus1d_w1", "s3dg_w1"]
@@ -121,3 +122,40 @@ def test_oracle_matches_live_reference_when_present():
         for k, v in ref.state_dict().items():
             if k.startswith("encoder_k."):
                 assert torch.equal(sd2[k], v), k
+
+
+def test_single_head_builder_oracle_matches_reference_golden():
+    """MoCoDiffLoss (builder:11-245): state_dict of the product's constructor and the oracle's forward / loss / gradients
+    against the fixture recorded from the unmodified reference (oracle/make_golden_single_head.py)."""
+    g = load_golden("r3d18_single_head")
+    cfg, hyper, rec = g["config"], g["hyper"], g["step"]
+    model = build_product_single_head(cfg, hyper)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    assert list(sd.keys()) == list(g["init"].keys())
+    for k, v in sd.items():
+        ref = g["init"][k]
+        s = summarize(v.float())
+        assert abs(s["sum"] - ref["sum"]) <= 1e-11 * max(ref["abssum"], 1.0) and torch.equal(s["head"], ref["head"]), k
+    names = oracle.param_names(sd, "encoder_q.")
+    leaves = {n: sd[n].clone().requires_grad_(True) for n in names}
+    sd.update(leaves)
+    im_q, im_k = make_inputs(cfg, 0, 0)
+    (l1, l2), (lp, ln) = oracle.single_head_forward(sd, im_q, im_k, rec["perm"],
+                                                    (rec["idx_shuffle_neg"], rec["idx_shuffle_pos"]),
+                                                    d=hyper["diff_speed"][0], m=hyper["m"], T=hyper["T"])
+    torch.testing.assert_close(l1.detach(), rec["logits1"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(l2.detach(), rec["logits2"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(lp.detach(), rec["l_pos"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(ln.detach(), rec["l_neg_speed"], rtol=1e-4, atol=1e-4)
+    total, ce, rank = oracle.loss((l1, l2), (lp, ln), hyper["margin"], hyper["A"], hyper["M"])
+    torch.testing.assert_close(torch.stack([total, ce, rank]).detach(), rec["loss"], rtol=1e-4, atol=1e-5)
+    assert int(sd["queue_ptr"]) == rec["queue_ptr"]
+    first = (rec["queue_ptr"] - cfg["batch"]) % cfg["K"]
+    torch.testing.assert_close(sd["queue"][:, first:first + cfg["batch"]], rec["queue_cols"], rtol=1e-5, atol=1e-6)
+    grads = torch.autograd.grad(total, [leaves[n] for n in names], allow_unused=True)
+    checked = 0
+    for n, gr in zip(names, grads):
+        if n in rec["grads"] and gr is not None:
+            check_packed(gr, rec["grads"][n], rtol=2e-3, atol=2e-5, what=n, norm_only=True)
+            checked += 1
+    assert checked >= 60

@@ -146,6 +146,54 @@ def test_step_matches_reference_golden(name):
         assert named[k].grad is None, k
 
 
+def test_single_head_builder_matches_reference_golden():
+    """MoCoDiffLoss.forward (builder:184-245, one projection head = the backbone's fc) on the B200 against the fixture of
+    the unmodified reference: integer state bit-exact, logits / loss within the stated bf16 tolerance of the conv path."""
+    from helpers import build_product_single_head
+    from rspnet_b200.moco import Loss
+    g = load_golden("r3d18_single_head")
+    cfg, hyper, rec = g["config"], g["hyper"], g["step"]
+    model = build_product_single_head(cfg, hyper).cuda()
+    crit = Loss(margin=hyper["margin"], A=hyper["A"], M=hyper["M"])
+    im_q, im_k = make_inputs(cfg, 0, 0)
+    draws = [rec["perm"], rec["idx_shuffle_neg"], rec["idx_shuffle_pos"]]
+    orig, calls = torch.randperm, []
+
+    def replay(n, *a, **k):
+        r = draws[len(calls)]
+        calls.append(n)
+        dev = k.get("device", None)
+        return r.to(dev) if dev is not None else r.clone()
+
+    torch.randperm = replay
+    try:
+        output, target, ranking_logits, ranking_target = model(im_q.cuda(), im_k.cuda())
+    finally:
+        torch.randperm = orig
+    loss, ce, rank = crit(output, target, ranking_logits, ranking_target)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert torch.equal(target.cpu(), rec["target"]) and torch.equal(ranking_target.cpu(), rec["ranking_target"])
+    assert int(model.queue_ptr) == rec["queue_ptr"]
+    assert (output[0].cpu() - rec["logits1"]).abs().max() < 0.35
+    assert (output[1].cpu() - rec["logits2"]).abs().max() < 0.35
+    assert (ranking_logits[0].cpu() - rec["l_pos"]).abs().max() < 0.35
+    assert (ranking_logits[1].cpu() - rec["l_neg_speed"]).abs().max() < 0.35
+    assert (torch.stack([loss, ce, rank]).cpu() - rec["loss"]).abs().max() < 0.15
+    first = (rec["queue_ptr"] - cfg["batch"]) % cfg["K"]
+    assert (model.queue[:, first:first + cfg["batch"]].cpu() - rec["queue_cols"]).abs().max() < 0.03
+    named = dict(model.named_parameters())
+    gots, refs = [], []
+    for k, ref in rec["grads"].items():
+        if isinstance(ref, dict) or ref.abs().max() < 1e-6:
+            continue
+        gots.append(named[k].grad.cpu().flatten())
+        refs.append(ref.flatten())
+    overall = _cos(torch.cat(gots), torch.cat(refs))
+    print(f"[single head] gradient cosine vs fp32 reference fixture over {len(gots)} tensors: {overall:.4f}")
+    assert len(gots) >= 10 and overall > 0.85, overall
+
+
 def test_objective_matches_oracle_fp32():
     """Everything after the encoders in fp32: EMA, logits, loss, enqueue vs the oracle at 1e-3 relative."""
     from rspnet_b200 import ops
