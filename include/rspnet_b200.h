@@ -88,6 +88,13 @@ int rsp_bn_finalize(float* sum, float* sumsq, int32_t clear_sums, int64_t count,
 /* out = act(x*scale + shift (+ residual)); relu != 0 applies max(0,.). residual may be NULL. */
 int rsp_bn_act_fwd(const void* x, const float* scale, const float* shift, const void* residual, int relu, void* out,
                    int64_t M, int32_t C, void* stream);
+/* rsp_bn_finalize + rsp_bn_act_fwd in one launch.  sum / sumsq: the batch sums of x (read only); clear_sums: 2*C floats
+ * zeroed for the layer's next forward (the other half of a double-buffered accumulator), may be NULL; rows: [4][C] =
+ * scale, shift, mean, invstd (written for the backward). */
+int rsp_bn_finalize_act_fwd(const void* x, const float* sum, const float* sumsq, float* clear_sums, int64_t count,
+                            const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                            float* running_var, float* rows, const void* residual, int relu, void* out, int64_t M,
+                            int32_t C, int32_t C_logical, void* stream);
 /* dz = dout * (out > 0 if relu); sum_dz[c] += sum dz, sum_dz_xhat[c] += sum dz * (x-mean)*invstd (caller zeroes). */
 int rsp_bn_act_bwd_reduce(const void* dout, const void* out, const void* x, const float* mean, const float* invstd,
                           int relu, float* sum_dz, float* sum_dz_xhat, int64_t M, int32_t C, void* stream);

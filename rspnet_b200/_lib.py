@@ -53,6 +53,8 @@ SIGNATURES = {
     "rsp_bn_stats": (c_i32, [_P, c_i64, c_i32, _P, _P, _P]),
     "rsp_bn_finalize": (c_i32, [_P, _P, c_i32, c_i64, _P, _P, c_f32, c_f32, _P, _P, _P, _P, _P, _P, c_i32, c_i32, _P]),
     "rsp_bn_act_fwd": (c_i32, [_P, _P, _P, _P, c_i32, _P, c_i64, c_i32, _P]),
+    "rsp_bn_finalize_act_fwd": (c_i32, [_P, _P, _P, _P, c_i64, _P, _P, c_f32, c_f32, _P, _P, _P, _P, c_i32, _P, c_i64,
+                                        c_i32, c_i32, _P]),
     "rsp_bn_act_bwd_reduce": (c_i32, [_P, _P, _P, _P, _P, c_i32, _P, _P, c_i64, c_i32, _P]),
     "rsp_bn_act_bwd_apply": (c_i32, [_P, _P, _P, _P, _P, _P, _P, _P, c_i32, _P, _P, c_i64, c_i32, c_i32, _P]),
     "rsp_maxpool3d_fwd": (c_i32, [C.POINTER(PoolDesc), _P, _P, _P, _P]),

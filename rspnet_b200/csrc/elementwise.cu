@@ -167,6 +167,65 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const uint4* __restrict
   }
 }
 
+// bn_finalize + bn_act_fwd in one launch: every block derives scale / shift of all channels from the batch sums (C rsqrt
+// per block is noise next to the activation pass); block 0 also publishes (scale, shift, mean, invstd) for the backward,
+// updates the running statistics and zeroes the OTHER parity's accumulators for the next forward of this layer (the
+// conv epilogue of that forward is stream-ordered after this kernel; the sums read here are cleared one call later).
+__global__ void __launch_bounds__(256) bn_finalize_act_fwd_kernel(
+    const uint4* __restrict__ x, const float* __restrict__ sum, const float* __restrict__ sumsq,
+    float* __restrict__ clear, float count, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+    float momentum, float* __restrict__ rmean, float* __restrict__ rvar, float* __restrict__ rows,
+    const uint4* __restrict__ res, int relu, uint4* __restrict__ out, size_t nvec, int C, int Cl) {
+  extern __shared__ float sm[];
+  float* ssc = sm;
+  float* ssh = sm + C;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float sc = 0.f, sh = 0.f, mu = 0.f, is = 0.f;
+    if (c < Cl) {
+      mu = sum[c] / count;
+      const float var = fmaxf(sumsq[c] / count - mu * mu, 0.f);
+      is = rsqrtf(var + eps);
+      sc = gamma[c] * is;
+      sh = beta[c] - mu * sc;
+      if (blockIdx.x == 0) {
+        if (rmean) rmean[c] = (1.f - momentum) * rmean[c] + momentum * mu;
+        if (rvar) {
+          const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
+          rvar[c] = (1.f - momentum) * rvar[c] + momentum * unbiased;
+        }
+      }
+    }
+    ssc[c] = sc;
+    ssh[c] = sh;
+    if (blockIdx.x == 0) {
+      rows[c] = sc;
+      rows[C + c] = sh;
+      rows[2 * C + c] = mu;
+      rows[3 * C + c] = is;
+      if (clear) {
+        clear[c] = 0.f;
+        clear[C + c] = 0.f;
+      }
+    }
+  }
+  __syncthreads();
+  const int G = C >> 3;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < nvec;
+       i += static_cast<size_t>(gridDim.x) * 256) {
+    int g = static_cast<int>(i % G);
+    float xv[8], rv[8];
+    unpack8(__ldg(x + i), xv);
+    if (res) unpack8(__ldg(res + i), rv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float y = fmaf(xv[e], ssc[g * 8 + e], ssh[g * 8 + e]);
+      if (res) y += rv[e];
+      xv[e] = relu ? fmaxf(y, 0.f) : y;
+    }
+    out[i] = pack8(xv);
+  }
+}
+
 __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
     const uint4* __restrict__ dout, const uint4* __restrict__ out, const uint4* __restrict__ x,
     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
@@ -531,6 +590,20 @@ int rsp_bn_act_fwd(const void* x, const float* scale, const float* shift, const 
       static_cast<const uint4*>(x), scale, shift, static_cast<const uint4*>(residual), relu, static_cast<uint4*>(out),
       nvec, C);
   return check_launch("bn_act_fwd");
+}
+
+int rsp_bn_finalize_act_fwd(const void* x, const float* sum, const float* sumsq, float* clear_sums, int64_t count,
+                            const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                            float* running_var, float* rows, const void* residual, int relu, void* out, int64_t M,
+                            int32_t C, int32_t C_logical, void* stream) {
+  RSP_REQUIRE(C % 8 == 0 && C <= 4096 && C_logical <= C && count > 0, "bn_finalize_act_fwd: bad channels / count");
+  if (M == 0) return RSP_OK;
+  size_t nvec = static_cast<size_t>(M) * (C / 8);
+  bn_finalize_act_fwd_kernel<<<ew_grid(nvec, 256), 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), sum, sumsq, clear_sums, static_cast<float>(count), gamma, beta, eps, momentum,
+      running_mean, running_var, rows, static_cast<const uint4*>(residual), relu, static_cast<uint4*>(out), nvec, C,
+      C_logical);
+  return check_launch("bn_finalize_act_fwd");
 }
 
 int rsp_bn_act_bwd_reduce(const void* dout, const void* out, const void* x, const float* mean, const float* invstd,

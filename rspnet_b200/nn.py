@@ -75,32 +75,53 @@ def _pad_vec(v: Optional[torch.Tensor], n: int):
     return out
 
 
-def _conv_bn_stats(x, weight, bias, gamma, beta, running_mean, running_var, kernel, stride, padding, eps, momentum):
-    """Conv fprop with the BN batch statistics taken in its epilogue, then bn_finalize. Returns desc, y, co and the
-    (scale, shift, mean, invstd) rows."""
+def _conv_stats(x, weight, bias, gamma, kernel, stride, padding):
+    """Conv fprop with the BN batch statistics taken in its epilogue.  The per-layer accumulator is double buffered:
+    this forward adds into one half (zero at rest), the BN kernel that consumes it zeroes the other half for the next
+    forward.  Returns desc, y, the sums of this forward and the half to clear."""
     co = ops.pad_channels(weight.shape[0])
     desc = ops.conv_desc(x.shape, co, kernel, stride, padding)
     wp = _pack_cache.get(weight, desc, 0)
-    # per-layer persistent statistics accumulator: zero at rest (bn_finalize clears it after reading)
     key = (id(gamma), co)
-    acc = _stats_acc.get(key)
-    if acc is None or acc.device != x.device:
-        acc = _stats_acc[key] = torch.zeros((2, co), dtype=torch.float32, device=x.device)
-    y = ops.conv3d_fprop(desc, x, wp, _pad_vec(bias, co), stats=acc)   # statistics fused into the conv epilogue
+    st = _stats_acc.get(key)
+    if st is None or st[0].device != x.device:
+        st = _stats_acc[key] = [torch.zeros((2, 2, co), dtype=torch.float32, device=x.device), 0]
+    acc, parity = st
+    st[1] = parity ^ 1
+    sums, other = acc[parity], acc[parity ^ 1]
+    y = ops.conv3d_fprop(desc, x, wp, _pad_vec(bias, co), stats=sums)   # statistics fused into the conv epilogue
     if not ops.conv3d_fprop.stats_done:
-        ops.bn_stats(y, out=acc)                                        # split-K layers: separate reduction
-    rows = ops.bn_finalize(acc[0], acc[1], y.numel() // co, gamma, beta, eps, momentum, running_mean, running_var, co,
+        ops.bn_stats(y, out=sums)                                        # split-K layers: separate reduction
+    return desc, y, sums, other
+
+
+def _conv_bn_stats(x, weight, bias, gamma, beta, running_mean, running_var, kernel, stride, padding, eps, momentum):
+    """_conv_stats followed by the stand-alone bn_finalize (used where the consumer is not the BN-apply kernel).
+    Returns desc, y and the (scale, shift, mean, invstd) rows."""
+    desc, y, sums, other = _conv_stats(x, weight, bias, gamma, kernel, stride, padding)
+    co = y.shape[-1]
+    # stand-alone finalize clears the half it read, so both halves are zero at rest on this path
+    rows = ops.bn_finalize(sums[0], sums[1], y.numel() // co, gamma, beta, eps, momentum, running_mean, running_var, co,
                            clear_sums=True)
     return desc, y, rows
+
+
+def _conv_bn_act_fwd(x, weight, bias, gamma, beta, running_mean, running_var, residual, kernel, stride, padding, eps,
+                     momentum, relu):
+    desc, y, sums, other = _conv_stats(x, weight, bias, gamma, kernel, stride, padding)
+    co = y.shape[-1]
+    out, rows = ops.bn_finalize_act_fwd(y, sums, other, y.numel() // co, gamma, beta, eps, momentum, running_mean,
+                                        running_var, residual, relu)
+    return desc, y, out, rows
 
 
 class ConvBNAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, residual, kernel, stride, padding, eps,
                 momentum, relu):
-        desc, y, (scale, shift, mean, invstd) = _conv_bn_stats(x, weight, bias, gamma, beta, running_mean, running_var,
-                                                               kernel, stride, padding, eps, momentum)
-        out = ops.bn_act_fwd(y, scale, shift, residual, relu)
+        desc, y, out, (scale, shift, mean, invstd) = _conv_bn_act_fwd(x, weight, bias, gamma, beta, running_mean,
+                                                                      running_var, residual, kernel, stride, padding,
+                                                                      eps, momentum, relu)
         ctx.desc = desc
         ctx.relu = relu
         ctx.has_bias = bias is not None
@@ -190,10 +211,8 @@ def conv_bn_act(x, conv: torch.nn.Conv3d, bn: torch.nn.BatchNorm3d, relu: bool =
     momentum = bn.momentum if bn.momentum is not None else 0.0
     if not torch.is_grad_enabled():
         # key-encoder passes: same kernels without the autograd.Function round trip
-        _, y, (scale, shift, _, _) = _conv_bn_stats(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean,
-                                                    bn.running_var, conv.kernel_size, conv.stride, conv.padding, bn.eps,
-                                                    momentum)
-        out = ops.bn_act_fwd(y, scale, shift, residual, relu)
+        out = _conv_bn_act_fwd(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual,
+                               conv.kernel_size, conv.stride, conv.padding, bn.eps, momentum, relu)[2]
     else:
         out = ConvBNAct.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual,
                               tuple(conv.kernel_size), tuple(conv.stride), tuple(conv.padding), bn.eps, momentum, relu)

@@ -120,6 +120,20 @@ def bn_finalize(s, ss, count, gamma, beta, eps, momentum, running_mean, running_
     return out.unbind(0)  # scale, shift, mean, invstd
 
 
+def bn_finalize_act_fwd(x, sums, clear, count, gamma, beta, eps, momentum, running_mean, running_var, residual,
+                        relu: bool):
+    """bn_finalize + bn_act_fwd in one launch; ``sums`` [2, C] are read, ``clear`` [2, C] (or None) is zeroed.
+    Returns out and the (scale, shift, mean, invstd) rows."""
+    c = x.shape[-1]
+    out = torch.empty_like(x)
+    rows = torch.empty((4, c), dtype=torch.float32, device=x.device)
+    base = sums.data_ptr()
+    call("rsp_bn_finalize_act_fwd", ptr(x), base, base + 4 * c, ptr(clear), count, ptr(gamma), ptr(beta), eps, momentum,
+         ptr(running_mean), ptr(running_var), ptr(rows), ptr(residual), int(relu), ptr(out), x.numel() // c, c,
+         gamma.numel(), stream_ptr())
+    return out, rows.unbind(0)
+
+
 def bn_act_fwd(x, scale, shift, residual, relu: bool):
     c = x.shape[-1]
     out = torch.empty_like(x)
