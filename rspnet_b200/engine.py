@@ -45,8 +45,11 @@ class PretrainEngine:
 
     def step(self, clip_q: torch.Tensor, clip_k: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """One optimisation step; returns (loss, loss_A, loss_M) as device scalars (no host sync)."""
-        self.ddp.flat_grad.zero_()
-        self._bind_grads()
+        # gradients are produced straight into their slots of the flat buffer (rnn.register_grad_slots); slots of
+        # parameters that receive nothing are zeroed by FlatDDP._finalize
+        for p in self.ddp._params:
+            p.grad = None
+        rnn.begin_grad_epoch()
         output, target, ranking_logits, ranking_target = self.ddp(clip_q, clip_k)
         loss, loss_a, loss_m = self.criterion(output, target, ranking_logits, ranking_target)
         loss.backward()

@@ -59,6 +59,8 @@ class FlatDDP(nn.Module):
         self.used_parameter_ids = None  # indices that received gradients in the last backward
         for i, p in enumerate(self._params):
             p.register_post_accumulate_grad_hook(self._make_hook(i))
+        from .. import nn as rnn
+        rnn.register_grad_slots(self._params, self._views)
 
     def forward(self, *args, **kwargs):
         return self.module(*args, **kwargs)

@@ -26,6 +26,42 @@ def bump_weight_epoch():
     _weight_epoch += 1
 
 
+# Gradient slots: when a data-parallel wrapper owns one flat gradient buffer it registers the slot of every parameter
+# here; the wgrad kernels then write straight into the slot and autograd adopts that tensor as ``param.grad``
+# (no temporary, no accumulate kernel).  Valid once per backward and parameter: a second use falls back to a temporary.
+_grad_slots = {}
+_grad_epoch = 0
+_grad_written = {}
+
+
+def register_grad_slots(params, views):
+    for p, v in zip(params, views):
+        _grad_slots[p.data_ptr()] = v
+
+
+def begin_grad_epoch():
+    """Called once per backward by the engine (after setting the parameters' ``.grad`` to None)."""
+    global _grad_epoch
+    _grad_epoch += 1
+
+
+def _grad_slot(weight):
+    key = weight.data_ptr()
+    v = _grad_slots.get(key)
+    if v is None or weight.grad is not None or _grad_written.get(key) == _grad_epoch or v.shape != weight.shape:
+        return None
+    _grad_written[key] = _grad_epoch
+    return v
+
+
+def _wgrad(desc, x, dy, weight):
+    slot = _grad_slot(weight)
+    if slot is None:
+        return ops.conv3d_wgrad(desc, x, dy, weight.shape)
+    ops.conv3d_wgrad(desc, x, dy, weight.shape, out=slot)
+    return slot.view(slot.shape)   # a fresh alias: autograd takes it over as param.grad without copying
+
+
 def refresh_packed_weights():
     """Batch re-pack of all stale filter operands (see _PackCache.refresh)."""
     _pack_cache.refresh()
@@ -135,7 +171,7 @@ class ConvBNAct(torch.autograd.Function):
         desc = ctx.desc
         dout = dout.contiguous()
         dy, dres, dgamma, dbeta = ops.bn_act_bwd(dout, out, y, mean, invstd, gamma, ctx.relu, ctx.has_res)
-        dw = ops.conv3d_wgrad(desc, x, dy, weight.shape)
+        dw = _wgrad(desc, x, dy, weight)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = ops.conv3d_dgrad(desc, dy, _pack_cache.get(weight, desc, 1))
@@ -166,7 +202,7 @@ class ConvBNReLUPool(torch.autograd.Function):
         desc = ctx.desc
         dy, dgamma, dbeta = ops.bn_relu_maxpool_bwd(ctx.pdesc, dout.contiguous(), idx, y, scale, shift, mean, invstd,
                                                     gamma)
-        dw = ops.conv3d_wgrad(desc, x, dy, weight.shape)
+        dw = _wgrad(desc, x, dy, weight)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = ops.conv3d_dgrad(desc, dy, _pack_cache.get(weight, desc, 1))
