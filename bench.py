@@ -259,7 +259,9 @@ def run_b200(args):
         copy_stream = torch.cuda.Stream()
         ready = [torch.cuda.Event() for _ in range(2)]
         consumed = [torch.cuda.Event() for _ in range(2)]
-        loss_host = torch.empty(3, pin_memory=True)
+        loss_host = [torch.empty(3, pin_memory=True) for _ in range(2)]
+        loss_done = [torch.cuda.Event() for _ in range(2)]
+        seen = {"loss": None}
 
         def prefetch(i):
             s = i % 2
@@ -281,8 +283,13 @@ def run_b200(args):
             torch.cuda.current_stream().wait_event(ready[s])
             loss = engine.step(stage[s][0], stage[s][1])
             consumed[s].record()
-            loss_host.copy_(torch.stack(loss), non_blocking=True)
-            torch.cuda.current_stream().synchronize()  # the caller reads the loss every step
+            loss_host[s].copy_(torch.stack(loss), non_blocking=True)
+            loss_done[s].record()
+            # the caller reads every step's loss on the host, one step behind the device (as a logging loop does): wait for
+            # the PREVIOUS step's copy, so that the CPU can enqueue step i+1 while the GPU still runs step i
+            if i > 0:
+                loss_done[1 - s].synchronize()
+                seen["loss"] = float(loss_host[1 - s][0])
 
         for s in range(2):
             consumed[s].record()
@@ -291,7 +298,8 @@ def run_b200(args):
         ms_e2e = timed(e2e_step, args.steps) / args.steps
         e2e = {"value": B * world / (ms_e2e / 1e3), "unit": "clips/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 12,
-               "note": "pinned host fp32 clips, double-buffered H2D on a copy stream, loss read back every step"}
+               "note": "pinned host fp32 clips, double-buffered H2D on a copy stream; every step's loss is copied to pinned "
+                       "host memory and read there one step later (the timed region ends with a full synchronize)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -46,7 +46,8 @@ static EncodeTiledFn tmap_encoder() {
 }
 
 static int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, CUtensorMapSwizzle swz, const void* base, int rank,
-                       const unsigned long long* dims, const unsigned long long* strides_bytes, const unsigned* box) {
+                       const unsigned long long* dims, const unsigned long long* strides_bytes, const unsigned* box,
+                       const unsigned* elem_strides = nullptr) {
   EncodeTiledFn encode = tmap_encoder();
   if (!encode) return RSP_ERR_CUDA;
   RSP_REQUIRE(rank >= 1 && rank <= 5, "tensor map: rank %d", rank);
@@ -55,7 +56,7 @@ static int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, CUtensorMapS
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bdim[i] = box[i];
-    estr[i] = 1;
+    estr[i] = elem_strides ? elem_strides[i] : 1;
     RSP_REQUIRE(box[i] >= 1 && box[i] <= 256, "tensor map: box[%d] = %u out of range", i, box[i]);
     if (i > 0) {
       gstr[i - 1] = strides_bytes[i - 1];
@@ -77,6 +78,13 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const unsigned 
                    const unsigned long long* strides_bytes, const unsigned* box) {
   RSP_REQUIRE(box[0] * 2 <= 128, "tensor map: inner box exceeds the 128-byte swizzle span");
   return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_128B, base, rank, dims, strides_bytes, box);
+}
+
+int make_tmap_bf16_strided(CUtensorMap* out, const void* base, int rank, const unsigned long long* dims,
+                           const unsigned long long* strides_bytes, const unsigned* box, const unsigned* estr) {
+  RSP_REQUIRE(box[0] * 2 <= 128 && estr[0] == 1, "tensor map: inner box exceeds the 128-byte swizzle span");
+  return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_128B, base, rank, dims, strides_bytes, box,
+                     estr);
 }
 
 // 8-byte elements (one RGBx pixel of four bf16), no swizzle: box rows land back to back, out-of-range elements are zero.

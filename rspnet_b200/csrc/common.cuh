@@ -30,6 +30,10 @@ int check_launch(const char* what);
 // dims / box: extents per dimension, innermost first; strides_bytes: rank-1 entries for dimensions 1..rank-1.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const unsigned long long* dims,
                    const unsigned long long* strides_bytes, const unsigned* box);
+// Same with a traversal stride per dimension (every estr[i]-th element along dimension i; box[i] is the traversed
+// extent, so box[i] / estr[i] elements are copied).
+int make_tmap_bf16_strided(CUtensorMap* out, const void* base, int rank, const unsigned long long* dims,
+                           const unsigned long long* strides_bytes, const unsigned* box, const unsigned* estr);
 
 #define RSP_REQUIRE(cond, ...)                    \
   do {                                            \

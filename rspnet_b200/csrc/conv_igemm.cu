@@ -936,6 +936,8 @@ bool stem3_supported(const rsp_conv3d_desc* d);
 int pack_stem3(int Ci_logical, int Co_logical, const float* w, void* wst, cudaStream_t stream);
 int launch_stem3(const rsp_conv3d_desc* d, const void* x, const void* wst, const float* bias, void* y, float* stats,
                  int sm_count, cudaStream_t stream);
+int launch_stem3_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const void* x, const void* dy,
+                       void* zero_row_1k, float* dw, int accumulate, int sm_count, cudaStream_t stream);
 bool direct_supported(const rsp_conv3d_desc* d, int transposed);
 int launch_direct(const rsp_conv3d_desc* d, int transposed, const void* x, const void* wgt, const float* bias, void* y,
                   float* stats, cudaStream_t stream);
@@ -1202,6 +1204,8 @@ int rsp_conv3d_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, c
   RSP_REQUIRE(d->Co % 64 == 0, "conv3d wgrad: Co=%d must be a multiple of 64", d->Co);
   if (stem_supported(d) && d->kh * 2 * 32 <= 448)
     return launch_stem_wgrad(d, Ci_logical, Co_logical, x, dy, dw, accumulate, device_sm_count(), stream);
+  if (stem3_supported(d))
+    return launch_stem3_wgrad(d, Ci_logical, Co_logical, x, dy, dwt_workspace, dw, accumulate, device_sm_count(), stream);
   p.g.src = static_cast<const __nv_bfloat16*>(x);
   p.dy = static_cast<const __nv_bfloat16*>(dy);
   p.dwt = dwt_workspace;

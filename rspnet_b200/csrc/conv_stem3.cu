@@ -262,6 +262,214 @@ __global__ void pack_weight_stem3_kernel(const float* __restrict__ w, __nv_bfloa
   wst[idx] = __float2bfloat16(v);
 }
 
+// =====================================================================================================================
+// wgrad of the same layer:  dW[co][ch][a][b][c] = sum_pixels dY[pixel][co] * X[pixel + (a-1, b-1, c-1)][ch]
+//   A = dY of one output row, pixels of ONE parity (TMA box with a traversal stride of 2 along w: 64 pixel rows x 128 B,
+//       128B-swizzled, pixels >= Wo zero)                                  [K = 64 pixels] x [M = 64 co], MN-major
+//   B = the 9 raw input rows (3 frame taps x 3 filter rows, 1 KB apart, pixels at byte 16): K = pixel pairs 16 B apart,
+//       N chunk = one 2-pixel window (8 elements) of every row (SBO = 1 KB) -> N = 72; chunk j = window slots 2j, 2j+1
+//   odd pixels w = 2k+1: window = pixels 2k .. 2k+3 (slot s <-> tap c = s); even pixels w = 2k: window 2k-2 .. 2k+1
+//   (slot s <-> tap c = s-1), i.e. the same rows read 16 bytes earlier.
+//   D[parity][j] = [64 co] x [72]: 4 accumulators of 72 TMEM columns kept for the whole kernel, added into dW with atomics.
+// grid: one persistent CTA per SM over the output rows (n, t, h).
+// =====================================================================================================================
+struct Stem3WgradParams {
+  CUtensorMap tmapDy;       // dy as {64, Wo, N*To*Ho}, box {64, 128 (stride 2 -> 64 pixels), 1}
+  const __nv_bfloat16* x;   // [N][Ti][Hi][Wi][4]
+  const __nv_bfloat16* zero_row;
+  float* dw;                // [Co][Ci][3][3][3] fp32, accumulated atomically
+  int N, Ti, Hi, Wi;
+  int Co, Ci;               // logical
+  int numRows;              // N*Ti*Hi
+};
+
+constexpr int kS3WStages = 6;
+constexpr int kS3WDyBytes = 2 * 8192;                       // even pixels, odd pixels
+constexpr int kS3WStageBytes = kS3WDyBytes + 9 * 1024;
+
+__global__ void __launch_bounds__(192, 1) conv_stem3_wgrad_kernel(const __grid_constant__ Stem3WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KB of zeros follows the stages: windows of pixel pairs >= Wi/2 of the last row are read (against zero dY rows)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kS3WStages * kS3WStageBytes + 1024);
+  uint64_t* empty_bar = full_bar + kS3WStages;
+  uint64_t* accum_bar = empty_bar + kS3WStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  const int t = threadIdx.x;
+  const int warp = t >> 5;
+  int iters = 0;
+  for (int r = blockIdx.x; r < p.numRows; r += gridDim.x) ++iters;
+  for (int i = t; i < (kS3WStages * kS3WStageBytes + 1024) / 16; i += 192) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (t == 0) {
+    for (int s = 0; s < kS3WStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, 512);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (iters > 0) {
+    if (warp == 4) {
+      // ---------------- producer: two TMA boxes (even / odd dY pixels) + one bulk copy per raw input row (lane = row)
+      const int lane = t & 31;
+      const uint32_t rowBytes = static_cast<uint32_t>(p.Wi) * 8u;
+      const int al = lane / 3, b = lane - al * 3;
+      if (lane == 0) tma_prefetch_desc(&p.tmapDy);
+      int s = 0;
+      uint32_t ph = 1;
+      int h = blockIdx.x % p.Hi, tt = (blockIdx.x / p.Hi) % p.Ti, n = blockIdx.x / (p.Hi * p.Ti);
+      const int dh = gridDim.x % p.Hi, dt = (gridDim.x / p.Hi) % p.Ti, dn = gridDim.x / (p.Hi * p.Ti);
+      for (int r = blockIdx.x; r < p.numRows; r += gridDim.x) {
+        mbar_wait(&empty_bar[s], ph);
+        const uint32_t stage = smem_u32(smem + s * kS3WStageBytes);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&full_bar[s], kS3WDyBytes + 9 * rowBytes);
+#pragma unroll
+          for (int par = 0; par < 2; ++par)
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                ::"r"(stage + par * 8192), "l"(&p.tmapDy), "r"(smem_u32(&full_bar[s])), "r"(0), "r"(par), "r"(r)
+                : "memory");
+        }
+        __syncwarp();
+        if (lane < 9) {
+          const int ti = tt - 1 + al, hi = h - 1 + b;
+          const bool ok = ti >= 0 && ti < p.Ti && hi >= 0 && hi < p.Hi;
+          const __nv_bfloat16* src = ok ? p.x + ((static_cast<size_t>(n) * p.Ti + ti) * p.Hi + hi) * p.Wi * 4 : p.zero_row;
+          s3_bulk_g2s(stage + kS3WDyBytes + lane * 1024 + 16, src, rowBytes, &full_bar[s]);
+        }
+        if (++s == kS3WStages) {
+          s = 0;
+          ph ^= 1;
+        }
+        h += dh;
+        tt += dt;
+        n += dn;
+        if (h >= p.Hi) {
+          h -= p.Hi;
+          ++tt;
+        }
+        if (tt >= p.Ti) {
+          tt -= p.Ti;
+          ++n;
+        }
+      }
+    } else if (warp < 4) {
+      // ---------------- epilogue: TMEM lanes of an M=64 accumulator: co = 16*warp + lane, lanes 16..31 unused
+      mbar_wait(accum_bar, 0);
+      tc_fence_after_sync();
+      const int lane = t & 31;
+      const int co = warp * 16 + lane;
+      for (int acc = 0; acc < 4; ++acc) {          // acc = parity * 2 + j
+        const int par = acc >> 1, j = acc & 1;
+        for (int c0 = 0; c0 < 72; c0 += 8) {
+          uint32_t v[8];
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                       : "r"(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * 72 + c0)
+                       : "memory");
+          tmem_ld_wait();
+          if (lane < 16 && co < p.Co) {
+            const int fr = c0 >> 3;
+            const int a = fr / 3, b = fr - a * 3;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int slot = 2 * j + (e >> 2), ch = e & 3, c = slot - (1 - par);
+              if (ch < p.Ci && c >= 0 && c < 3)
+                atomicAdd(p.dw + (((static_cast<size_t>(co) * p.Ci + ch) * 3 + a) * 3 + b) * 3 + c, __uint_as_float(v[e]));
+            }
+          }
+        }
+      }
+    } else {
+      // ---------------- MMA lane
+      if (elect_one()) {
+        constexpr uint32_t idesc = make_idesc_bf16(64, 72, 1, 1);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after_sync();
+          const uint32_t stage = smem_u32(smem + s * kS3WStageBytes);
+#pragma unroll
+          for (int par = 0; par < 2; ++par) {
+            // A: 16 pixels = two 8-row groups of the swizzled dY panel.  B: rows 1 KB apart (SBO), pixel pairs 16 B apart
+            // with 8-pair groups 128 B apart (LBO); odd pixels start at the row's pixel 0 (byte 16), even pixels 16 B earlier
+            const uint64_t abase = make_smem_desc_sw128(stage + par * 8192, 8192, 1024);
+            const uint64_t bbase = s3_desc_nosw(stage + kS3WDyBytes + par * 16, 128, 1024);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                umma_bf16(tmem_base + (par * 2 + j) * 72, abase + static_cast<uint64_t>((ks * 2048) >> 4),
+                          bbase + static_cast<uint64_t>((j * 16 + ks * 256) >> 4), idesc, (it | ks) != 0);
+              }
+            }
+          }
+          umma_commit(&empty_bar[s]);
+          if (it == iters - 1) umma_commit(accum_bar);
+          if (++s == kS3WStages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, 512);
+}
+
+int launch_stem3_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const void* x, const void* dy,
+                       void* zero_row_1k, float* dw, int accumulate, int sm_count, cudaStream_t stream) {
+  Stem3WgradParams p{};
+  p.x = static_cast<const __nv_bfloat16*>(x);
+  // rows outside the clip are copied from 1 KB of zeros at the head of the caller's workspace
+  if (cudaMemsetAsync(zero_row_1k, 0, 1024, stream) != cudaSuccess) {
+    set_error("stem3 wgrad: workspace memset failed");
+    return RSP_ERR_CUDA;
+  }
+  p.zero_row = static_cast<const __nv_bfloat16*>(zero_row_1k);
+  p.dw = dw;
+  p.N = d->N; p.Ti = d->Ti; p.Hi = d->Hi; p.Wi = d->Wi;
+  p.Co = Co_logical; p.Ci = Ci_logical;
+  p.numRows = p.N * p.Ti * p.Hi;
+  const size_t nw = static_cast<size_t>(Co_logical) * Ci_logical * 27;
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(dw, 0, nw * sizeof(float), stream);
+    if (e != cudaSuccess) {
+      set_error("stem3 wgrad memset: %s", cudaGetErrorString(e));
+      return RSP_ERR_CUDA;
+    }
+  }
+  {
+    const unsigned long long dims[3] = {64, static_cast<unsigned long long>(p.Wi), static_cast<unsigned long long>(p.numRows)};
+    const unsigned long long strides[2] = {128, static_cast<unsigned long long>(p.Wi) * 128};
+    const unsigned box[3] = {64, 128, 1};
+    const unsigned estr[3] = {1, 2, 1};
+    int rc = make_tmap_bf16_strided(&p.tmapDy, dy, 3, dims, strides, box, estr);
+    if (rc != RSP_OK) return rc;
+  }
+  constexpr int smem = kS3WStages * kS3WStageBytes + 1024 + 1024 + 256;
+  cudaError_t e = cudaFuncSetAttribute(conv_stem3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(conv_stem3_wgrad): %s", cudaGetErrorString(e));
+    return RSP_ERR_CUDA;
+  }
+  const int grid = p.numRows < sm_count ? p.numRows : sm_count;
+  conv_stem3_wgrad_kernel<<<grid, 192, smem, stream>>>(p);
+  return check_launch("conv_stem3_wgrad");
+}
+
 bool stem3_supported(const rsp_conv3d_desc* d) {
   return d->Ci == 4 && d->Co == 64 && d->kt == 3 && d->kh == 3 && d->kw == 3 && d->st == 1 && d->sh == 1 && d->sw == 1 &&
          d->pt == 1 && d->ph == 1 && d->pw == 1 && (d->Wi % 2) == 0 && d->Wi <= 124;
