@@ -138,7 +138,9 @@ def run_reference(args):
         "impl": "reference", "metric": "pretrain clips/sec", "value": v, "unit": "clips/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": f"RSPNet {args.arch} pretraining step, 16x112x112 clips (CPU sample: batch {batch})"},
+        "config": {"workload": f"RSPNet {args.arch} pretraining step (MoCoDiffLossTwoFc), per-GPU batch {args.batch} videos, "
+                               f"2x{args.frames // 2}x{args.size}x{args.size} clips, K={HYPER['K']}, dim 128",
+                   "sample": f"each CPU step is a batch of {batch} videos of that workload (same clip size, K and loss)"},
         "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -355,6 +357,8 @@ def conv_roofline(args, B, ms_step):
     ops.conv3d_fprop = orig
     del net
     tot_ms = {"fprop": 0.0, "dgrad": 0.0, "wgrad": 0.0}
+    per_launch = []   # (ms weighted as in a step, pass, layer, GFLOP, ms per launch)
+    weight = {"fprop": 3, "dgrad": 1, "wgrad": 1}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for li, (desc, xshape, _) in enumerate(shapes):
         x = torch.randn(xshape, device="cuda").bfloat16()
@@ -377,13 +381,27 @@ def conv_roofline(args, B, ms_step):
                 fn()
             e1.record()
             torch.cuda.synchronize()
-            tot_ms[name] += e0.elapsed_time(e1) / 3
+            ms = e0.elapsed_time(e1) / 3
+            tot_ms[name] += ms
+            to, ho, wo = desc.out_dims()
+            gf = 2.0 * desc.N * to * ho * wo * desc.Co * ci_l * desc.kt * desc.kh * desc.kw / 1e9
+            per_launch.append((ms * weight[name], name, li, gf, ms))
         del x, y, dy, w, wp
     conv_ms = 3 * tot_ms["fprop"] + tot_ms["dgrad"] + tot_ms["wgrad"]
     flops = (3 * fwd + (2 * fwd - first)) * 1e9 * B
     achieved = flops / (conv_ms / 1e3) / 1e12
+    per_launch.sort(reverse=True)
+    top = [{"pass": n, "conv_layer": li, "gflop_per_launch": round(gf, 1), "ms_per_launch": round(ms, 4),
+            "tflops": round(gf / ms, 1), "frac": round(gf / ms / peak, 3), "launches_per_step": weight[n]}
+           for _, n, li, gf, ms in per_launch[:4]]
+    # DRAM traffic of the most expensive single launch (R3D-18 stem fprop, batch 64) from the committed ncu --set full capture
+    traffic = 4.61e8 if (args.arch == "resnet18" and B == 64 and args.size == 112) else None
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": src, "kernel": "conv_igemm_kernel / conv_wgrad_kernel (tcgen05)",
+            "traffic": traffic,
+            "traffic_note": "dram__bytes_read+write of one conv_stem_kernel launch (algorithmic 5.14e8: 1.03e8 in, 4.11e8 out), "
+                            "profiles/r01_ncu_full_conv_r18.txt" if traffic else None,
+            "peak_source": src, "kernel": "tcgen05 conv kernels (conv_direct / conv_igemm / conv_stem / conv_stem3 / conv_wgrad)",
+            "top_launches": top,
             "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / ms_step,
             "per_pass_ms": tot_ms, "algorithmic_gflop_per_step": flops / 1e9}
 
