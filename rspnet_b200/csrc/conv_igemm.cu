@@ -906,11 +906,23 @@ static int launch_wgrad(WgradParams& p, int sm_count, cudaStream_t stream) {
   }
   const int mt = (p.g.numKb + 1) / 2, nt = p.Nout / NT;
   const long long totalPb = (p.g.M + 63) / 64;
-  // enough pixel splits for ~2 waves of CTAs (2 CTAs/SM), at least 8 pixel blocks per split
-  long long splits = (4ll * sm_count + mt * nt - 1) / (mt * nt);
-  if (splits > (totalPb + 7) / 8) splits = (totalPb + 7) / 8;
-  if (splits < 1) splits = 1;
-  if (splits > 65535) splits = 65535;
+  // pixel splits: the CTAs run in waves of 2 per SM, so pick the split count that minimises
+  // (number of waves) x (pixel blocks per CTA + a fixed per-CTA cost for the prologue and the atomic epilogue);
+  // at least 8 pixel blocks per split.  (602 CTAs on 592 slots is three waves, 588 is two.)
+  const long long slots = 2ll * sm_count, tiles = static_cast<long long>(mt) * nt;
+  long long maxSplits = (totalPb + 7) / 8;
+  if (maxSplits < 1) maxSplits = 1;
+  if (maxSplits > 4096) maxSplits = 4096;
+  long long splits = 1, best = -1;
+  for (long long sp = 1; sp <= maxSplits; ++sp) {
+    const long long waves = (tiles * sp + slots - 1) / slots;
+    const long long cost = waves * ((totalPb + sp - 1) / sp + 24);
+    if (best < 0 || cost < best) {
+      best = cost;
+      splits = sp;
+    }
+    if (tiles * sp > 8 * slots) break;
+  }
   p.pbPerSplit = static_cast<int>((totalPb + splits - 1) / splits);
   splits = (totalPb + p.pbPerSplit - 1) / p.pbPerSplit;
   dim3 grid(mt, nt, static_cast<unsigned>(splits));
