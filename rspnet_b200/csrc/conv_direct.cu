@@ -100,14 +100,17 @@ __global__ void __launch_bounds__(kDirThreads, 1) conv_direct_kernel(const __gri
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  // work item -> (ntile, n, to, group); group fastest so that neighbouring CTAs share planes and filters in L2
+  // work item -> (group, to, ntile, n) with n fastest.  Items differ in cost (the last group of a plane has fewer position
+  // chunks, the first / last frame skips a frame tap); a CTA takes every gridDim.x-th item, so the cost classes are the
+  // slow indices: every CTA then gets its share of each class, and neighbouring CTAs still share the filter tile in L2.
+  const int ntiles = p.Nout / NT;
   auto decode_item = [&](int it, int& nt, int& n, int& to, int& grp) {
-    grp = it % p.groups;
-    int q = it / p.groups;
+    n = it % p.N;
+    int q = it / p.N;
+    nt = q % ntiles;
+    q /= ntiles;
     to = q % p.To;
-    q /= p.To;
-    n = q % p.N;
-    nt = q / p.N;
+    grp = q / p.To;
   };
 
   if (warp == 4) {

@@ -327,28 +327,32 @@ int pack_stem(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const fl
 
 // =====================================================================================================================
 // Stem wgrad with the same raw-row trick:  dW[co][c][a][b][kw] = sum_pixels dY[pixel][co] * X[patch(pixel)][kw, c].
-//   A = dY row panel   [64 px (K)] x [64 co (M)]   MN-major, 128 B swizzle (one pixel = one 128 B row)
-//   B = raw input row  [64 px (K)] x [32 k-slots (N)] MN-major, no swizzle: pixel pitch 16 B (K), 8-element N chunks 16 B
-//       apart (overlapping windows), 8-pixel K groups 128 B apart
-//   D = [64 co] x [32] per filter row (a, b); one CTA keeps the accumulators of two frame taps (2*kh*32 <= 448 TMEM
-//       columns) while it streams output rows, then adds them into dW with fp32 atomics.
-// grid: x = workers over output rows, y = pairs of frame taps.
+//   A = raw input rows of up to 32 filter rows (a, b)   [64 px (K)] x [M = 16 rows x 8 k-slots], MN-major, no swizzle:
+//       pixel pitch 16 B (K; overlapping windows), 8-pixel K groups 128 B apart (LBO), the same 2-pixel window of the
+//       next filter row 1 KB further (SBO) -> one instruction covers 16 filter rows (M = 128)
+//   B = dY row panel   [64 px (K)] x [64 co (N)]   MN-major, 128 B swizzle (one pixel = one 128 B row; TMA box, pixels
+//       >= Wo zero-filled)
+//   D[set][j] = [16 rows x 8 slots] x [64 co]: window chunk j (slots 2j, 2j+1) of filter-row set `set`; a CTA keeps
+//       2 sets x 4 chunks = 512 TMEM columns while it streams output rows, then adds them into dW with fp32 atomics.
+// The 49 filter rows are split over two groups of CTAs (25 + 24 rows), so dY is read twice (an M = 64 formulation with
+// the roles swapped needs four groups and runs the tensor core at half rate).
+// grid: x = workers over output rows within a group, y = group.
 // =====================================================================================================================
 struct StemWgradParams {
   CUtensorMap tmapDy;       // dy as {64, Wo, N*To*Ho}, box {64, 64, 1}: one output row per copy, pixels >= Wo zero-filled
   const __nv_bfloat16* x;   // [N][Ti][Hi][Wi][4]
-  const __nv_bfloat16* dy;  // [N][To][Ho][Wo][64]
   float* dw;                // [Co][Ci][kt][kh][kw] fp32, accumulated atomically
   int N, Ti, Hi, Wi, To, Ho, Wo;
   int kt, kh, kw, st, sh, pt, ph;
   int Co, Ci;               // logical
   int numRows;              // N*To*Ho
+  int rowsPerGroup;         // filter rows (a, b) per CTA group (<= 32)
 };
 
-constexpr int kSWStages = 6;
+constexpr int kSWStages = 5;
 constexpr int kSWDyBytes = 64 * 128;
-constexpr int kSWRowsMax = 14;
-constexpr int kSWStageBytes = kSWDyBytes + kSWRowsMax * kStemRowBytes;
+constexpr int kSWRowSlots = 32;
+constexpr int kSWStageBytes = kSWDyBytes + kSWRowSlots * kStemRowBytes;
 
 __global__ void __launch_bounds__(192, 1) conv_stem_wgrad_kernel(const __grid_constant__ StemWgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -362,12 +366,14 @@ __global__ void __launch_bounds__(192, 1) conv_stem_wgrad_kernel(const __grid_co
 
   const int t = threadIdx.x;
   const int warp = t >> 5;
-  const int a0 = blockIdx.y * 2;                       // first frame tap of this CTA
-  const int na = (p.kt - a0) < 2 ? (p.kt - a0) : 2;    // frame taps handled (1 or 2)
-  const int nrows = na * p.kh;                         // filter rows = accumulators
+  const int frTotal = p.kt * p.kh;
+  const int f0 = blockIdx.y * p.rowsPerGroup;                               // first filter row of this CTA
+  const int nr = (frTotal - f0) < p.rowsPerGroup ? (frTotal - f0) : p.rowsPerGroup;
+  const int nsets = (nr + 15) >> 4;                                          // 1 or 2 sets of 16 filter rows
   int iters = 0;
   for (int r = blockIdx.x; r < p.numRows; r += gridDim.x) ++iters;
 
+  // zero everything once: halo pixel slots and unused row slots are never written afterwards
   for (int i = t; i < (kSWStages * kSWStageBytes + 1024) / 16; i += 192)
     reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (t == 0) {
@@ -385,15 +391,14 @@ __global__ void __launch_bounds__(192, 1) conv_stem_wgrad_kernel(const __grid_co
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (iters > 0) {
+  if (iters > 0 && nr > 0) {
     if (warp == 4) {
       // ---------------- producer: one TMA box for the dY row, one bulk copy per raw input row (lane fr owns filter row fr)
       const int lane = t & 31;
       const uint32_t rowBytes = static_cast<uint32_t>(p.Wi) * 8u;
-      const int al = lane / p.kh, b = lane - al * p.kh;
+      const int fr = f0 + lane;
+      const int al = fr / p.kh, b = fr - al * p.kh;
       if (lane == 0) tma_prefetch_desc(&p.tmapDy);
-      // (n, to, ho) of output row r advance incrementally: the producer is a single serial instruction stream and four
-      // integer divisions per stage were most of it
       int s = 0;
       uint32_t ph = 0;
       int ho = blockIdx.x % p.Ho, to = (blockIdx.x / p.Ho) % p.To, n = blockIdx.x / (p.Ho * p.To);
@@ -401,9 +406,9 @@ __global__ void __launch_bounds__(192, 1) conv_stem_wgrad_kernel(const __grid_co
       for (int r = blockIdx.x; r < p.numRows; r += gridDim.x) {
         mbar_wait(&empty_bar[s], ph ^ 1);
         const uint32_t stage = smem_u32(smem + s * kSWStageBytes);
-        const int ti = to * p.st - p.pt + a0 + al;
+        const int ti = to * p.st - p.pt + al;
         const int hi = ho * p.sh - p.ph + b;
-        const bool mine = lane < nrows;
+        const bool mine = lane < nr;
         const bool ok = mine && ti >= 0 && ti < p.Ti && hi >= 0 && hi < p.Hi;
         const unsigned okmask = __ballot_sync(0xffffffffu, ok);
         const unsigned zmask = __ballot_sync(0xffffffffu, mine && !ok);
@@ -443,36 +448,38 @@ __global__ void __launch_bounds__(192, 1) conv_stem_wgrad_kernel(const __grid_co
         }
       }
     } else if (warp < 4) {
-      // ---------------- epilogue: TMEM lanes of an M=64 accumulator: co = 16*warp + lane, lanes 16..31 unused
+      // ---------------- epilogue: D lane = (filter row within the set) * 8 + k-slot element, columns = co
       mbar_wait(accum_bar, 0);
       tc_fence_after_sync();
       const int lane = t & 31;
-      const int co = warp * 16 + lane;
-      const int ncol = nrows * 8;
-      for (int j = 0; j < 4; ++j) {
-        for (int c0 = 0; c0 < ncol; c0 += 8) {
-          uint32_t v[8];
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                       : "r"(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + j * ncol + c0)
-                       : "memory");
-          tmem_ld_wait();
-          if (lane < 16 && co < p.Co) {
-            const int fr = c0 >> 3;
-            const int a = a0 + fr / p.kh, b = fr % p.kh;
+      const int l = warp * 32 + lane;
+      const int frl = l >> 3, e = l & 7;
+      const int ch = e & 3;
+      for (int set = 0; set < nsets; ++set) {
+        const int fr = f0 + set * 16 + frl;
+        const bool row_ok = (set * 16 + frl) < nr;
+        const int a = fr / p.kh, b = fr - a * p.kh;
+        for (int j = 0; j < 4; ++j) {
+          const int c = 2 * j + (e >> 2) - 1;           // window slot 2j + e/4 holds tap c = slot - 1
+          const bool ok = row_ok && ch < p.Ci && c >= 0 && c < p.kw;
+          float* dst = p.dw + ((static_cast<size_t>(ok ? ch : 0) * p.kt + (ok ? a : 0)) * p.kh + (ok ? b : 0)) * p.kw + (ok ? c : 0);
+          const size_t co_stride = static_cast<size_t>(p.Ci) * p.kt * p.kh * p.kw;
+#pragma unroll 1
+          for (int c0 = 0; c0 < 64; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + (set * 4 + j) * 64 + c0, v);
+            tmem_ld_wait();
+            if (ok) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int slot = 2 * j + (e >> 2), ch = e & 3, c = slot - 1;
-              if (ch < p.Ci && c >= 0 && c < p.kw)
-                atomicAdd(p.dw + (((static_cast<size_t>(co) * p.Ci + ch) * p.kt + a) * p.kh + b) * p.kw + c,
-                          __uint_as_float(v[e]));
+              for (int q = 0; q < 32; ++q)
+                if (c0 + q < p.Co) atomicAdd(dst + static_cast<size_t>(c0 + q) * co_stride, __uint_as_float(v[q]));
             }
           }
         }
       }
     } else {
-      const int ncol = nrows * 8;                                    // accumulator columns per pixel-pair window
-      const uint32_t idesc = make_idesc_bf16(64, ncol, 1, 1);
+      // ---------------- MMA lane
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
       const bool leader = elect_one();
       int s = 0;
       uint32_t ph = 0;
@@ -481,17 +488,19 @@ __global__ void __launch_bounds__(192, 1) conv_stem_wgrad_kernel(const __grid_co
         fence_proxy_async_smem();
         tc_fence_after_sync();
         const uint32_t stage = smem_u32(smem + s * kSWStageBytes);
-        // A: 16 pixels = two 8-row groups of the swizzled dY panel.
-        // B: N chunk = the same 2-pixel window (16 B) of every filter row (rows are 1 KB apart -> SBO = 1024), so one
-        //    instruction covers all nrows filter rows (N = 8*nrows <= 112); K: 8-pixel groups 128 B apart (LBO).
-        const uint64_t abase = make_smem_desc_sw128(stage, 8192, 1024);
-        const uint64_t bbase = make_smem_desc_nosw(stage + kSWDyBytes, 128, kStemRowBytes);
+        // A: raw rows; M chunk = the same 2-pixel window (16 B) of 16 consecutive filter rows (rows are 1 KB apart -> SBO),
+        //    K: pixels 16 B apart, 8-pixel groups 128 B apart (LBO).  B: 16 pixels = two 8-row groups of the dY panel.
+        const uint64_t abase = make_smem_desc_nosw(stage + kSWDyBytes, 128, kStemRowBytes);
+        const uint64_t bbase = make_smem_desc_sw128(stage, 8192, 1024);
+        for (int set = 0; set < nsets; ++set) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < 4; ++j) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            umma_bf16(tmem_base + j * ncol, abase + static_cast<uint64_t>((ks * 2048) >> 4),
-                      bbase + static_cast<uint64_t>((j * 16 + ks * 256) >> 4), idesc, (it | ks) != 0);
+            for (int ks = 0; ks < 4; ++ks) {
+              umma_bf16(tmem_base + (set * 4 + j) * 64,
+                        abase + static_cast<uint64_t>((set * 16 * kStemRowBytes + j * 16 + ks * 256) >> 4),
+                        bbase + static_cast<uint64_t>((ks * 2048) >> 4), idesc, (it | ks) != 0);
+            }
           }
         }
         umma_commit(&empty_bar[s]);
@@ -512,7 +521,6 @@ int launch_stem_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, 
                       float* dw, int accumulate, int sm_count, cudaStream_t stream) {
   StemWgradParams p{};
   p.x = static_cast<const __nv_bfloat16*>(x);
-  p.dy = static_cast<const __nv_bfloat16*>(dy);
   p.dw = dw;
   p.N = d->N; p.Ti = d->Ti; p.Hi = d->Hi; p.Wi = d->Wi;
   p.To = (d->Ti + 2 * d->pt - d->kt) / d->st + 1;
@@ -535,7 +543,9 @@ int launch_stem_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, 
     set_error("cudaFuncSetAttribute(conv_stem_wgrad): %s", cudaGetErrorString(e));
     return RSP_ERR_CUDA;
   }
-  const int groups = (d->kt + 1) / 2;
+  const int frTotal = d->kt * d->kh;
+  const int groups = (frTotal + kSWRowSlots - 1) / kSWRowSlots;
+  p.rowsPerGroup = (frTotal + groups - 1) / groups;
   int workers = sm_count / groups;
   if (workers < 1) workers = 1;
   if (workers > p.numRows) workers = p.numRows;
