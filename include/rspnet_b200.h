@@ -174,6 +174,13 @@ int rsp_ndhwc_bf16_to_ncdhw(const void* x, float* y, int32_t N, int32_t C, int32
 int rsp_clip_sample(const uint8_t* frames, const int32_t* frame_idx, const int32_t* box, const uint8_t* flags,
                     const float* mean3, const float* std3, int32_t n_clips, int32_t T, int32_t Hs, int32_t Ws,
                     int32_t S, int32_t layout, void* out, void* stream);
+/* The same with ColorJitter (transforms_tensor.py:54-145; colour kernels functional_tensor.py:88-162,253-415) between
+ * RandomGrayScale and the flip: jitter is a device table of n_clips records {float factor[4]; uint8 order[4]} — factors
+ * of brightness / contrast / saturation / hue and the order of application (op ids 0..3 in that sequence, 255 = skip);
+ * gray_sums: fp32 [n_clips] workspace (the contrast op blends with the clip-wide mean gray level, taken by a first pass). */
+int rsp_clip_sample_jitter(const uint8_t* frames, const int32_t* frame_idx, const int32_t* box, const uint8_t* flags,
+                           const void* jitter, float* gray_sums, const float* mean3, const float* std3, int32_t n_clips,
+                           int32_t T, int32_t Hs, int32_t Ws, int32_t S, int32_t layout, void* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * MoCo / RSP objective (reference: moco/builder_diffspeed_diffloss.py)

@@ -71,6 +71,8 @@ SIGNATURES = {
     "rsp_ndhwc_bf16_to_ncdhw": (c_i32, [_P, _P, c_i32, c_i32, c_i32, c_i64, _P]),
     "rsp_clip_sample": (c_i32, [_P, _P, _P, _P, C.POINTER(c_f32), C.POINTER(c_f32), c_i32, c_i32, c_i32, c_i32, c_i32,
                                 c_i32, _P, _P]),
+    "rsp_clip_sample_jitter": (c_i32, [_P, _P, _P, _P, _P, _P, C.POINTER(c_f32), C.POINTER(c_f32), c_i32, c_i32, c_i32,
+                                       c_i32, c_i32, c_i32, _P, _P]),
     "rsp_ema_update": (c_i32, [_P, _P, c_i64, c_f32, c_f32, _P]),
     "rsp_sgd_step": (c_i32, [_P, _P, _P, c_i64, c_f32, c_f32, c_f32, c_f32, c_i32, _P]),
     "rsp_speed_gather": (c_i32, [_P, _P, _P, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P, _P, _P, _P]),

@@ -710,11 +710,137 @@ struct ClipGeom {
   float mean[3], inv_std_unused[3], stdv[3];
 };
 
+// ColorJitter state of one clip (transforms_tensor.py:54-145): the four factors and the order in which the adjustments
+// are applied (op ids: 0 brightness, 1 contrast, 2 saturation, 3 hue, 255 = none).
+struct ClipJitter {
+  float factor[4];
+  uint8_t order[4];
+};
+
+__device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
+__device__ __forceinline__ float luma(const float (&v)[3]) { return 0.2989f * v[0] + 0.5870f * v[1] + 0.1140f * v[2]; }
+
+// functional_tensor.py:253-415: RGB -> HSV, h = (h + shift) mod 1, HSV -> RGB
+__device__ __forceinline__ void hue_shift(float (&v)[3], float shift) {
+  const float r = v[0], g = v[1], b = v[2];
+  const float maxc = fmaxf(r, fmaxf(g, b)), minc = fminf(r, fminf(g, b));
+  const float delta = maxc - minc;
+  const float sat = maxc == 0.f ? 0.f : delta / maxc;
+  float h;
+  if (delta == 0.f) h = 0.f;
+  else if (r == maxc) h = (g - b) / delta;           // torch.max returns the first maximal channel
+  else if (g == maxc) h = (b - r) / delta + 2.0f;
+  else h = (r - g) / delta + 4.0f;
+  h = h / 6.0f;
+  h = h - floorf(h);                                  // python-style mod 1
+  h = h + shift;
+  h = h - floorf(h);
+  const float h6 = h * 6.f;
+  const float hi = floorf(h6);
+  const float f = h6 - hi;
+  const float val = maxc;
+  const float vt[4] = {val, val * (1.f - (1.f - f) * sat), val * (1.f - sat), val * (1.f - f * sat)};
+  int idx = static_cast<int>(hi) % 6;
+  if (idx < 0) idx += 6;
+  const int map[3][6] = {{0, 3, 2, 2, 1, 0}, {1, 0, 0, 3, 2, 2}, {2, 2, 1, 0, 0, 3}};
+  v[0] = vt[map[0][idx]];
+  v[1] = vt[map[1][idx]];
+  v[2] = vt[map[2][idx]];
+}
+
+// Resized (bilinear, align_corners=False), optionally gray-scaled pixel of the cropped frame, in [0, 1].
+__device__ __forceinline__ void clip_pixel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ frame_idx,
+                                           const int32_t* __restrict__ box, uint8_t fl, const ClipGeom& g, int clip, int t,
+                                           int y, int xs, float (&v)[3]) {
+  const int bi = box[clip * 4 + 0], bj = box[clip * 4 + 1], bh = box[clip * 4 + 2], bw = box[clip * 4 + 3];
+  // torch upsample_bilinear2d, align_corners=False: src = scale*(dst+0.5)-0.5 clamped at 0
+  const float sh = static_cast<float>(bh) / g.S, sw = static_cast<float>(bw) / g.S;
+  float fy = sh * (y + 0.5f) - 0.5f, fx = sw * (xs + 0.5f) - 0.5f;
+  fy = fy < 0.f ? 0.f : fy;
+  fx = fx < 0.f ? 0.f : fx;
+  const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+  const int y1 = y0 + (y0 < bh - 1 ? 1 : 0), x1 = x0 + (x0 < bw - 1 ? 1 : 0);
+  const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
+  const uint8_t* f = frames + static_cast<size_t>(frame_idx[clip * g.T + t]) * g.Hs * g.Ws * 3;
+  const uint8_t* p00 = f + (static_cast<size_t>(bi + y0) * g.Ws + bj + x0) * 3;
+  const uint8_t* p01 = f + (static_cast<size_t>(bi + y0) * g.Ws + bj + x1) * 3;
+  const uint8_t* p10 = f + (static_cast<size_t>(bi + y1) * g.Ws + bj + x0) * 3;
+  const uint8_t* p11 = f + (static_cast<size_t>(bi + y1) * g.Ws + bj + x1) * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float a = p00[c] / 255.0f, b = p01[c] / 255.0f, cc = p10[c] / 255.0f, d = p11[c] / 255.0f;
+    v[c] = hy * (hx * a + lx * b) + ly * (hx * cc + lx * d);
+  }
+  if (fl & 2) {  // RandomGrayScale: ITU-R 601-2 luma, replicated on the three channels
+    const float gray = luma(v);
+    v[0] = v[1] = v[2] = gray;
+  }
+}
+
+// Applies the jitter ops order[first .. last) to one pixel; `mean` is the clip-wide gray mean the contrast op blends with.
+__device__ __forceinline__ void jitter_ops(float (&v)[3], const ClipJitter& jt, int first, int last, float mean) {
+  for (int k = first; k < last; ++k) {
+    const int op = jt.order[k];
+    const float fac = op < 4 ? jt.factor[op] : 0.f;
+    if (op == 0) {                     // adjust_brightness: blend with black
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[c] = clamp01(fac * v[c] + (1.f - fac) * 0.f);
+    } else if (op == 1) {              // adjust_contrast: blend with the mean gray level of the whole clip
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[c] = clamp01(fac * v[c] + (1.f - fac) * mean);
+    } else if (op == 2) {              // adjust_saturation: blend with the pixel's gray level
+      const float gray = luma(v);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[c] = clamp01(fac * v[c] + (1.f - fac) * gray);
+    } else if (op == 3) {
+      hue_shift(v, fac);
+    }
+  }
+}
+
+// Pass 1 (only when a contrast op is present): sum over the clip of the gray level right before the contrast op.
+__global__ void __launch_bounds__(256) clip_gray_sum_kernel(const uint8_t* __restrict__ frames,
+                                                            const int32_t* __restrict__ frame_idx,
+                                                            const int32_t* __restrict__ box,
+                                                            const uint8_t* __restrict__ flags,
+                                                            const ClipJitter* __restrict__ jitter, ClipGeom g,
+                                                            float* __restrict__ sums, int per_clip_blocks) {
+  const int clip = blockIdx.x / per_clip_blocks, blk = blockIdx.x - clip * per_clip_blocks;
+  const ClipJitter jt = jitter[clip];
+  int cpos = -1;
+  for (int k = 0; k < 4; ++k)
+    if (jt.order[k] == 1) cpos = k;
+  float acc = 0.f;
+  if (cpos >= 0) {
+    const int per = g.T * g.S * g.S;
+    const uint8_t fl = flags[clip];
+    for (int i = blk * 256 + threadIdx.x; i < per; i += per_clip_blocks * 256) {
+      const int x = i % g.S, y = (i / g.S) % g.S, t = i / (g.S * g.S);
+      float v[3];
+      clip_pixel(frames, frame_idx, box, fl, g, clip, t, y, x, v);   // the mean does not depend on the flip
+      jitter_ops(v, jt, 0, cpos, 0.f);
+      acc += luma(v);
+    }
+  }
+  __shared__ float red[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0 && cpos >= 0) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    atomicAdd(sums + clip, s);
+  }
+}
+
 template <int LAYOUT>
 __global__ void __launch_bounds__(256) clip_sample_kernel(const uint8_t* __restrict__ frames,
                                                           const int32_t* __restrict__ frame_idx,
                                                           const int32_t* __restrict__ box,
-                                                          const uint8_t* __restrict__ flags, ClipGeom g,
+                                                          const uint8_t* __restrict__ flags,
+                                                          const ClipJitter* __restrict__ jitter,
+                                                          const float* __restrict__ gray_sums, ClipGeom g,
                                                           void* __restrict__ outv, size_t total) {
   for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * 256) {
@@ -724,31 +850,13 @@ __global__ void __launch_bounds__(256) clip_sample_kernel(const uint8_t* __restr
     q /= g.S;
     const int t = static_cast<int>(q % g.T);
     const int clip = static_cast<int>(q / g.T);
-    const int bi = box[clip * 4 + 0], bj = box[clip * 4 + 1], bh = box[clip * 4 + 2], bw = box[clip * 4 + 3];
     const uint8_t fl = flags[clip];
     const int xs = (fl & 1) ? (g.S - 1 - x) : x;                 // horizontal flip acts on the resized clip
-    // torch upsample_bilinear2d, align_corners=False: src = scale*(dst+0.5)-0.5 clamped at 0
-    const float sh = static_cast<float>(bh) / g.S, sw = static_cast<float>(bw) / g.S;
-    float fy = sh * (y + 0.5f) - 0.5f, fx = sw * (xs + 0.5f) - 0.5f;
-    fy = fy < 0.f ? 0.f : fy;
-    fx = fx < 0.f ? 0.f : fx;
-    const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
-    const int y1 = y0 + (y0 < bh - 1 ? 1 : 0), x1 = x0 + (x0 < bw - 1 ? 1 : 0);
-    const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
-    const uint8_t* f = frames + static_cast<size_t>(frame_idx[clip * g.T + t]) * g.Hs * g.Ws * 3;
-    const uint8_t* p00 = f + (static_cast<size_t>(bi + y0) * g.Ws + bj + x0) * 3;
-    const uint8_t* p01 = f + (static_cast<size_t>(bi + y0) * g.Ws + bj + x1) * 3;
-    const uint8_t* p10 = f + (static_cast<size_t>(bi + y1) * g.Ws + bj + x0) * 3;
-    const uint8_t* p11 = f + (static_cast<size_t>(bi + y1) * g.Ws + bj + x1) * 3;
     float v[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float a = p00[c] / 255.0f, b = p01[c] / 255.0f, cc = p10[c] / 255.0f, d = p11[c] / 255.0f;
-      v[c] = hy * (hx * a + lx * b) + ly * (hx * cc + lx * d);
-    }
-    if (fl & 2) {  // RandomGrayScale: ITU-R 601-2 luma, replicated on the three channels
-      const float gray = 0.2989f * v[0] + 0.5870f * v[1] + 0.1140f * v[2];
-      v[0] = v[1] = v[2] = gray;
+    clip_pixel(frames, frame_idx, box, fl, g, clip, t, y, xs, v);
+    if (jitter) {
+      const float mean = gray_sums[clip] / (static_cast<float>(g.T) * g.S * g.S);
+      jitter_ops(v, jitter[clip], 0, 4, mean);
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) v[c] = (v[c] - g.mean[c]) / g.stdv[c];
@@ -770,11 +878,12 @@ __global__ void __launch_bounds__(256) clip_sample_kernel(const uint8_t* __restr
 
 }  // namespace rsp
 
-extern "C" int rsp_clip_sample(const uint8_t* frames, const int32_t* frame_idx, const int32_t* box,
-                               const uint8_t* flags, const float* mean3, const float* std3, int32_t n_clips, int32_t T,
-                               int32_t Hs, int32_t Ws, int32_t S, int32_t layout, void* out, void* stream) {
+static int clip_sample_impl(const uint8_t* frames, const int32_t* frame_idx, const int32_t* box, const uint8_t* flags,
+                            const void* jitter, float* gray_sums, const float* mean3, const float* std3, int32_t n_clips,
+                            int32_t T, int32_t Hs, int32_t Ws, int32_t S, int32_t layout, void* out, void* stream) {
   RSP_REQUIRE(n_clips >= 0 && T > 0 && Hs > 0 && Ws > 0 && S > 0, "clip_sample: bad sizes");
   RSP_REQUIRE(layout == 0 || layout == 1, "clip_sample: layout must be 0 (fp32 NCDHW) or 1 (bf16 NDHWC4)");
+  RSP_REQUIRE((jitter == nullptr) == (gray_sums == nullptr), "clip_sample: jitter and gray_sums go together");
   size_t total = static_cast<size_t>(n_clips) * T * S * S;
   if (total == 0) return rsp::RSP_OK;
   rsp::ClipGeom g{};
@@ -783,14 +892,43 @@ extern "C" int rsp_clip_sample(const uint8_t* frames, const int32_t* frame_idx, 
     g.mean[c] = mean3[c];
     g.stdv[c] = std3[c];
   }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const rsp::ClipJitter* jt = static_cast<const rsp::ClipJitter*>(jitter);
+  if (jt) {
+    if (cudaMemsetAsync(gray_sums, 0, sizeof(float) * n_clips, st) != cudaSuccess) {
+      rsp::set_error("clip_sample: memset failed");
+      return rsp::RSP_ERR_CUDA;
+    }
+    int per_clip_blocks = (T * S * S + 256 * 8 - 1) / (256 * 8);
+    if (per_clip_blocks < 1) per_clip_blocks = 1;
+    if (per_clip_blocks > 64) per_clip_blocks = 64;
+    rsp::clip_gray_sum_kernel<<<n_clips * per_clip_blocks, 256, 0, st>>>(frames, frame_idx, box, flags, jt, g, gray_sums,
+                                                                         per_clip_blocks);
+    int rc = rsp::check_launch("clip_gray_sum");
+    if (rc != rsp::RSP_OK) return rc;
+  }
   unsigned grid = rsp::ew_grid(total, 256);
   if (layout == 0)
-    rsp::clip_sample_kernel<0><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(frames, frame_idx, box, flags, g,
-                                                                                     out, total);
+    rsp::clip_sample_kernel<0><<<grid, 256, 0, st>>>(frames, frame_idx, box, flags, jt, gray_sums, g, out, total);
   else
-    rsp::clip_sample_kernel<1><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(frames, frame_idx, box, flags, g,
-                                                                                     out, total);
+    rsp::clip_sample_kernel<1><<<grid, 256, 0, st>>>(frames, frame_idx, box, flags, jt, gray_sums, g, out, total);
   return rsp::check_launch("clip_sample");
+}
+
+extern "C" int rsp_clip_sample(const uint8_t* frames, const int32_t* frame_idx, const int32_t* box,
+                               const uint8_t* flags, const float* mean3, const float* std3, int32_t n_clips, int32_t T,
+                               int32_t Hs, int32_t Ws, int32_t S, int32_t layout, void* out, void* stream) {
+  return clip_sample_impl(frames, frame_idx, box, flags, nullptr, nullptr, mean3, std3, n_clips, T, Hs, Ws, S, layout, out,
+                          stream);
+}
+
+extern "C" int rsp_clip_sample_jitter(const uint8_t* frames, const int32_t* frame_idx, const int32_t* box,
+                                      const uint8_t* flags, const void* jitter, float* gray_sums, const float* mean3,
+                                      const float* std3, int32_t n_clips, int32_t T, int32_t Hs, int32_t Ws, int32_t S,
+                                      int32_t layout, void* out, void* stream) {
+  RSP_REQUIRE(jitter && gray_sums, "clip_sample_jitter: jitter table and gray_sums workspace are required");
+  return clip_sample_impl(frames, frame_idx, box, flags, jitter, gray_sums, mean3, std3, n_clips, T, Hs, Ws, S, layout, out,
+                          stream);
 }
 
 // =====================================================================================================================

@@ -4,12 +4,14 @@ Host side: the reference's random decisions, drawn from python's ``random`` in t
 (SURVEY.md appendix B): per video ``RandomStrideCrop`` twice (two clips; datasets/transforms_video/
 transforms_temporal.py:25-50, fallback :16-22), then per clip ``RawVideoRandomCrop.get_params``
 (transforms_spatial.py:50-83), then per clip on the main process ``RandomGrayScale`` and
-``RandomHorizontalFlipVideo`` (transforms_tensor.py:13-31; torchvision).  Device side: ONE kernel
-(``rsp_clip_sample``) replaces the per-clip loop of ``SequentialGPUCollateFn`` (transforms_tensor.py:214-233):
-uint8 frame gather + crop + bilinear resize + gray + flip + normalise for the whole batch.
+``ColorJitter`` (four ``random.uniform`` factors then ``random.shuffle`` of the op list, transforms_tensor.py:97-125) and
+``RandomHorizontalFlipVideo`` (transforms_tensor.py:13-31; torchvision) — the order of the non-``aug_plus`` chain
+of datasets/classification/__init__.py:188-202.  Device side: ``rsp_clip_sample`` / ``rsp_clip_sample_jitter``
+replace the per-clip loop of ``SequentialGPUCollateFn`` (transforms_tensor.py:214-233): uint8 frame gather + crop +
+bilinear resize + gray + colour jitter + flip + normalise for the whole batch in one kernel (plus one reduction
+pass for the clip-wide gray mean the contrast op blends with).
 
-ColorJitter (brightness/contrast/saturation/hue in random order) is the "next" row of SURVEY.md §8f and is not
-implemented: construct the sampler from a config patched with ``add.no_color_jitter``.
+The ``aug_plus`` chain (RandomApply(ColorJitter) / GaussianBlur) is not implemented.
 """
 import ctypes as C
 import math
@@ -99,9 +101,53 @@ class RawVideoRandomCrop:
         return (height - h) // 2, (width - w) // 2, h, w
 
 
+JITTER_DTYPE = np.dtype([("factor", np.float32, (4,)), ("order", np.uint8, (4,))])   # struct ClipJitter of the C ABI
+JITTER_OPS = ("brightness", "contrast", "saturation", "hue")
+
+
+class ColorJitter:
+    """Random decisions of the reference's ColorJitter (transforms_tensor.py:54-145): ranges as ``_check_input`` builds
+    them, one ``random.uniform`` per enabled op in the fixed order brightness, contrast, saturation, hue, then
+    ``random.shuffle`` of the enabled ops."""
+
+    def __init__(self, brightness=0.0, contrast=0.0, saturation=0.0, hue=0.0):
+        self.ranges = [self._range(brightness, "brightness"), self._range(contrast, "contrast"),
+                       self._range(saturation, "saturation"),
+                       self._range(hue, "hue", center=0, bound=(-0.5, 0.5), clip_first_on_zero=False)]
+
+    @staticmethod
+    def _range(value, name, center=1, bound=(0, float("inf")), clip_first_on_zero=True):
+        if isinstance(value, (int, float)):
+            if value < 0:
+                raise ValueError("If {} is a single number, it must be non negative.".format(name))
+            value = [center - value, center + value]
+            if clip_first_on_zero:
+                value[0] = max(value[0], 0)
+        elif isinstance(value, (tuple, list)) and len(value) == 2:
+            if not bound[0] <= value[0] <= value[1] <= bound[1]:
+                raise ValueError("{} values should be between {}".format(name, bound))
+        else:
+            raise TypeError("{} should be a single number or a list/tuple with lenght 2.".format(name))
+        return None if value[0] == value[1] == center else value
+
+    def get_params(self):
+        """Returns (factor[4], order[4]) — op ids in application order, 255-padded."""
+        factor, ops = [0.0] * 4, []
+        for op, rng in enumerate(self.ranges):
+            if rng is not None:
+                factor[op] = random.uniform(rng[0], rng[1])
+                ops.append(op)
+        random.shuffle(ops)
+        if not -0.5 <= factor[3] <= 0.5:
+            raise ValueError("hue_factor is not in [-0.5, 0.5].")
+        return factor, ops + [255] * (4 - len(ops))
+
+
 def clip_sample(frames: torch.Tensor, frame_idx: torch.Tensor, boxes: torch.Tensor, flags: torch.Tensor,
-                mean: Sequence[float], std: Sequence[float], size: int, layout: int = 0) -> torch.Tensor:
-    """frames uint8 [F,H,W,3] (device); frame_idx int32 [n,T]; boxes int32 [n,4]; flags uint8 [n]."""
+                mean: Sequence[float], std: Sequence[float], size: int, layout: int = 0,
+                jitter: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """frames uint8 [F,H,W,3] (device); frame_idx int32 [n,T]; boxes int32 [n,4]; flags uint8 [n]; jitter: uint8
+    [n, 20] device view of a ``JITTER_DTYPE`` table, or None."""
     assert frames.dtype == torch.uint8 and frames.is_contiguous() and frames.shape[-1] == 3
     n, t = frame_idx.shape
     _, hs, ws, _ = frames.shape
@@ -112,9 +158,24 @@ def clip_sample(frames: torch.Tensor, frame_idx: torch.Tensor, boxes: torch.Tens
         out = torch.empty((n, t, size, size, 4), dtype=torch.bfloat16, device=dev)
     m3 = (C.c_float * 3)(*[float(v) for v in mean])
     s3 = (C.c_float * 3)(*[float(v) for v in std])
-    call("rsp_clip_sample", ptr(frames), ptr(frame_idx), ptr(boxes), ptr(flags), m3, s3, n, t, hs, ws, size, layout,
-         ptr(out), stream_ptr())
+    if jitter is None:
+        call("rsp_clip_sample", ptr(frames), ptr(frame_idx), ptr(boxes), ptr(flags), m3, s3, n, t, hs, ws, size,
+             layout, ptr(out), stream_ptr())
+    else:
+        assert jitter.dtype == torch.uint8 and jitter.shape == (n, JITTER_DTYPE.itemsize) and jitter.is_contiguous()
+        sums = torch.empty(n, dtype=torch.float32, device=dev)
+        call("rsp_clip_sample_jitter", ptr(frames), ptr(frame_idx), ptr(boxes), ptr(flags), ptr(jitter), ptr(sums),
+             m3, s3, n, t, hs, ws, size, layout, ptr(out), stream_ptr())
     return out
+
+
+def jitter_table(records) -> torch.Tensor:
+    """[(factor[4], order[4]), ...] -> host uint8 [n, 20] tensor laid out as ``struct ClipJitter``."""
+    tab = np.zeros(len(records), dtype=JITTER_DTYPE)
+    for i, (factor, order) in enumerate(records):
+        tab[i]["factor"] = factor
+        tab[i]["order"] = order
+    return torch.from_numpy(tab.view(np.uint8).reshape(len(records), JITTER_DTYPE.itemsize))
 
 
 class GPUClipSampler:
@@ -124,7 +185,14 @@ class GPUClipSampler:
 
     def __init__(self, size: int = 112, temporal_size: int = 32, strides=({'stride': 1, 'weight': 1},),
                  crop_scale=(0.4, 1.0), gray_p: float = 0.2, flip_p: float = 0.5,
-                 mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
+                 mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225), color_jitter=None):
+        """``color_jitter``: None (the ``no_color_jitter`` configs) or a dict / 4-tuple of ColorJitter arguments —
+        the reference's pretraining chain uses ``dict(brightness=.4, contrast=.4, saturation=.4, hue=.4)``."""
+        if isinstance(color_jitter, dict):
+            color_jitter = ColorJitter(**color_jitter)
+        elif isinstance(color_jitter, (tuple, list)):
+            color_jitter = ColorJitter(*color_jitter)
+        self.jitter = color_jitter
         self.size = size
         self.temporal = RandomStrideCrop(temporal_size, strides)
         self.crop = RawVideoRandomCrop(scale=crop_scale)
@@ -133,7 +201,7 @@ class GPUClipSampler:
 
     def draw(self, video_lengths: Sequence[int], height: int, width: int):
         """All random decisions for one batch, in the reference's order. Returns numpy arrays in clip-major layout
-        [2][B]: frame indices (video-relative), boxes, flags."""
+        [2][B]: frame indices (video-relative), boxes, flags, and the colour-jitter table (None without jitter)."""
         b = len(video_lengths)
         t = self.temporal.size
         idx = np.zeros((2, b, t), dtype=np.int32)
@@ -145,22 +213,26 @@ class GPUClipSampler:
                 idx[c, v] = self.temporal(base)
             for c in range(2):
                 box[c, v] = self.crop.get_params(height, width)
+        jit = [[None] * b, [None] * b] if self.jitter is not None else None
         for v in range(b):                                     # main process: per video, per clip GPU transforms
             for c in range(2):
                 gray = random.random() < self.gray_p
+                if jit is not None:
+                    jit[c][v] = self.jitter.get_params()
                 flip = random.random() < self.flip_p
                 flags[c, v] = (1 if flip else 0) | (2 if gray else 0)
-        return idx, box, flags
+        return idx, box, flags, (jitter_table(jit[0] + jit[1]) if jit is not None else None)
 
     def __call__(self, frames: torch.Tensor, video_offsets: Sequence[int], video_lengths: Sequence[int],
                  layout: int = 0):
         _, h, w, _ = frames.shape
-        idx, box, flags = self.draw(video_lengths, h, w)
+        idx, box, flags, jit = self.draw(video_lengths, h, w)
         b = len(video_lengths)
         idx = idx + np.asarray(video_offsets, dtype=np.int32)[None, :, None]
         dev = frames.device
         t_idx = torch.from_numpy(idx.reshape(2 * b, -1)).to(dev, non_blocking=True)
         t_box = torch.from_numpy(box.reshape(2 * b, 4)).to(dev, non_blocking=True)
         t_flags = torch.from_numpy(flags.reshape(2 * b)).to(dev, non_blocking=True)
-        out = clip_sample(frames, t_idx, t_box, t_flags, self.mean, self.std, self.size, layout)
+        t_jit = jit.to(dev, non_blocking=True) if jit is not None else None
+        out = clip_sample(frames, t_idx, t_box, t_flags, self.mean, self.std, self.size, layout, jitter=t_jit)
         return (out[:b], out[b:]), None

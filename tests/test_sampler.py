@@ -39,6 +39,100 @@ def test_fallback_select_edges():
         fallback_select(4, 1, 0)
 
 
+def test_color_jitter_draws_match_reference_fixture():
+    """gray -> 4 uniforms -> shuffle -> flip per clip, as the reference chain consumes python's random."""
+    from rspnet_b200.sampler import ColorJitter
+    g = torch.load(GOLDEN / "sampler_jitter.pt")
+    cj = ColorJitter(brightness=0.4, contrast=0.4, saturation=0.4, hue=0.4)
+    assert cj.ranges == [[0.6, 1.4], [0.6, 1.4], [0.6, 1.4], [-0.4, 0.4]]
+    random.seed(g["seed"])
+    for c in range(g["idx"].shape[0]):
+        gray = random.random() < 0.2
+        factor, order = cj.get_params()
+        flip = random.random() < 0.5
+        assert ((1 if flip else 0) | (2 if gray else 0)) == int(g["flags"][c])
+        assert factor == g["factors"][c].tolist() and order == g["orders"][c].tolist()
+    assert random.random() == g["end_state"]
+    assert ColorJitter().ranges == [None] * 4 and ColorJitter().get_params() == ([0.0] * 4, [255] * 4)
+    with pytest.raises(ValueError):
+        ColorJitter(brightness=-1)
+    with pytest.raises(ValueError):
+        ColorJitter(hue=(-0.7, 0.2))
+    with pytest.raises(TypeError):
+        ColorJitter(contrast="x")
+
+
+def test_sampler_draw_order_with_jitter():
+    """GPUClipSampler.draw: worker-side draws for every video first, then per clip gray / jitter / flip."""
+    from rspnet_b200.sampler import GPUClipSampler, JITTER_DTYPE
+    s = GPUClipSampler(size=16, temporal_size=4, color_jitter=dict(brightness=.4, contrast=.4, saturation=.4, hue=.4))
+    random.seed(5)
+    idx, box, flags, jit = s.draw([30, 40], 40, 52)
+    random.seed(5)
+    for n in (30, 40):
+        for _ in range(2):
+            s.temporal(np.arange(n))
+        for _ in range(2):
+            s.crop.get_params(40, 52)
+    tab = jit.numpy().view(JITTER_DTYPE).reshape(2, 2)
+    for v in range(2):
+        for c in range(2):
+            gray = random.random() < 0.2
+            factor, order = s.jitter.get_params()
+            flip = random.random() < 0.5
+            assert flags[c, v] == ((1 if flip else 0) | (2 if gray else 0))
+            assert tab[c, v]["factor"].tolist() == np.asarray(factor, dtype=np.float32).tolist()
+            assert tab[c, v]["order"].tolist() == order
+    assert jit.shape == (4, 20) and idx.shape == (2, 2, 4) and box.shape == (2, 2, 4)
+    plain = GPUClipSampler(size=16, temporal_size=4)
+    assert plain.draw([30], 40, 52)[3] is None
+
+
+def test_clip_oracle_matches_reference_chain():
+    from oracle import clip_oracle
+    g = torch.load(GOLDEN / "sampler_clip.pt")
+    for c in range(g["idx"].shape[0]):
+        out = clip_oracle.clip_chain(g["frames"], g["idx"][c], g["box"][c], g["flags"][c], g["mean"], g["std"], g["size"])
+        torch.testing.assert_close(out, g["out"][c], rtol=1e-6, atol=1e-6)
+    g = torch.load(GOLDEN / "sampler_jitter.pt")
+    for c in range(g["idx"].shape[0]):
+        out = clip_oracle.clip_chain(g["frames"], g["idx"][c], g["box"][c], g["flags"][c], g["mean"], g["std"], g["size"],
+                                     factor=g["factors"][c], order=g["orders"][c])
+        torch.testing.assert_close(out, g["out"][c], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_clip_kernel_color_jitter_matches_reference_chain():
+    """rsp_clip_sample_jitter against the unmodified reference chain (RandomGrayScale -> ColorJitter -> flip)."""
+    from rspnet_b200 import sampler
+    g = torch.load(GOLDEN / "sampler_jitter.pt")
+    n = g["idx"].shape[0]
+    tab = sampler.jitter_table([(g["factors"][c].tolist(), g["orders"][c].tolist()) for c in range(n)]).cuda()
+    args = (g["frames"].cuda(), g["idx"].cuda(), g["box"].cuda(), g["flags"].cuda(), g["mean"], g["std"], g["size"])
+    out = sampler.clip_sample(*args, layout=0, jitter=tab).cpu()
+    # hue runs through (x - y) / delta with delta down to 1/255 of fp32 inputs that already differ in the last bit
+    # between the fused bilinear taps here and torch's: errors up to ~1e-4 / std on isolated pixels
+    err = (out - g["out"]).abs()
+    assert err.max() < 2e-3 and err.mean() < 2e-5, (err.max().item(), err.mean().item())
+    out1 = sampler.clip_sample(*args, layout=1, jitter=tab)
+    exp = g["out"].permute(0, 2, 3, 4, 1).bfloat16()
+    assert (out1[..., :3].cpu().float() - exp.float()).abs().max() < 3e-2
+    # every order / subset of ops: against the CPU restatement (pinned to the reference above)
+    from oracle import clip_oracle
+    import itertools
+    orders = [list(p) for p in itertools.permutations(range(4))][:n]
+    orders[0] = [1, 255, 255, 255]
+    orders[1] = [3, 1, 255, 255]
+    orders[2] = [255, 255, 255, 255]
+    tab = sampler.jitter_table([(g["factors"][c].tolist(), orders[c]) for c in range(n)]).cuda()
+    out = sampler.clip_sample(*args, layout=0, jitter=tab).cpu()
+    for c in range(n):
+        exp = clip_oracle.clip_chain(g["frames"], g["idx"][c], g["box"][c], g["flags"][c], g["mean"], g["std"], g["size"],
+                                     factor=g["factors"][c], order=[o for o in orders[c] if o != 255])
+        err = (out[c] - exp).abs()
+        assert err.max() < 2e-3 and err.mean() < 2e-5, (c, orders[c], err.max().item(), err.mean().item())
+
+
 @pytest.mark.gpu
 def test_clip_kernel_matches_reference_chain():
     from rspnet_b200 import sampler
@@ -58,7 +152,8 @@ def test_gpu_clip_sampler_contract():
     from rspnet_b200.sampler import GPUClipSampler
     random.seed(0)
     frames = torch.randint(0, 256, (96 * 3, 64, 80, 3), dtype=torch.uint8, device="cuda")
-    s = GPUClipSampler(size=32, temporal_size=8)
-    (clip_q, clip_k), label = s(frames, [0, 96, 192], [96, 96, 96])
-    assert label is None and clip_q.shape == clip_k.shape == (3, 3, 8, 32, 32) and clip_q.dtype == torch.float32
-    assert torch.isfinite(clip_q).all() and torch.isfinite(clip_k).all()
+    for jitter in (None, dict(brightness=0.4, contrast=0.4, saturation=0.4, hue=0.4)):
+        s = GPUClipSampler(size=32, temporal_size=8, color_jitter=jitter)
+        (clip_q, clip_k), label = s(frames, [0, 96, 192], [96, 96, 96])
+        assert label is None and clip_q.shape == clip_k.shape == (3, 3, 8, 32, 32) and clip_q.dtype == torch.float32
+        assert torch.isfinite(clip_q).all() and torch.isfinite(clip_k).all()
