@@ -97,6 +97,20 @@ struct ConvParams {
   float* stats;              // optional [2][Nout]: += per-channel sum / sum of squares of the stored (bf16) output
 };
 
+// All parity classes of a strided dgrad in ONE launch: blockIdx.x walks the M tiles of the classes back to back
+// (tileEnd = running tile count), each class with its own geometry; the filter operand (and its tensor map) is shared.
+constexpr int kMaxClasses = 8;
+struct ConvParamsMulti {
+  ConvParams base;
+  int ncls;
+  int tileEnd[kMaxClasses];
+  GatherGeom gx[kMaxClasses];
+};
+__device__ __forceinline__ const ConvParams& base_of(const ConvParams& p) { return p; }
+__device__ __forceinline__ const ConvParams& base_of(const ConvParamsMulti& p) { return p.base; }
+template <typename P> struct is_multi { static constexpr bool value = false; };
+template <> struct is_multi<ConvParamsMulti> { static constexpr bool value = true; };
+
 struct WgradParams {
   GatherGeom g;
   const __nv_bfloat16* dy;   // [M][Nout]
@@ -231,8 +245,9 @@ __device__ __forceinline__ void load_rows(uint32_t panel, const __nv_bfloat16* b
 // ---------------------------------------------------------------------------------------------
 // fprop / dgrad kernel:  out[M][Nout] = gather(src)[M][K] * wgt[Nout][K]^T (+ bias)
 // ---------------------------------------------------------------------------------------------
-template <int NT, int STAGES, int MODE>
-__global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+template <int NT, int STAGES, int MODE, typename P>
+__global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_constant__ P pp) {
+  const ConvParams& p = base_of(pp);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int A_BYTES = 128 * 128;
   constexpr int B_BYTES = NT * 128;
@@ -249,9 +264,17 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
 
   const int t = threadIdx.x;
   const int warp = t >> 5;
-  const long long m0 = static_cast<long long>(blockIdx.x) * 128;
+  unsigned tile = blockIdx.x;
+  const GatherGeom* gp = &p.g;
+  if constexpr (is_multi<P>::value) {
+    int cls = 0;
+    while (cls + 1 < pp.ncls && tile >= static_cast<unsigned>(pp.tileEnd[cls])) ++cls;
+    if (cls) tile -= pp.tileEnd[cls - 1];
+    gp = &pp.gx[cls];
+  }
+  const GatherGeom& g = *gp;
+  const long long m0 = static_cast<long long>(tile) * 128;
   const int n0 = blockIdx.y * NT;
-  const GatherGeom& g = p.g;
   // split-K: z-slice handles K blocks [kbBegin, kbBegin + numKb)
   const int kbBegin = blockIdx.z * p.kbPerSplit;
   const int numKb = (g.numKb - kbBegin) < p.kbPerSplit ? (g.numKb - kbBegin) : p.kbPerSplit;
@@ -709,15 +732,39 @@ __global__ void __launch_bounds__(256) pack_weight_fprop_batch_kernel(const __gr
   const int co = blockIdx.x - J.blk0;
   const int taps = J.kt * J.kh * J.kw;
   const int per = J.Ci * taps;
-  if (co < J.Co)
-    for (int i = threadIdx.x; i < per; i += 256) sw[i] = J.w[static_cast<size_t>(co) * per + i];
+  if (co < J.Co) {
+    const float* src = J.w + static_cast<size_t>(co) * per;
+    if ((per & 3) == 0) {
+      for (int i = threadIdx.x; i < (per >> 2); i += 256)
+        reinterpret_cast<float4*>(sw)[i] = reinterpret_cast<const float4*>(src)[i];
+    } else {
+      for (int i = threadIdx.x; i < per; i += 256) sw[i] = src[i];
+    }
+  }
   __syncthreads();
+  __nv_bfloat16* dst = J.wp + static_cast<size_t>(co) * J.Kpad;
+  if (J.mode == MODE_GENERIC && (J.Cs & 1) == 0) {
+    // k = tap * Cs + ci, walked without divisions; one thread packs two adjacent channels (one 32-bit store)
+    int tap = 0, ci = 2 * threadIdx.x;
+    while (ci >= J.Cs) { ci -= J.Cs; ++tap; }
+    for (int k = 2 * threadIdx.x; k < J.Kpad; k += 512) {
+      float v0 = 0.f, v1 = 0.f;
+      if (co < J.Co && tap < taps) {
+        if (ci < J.Ci) v0 = sw[ci * taps + tap];
+        if (ci + 1 < J.Ci) v1 = sw[(ci + 1) * taps + tap];
+      }
+      *reinterpret_cast<uint32_t*>(dst + k) = pack_bf16x2(v0, v1);
+      ci += 512;
+      while (ci >= J.Cs) { ci -= J.Cs; ++tap; }
+    }
+    return;
+  }
   for (int k = threadIdx.x; k < J.Kpad; k += 256) {
     int ci, a, bb, c;
     float v = 0.f;
     if (co < J.Co && k_to_filter(J.mode, k, J.Cs, J.Ci, J.kt, J.kh, J.kw, J.pxs, ci, a, bb, c))
       v = sw[ci * taps + (a * J.kh + bb) * J.kw + c];
-    J.wp[static_cast<size_t>(co) * J.Kpad + k] = __float2bfloat16(v);
+    dst[k] = __float2bfloat16(v);
   }
 }
 
@@ -760,6 +807,37 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwt, float* __rest
   size_t o = (((static_cast<size_t>(co) * Ci + ci) * kt + a) * kh + b) * kw + c;
   float v = dwt[idx];
   dw[o] = accumulate ? dw[o] + v : v;
+}
+
+// The generic-mode unpack as a tiled transpose: dwt rows are k = tap * Cs + ci, dw rows are co with r = ci * taps + tap
+// contiguous.  A CTA moves 32 output channels x ciTile input channels x all taps through shared memory: 128-byte
+// coalesced reads along co, contiguous ciTile * taps float runs on the way out.
+__global__ void __launch_bounds__(256) unpack_wgrad_tiled_kernel(const float* __restrict__ dwt, float* __restrict__ dw,
+                                                                 int Co, int CoPad, int Ci, int Cs, int taps, int ciTile,
+                                                                 int accumulate) {
+  extern __shared__ float tile[];
+  const int R = ciTile * taps, pitch = R | 1;
+  const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * ciTile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int j = warp; j < R; j += 8) {
+    const int tap = j / ciTile, cl = j - tap * ciTile;
+    const int ci = ci0 + cl;
+    float v = 0.f;
+    if (ci < Ci && co0 + lane < CoPad) v = dwt[(static_cast<size_t>(tap) * Cs + ci) * CoPad + co0 + lane];
+    tile[lane * pitch + cl * taps + tap] = v;
+  }
+  __syncthreads();
+  const int valid = (Ci - ci0 < ciTile ? Ci - ci0 : ciTile) * taps;
+  for (int row = warp; row < 32; row += 8) {
+    const int co = co0 + row;
+    if (co >= Co) break;
+    float* dst = dw + (static_cast<size_t>(co) * Ci + ci0) * taps;
+    const float* srow = tile + row * pitch;
+    if (accumulate)
+      for (int r = lane; r < valid; r += 32) dst[r] += srow[r];
+    else
+      for (int r = lane; r < valid; r += 32) dst[r] = srow[r];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -869,7 +947,7 @@ static int launch_igemm(ConvParams& p, cudaStream_t stream) {
     if (rc != RSP_OK) return rc;
   }
   constexpr int smem = STAGES * (128 * 128 + NT * 128) + 1024 + 256 + 2 * NT * 4;
-  auto kern = conv_igemm_kernel<NT, STAGES, MODE>;
+  auto kern = conv_igemm_kernel<NT, STAGES, MODE, ConvParams>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(conv_igemm): %s", cudaGetErrorString(e));
@@ -893,6 +971,31 @@ static int dispatch_igemm(ConvParams& p, cudaStream_t stream, int wgtKb = 0) {
   p.wgtKb = wgtKb > 0 ? wgtKb : p.g.numKb;
   if (p.Nout % 128 == 0) return launch_igemm<128, 3, MODE>(p, stream);
   return launch_igemm<64, 4, MODE>(p, stream);
+}
+
+template <int NT, int STAGES>
+static int launch_igemm_multi(ConvParamsMulti& pm, cudaStream_t stream) {
+  ConvParams& p = pm.base;
+  p.acc = nullptr;
+  p.stats = nullptr;
+  p.kbPerSplit = 0;
+  for (int i = 0; i < pm.ncls; ++i)
+    if (pm.gx[i].numKb > p.kbPerSplit) p.kbPerSplit = pm.gx[i].numKb;
+  const unsigned long long dims[2] = {static_cast<unsigned long long>(p.wgtKb) * 64, static_cast<unsigned long long>(p.Nout)};
+  const unsigned long long strides[1] = {static_cast<unsigned long long>(p.wgtKb) * 64 * 2};
+  const unsigned box[2] = {64, NT};
+  int rc = make_tmap_bf16(&p.tmapW, p.wgt, 2, dims, strides, box);
+  if (rc != RSP_OK) return rc;
+  constexpr int smem = STAGES * (128 * 128 + NT * 128) + 1024 + 256 + 2 * NT * 4;
+  auto kern = conv_igemm_kernel<NT, STAGES, MODE_GENERIC, ConvParamsMulti>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(conv_igemm multi): %s", cudaGetErrorString(e));
+    return RSP_ERR_CUDA;
+  }
+  dim3 grid(static_cast<unsigned>(pm.tileEnd[pm.ncls - 1]), static_cast<unsigned>(p.Nout / NT), 1);
+  kern<<<grid, kThreads, smem, stream>>>(pm);
+  return check_launch("conv_igemm (dgrad classes)");
 }
 
 template <int NT, int STAGES, int MODE>
@@ -1114,8 +1217,7 @@ int rsp_conv3d_fprop(const rsp_conv3d_desc* d, const void* x, const void* wp, co
 
 // One parity class of a strided dgrad: destination pixels (st*t'+par_t, ...) only see the taps a = a0 + st*i with
 // a0 = (par_t + pt) % st, and source (dY) index t' + (par_t + pt - a0)/st - i: a unit-stride transposed conv in class space.
-static int dgrad_class(const rsp_conv3d_desc* d, const int par[3], const void* dy, const void* wd, void* dx,
-                       cudaStream_t stream) {
+static bool class_geom(const rsp_conv3d_desc* d, const int par[3], const void* dy, GatherGeom& g) {
   const int k[3] = {d->kt, d->kh, d->kw}, s[3] = {d->st, d->sh, d->sw}, pd[3] = {d->pt, d->ph, d->pw};
   const int in[3] = {d->Ti, d->Hi, d->Wi};
   int a0[3], na[3], off[3], cd[3];
@@ -1124,10 +1226,9 @@ static int dgrad_class(const rsp_conv3d_desc* d, const int par[3], const void* d
     na[i] = a0[i] < k[i] ? (k[i] - a0[i] + s[i] - 1) / s[i] : 0;
     off[i] = (par[i] + pd[i] - a0[i]) / s[i];
     cd[i] = in[i] > par[i] ? (in[i] - par[i] + s[i] - 1) / s[i] : 0;
-    if (na[i] == 0 || cd[i] == 0) return RSP_OK;  // no tap reaches this class: dx stays zero (memset by the caller)
+    if (na[i] == 0 || cd[i] == 0) return false;  // no tap reaches this class: dx stays zero (memset by the caller)
   }
-  ConvParams p{};
-  GatherGeom& g = p.g;
+  g = GatherGeom{};
   g.N = d->N;
   g.Ts = (d->Ti + 2 * d->pt - d->kt) / d->st + 1;
   g.Hs = (d->Hi + 2 * d->ph - d->kh) / d->sh + 1;
@@ -1158,12 +1259,7 @@ static int dgrad_class(const rsp_conv3d_desc* d, const int par[3], const void* d
   g.ost = s[0]; g.osh = s[1]; g.osw = s[2];
   g.oot = par[0]; g.ooh = par[1]; g.oow = par[2];
   g.src = static_cast<const __nv_bfloat16*>(dy);
-  p.wgt = static_cast<const __nv_bfloat16*>(wd);
-  p.out = static_cast<__nv_bfloat16*>(dx);
-  p.bias = nullptr;
-  p.Nout = d->Ci;
-  // the kernel addresses filter rows with the full K extent of the dgrad operand
-  return dispatch_igemm<MODE_GENERIC>(p, stream, d->kt * d->kh * d->kw * (d->Co / 64));
+  return g.M > 0;
 }
 
 int rsp_conv3d_dgrad(const rsp_conv3d_desc* d, const void* dy, const void* wd, void* dx, void* workspace,
@@ -1185,14 +1281,35 @@ int rsp_conv3d_dgrad(const rsp_conv3d_desc* d, const void* dy, const void* wd, v
         return RSP_ERR_CUDA;
       }
     }
-    for (int a = 0; a < d->st; ++a)
-      for (int b = 0; b < d->sh; ++b)
-        for (int c = 0; c < d->sw; ++c) {
+    // every parity class with at least one tap, kMaxClasses per launch
+    ConvParamsMulti pm{};
+    pm.base.wgt = static_cast<const __nv_bfloat16*>(wd);
+    pm.base.out = static_cast<__nv_bfloat16*>(dx);
+    pm.base.Nout = d->Ci;
+    pm.base.wgtKb = d->kt * d->kh * d->kw * (d->Co / 64);  // filter rows carry the full K extent of the dgrad operand
+    auto flush = [&]() -> int {
+      if (pm.ncls == 0) return RSP_OK;
+      pm.base.g = pm.gx[0];
+      // short K loops (a class sees 1..8 of the 27 taps): two stages are enough and leave room for 4 CTAs per SM
+      int rc = d->Ci % 128 == 0 ? launch_igemm_multi<128, 3>(pm, stream) : launch_igemm_multi<64, 2>(pm, stream);
+      pm.ncls = 0;
+      return rc;
+    };
+    // odd parities first: they see the most taps, so the longest CTAs start first
+    for (int a = d->st - 1; a >= 0; --a)
+      for (int b = d->sh - 1; b >= 0; --b)
+        for (int c = d->sw - 1; c >= 0; --c) {
           const int par[3] = {a, b, c};
-          int rc = dgrad_class(d, par, dy, wd, dx, stream);
-          if (rc != RSP_OK) return rc;
+          if (!class_geom(d, par, dy, pm.gx[pm.ncls])) continue;
+          const long long tiles = (pm.gx[pm.ncls].M + 127) / 128 + (pm.ncls ? pm.tileEnd[pm.ncls - 1] : 0);
+          RSP_REQUIRE(tiles < (1ll << 31), "conv3d dgrad: too many tiles");
+          pm.tileEnd[pm.ncls] = static_cast<int>(tiles);
+          if (++pm.ncls == kMaxClasses) {
+            int rc = flush();
+            if (rc != RSP_OK) return rc;
+          }
         }
-    return RSP_OK;
+    return flush();
   }
   if (direct_supported(d, 1)) return launch_direct(d, 1, dy, wd, nullptr, dx, nullptr, stream);
   int rc = fill_geom(p.g, d, MODE_GENERIC, 1);
@@ -1231,6 +1348,16 @@ int rsp_conv3d_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, c
   const int sms = device_sm_count();
   rc = mode == MODE_GENERIC ? dispatch_wgrad<MODE_GENERIC>(p, sms, stream) : dispatch_wgrad<MODE_SMALLC>(p, sms, stream);
   if (rc != RSP_OK) return rc;
+  const int taps = d->kt * d->kh * d->kw;
+  if (mode == MODE_GENERIC && taps <= 343) {
+    int ciTile = taps == 27 ? 8 : 256 / taps;
+    ciTile = ciTile < 1 ? 1 : (ciTile > 64 ? 64 : ciTile);
+    dim3 grid(d->Co / 32, (Ci_logical + ciTile - 1) / ciTile);
+    const size_t smem = static_cast<size_t>(32) * ((ciTile * taps) | 1) * sizeof(float);
+    unpack_wgrad_tiled_kernel<<<grid, 256, smem, stream>>>(dwt_workspace, dw, Co_logical, d->Co, Ci_logical, d->Ci, taps,
+                                                           ciTile, accumulate);
+    return check_launch("unpack_wgrad_tiled");
+  }
   size_t total = static_cast<size_t>(d->Co) * Kpad;
   unpack_wgrad_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
       dwt_workspace, dw, mode, Co_logical, d->Co, Ci_logical, d->Ci, d->kt, d->kh, d->kw, p.g.pxs, Kpad, accumulate);
