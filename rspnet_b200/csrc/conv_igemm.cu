@@ -112,6 +112,7 @@ template <typename P> struct is_multi { static constexpr bool value = false; };
 template <> struct is_multi<ConvParamsMulti> { static constexpr bool value = true; };
 
 struct WgradParams {
+  CUtensorMap tmapDy;        // dy as a 2-D tensor {Nout, M}, box {64, 64}, 128 B swizzle: one TMA per 64-channel panel
   GatherGeom g;
   const __nv_bfloat16* dy;   // [M][Nout]
   float* dwt;                // [numKb*64][Nout], accumulated with atomics
@@ -484,8 +485,11 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
 // wgrad kernel: dwt[kb*64 + kk][cout] += sum_pixel gather(src)[pixel][kb*64+kk] * dy[pixel][cout]
 // grid: x = pairs of K blocks (M tile = 128 rows of the K axis), y = cout tile, z = pixel split
 // ---------------------------------------------------------------------------------------------
+// threads: warps 0-3 gather + epilogue, warp 4 issues the MMAs, warps 5-8 gather only (fast path): one producer warp per
+// scheduler retires ~0.5 instructions per clock, which made the gather the bound; dy arrives by TMA.
+constexpr int kWgradThreads = 288;
 template <int NT, int STAGES, int MODE>
-__global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const WgradParams p) {
+__global__ void __launch_bounds__(kWgradThreads) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int PANEL = 64 * 128;  // 64 pixel rows x 128 B
   constexpr int NB = NT / 64;
@@ -509,9 +513,10 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const WgradParams 
   if (pbEnd > totalPb) pbEnd = totalPb;
   const int iters = pbEnd > pbBegin ? static_cast<int>(pbEnd - pbBegin) : 0;
 
+  const bool fastpath = MODE == MODE_GENERIC && !g.transposed && g.fast;
   if (t == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], kProducerThreads);
+      mbar_init(&full_bar[s], fastpath ? 2 * kProducerThreads : kProducerThreads);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(accum_bar, 1);
@@ -524,10 +529,11 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const WgradParams 
   const uint32_t tmem_base = *tmem_slot;
 
   if (iters > 0) {
-    if (warp < 4) {
-      if (MODE == MODE_GENERIC && !g.transposed && g.fast) {
-        const int chunk = t & 7;
-        const uint32_t dst0 = swz(t >> 3, chunk * 16);
+    if (warp != 4) {
+      if (fastpath) {
+        const int pt = warp < 4 ? t : t - 32;          // producer index 0..255: pixel rows (pt>>3) + 32 i, 16 B chunk pt&7
+        const int chunk = pt & 7;
+        const uint32_t dst0 = swz(pt >> 3, chunk * 16);
         const int cchunks = g.Cs >> 6;
         int ta[2], tb[2], tc[2], koff[2];
         bool kbok[2];
@@ -542,16 +548,15 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const WgradParams 
           tc[j] = rem - tb[j] * g.kw;
           koff[j] = ((ta[j] * g.Hs + tb[j]) * g.Ws + tc[j]) * g.Cs + cc * 64;
         }
-        const __nv_bfloat16* dybase = p.dy + n0 + chunk * 8;
         for (int it = 0; it < iters; ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          const uint32_t prow0 = static_cast<uint32_t>((pbBegin + it) * 64) + (t >> 3);
-          int base[4], t0[4], h0[4], w0[4];
-          bool ok[4];
+          const uint32_t prow0 = static_cast<uint32_t>((pbBegin + it) * 64) + (pt >> 3);
+          int base[2], t0[2], h0[2], w0[2];
+          bool ok[2];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint32_t m = prow0 + 16 * i;
+          for (int i = 0; i < 2; ++i) {
+            const uint32_t m = prow0 + 32 * i;
             ok[i] = m < static_cast<uint32_t>(g.M);
             int n, td, hd, wd;
             decode_fast(g, ok[i] ? m : 0u, n, td, hd, wd);
@@ -561,28 +566,30 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const WgradParams 
             base[i] = (((n * g.Ts + t0[i]) * g.Hs + h0[i]) * g.Ws + w0[i]) * g.Cs + chunk * 8;
           }
           mbar_wait(&empty_bar[s], ph ^ 1);
-          const uint32_t stage = smem_u32(smem + s * STAGE_BYTES) + dst0;
+          const uint32_t stage0 = smem_u32(smem + s * STAGE_BYTES);
+          if (pt == 0) {   // the dy panels of this pixel block: rows beyond M are zero-filled by the TMA unit
+            mbar_arrive_expect_tx(&full_bar[s], NB * PANEL);
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
+              tma_load_2d(stage0 + (2 + j) * PANEL, &p.tmapDy, &full_bar[s], n0 + j * 64,
+                          static_cast<int>((pbBegin + it) * 64));
+          }
+          const uint32_t stage = stage0 + dst0;
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < 2; ++i) {
               const bool v = ok[i] && kbok[j] && static_cast<unsigned>(t0[i] + ta[j]) < static_cast<unsigned>(g.Ts) &&
                              static_cast<unsigned>(h0[i] + tb[j]) < static_cast<unsigned>(g.Hs) &&
                              static_cast<unsigned>(w0[i] + tc[j]) < static_cast<unsigned>(g.Ws);
-              cp_async16(stage + j * PANEL + i * 2048, g.src + (v ? static_cast<ptrdiff_t>(base[i] + koff[j]) : 0),
+              cp_async16(stage + j * PANEL + i * 4096, g.src + (v ? static_cast<ptrdiff_t>(base[i] + koff[j]) : 0),
                          v ? 16u : 0u);
             }
           }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const __nv_bfloat16* dsrc = dybase + (ok[i] ? static_cast<size_t>(prow0 + 16 * i) * p.Nout : 0);
-#pragma unroll
-            for (int j = 0; j < NB; ++j) cp_async16(stage + (2 + j) * PANEL + i * 2048, dsrc + j * 64, ok[i] ? 16u : 0u);
-          }
           cp_async_mbar_arrive(&full_bar[s]);
-          mbar_arrive(&full_bar[s]);
+          if (pt != 0) mbar_arrive(&full_bar[s]);
         }
-      } else
+      } else if (warp < 4)
       for (int it = 0; it < iters; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
@@ -595,14 +602,18 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const WgradParams 
         }
         mbar_wait(&empty_bar[s], ph ^ 1);
         const uint32_t stage = smem_u32(smem + s * STAGE_BYTES);
+        if (t == 0) {
+          mbar_arrive_expect_tx(&full_bar[s], NB * PANEL);
+#pragma unroll
+          for (int j = 0; j < NB; ++j)
+            tma_load_2d(stage + (2 + j) * PANEL, &p.tmapDy, &full_bar[s], n0 + j * 64, static_cast<int>(prow0));
+        }
         gather_panel<MODE, 64>(g, stage, kb0, t, rows);
         gather_panel<MODE, 64>(g, stage + PANEL, kb0 + 1, t, rows);
-#pragma unroll
-        for (int j = 0; j < NB; ++j)
-          load_rows<64>(stage + (2 + j) * PANEL, p.dy + n0 + j * 64, prow0, g.M, p.Nout, t);
         cp_async_mbar_arrive(&full_bar[s]);
-        mbar_arrive(&full_bar[s]);
+        if (t != 0) mbar_arrive(&full_bar[s]);
       }
+      if (warp < 4) {
       // epilogue: D row = K index inside the pair of K blocks, columns = cout
       mbar_wait(accum_bar, 0);
       tc_fence_after_sync();
@@ -623,6 +634,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const WgradParams 
                          : "memory");
           }
         }
+      }
       }
     } else {
       constexpr uint32_t idesc = make_idesc_bf16(128, NT, 1, 1);
@@ -1028,8 +1040,15 @@ static int launch_wgrad(WgradParams& p, int sm_count, cudaStream_t stream) {
   }
   p.pbPerSplit = static_cast<int>((totalPb + splits - 1) / splits);
   splits = (totalPb + p.pbPerSplit - 1) / p.pbPerSplit;
+  {
+    const unsigned long long dims[2] = {static_cast<unsigned long long>(p.Nout), static_cast<unsigned long long>(p.g.M)};
+    const unsigned long long strides[1] = {static_cast<unsigned long long>(p.Nout) * 2};
+    const unsigned box[2] = {64, 64};
+    int rc = make_tmap_bf16(&p.tmapDy, p.dy, 2, dims, strides, box);
+    if (rc != RSP_OK) return rc;
+  }
   dim3 grid(mt, nt, static_cast<unsigned>(splits));
-  kern<<<grid, kThreads, smem, stream>>>(p);
+  kern<<<grid, kWgradThreads, smem, stream>>>(p);
   return check_launch("conv_wgrad");
 }
 
