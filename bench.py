@@ -147,7 +147,7 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
-KERNELS_PER_CALL = {"rsp_conv3d_wgrad": 2, "rsp_queue_enqueue": 2, "rsp_moco_logits_fwd": 3,
+KERNELS_PER_CALL = {"rsp_conv3d_wgrad": 2, "rsp_queue_enqueue": 2, "rsp_moco_logits_fwd": 3, "rsp_moco_logits_fwd_ranked": 3,
                     "rsp_moco_logits_bwd": 2}
 
 

@@ -216,6 +216,19 @@ int rsp_moco_logits_fwd(const float* q_a, const float* q_m, const float* k_a, co
                         const float* kn_m, const float* queue, int32_t N, int32_t D, int32_t K, float temperature,
                         float* logits1, float* logits2, float* lpos_m, float* lneg_m, float* lse1, float* lse2,
                         float* pos1, float* pos2, float* workspace, void* stream);
+/* The same, also counting per row how many queue negatives beat each positive: ranks int32 [2][N] (ranks[0][n] =
+ * #{k : logits1[n][1+k] > logits1[n][0]}, ranks[1] for logits2).  accuracy(output, target, topk=(1,5)) of
+ * pretrain.py:169-175 (framework/metrics/classification.py:6-20) is then rank == 0 / rank < 5 — no top-k pass over
+ * [N][1+K] and no materialised logits. */
+int rsp_moco_logits_fwd_ranked(const float* q_a, const float* q_m, const float* k_a, const float* k_m, const float* kn_a,
+                               const float* kn_m, const float* queue, int32_t N, int32_t D, int32_t K, float temperature,
+                               float* logits1, float* logits2, float* lpos_m, float* lneg_m, float* lse1, float* lse2,
+                               float* pos1, float* pos2, float* workspace, int32_t* ranks, void* stream);
+/* Device-side AverageMeters (framework/meters/average.py:4-44) of the eight values pretrain.py:169-196 logs, in the
+ * order Loss, Loss_A, Acc@1_A, Acc@5_A, Acc@1_A_n, Acc@5_A_n, Loss_M, Acc@1_M: meters = float val[8], float sum[8],
+ * int32 count.  loss3 = Loss.forward's triple; val = this step's value, sum += val * N, count += N.  No host sync. */
+int rsp_metrics_update(const float* loss3, const int32_t* ranks, const float* lpos_m, const float* lneg_m, int32_t N,
+                       float* meters, void* stream);
 /* Gradient w.r.t. q_a / q_m given per-row gradients of lse1, lse2, pos1, pos2, lpos_m, lneg_m and (optionally,
  * may be NULL) dense gradients of the materialised logits. dq_a/dq_m overwritten. */
 int rsp_moco_logits_bwd(const float* q_a, const float* q_m, const float* k_a, const float* k_m, const float* kn_a,

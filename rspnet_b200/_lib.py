@@ -80,6 +80,8 @@ SIGNATURES = {
     "rsp_queue_enqueue": (c_i32, [_P, _P, _P, c_i32, c_i32, c_i32, _P]),
     "rsp_moco_logits_workspace": (c_i64, [c_i32, c_i32]),
     "rsp_moco_logits_fwd": (c_i32, [_P] * 7 + [c_i32, c_i32, c_i32, c_f32] + [_P] * 9 + [_P]),
+    "rsp_moco_logits_fwd_ranked": (c_i32, [_P] * 7 + [c_i32, c_i32, c_i32, c_f32] + [_P] * 10 + [_P]),
+    "rsp_metrics_update": (c_i32, [_P, _P, _P, _P, c_i32, _P, _P]),
     "rsp_moco_logits_bwd": (c_i32, [_P] * 7 + [c_i32, c_i32, c_i32, c_f32] + [_P] * 14 + [_P]),
     "rsp_moco_loss_fwd": (c_i32, [_P] * 6 + [c_i32, c_f32, c_f32, c_f32, _P, _P]),
     "rsp_moco_loss_bwd": (c_i32, [_P, _P, c_i32, c_f32, c_f32, c_f32] + [_P] * 7 + [_P]),

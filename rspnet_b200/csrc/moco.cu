@@ -201,7 +201,9 @@ __global__ void __launch_bounds__(kNegCols) neg_logits_kernel(const float* __res
                                                               const float* __restrict__ queue, int N, int D, int K,
                                                               float T, float* __restrict__ logits1,
                                                               float* __restrict__ logits2, float* __restrict__ ws,
-                                                              int tiles) {
+                                                              int tiles, const float* __restrict__ pos1,
+                                                              const float* __restrict__ pos2,
+                                                              int32_t* __restrict__ ranks) {
   extern __shared__ float sm[];  // [kNegRows][D] query rows, then [8][kNegRows][2] reduction scratch
   float* qs = sm;
   float* red = sm + kNegRows * D;
@@ -230,6 +232,13 @@ __global__ void __launch_bounds__(kNegCols) neg_logits_kernel(const float* __res
       size_t o = static_cast<size_t>(n0 + r) * (K + 1) + 1 + k;
       if (logits1) logits1[o] = l;
       if (logits2) logits2[o] = l;
+    }
+    if (ranks) {   // contrastive accuracy without top-k: how many negatives beat each positive (uniform branch)
+      const bool rv = k < K && n0 + r < N;
+      const unsigned b1 = __ballot_sync(0xffffffffu, rv && l > pos1[n0 + r]);
+      const unsigned b2 = __ballot_sync(0xffffffffu, rv && l > pos2[n0 + r]);
+      if (lane == 0 && b1) atomicAdd(ranks + n0 + r, __popc(b1));
+      if (lane == 0 && b2) atomicAdd(ranks + N + n0 + r, __popc(b2));
     }
     float lm = k < K ? l : -INFINITY;
     float mx = warp_max(lm);
@@ -471,6 +480,43 @@ __global__ void __launch_bounds__(256) ce0_bwd_kernel(const float* __restrict__ 
 
 using namespace rsp;
 
+__global__ void __launch_bounds__(256) metrics_update_kernel(const float* __restrict__ loss3,
+                                                             const int32_t* __restrict__ ranks,
+                                                             const float* __restrict__ lpos_m,
+                                                             const float* __restrict__ lneg_m, int N,
+                                                             float* __restrict__ meters) {
+  __shared__ int cnt[5];
+  if (threadIdx.x < 5) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  int c[5] = {0, 0, 0, 0, 0};
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const int r1 = ranks[n], r2 = ranks[N + n];
+    c[0] += r1 == 0;                     // top-1 of logits1: nothing in the queue beats the positive
+    c[1] += r1 < 5;                      // top-5
+    c[2] += r2 == 0;
+    c[3] += r2 < 5;
+    c[4] += lpos_m[n] >= lneg_m[n];      // top-1 of cat(l_pos_M, l_neg_M) against class 0 (ties go to the lower index)
+  }
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    int v = c[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&cnt[i], v);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float scale = 100.0f / N;
+    const float val[8] = {loss3[0],       loss3[1],       cnt[0] * scale, cnt[1] * scale,
+                          cnt[2] * scale, cnt[3] * scale, loss3[2],       cnt[4] * scale};
+    for (int i = 0; i < 8; ++i) {
+      meters[i] = val[i];
+      meters[8 + i] += val[i] * N;
+    }
+    reinterpret_cast<int32_t*>(meters)[16] += N;
+  }
+}
+
 extern "C" {
 
 int rsp_ema_update(float* k, const float* q, int64_t n, float m, float one_minus_m, void* stream) {
@@ -542,20 +588,54 @@ int64_t rsp_moco_logits_workspace(int32_t N, int32_t K) {
   return static_cast<int64_t>(N) * ((K + kNegCols - 1) / kNegCols) * 2 * sizeof(float);
 }
 
-int rsp_moco_logits_fwd(const float* q_a, const float* q_m, const float* k_a, const float* k_m, const float* kn_a,
-                        const float* kn_m, const float* queue, int32_t N, int32_t D, int32_t K, float temperature,
-                        float* logits1, float* logits2, float* lpos_m, float* lneg_m, float* lse1, float* lse2,
-                        float* pos1, float* pos2, float* workspace, void* stream) {
+static int moco_logits_fwd_impl(const float* q_a, const float* q_m, const float* k_a, const float* k_m, const float* kn_a,
+                                const float* kn_m, const float* queue, int32_t N, int32_t D, int32_t K, float temperature,
+                                float* logits1, float* logits2, float* lpos_m, float* lneg_m, float* lse1, float* lse2,
+                                float* pos1, float* pos2, float* workspace, int32_t* ranks, void* stream) {
   RSP_REQUIRE(N > 0 && D > 0 && K > 0 && D <= 512, "moco_logits: bad sizes N=%d D=%d K=%d", N, D, K);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (ranks && cudaMemsetAsync(ranks, 0, sizeof(int32_t) * 2 * N, s) != cudaSuccess) {
+    set_error("moco_logits: memset failed");
+    return RSP_ERR_CUDA;
+  }
   rowdots_kernel<<<(N + 7) / 8, 256, 0, s>>>(q_a, q_m, k_a, k_m, kn_a, kn_m, N, D, K, temperature, logits1, logits2,
                                              lpos_m, lneg_m, pos1, pos2);
   const int tiles = (K + kNegCols - 1) / kNegCols;
   dim3 grid(tiles, (N + kNegRows - 1) / kNegRows);
   size_t smem = (static_cast<size_t>(kNegRows) * D + (kNegCols / 32) * kNegRows * 2) * sizeof(float);
-  neg_logits_kernel<<<grid, kNegCols, smem, s>>>(q_a, queue, N, D, K, temperature, logits1, logits2, workspace, tiles);
+  neg_logits_kernel<<<grid, kNegCols, smem, s>>>(q_a, queue, N, D, K, temperature, logits1, logits2, workspace, tiles,
+                                                 pos1, pos2, ranks);
   lse_finalize_kernel<<<(N + 7) / 8, 256, 0, s>>>(workspace, pos1, pos2, N, tiles, lse1, lse2);
   return check_launch("moco_logits_fwd");
+}
+
+int rsp_moco_logits_fwd(const float* q_a, const float* q_m, const float* k_a, const float* k_m, const float* kn_a,
+                        const float* kn_m, const float* queue, int32_t N, int32_t D, int32_t K, float temperature,
+                        float* logits1, float* logits2, float* lpos_m, float* lneg_m, float* lse1, float* lse2,
+                        float* pos1, float* pos2, float* workspace, void* stream) {
+  return moco_logits_fwd_impl(q_a, q_m, k_a, k_m, kn_a, kn_m, queue, N, D, K, temperature, logits1, logits2, lpos_m, lneg_m,
+                              lse1, lse2, pos1, pos2, workspace, nullptr, stream);
+}
+
+int rsp_moco_logits_fwd_ranked(const float* q_a, const float* q_m, const float* k_a, const float* k_m, const float* kn_a,
+                               const float* kn_m, const float* queue, int32_t N, int32_t D, int32_t K, float temperature,
+                               float* logits1, float* logits2, float* lpos_m, float* lneg_m, float* lse1, float* lse2,
+                               float* pos1, float* pos2, float* workspace, int32_t* ranks, void* stream) {
+  RSP_REQUIRE(ranks != nullptr, "moco_logits_fwd_ranked: ranks must not be null");
+  return moco_logits_fwd_impl(q_a, q_m, k_a, k_m, kn_a, kn_m, queue, N, D, K, temperature, logits1, logits2, lpos_m, lneg_m,
+                              lse1, lse2, pos1, pos2, workspace, ranks, stream);
+}
+
+// Device-side AverageMeters of the training loop (pretrain.py:97-106,169-196; framework/meters/average.py:4-44;
+// framework/metrics/classification.py:6-20): one thread block turns the step's loss triple, the rank counters and the
+// ranking pair into the eight logged values and folds them into val / sum / count without a host round trip.
+// meters: float val[8], float sum[8], then int32 count — order Loss, Loss_A, Acc@1_A, Acc@5_A, Acc@1_A_n, Acc@5_A_n,
+// Loss_M, Acc@1_M.
+int rsp_metrics_update(const float* loss3, const int32_t* ranks, const float* lpos_m, const float* lneg_m, int32_t N,
+                       float* meters, void* stream) {
+  RSP_REQUIRE(N > 0, "metrics_update: empty batch");
+  metrics_update_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(loss3, ranks, lpos_m, lneg_m, N, meters);
+  return check_launch("metrics_update");
 }
 
 int rsp_moco_logits_bwd(const float* q_a, const float* q_m, const float* k_a, const float* k_m, const float* kn_a,

@@ -20,7 +20,7 @@ def scale_learning_rate(lr: float, world_size: int, batch_size: int, base_batch:
 
 class PretrainEngine:
     def __init__(self, model, criterion: Loss, lr: float, momentum: float = 0.9, weight_decay: float = 1e-4,
-                 num_epochs: int = 200):
+                 num_epochs: int = 200, track_metrics: bool = False):
         self.ddp = model if isinstance(model, FlatDDP) else FlatDDP(model)
         self.model = self.ddp.module
         self.criterion = criterion
@@ -32,6 +32,11 @@ class PretrainEngine:
         self.flat_q, _ = self.model.flat_parameters()
         self.momentum_buf = torch.zeros_like(self.flat_q)
         self._first = True
+        # the eight AverageMeters of pretrain.py:97-106, kept on the device (meters.py); off by default like any logging
+        self.meters = None
+        if track_metrics:
+            from .meters import ContrastiveMeters
+            self.meters = ContrastiveMeters(self.flat_q.device)
         self._bind_grads()
 
     def _bind_grads(self):
@@ -58,5 +63,7 @@ class PretrainEngine:
                           self.momentum, self.weight_decay, 1.0, self._first)
         self._first = False
         rnn.bump_weight_epoch()
+        if self.meters is not None:
+            self.meters.update((loss, loss_a, loss_m), output, ranking_logits)
         self.last_output = (output, ranking_logits)
         return loss.detach(), loss_a.detach(), loss_m.detach()

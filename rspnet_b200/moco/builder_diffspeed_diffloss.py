@@ -46,16 +46,17 @@ class _LogitsFn(torch.autograd.Function):
             # the queue is overwritten in place by _dequeue_and_enqueue before backward runs; backward recomputes the
             # negative logits, so it needs the queue as it was (the reference clones it for the same reason, :529)
             queue = queue.clone()
-        logits, rows = ops.moco_logits_fwd(*args, queue, temperature, materialize)
+        logits, rows, ranks = ops.moco_logits_fwd(*args, queue, temperature, materialize)
         ctx.temperature = temperature
         ctx.save_for_backward(*args, queue, rows)
         ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(ranks)
         l1 = logits[0] if materialize else None
         l2 = logits[1] if materialize else None
-        return l1, l2, rows[0].unsqueeze(-1), rows[1].unsqueeze(-1), rows
+        return l1, l2, rows[0].unsqueeze(-1), rows[1].unsqueeze(-1), rows, ranks
 
     @staticmethod
-    def backward(ctx, g_l1, g_l2, g_lpm, g_lnm, g_rows):
+    def backward(ctx, g_l1, g_l2, g_lpm, g_lnm, g_rows, _g_ranks):
         *args, queue, rows = ctx.saved_tensors
         g = torch.zeros_like(rows) if g_rows is None else g_rows.contiguous().clone()
         if g_lpm is not None:
@@ -242,12 +243,14 @@ class _MoCoBase(nn.Module):
         return ops.speed_gather(im_q.float(), im_k.float(), random_indices, int(B * self.alpha), int(diff_speed), 1)
 
     def _logits(self, q_a, q_m, k_a, k_m, kn_a, kn_m):
-        l1, l2, lpm, lnm, rows = _LogitsFn.apply(q_a, q_m, k_a, k_m, kn_a, kn_m, self.queue, self.T,
-                                                 self.materialize_logits)
+        l1, l2, lpm, lnm, rows, ranks = _LogitsFn.apply(q_a, q_m, k_a, k_m, kn_a, kn_m, self.queue, self.T,
+                                                        self.materialize_logits)
         if l1 is None:  # statistics-only mode: hand the Loss something to hold on to
             l1, l2 = rows[2].unsqueeze(-1), rows[3].unsqueeze(-1)
         for t in (l1, l2, lpm, lnm):
             t._rsp_rows = rows
+            t._rsp_ranks = ranks     # [2][N] negatives beating each positive: accuracy without top-k (meters.py)
+        l1._rsp_slot, l2._rsp_slot = 0, 1
         return (l1, l2), (lpm, lnm)
 
 

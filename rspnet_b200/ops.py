@@ -303,10 +303,18 @@ def moco_logits_fwd(q_a, q_m, k_a, k_m, kn_a, kn_m, queue, temperature: float, m
     logits = torch.empty((2, n, k + 1), dtype=torch.float32, device=dev) if materialize else None
     rows = torch.empty((6, n), dtype=torch.float32, device=dev)  # lpos_m, lneg_m, lse1, lse2, pos1, pos2
     ws = torch.empty((_lib.load().rsp_moco_logits_workspace(n, k) // 4,), dtype=torch.float32, device=dev)
-    call("rsp_moco_logits_fwd", ptr(q_a), ptr(q_m), ptr(k_a), ptr(k_m), ptr(kn_a), ptr(kn_m), ptr(queue), n, d, k,
+    ranks = torch.empty((2, n), dtype=torch.int32, device=dev)   # negatives beating each positive (zeroed by the call)
+    call("rsp_moco_logits_fwd_ranked", ptr(q_a), ptr(q_m), ptr(k_a), ptr(k_m), ptr(kn_a), ptr(kn_m), ptr(queue), n, d, k,
          float(temperature), ptr(logits[0]) if materialize else None, ptr(logits[1]) if materialize else None,
-         ptr(rows[0]), ptr(rows[1]), ptr(rows[2]), ptr(rows[3]), ptr(rows[4]), ptr(rows[5]), ptr(ws), stream_ptr())
-    return logits, rows
+         ptr(rows[0]), ptr(rows[1]), ptr(rows[2]), ptr(rows[3]), ptr(rows[4]), ptr(rows[5]), ptr(ws), ptr(ranks),
+         stream_ptr())
+    return logits, rows, ranks
+
+
+def metrics_update(loss3, ranks, lpos_m, lneg_m, meters):
+    """meters: fp32 [17] device buffer (val[8], sum[8], int32 count) — see rsp_metrics_update."""
+    call("rsp_metrics_update", ptr(loss3), ptr(ranks), ptr(lpos_m), ptr(lneg_m), ranks.shape[1], ptr(meters),
+         stream_ptr())
 
 
 def moco_logits_bwd(q_a, q_m, k_a, k_m, kn_a, kn_m, queue, temperature, rows, g_rows, g_logits1, g_logits2):

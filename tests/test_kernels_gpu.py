@@ -137,7 +137,10 @@ def test_moco_logits_loss_fwd_bwd(n, k):
     loss = A * ce + M * rank
     loss.backward()
 
-    logits, rows = ops.moco_logits_fwd(feats[0], feats[1], *feats[2:], queue, T, materialize=True)
+    logits, rows, ranks = ops.moco_logits_fwd(feats[0], feats[1], *feats[2:], queue, T, materialize=True)
+    assert ranks.dtype == torch.int32 and ranks.shape == (2, n)
+    for i in range(2):   # the counters against the logits the same call materialised: exact
+        assert torch.equal(ranks[i].long(), (logits[i][:, 1:] > logits[i][:, :1]).sum(1))
     torch.testing.assert_close(logits[0], l1.detach(), rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(logits[1], l2.detach(), rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(rows[0], lpm.detach().squeeze(1), rtol=1e-4, atol=1e-4)
@@ -164,6 +167,62 @@ def test_moco_logits_loss_fwd_bwd(n, k):
     r1, r2, _, _ = _logits_ref(q_a2, feats[1], *feats[2:], queue, T)
     (F.cross_entropy(r1, tgt) + F.cross_entropy(r2, tgt)).backward()
     torch.testing.assert_close(dq_a2, q_a2.grad, rtol=1e-3, atol=1e-5)
+
+
+def test_contrastive_meters_match_reference_accuracy():
+    """Rank counters + device meters against the reference's accuracy() (top-k over [N, 1+K]) and AverageMeter
+    arithmetic (framework/metrics/classification.py:6-20, framework/meters/average.py:23-30, pretrain.py:169-196)."""
+    from rspnet_b200 import meters as M
+    ops = _ops()
+    n, d, k, T = 64, 128, 4096, 0.07
+    queue = F.normalize(rand(d, k, seed=9), dim=0)
+
+    def ref_accuracy(output, target, topk):
+        maxk = max(topk)
+        _, pred = output.topk(maxk, 1, True, True)
+        correct = pred.t().eq(target[None])
+        return [correct[:kk].flatten().sum(dtype=torch.float) * (100.0 / target.size(0)) for kk in topk]
+
+    meters = M.ContrastiveMeters(DEV)
+    ref_sum, ref_count, ref_val, seen_mid = torch.zeros(8, dtype=torch.float64), 0, None, 0
+    tgt = torch.zeros(n, dtype=torch.long, device=DEV)
+    for step in range(3):
+        q_a = F.normalize(rand(n, d, seed=20 + step), dim=1)
+        # keys at graded distances from the queries so that ranks cover 0, 1..4 and >= 5
+        noise = F.normalize(rand(n, d, seed=30 + step), dim=1)
+        scale = torch.linspace(0.0, 5.0, n, device=DEV)[:, None]
+        k_a = F.normalize(q_a + scale * noise, dim=1)
+        kn_a = F.normalize(q_a + scale.flip(0) * noise, dim=1)
+        q_m, k_m, kn_m = [F.normalize(rand(n, d, seed=40 + 3 * step + i), dim=1) for i in range(3)]
+        logits, rows, ranks = ops.moco_logits_fwd(q_a, q_m, k_a, k_m, kn_a, kn_m, queue, T, materialize=True)
+        loss3 = ops.moco_loss_fwd(rows, 2.0, 1.0, 1.0)
+        l1, l2 = logits[0], logits[1]
+        l1._rsp_ranks = l2._rsp_ranks = ranks
+        l1._rsp_slot, l2._rsp_slot = 0, 1
+        lpm, lnm = rows[0].unsqueeze(1), rows[1].unsqueeze(1)
+        meters.update(loss3, (l1, l2), (lpm, lnm))
+        a1, a5 = ref_accuracy(l1, tgt, (1, 5))
+        n1, n5 = ref_accuracy(l2, tgt, (1, 5))
+        m1, = ref_accuracy(torch.cat([lpm, lnm], dim=1), tgt, (1,))
+        assert 0 < float(a1) <= float(a5) < 100          # the case is not degenerate
+        seen_mid += int(((ranks > 0) & (ranks < 5)).sum())
+        got = M.accuracy(l1, tgt, topk=(1, 5))
+        assert float(got[0]) == float(a1) and float(got[1]) == float(a5)
+        got = M.accuracy(l2, tgt, topk=(1, 5))
+        assert float(got[0]) == float(n1) and float(got[1]) == float(n5)
+        assert float(M.accuracy(torch.cat([lpm, lnm], dim=1), tgt, topk=(1,))[0]) == float(m1)   # plain-tensor route
+        ref_val = torch.tensor([float(loss3[0]), float(loss3[1]), float(a1), float(a5), float(n1), float(n5),
+                                float(loss3[2]), float(m1)], dtype=torch.float64)
+        ref_sum += ref_val * n
+        ref_count += n
+    assert seen_mid > 0                                   # some positives sit between top-1 and top-5
+    s = meters.summary()
+    for i, name in enumerate(M.NAMES):
+        assert abs(s[name]["val"] - float(ref_val[i])) <= 1e-4 * max(1.0, abs(float(ref_val[i]))), name
+        assert abs(s[name]["avg"] - float(ref_sum[i]) / ref_count) <= 1e-4 * max(1.0, abs(float(ref_sum[i]) / ref_count)), name
+    assert "Acc@1_A" in str(meters)
+    meters.reset()
+    assert meters.summary()["Loss"]["avg"] == 0.0
 
 
 # ------------------------------------------------------------------------------------------------ BN / pool / head

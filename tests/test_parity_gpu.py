@@ -207,7 +207,7 @@ def test_objective_matches_oracle_fp32():
     total, ce, rank = oracle.loss(la, lm, 2.0, 1.0, 1.0)
     total.backward()
     gq_a, gq_m = f[0].cuda().requires_grad_(True), f[1].cuda().requires_grad_(True)
-    l1, l2, lpm, lnm, rows = _LogitsFn.apply(gq_a, gq_m, *[t.cuda() for t in f[2:]], queue.cuda(), T, True)
+    l1, l2, lpm, lnm, rows, _ranks = _LogitsFn.apply(gq_a, gq_m, *[t.cuda() for t in f[2:]], queue.cuda(), T, True)
     for t in (l1, l2, lpm, lnm):
         t._rsp_rows = rows
     out = Loss(2.0, 1.0, 1.0)((l1, l2), torch.zeros(n, dtype=torch.long), (lpm, lnm), torch.ones(n, dtype=torch.long))
@@ -233,8 +233,9 @@ def test_engine_two_steps_track_oracle():
     cfg, hyper = g["config"], g["hyper"]
     model = build_product_moco(cfg, hyper, rank=0).cuda()
     eng = PretrainEngine(model, Loss(hyper["margin"], hyper["A"], hyper["M"]), lr=hyper["lr"],
-                         momentum=hyper["momentum"], weight_decay=hyper["weight_decay"])
+                         momentum=hyper["momentum"], weight_decay=hyper["weight_decay"], track_metrics=True)
     orig = torch.randperm
+    loss_sum = torch.zeros(3)
     for step in range(2):
         rec = g["ranks"][0]["steps"][step]
         draws = [rec["perm"], rec["idx_shuffle_neg"], rec["idx_shuffle_pos"]]
@@ -247,9 +248,17 @@ def test_engine_two_steps_track_oracle():
             torch.randperm = orig
         got = torch.stack(losses).cpu()
         assert torch.isfinite(got).all()
+        loss_sum += got
         # step 0 sees identical weights; step 1 additionally checks that EMA + SGD moved the weights the same way
         assert (got - rec["loss"]).abs().max() < (0.15 if step == 0 else 0.6), (step, got, rec["loss"])
         assert int(model.queue_ptr) == rec["queue_ptr"]
+    # device-side meters (pretrain.py:97-106): averages of the two steps, read once
+    summ = eng.meters.summary()
+    for name, idx in (("Loss", 0), ("Loss_A", 1), ("Loss_M", 2)):
+        assert abs(summ[name]["avg"] - float(loss_sum[idx]) / 2) < 1e-4 * max(1.0, abs(float(loss_sum[idx])))
+        assert abs(summ[name]["val"] - float(got[idx])) < 1e-5 * max(1.0, abs(float(got[idx])))
+    for name in ("Acc@1_A", "Acc@5_A", "Acc@1_A_n", "Acc@5_A_n", "Acc@1_M"):
+        assert 0.0 <= summ[name]["avg"] <= 100.0
     sd = model.state_dict()
     ref_after = g["ranks"][0]["steps"][1]["params_after"]
     for k in ("encoder_q.fc1.2.bias", "encoder_q.encoder.bn1.weight", "encoder_k.encoder.bn1.weight"):

@@ -27,7 +27,7 @@ for (n, k, degenerate) in [(4, 64, False), (4, 64, True), (64, 16384, True), (4,
     rank = torch.clamp(-(lpm - lnm) + 2.0, min=0).mean()
     (ce + rank).backward()
     gq_a, gq_m = f[0].cuda().requires_grad_(True), f[1].cuda().requires_grad_(True)
-    l1, l2, a, b, rows = _LogitsFn.apply(gq_a, gq_m, *[t.cuda() for t in f[2:]], queue.cuda(), T, True)
+    l1, l2, a, b, rows, _ranks = _LogitsFn.apply(gq_a, gq_m, *[t.cuda() for t in f[2:]], queue.cuda(), T, True)
     for t in (l1, l2, a, b):
         t._rsp_rows = rows
     out = Loss(2.0, 1.0, 1.0)((l1, l2), tgt.cuda(), (a, b), torch.ones(n, dtype=torch.long).cuda())
@@ -35,7 +35,7 @@ for (n, k, degenerate) in [(4, 64, False), (4, 64, True), (64, 16384, True), (4,
     print(n, k, degenerate, "loss", float(out[0]), float(ce + rank), "dq_a err", (gq_a.grad.cpu() - qa.grad).abs().max().item(),
           "ref max", qa.grad.abs().max().item(), "dq_m err", (gq_m.grad.cpu() - qm.grad).abs().max().item())
     # direct ops call
-    logits, rows2 = ops.moco_logits_fwd(*[t.cuda() for t in f], queue.cuda(), T, True)
+    logits, rows2, _ = ops.moco_logits_fwd(*[t.cuda() for t in f], queue.cuda(), T, True)
     g3 = torch.tensor([1.0, 0, 0], device="cuda")
     g_rows = ops.moco_loss_bwd(rows2, 2.0, 1.0, 1.0, g3)
     dqa, dqm = ops.moco_logits_bwd(*[t.cuda() for t in f], queue.cuda(), T, rows2, g_rows, None, None)
