@@ -1,8 +1,14 @@
 """Training-step driver for the pretraining hot path (the loop body of the reference's
 ``pretrain.Engine.train_epoch``, pretrain.py:154-165): forward, 3-term loss, backward, gradient all-reduce and
 SGD(momentum, weight decay) — with the optimizer running as one fused pass over the flat parameter buffer.
+
+Checkpoint hand-off: ``checkpoint_state`` / ``load_checkpoint`` speak the dictionary the
+reference writes and reads (pretrain.py:118-125,249-259) — ``model`` with the reference's state_dict names, ``optimizer``
+and ``scheduler`` in ``torch.optim.SGD`` / ``CosineAnnealingLR`` format — so a run can move between the two code bases
+and ``finetune.py:273-310`` / ``retrieval.py:84-101`` load the encoder unchanged.
 """
 import math
+import warnings
 from typing import Optional, Tuple
 
 import torch
@@ -67,3 +73,59 @@ class PretrainEngine:
             self.meters.update((loss, loss_a, loss_m), output, ranking_logits)
         self.last_output = (output, ranking_logits)
         return loss.detach(), loss_a.detach(), loss_m.detach()
+
+    # ------------------------------------------------------------------------------------------------ checkpoints
+    def _momentum_views(self):
+        return [self.momentum_buf[lo:lo + p.numel()].view_as(p)
+                for p, (lo, _) in zip(self.ddp._params, self.ddp._bounds)]
+
+    def _torch_optimizer(self, epoch: int):
+        """A ``torch.optim.SGD`` / ``CosineAnnealingLR`` pair over ``model.parameters()`` (what pretrain.py:64-79
+        builds) holding this engine's state; used for (de)serialisation only, never stepped."""
+        opt = torch.optim.SGD(self.model.parameters(), lr=self.base_lr, momentum=self.momentum, dampening=0.0,
+                              weight_decay=self.weight_decay, nesterov=False)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=self.num_epochs, eta_min=self.base_lr / 1000)
+        return opt, sched
+
+    def checkpoint_state(self, epoch: int, arch: str, best_loss: float = float("inf")) -> dict:
+        """The dictionary of pretrain.py:249-259 (``model`` is ``self.model.state_dict()``, i.e. DDP's ``.module``)."""
+        opt, sched = self._torch_optimizer(epoch)
+        used = self.ddp.used_parameter_ids if not self._first else []
+        views = self._momentum_views()
+        for i in (used or []):          # torch.optim.SGD only holds a buffer for parameters that received a gradient
+            opt.state[self.ddp._params[i]]["momentum_buffer"] = views[i].detach().clone()
+        self.set_epoch(epoch)
+        opt.param_groups[0]["lr"] = self.lr
+        sched.last_epoch = epoch
+        sched._step_count = epoch + 1
+        sched._last_lr = [self.lr]
+        return {"epoch": epoch, "arch": arch, "model": self.model.state_dict(), "best_loss": best_loss,
+                "optimizer": opt.state_dict(), "scheduler": sched.state_dict()}
+
+    def load_checkpoint(self, states: dict, arch: Optional[str] = None) -> int:
+        """pretrain.py:112-125.  Returns the epoch to continue from."""
+        if arch is not None and states["arch"] != arch:
+            raise ValueError(f'Loading checkpoint arch {states["arch"]} does not match current arch {arch}')
+        self.model.load_state_dict(states["model"])
+        rnn.bump_weight_epoch()                      # packed bf16 filters are stale now
+        opt, sched = self._torch_optimizer(0)
+        opt.load_state_dict(states["optimizer"])
+        sched.load_state_dict(states["scheduler"])
+        self.momentum_buf.zero_()
+        any_state = False
+        for p, view in zip(self.ddp._params, self._momentum_views()):
+            buf = opt.state.get(p, {}).get("momentum_buffer")
+            if buf is not None:
+                view.copy_(buf)
+                any_state = True
+        # without buffers the next step is torch's first step (buf = grad); with them, parameters that never had a
+        # gradient keep a zero buffer, which gives the same update as torch's lazy initialisation (momentum * 0 + grad)
+        self._first = not any_state
+        group = opt.param_groups[0]
+        self.momentum, self.weight_decay = group["momentum"], group["weight_decay"]
+        self.base_lr = group.get("initial_lr", self.base_lr)
+        self.num_epochs = sched.T_max
+        self.set_epoch(states["epoch"])
+        return states["epoch"]

@@ -257,6 +257,40 @@ def conv_bn_act(x, conv: torch.nn.Conv3d, bn: torch.nn.BatchNorm3d, relu: bool =
     return out
 
 
+class ConvBiasAct(torch.autograd.Function):
+    """Conv3d (+bias) -> optional ReLU on NDHWC bf16 without a BatchNorm behind it (the 'conv' projection heads,
+    reference moco/split_wrapper.py:17-40).  The convolutions run on the tcgen05 kernels; the ReLU mask and the bias
+    gradient of this non-hot variant are plain elementwise / reduction ops."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, kernel, stride, padding, relu):
+        co = ops.pad_channels(weight.shape[0])
+        desc = ops.conv_desc(x.shape, co, kernel, stride, padding)
+        y = ops.conv3d_fprop(desc, x, _pack_cache.get(weight, desc, 0), _pad_vec(bias, co))
+        out = torch.relu_(y) if relu else y
+        ctx.desc, ctx.relu, ctx.has_bias = desc, relu, bias is not None
+        ctx.save_for_backward(x, weight, out if relu else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight, out = ctx.saved_tensors
+        dy = dout.contiguous()
+        if ctx.relu:
+            dy = dy * (out > 0)
+        dw = _wgrad(ctx.desc, x, dy, weight)
+        dx = ops.conv3d_dgrad(ctx.desc, dy, _pack_cache.get(weight, ctx.desc, 1)) if ctx.needs_input_grad[0] else None
+        dbias = dy.float().sum(dim=(0, 1, 2, 3))[:weight.shape[0]] if ctx.has_bias else None
+        return dx, dw, dbias, None, None, None, None
+
+
+def conv_bias_act(x, conv: torch.nn.Conv3d, relu: bool = False):
+    if conv.groups != 1 or tuple(conv.dilation) != (1, 1, 1):
+        raise NotImplementedError("rspnet_b200: grouped / dilated Conv3d is not on the pretraining path")
+    return ConvBiasAct.apply(x, conv.weight, conv.bias, tuple(conv.kernel_size), tuple(conv.stride), tuple(conv.padding),
+                             relu)
+
+
 def batch_bn_counters(module: torch.nn.Module):
     """Re-homes every BatchNorm ``num_batches_tracked`` of ``module`` into one int64 buffer (the per-layer buffers become
     views, names/values unchanged) so that one increment per forward replaces one tiny kernel per layer.

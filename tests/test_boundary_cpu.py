@@ -76,6 +76,102 @@ def test_registry_and_state_dict_surface():
     torch.testing.assert_close(sd["queue"].norm(dim=0), torch.ones(64))
 
 
+def test_head_variants_state_dict_matches_reference_fixture():
+    """fc_type conv / convbn / finetune wrappers: same state_dict keys, order and initial values under the same seed as
+    the reference (fixture recorded by oracle/make_golden_heads.py from moco/split_wrapper.py)."""
+    from helpers import check_packed, initialize_seed, load_golden
+    from rspnet_b200.models import get_model_class
+    from rspnet_b200.moco import MultiTaskWrapper
+    g = load_golden("r3d18_heads")
+    for rec in g["cases"]:
+        initialize_seed(g["seed"])
+        model = MultiTaskWrapper(get_model_class(arch="resnet18"), num_classes=128, **rec["case"])
+        sd = model.state_dict()
+        assert list(sd.keys()) == rec["keys"], rec["case"]
+        for k, v in sd.items():
+            check_packed(v.float(), rec["init"][k], rtol=0, atol=0, what=f"{rec['case']} {k}")
+
+
+def test_checkpoint_hand_off_to_reference_loaders(tmp_path):
+    """PretrainEngine.checkpoint_state writes the dictionary of pretrain.py:249-259; the loaders of finetune.py:273-303
+    and retrieval.py:84-101 (their key filters restated here, and the reference's own modules when /root/reference is
+    present) accept it, torch.optim.SGD / CosineAnnealingLR load its optimizer / scheduler entries, and
+    load_checkpoint round-trips it."""
+    import math
+    from helpers import build_product_moco
+    from rspnet_b200.engine import PretrainEngine
+    from rspnet_b200.models import get_model_class
+    from rspnet_b200.moco import Loss, MultiTaskWrapper
+    cfg = dict(arch="resnet18", seed=0, K=64)
+    hyper = dict(dim=128, m=0.999, T=0.07, diff_speed=[2])
+    model = build_product_moco(cfg, hyper)
+    eng = PretrainEngine(model, Loss(2.0, 1.0, 1.0), lr=0.1, momentum=0.9, weight_decay=1e-4, num_epochs=200)
+    # state as after some steps: momentum everywhere except the unused backbone fc (it never receives a gradient)
+    names = [n for n, _ in model.encoder_q.named_parameters()]
+    used = [i for i, n in enumerate(names) if not n.startswith("encoder.fc.")]
+    torch.manual_seed(5)
+    eng.momentum_buf.normal_()
+    eng.ddp.used_parameter_ids = used
+    eng._first = False
+    path = tmp_path / "checkpoint.pth.tar"
+    torch.save(eng.checkpoint_state(epoch=7, arch="resnet18", best_loss=3.5), path)
+    cp = torch.load(path, weights_only=False)
+    assert set(cp) == {"epoch", "arch", "model", "best_loss", "optimizer", "scheduler"} and cp["epoch"] == 7
+    assert list(cp["model"].keys()) == list(model.state_dict().keys())
+
+    def filtered(prefix, blacklist):
+        keep = lambda k: k.startswith(prefix) and not any(k.startswith(f"{prefix}{fc}") for fc in blacklist)
+        return {k[len(prefix):]: v for k, v in cp["model"].items() if keep(k)}
+
+    # finetune.py:273-303
+    ft_state = filtered("encoder_q.", ["fc.", "linear", "head", "new_fc", "fc8", "encoder_fuse"])
+    targets = [MultiTaskWrapper(get_model_class(arch="resnet18"), num_classes=101, finetune=True)]
+    # retrieval.py:84-101
+    rt_state = filtered("encoder_q.encoder.", ["fc", "linear", "head", "new_fc"])
+    backbones = [get_model_class(arch="resnet18")(num_classes=101)]
+    if Path("/root/reference").exists():
+        from oracle import ref_loader
+        mods = ref_loader.modules()
+        targets.append(mods["wrapper"].MultiTaskWrapper(ref_loader.backbone_ctor("resnet18"), num_classes=101,
+                                                        finetune=True))
+        backbones.append(ref_loader.backbone_ctor("resnet18")(num_classes=101))
+    for tgt in targets:
+        msg = tgt.load_state_dict(ft_state, strict=False)
+        assert set(msg.missing_keys) == {"fc.weight", "fc.bias"}, msg
+        assert all(k.startswith(("fc1.", "fc2.")) for k in msg.unexpected_keys), msg
+        assert torch.equal(tgt.state_dict()["encoder.layer4.1.conv2.weight"],
+                           cp["model"]["encoder_q.encoder.layer4.1.conv2.weight"])
+    for tgt in backbones:
+        msg = tgt.load_state_dict(rt_state, strict=False)
+        assert set(msg.missing_keys) == {"fc.weight", "fc.bias"} and not msg.unexpected_keys, msg
+
+    # optimizer / scheduler entries in torch's own format (pretrain.py:64-79,123-124)
+    other = build_product_moco(cfg, hyper)
+    opt = torch.optim.SGD(other.parameters(), lr=1.0, momentum=0.5)
+    opt.load_state_dict(cp["optimizer"])
+    lr7 = 1e-4 + (0.1 - 1e-4) * (1 + math.cos(math.pi * 7 / 200)) / 2
+    assert abs(opt.param_groups[0]["lr"] - lr7) < 1e-12 and opt.param_groups[0]["momentum"] == 0.9
+    params = list(other.parameters())
+    views = eng._momentum_views()
+    assert sum("momentum_buffer" in opt.state.get(p, {}) for p in params) == len(used)
+    for i in (used[0], used[-1]):
+        assert torch.equal(opt.state[params[i]]["momentum_buffer"], views[i])
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=10, eta_min=0.0)
+    sched.load_state_dict(cp["scheduler"])
+    assert sched.last_epoch == 7 and sched.T_max == 200 and abs(sched.get_last_lr()[0] - lr7) < 1e-12
+
+    # round trip into a fresh engine
+    eng2 = PretrainEngine(other, Loss(2.0, 1.0, 1.0), lr=0.05, momentum=0.0, weight_decay=0.0, num_epochs=5)
+    with pytest.raises(ValueError):
+        eng2.load_checkpoint(cp, arch="c3d")
+    assert eng2.load_checkpoint(cp, arch="resnet18") == 7
+    assert abs(eng2.lr - lr7) < 1e-12 and eng2.momentum == 0.9 and eng2.weight_decay == 1e-4 and not eng2._first
+    for i in used:
+        assert torch.equal(eng2._momentum_views()[i], views[i])
+    for (k, a), b in zip(other.state_dict().items(), model.state_dict().values()):
+        assert torch.equal(a, b), k
+
+
 def test_flat_parameters_are_views_and_keep_values():
     from rspnet_b200.models import get_model_class
     from rspnet_b200.moco import MoCoDiffLossTwoFc, MultiTaskWrapper

@@ -372,3 +372,41 @@ def test_s3dg_front_slice_tight():
     # observed over several boxes: rel 0.017-0.020, worst cosine 0.937-0.955 with norm ratio 0.85-0.88 (always the BN bias
     # of the 16-channel branch2.0 of sepInc_3b, whose gradient is a small difference of large terms)
     assert rel < 0.05 and worst[0] > 0.90 and 0.80 < worst[2] < 1.20, (rel, worst)
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2, 3])
+def test_head_variants_match_reference_golden(idx):
+    """MultiTaskWrapper with fc_type 'conv' / 'convbn' (groups 1 and 2) and the finetune=True classifier branch against
+    the unmodified reference (oracle/make_golden_heads.py): outputs, loss and gradients."""
+    from helpers import initialize_seed
+    from oracle.make_golden_heads import inputs
+    from rspnet_b200.models import get_model_class
+    from rspnet_b200.moco import MultiTaskWrapper
+    g = load_golden("r3d18_heads")
+    rec = g["cases"][idx]
+    initialize_seed(g["seed"])
+    model = MultiTaskWrapper(get_model_class(arch="resnet18"), num_classes=128, **rec["case"]).cuda().train()
+    x, w1, w2 = [t.cuda() for t in inputs()]
+    y = model(x)
+    outs = [y] if rec["case"]["finetune"] else list(y)
+    loss = (outs[0] * w1).sum() if rec["case"]["finetune"] else (outs[0] * w1).sum() + (outs[1] * w2).sum()
+    loss.backward()
+    for got, ref in zip(outs, rec["outs"]):
+        # L2-normalised rows (|x| <= 1) through a bf16 backbone; the finetune logits are O(1) as well
+        assert (got.detach().float().cpu() - ref).abs().max() < 0.06, (got.detach().float().cpu() - ref).abs().max()
+        assert _cos(got.detach().float().cpu(), ref) > 0.995
+    named = dict(model.named_parameters())
+    gots, refs = [], []
+    for k, gref in rec["grads"].items():
+        assert named[k].grad is not None, k
+        if isinstance(gref, dict):   # large tensors are stored as (first 32 values, sum, abs-sum)
+            gk = named[k].grad.detach().float().cpu().flatten()
+            ratio = float(gk.abs().sum()) / max(gref["abssum"], 1e-12)
+            assert 0.8 < ratio < 1.25, (k, ratio)
+            assert _cos(gk[:32], gref["head"]) > 0.8, (k, _cos(gk[:32], gref["head"]))
+            continue
+        gots.append(named[k].grad.detach().float().cpu().flatten())
+        refs.append(gref.flatten())
+        if gref.abs().max() > 1e-6 and not k.endswith("conv1.bias"):
+            assert _cos(gots[-1], refs[-1]) > 0.85, (k, _cos(gots[-1], refs[-1]))
+    assert _cos(torch.cat(gots), torch.cat(refs)) > 0.9
