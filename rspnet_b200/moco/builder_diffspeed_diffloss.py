@@ -166,6 +166,8 @@ class _MoCoBase(nn.Module):
         self.register_buffer("queue_ptr", torch.zeros(1, dtype=torch.long))
         self.alpha = 0.5
         self.materialize_logits = True   # forward() returns [N, 1+K] logits like the reference
+        self.overlap_key_passes = True   # key-encoder passes on a side stream next to the query pass (forward())
+        self._side_stream = None
         self._flat_q: Optional[Tensor] = None
         self._flat_k: Optional[Tensor] = None
         assert self.diff_speed is not None, "This branch is for diff speed"
@@ -278,11 +280,33 @@ class MoCoDiffLossTwoFc(_MoCoBase):
         Input: im_q, im_k: [B, 3, T, H, W] clips (T = diff_speed * clip length).
         Output: (logits1, logits2), labels_A (zeros), (l_pos_M, l_neg_M), labels_M (ones) — as the reference.
         """
-        with torch.no_grad():
-            self._momentum_update_key_encoder()
-            im_q, im_k, k_neg_A, k_neg_M = self._diff_speed(im_q, im_k)
-            k_A, k_M = self._forward_encoder_k(im_k)
-        q_A, q_M = self.encoder_q(im_q)
+        if not (self.overlap_key_passes and im_q.is_cuda):
+            with torch.no_grad():
+                self._momentum_update_key_encoder()
+                im_q, im_k, k_neg_A, k_neg_M = self._diff_speed(im_q, im_k)
+                k_A, k_M = self._forward_encoder_k(im_k)
+            q_A, q_M = self.encoder_q(im_q)
+        else:
+            # The two key-encoder passes (no grad) and the query pass are independent: the key passes go to a side
+            # stream so that the small layer3 / layer4 kernels of one pass fill the SMs the other leaves idle.  Order
+            # of the random draws is the reference's (speed perm, shuffle of k_neg, shuffle of k).
+            main = torch.cuda.current_stream()
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream()
+            side = self._side_stream
+            with torch.no_grad():
+                self._momentum_update_key_encoder()
+                im_q, im_k, k_neg = self._speed_views(im_q, im_k)
+            side.wait_stream(main)
+            with torch.cuda.stream(side), torch.no_grad():
+                im_k.record_stream(side)
+                k_neg.record_stream(side)
+                k_neg_A, k_neg_M, self._enqueue_payload = self._forward_encoder_k(k_neg, return_all=True)
+                k_A, k_M = self._forward_encoder_k(im_k)
+            q_A, q_M = self.encoder_q(im_q)
+            main.wait_stream(side)
+            for t in (k_neg_A, k_neg_M, self._enqueue_payload, k_A, k_M):
+                t.record_stream(main)
         logits_A, logits_M = self._logits(q_A, q_M, k_A, k_M, k_neg_A, k_neg_M)
         labels_A = torch.zeros(q_A.shape[0], dtype=torch.long, device=q_A.device)
         labels_M = torch.ones_like(labels_A)
