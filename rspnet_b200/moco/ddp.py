@@ -96,6 +96,9 @@ class FlatDDP(nn.Module):
         seg = self.flat_grad[lo:hi]
         if self._comm_stream is not None:
             self._comm_stream.wait_stream(torch.cuda.current_stream())
+            from .. import nn as rnn
+            if rnn.wgrad_stream() is not None:      # filter gradients are produced on their own stream
+                self._comm_stream.wait_stream(rnn.wgrad_stream())
             with torch.cuda.stream(self._comm_stream):
                 dist.all_reduce(seg)
                 seg.mul_(1.0 / self.world)

@@ -54,12 +54,45 @@ def _grad_slot(weight):
     return v
 
 
+# Filter gradients are off the critical path of backward (only the optimizer / the all-reduce read them), so they run
+# on a side stream while the main stream carries on with dgrad and the next layer; a callback queued on the autograd
+# graph task joins the streams when backward ends (FlatDDP waits on the same stream before it reduces a bucket).
+wgrad_overlap = True
+_wgrad_stream = None
+_wgrad_task = -1          # autograd graph task that already has the join callback queued
+
+
+def wgrad_stream():
+    return _wgrad_stream
+
+
+def _join_wgrad():
+    global _wgrad_task
+    _wgrad_task = -1
+    torch.cuda.current_stream().wait_stream(_wgrad_stream)
+
+
 def _wgrad(desc, x, dy, weight):
+    global _wgrad_stream, _wgrad_task
     slot = _grad_slot(weight)
-    if slot is None:
-        return ops.conv3d_wgrad(desc, x, dy, weight.shape)
-    ops.conv3d_wgrad(desc, x, dy, weight.shape, out=slot)
-    return slot.view(slot.shape)   # a fresh alias: autograd takes it over as param.grad without copying
+    task = torch._C._current_graph_task_id()
+    if not (wgrad_overlap and x.is_cuda and task != -1):
+        if slot is None:
+            return ops.conv3d_wgrad(desc, x, dy, weight.shape)
+        ops.conv3d_wgrad(desc, x, dy, weight.shape, out=slot)
+        return slot.view(slot.shape)   # a fresh alias: autograd takes it over as param.grad without copying
+    if _wgrad_stream is None:
+        _wgrad_stream = torch.cuda.Stream()
+    if task != _wgrad_task:
+        torch.autograd.Variable._execution_engine.queue_callback(_join_wgrad)
+        _wgrad_task = task
+    side = _wgrad_stream
+    side.wait_stream(torch.cuda.current_stream())
+    x.record_stream(side)
+    dy.record_stream(side)
+    with torch.cuda.stream(side):
+        out = ops.conv3d_wgrad(desc, x, dy, weight.shape, out=slot)
+    return out if slot is None else slot.view(slot.shape)
 
 
 def refresh_packed_weights():
