@@ -9,9 +9,11 @@ speed re-sampling, two key-encoder forwards (shuffle-BN), query forward, logits 
 gradient all-reduce, SGD, queue update.  One "clip"  = one video = one (clip_q, clip_k) pair.
 
 `value`  : clips/s with the fp32 input clips already resident in HBM (a ring of batches larger than L2).
-`e2e`    : clips/s through the public API (PretrainEngine.step) from PINNED HOST buffers; every step copies its two
-           input tensors host->device (double-buffered on a copy stream, inside the timed region) and reads the
-           loss back device->host.
+`e2e`    : clips/s through the public API from PINNED HOST buffers (double-buffered H2D on a copy stream inside the timed
+           region, loss read back device->host every step).  Two feeds are measured and both kept in `e2e_feeds`:
+           "uint8_frames" — the reference loader's hand-off: uint8 frames cross PCIe, GPUClipSampler (the
+           SequentialGPUCollateFn replacement) builds the clips on the device; "fp32_clips" — ready-made fp32 clips, the
+           bare model(clip_q, clip_k) contract.  `e2e` repeats the faster of the two and names it in "feed".
 Prints one JSON line on rank 0.
 """
 import argparse
@@ -204,21 +206,27 @@ def run_b200(args):
 
     host_t = {}
 
-    def timed(fn, steps):
+    def timed(fn, steps, detail=None):
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        marks[0].record()
         t0 = time.perf_counter()
         for i in range(steps):
             fn(i)
+            marks[i + 1].record()
         host_t["ms"] = (time.perf_counter() - t0) * 1e3 / steps   # CPU time to enqueue one step (no device sync inside)
-        e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)
+        ms = marks[0].elapsed_time(marks[-1])
+        per = [marks[i].elapsed_time(marks[i + 1]) for i in range(steps)]
+        stall = 1.0 if max(per) > 2.5 * statistics.median(per) else 0.0
         if world > 1:
-            t = torch.tensor([ms], device=dev)
+            t = torch.tensor([ms, stall], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t)
+            ms, stall = float(t[0]), float(t[1])
+        if detail is not None:
+            detail["stall"] = stall > 0
+            detail["max_step_ms"] = max(per)
+            detail["median_step_ms"] = statistics.median(per)
         return ms
 
     last = {}
@@ -233,7 +241,18 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     counter["on"], counter["n"] = True, 0
-    ms_total = timed(resident_step, args.steps)
+    detail = {}
+    ms_total = timed(resident_step, args.steps, detail)
+    remeasured = None
+    if detail["stall"]:
+        # one step took > 2.5x the median (a driver / allocator hiccup, seen once in ~10 runs as a 270 ms gap): the
+        # region is measured once more and the first figure is kept in the line, as the clocks rule does for throttling
+        remeasured = {"first_ms_per_step": ms_total / args.steps, "first_max_step_ms": detail["max_step_ms"],
+                      "first_median_step_ms": detail["median_step_ms"]}
+        counter["n"] = 0
+        ms_total = timed(resident_step, args.steps, detail)
+    counter["on"] = False
+    launches = counter["n"]          # C-ABI kernel launches inside the timed region (K steps)
     # host cost of enqueueing one step, measured on an empty launch queue (in the timed loop the CPU runs ahead until the
     # driver's launch queue fills and then advances at the GPU's pace)
     host_ms_step = float("inf")
@@ -243,65 +262,111 @@ def run_b200(args):
         resident_step(i)
         host_ms_step = min(host_ms_step, (time.perf_counter() - t0) * 1e3)
     barrier()
-    counter["on"] = False
     clocks = sampler.stop() if rank == 0 else None
     loss_val = float(last["loss"][0])
     ms_step = ms_total / args.steps
     value = B * world / (ms_step / 1e3)
-    launches = counter["n"]
 
     # ---- dominant kernel roofline: conv kernels (fprop+dgrad+wgrad) timed over a pass of the same shapes ------
     roofline = None if args.no_roofline else conv_roofline(args, B, ms_step)
 
     # ---- end to end from pinned host memory --------------------------------------------------------------------
-    e2e = None
+    # Two feeds, both double-buffered on a copy stream inside the timed region, both reading every step's loss back:
+    #  e2e            : the reference's loader hand-off (datasets/classification/__init__.py:22-50 +
+    #                   SequentialGPUCollateFn, transforms_tensor.py:214-233): uint8 decoded frames cross PCIe, the clip
+    #                   sampler kernel (crop / resize / gray / colour jitter / flip / normalise, random decisions drawn on
+    #                   the host in the reference's order) builds (clip_q, clip_k) on the device, then the step runs;
+    #  e2e_fp32_clips : the model-API contract alone — ready-made fp32 clips [B,3,32,H,W] x 2 cross PCIe (617 MB/step).
+    e2e = e2e_feeds = None
     if not args.no_e2e:
-        host = [(torch.randn(shape).pin_memory(), torch.randn(shape).pin_memory()) for _ in range(2)]
-        stage = [(torch.empty(shape, device=dev), torch.empty(shape, device=dev)) for _ in range(2)]
+        import random as pyrandom
+        from rspnet_b200.sampler import GPUClipSampler
         copy_stream = torch.cuda.Stream()
-        ready = [torch.cuda.Event() for _ in range(2)]
-        consumed = [torch.cuda.Event() for _ in range(2)]
         loss_host = [torch.empty(3, pin_memory=True) for _ in range(2)]
         loss_done = [torch.cuda.Event() for _ in range(2)]
         seen = {"loss": None}
 
-        def prefetch(i):
-            s = i % 2
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(consumed[s])
-                stage[s][0].copy_(host[s][0], non_blocking=True)
-                stage[s][1].copy_(host[s][1], non_blocking=True)
-                ready[s].record(copy_stream)
+        def run_feed(host, stage, make_inputs, stage_free_after_inputs):
+            ready = [torch.cuda.Event() for _ in range(2)]
+            consumed = [torch.cuda.Event() for _ in range(2)]
 
-        tick = {"i": 0}
+            def prefetch(i):
+                s = i % 2
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(consumed[s])
+                    for dst, src in zip(stage[s], host[s]):
+                        dst.copy_(src, non_blocking=True)
+                    ready[s].record(copy_stream)
 
-        def e2e_step(_):
-            i = tick["i"]
-            tick["i"] += 1
-            s = i % 2
-            if i == 0:
-                prefetch(0)
-            prefetch(i + 1)  # next step's inputs move while this step computes
-            torch.cuda.current_stream().wait_event(ready[s])
-            loss = engine.step(stage[s][0], stage[s][1])
-            consumed[s].record()
-            loss_host[s].copy_(torch.stack(loss), non_blocking=True)
-            loss_done[s].record()
-            # the caller reads every step's loss on the host, one step behind the device (as a logging loop does): wait for
-            # the PREVIOUS step's copy, so that the CPU can enqueue step i+1 while the GPU still runs step i
-            if i > 0:
-                loss_done[1 - s].synchronize()
-                seen["loss"] = float(loss_host[1 - s][0])
+            tick = {"i": 0}
 
-        for s in range(2):
-            consumed[s].record()
-        for i in range(2):
-            e2e_step(i)
-        ms_e2e = timed(e2e_step, args.steps) / args.steps
-        e2e = {"value": B * world / (ms_e2e / 1e3), "unit": "clips/s", "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 12,
-               "note": "pinned host fp32 clips, double-buffered H2D on a copy stream; every step's loss is copied to pinned "
-                       "host memory and read there one step later (the timed region ends with a full synchronize)"}
+            def e2e_step(_):
+                i = tick["i"]
+                tick["i"] += 1
+                s = i % 2
+                if i == 0:
+                    prefetch(0)
+                prefetch(i + 1)  # next step's inputs move while this step computes
+                torch.cuda.current_stream().wait_event(ready[s])
+                clip_q, clip_k = make_inputs(stage[s])
+                if stage_free_after_inputs:     # the sampler has read the frames: the next copy may overwrite them
+                    consumed[s].record()
+                loss = engine.step(clip_q, clip_k)
+                if not stage_free_after_inputs:
+                    consumed[s].record()
+                loss_host[s].copy_(torch.stack(loss), non_blocking=True)
+                loss_done[s].record()
+                # the caller reads every step's loss on the host, one step behind the device (as a logging loop does):
+                # wait for the PREVIOUS step's copy, so that the CPU can enqueue step i+1 while the GPU still runs step i
+                if i > 0:
+                    loss_done[1 - s].synchronize()
+                    seen["loss"] = float(loss_host[1 - s][0])
+
+            for s in range(2):
+                consumed[s].record()
+            for i in range(max(2, args.warmup)):
+                e2e_step(i)
+            return timed(e2e_step, args.steps) / args.steps
+
+        # (1) uint8 frames -> sampler -> step.  Per video the 64 frames its two 32-frame clips are cut from, 128x171
+        # (SURVEY.md 8d "pipeline benchmark" frame size); frame indices / boxes / gray / jitter / flip drawn per step.
+        FV, HS, WS = 2 * args.frames, 128, 171
+        pyrandom.seed(1234 + rank)
+        sampler_k = GPUClipSampler(size=args.size, temporal_size=args.frames, strides=[{"stride": 1, "weight": 1}],
+                                   crop_scale=(0.4, 1.0),
+                                   color_jitter=dict(brightness=0.4, contrast=0.4, saturation=0.4, hue=0.4))
+        host_u8 = [(torch.randint(0, 256, (B * FV, HS, WS, 3), dtype=torch.uint8).pin_memory(),) for _ in range(2)]
+        stage_u8 = [(torch.empty((B * FV, HS, WS, 3), dtype=torch.uint8, device=dev),) for _ in range(2)]
+        offsets, lengths = [v * FV for v in range(B)], [FV] * B
+
+        def from_frames(st):
+            (clip_q, clip_k), _ = sampler_k(st[0], offsets, lengths)
+            return clip_q, clip_k
+
+        ms_u8 = run_feed(host_u8, stage_u8, from_frames, True)
+        u8_bytes = B * FV * HS * WS * 3
+        e2e_u8 = {"value": B * world / (ms_u8 / 1e3), "unit": "clips/s", "ms_per_step": ms_u8, "feed": "uint8_frames",
+               "h2d_bytes_per_step": u8_bytes + 2 * B * (args.frames * 4 + 16 + 1 + 20), "d2h_bytes_per_step": 12,
+               "note": f"loader hand-off as in the reference: pinned host uint8 frames ({FV} frames of {HS}x{WS} per video) "
+                       "-> double-buffered H2D on a copy stream -> clip sampler kernel (crop, bilinear resize, gray, "
+                       "colour jitter, flip, normalise; decisions drawn on the host per step) -> PretrainEngine.step; "
+                       "every step's loss is copied to pinned host memory and read there one step later (the timed "
+                       "region ends with a full synchronize)"}
+        del host_u8, stage_u8
+        # (2) ready-made fp32 clips
+        host_f = [(torch.randn(shape).pin_memory(), torch.randn(shape).pin_memory()) for _ in range(2)]
+        stage_f = [(torch.empty(shape, device=dev), torch.empty(shape, device=dev)) for _ in range(2)]
+        ms_f = run_feed(host_f, stage_f, lambda st: (st[0], st[1]), False)
+        e2e_fp32 = {"value": B * world / (ms_f / 1e3), "unit": "clips/s", "ms_per_step": ms_f, "feed": "fp32_clips",
+                    "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 12,
+                    "note": "pinned host fp32 clips [B,3,32,H,W] x 2 straight into PretrainEngine.step (PCIe-bound: "
+                            "617 MB per step)"}
+        del host_f, stage_f
+        # both feeds are the public API with host buffers; `e2e` is the one a user would run on this node (the faster):
+        # one GPU is not PCIe-bound and skips the sampler's ~1.5 ms, eight GPUs share the host's memory bandwidth and
+        # win by moving uint8.  Both measurements stay in the line.
+        e2e = dict(e2e_u8 if e2e_u8["value"] >= e2e_fp32["value"] else e2e_fp32)
+        e2e_feeds = {"uint8_frames": e2e_u8, "fp32_clips": e2e_fp32}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -319,7 +384,7 @@ def run_b200(args):
                                    f"2x{args.frames // 2}x{args.size}x{args.size} clips, K={HYPER['K']}, dim 128",
                        "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "inputs alternate between two 617 MB device batches (> 126 MB L2)"},
-            "loss": loss_val, "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms_step, "clocks": clocks, "e2e": e2e, "roofline": roofline,
+            "loss": loss_val, "remeasured": remeasured, "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms_step, "clocks": clocks, "e2e": e2e, "e2e_feeds": e2e_feeds, "roofline": roofline,
             "cpu_baseline": cpu,
         }))
     if world > 1:

@@ -74,6 +74,27 @@ static int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, CUtensorMapS
   return RSP_OK;
 }
 
+__global__ void __launch_bounds__(256) zero_fill_kernel(uint4* __restrict__ p16, size_t n16, unsigned char* __restrict__ tail,
+                                                        int ntail) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride)
+    p16[i] = make_uint4(0, 0, 0, 0);
+  if (blockIdx.x == 0 && static_cast<int>(threadIdx.x) < ntail) tail[threadIdx.x] = 0;
+}
+
+cudaError_t zero_async(void* p, size_t bytes, cudaStream_t stream) {
+  if (bytes == 0) return cudaSuccess;
+  if ((reinterpret_cast<uintptr_t>(p) & 15) != 0) return cudaMemsetAsync(p, 0, bytes, stream);   // never on the hot path
+  const size_t n16 = bytes >> 4;
+  const int ntail = static_cast<int>(bytes & 15);
+  size_t blocks = (n16 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks == 0) blocks = 1;
+  zero_fill_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(static_cast<uint4*>(p), n16,
+                                                                      static_cast<unsigned char*>(p) + (n16 << 4), ntail);
+  return cudaGetLastError();
+}
+
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const unsigned long long* dims,
                    const unsigned long long* strides_bytes, const unsigned* box) {
   RSP_REQUIRE(box[0] * 2 <= 128, "tensor map: inner box exceeds the 128-byte swizzle span");

@@ -28,6 +28,10 @@ int check_launch(const char* what);
 
 // Tiled bf16 tensor map with 128-byte swizzle and zero fill outside the tensor (cuTensorMapEncodeTiled).
 // dims / box: extents per dimension, innermost first; strides_bytes: rank-1 entries for dimensions 1..rank-1.
+// Zero-fill as a kernel on `stream`.  cudaMemsetAsync may be serviced by a copy engine, where it queues behind the
+// loader's multi-hundred-MB host->device transfers and stalls the compute stream for milliseconds.
+cudaError_t zero_async(void* p, size_t bytes, cudaStream_t stream);
+
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const unsigned long long* dims,
                    const unsigned long long* strides_bytes, const unsigned* box);
 // Same with a traversal stride per dimension (every estr[i]-th element along dimension i; box[i] is the traversed

@@ -945,7 +945,7 @@ static int launch_igemm(ConvParams& p, cudaStream_t stream) {
   p.kbPerSplit = (p.g.numKb + splits - 1) / splits;
   splits = (p.g.numKb + p.kbPerSplit - 1) / p.kbPerSplit;
   if (acc) {
-    cudaError_t e = cudaMemsetAsync(acc, 0, static_cast<size_t>(p.g.M) * p.Nout * sizeof(float), stream);
+    cudaError_t e = rsp::zero_async(acc, static_cast<size_t>(p.g.M) * p.Nout * sizeof(float), stream);
     if (e != cudaSuccess) {
       set_error("split-K memset: %s", cudaGetErrorString(e));
       return RSP_ERR_CUDA;
@@ -1294,7 +1294,7 @@ int rsp_conv3d_dgrad(const rsp_conv3d_desc* d, const void* dy, const void* wd, v
                     static_cast<long long>(d->N) * d->Ti * d->Hi * d->Wi < (1ll << 31),
                 "conv3d dgrad: tensor too large");
     if (d->kt < d->st || d->kh < d->sh || d->kw < d->sw) {  // some parity classes receive nothing
-      cudaError_t e = cudaMemsetAsync(dx, 0, static_cast<size_t>(d->N) * d->Ti * d->Hi * d->Wi * d->Ci * 2, stream);
+      cudaError_t e = rsp::zero_async(dx, static_cast<size_t>(d->N) * d->Ti * d->Hi * d->Wi * d->Ci * 2, stream);
       if (e != cudaSuccess) {
         set_error("dgrad memset: %s", cudaGetErrorString(e));
         return RSP_ERR_CUDA;
@@ -1359,7 +1359,7 @@ int rsp_conv3d_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, c
   p.dwt = dwt_workspace;
   p.Nout = d->Co;
   const int Kpad = p.g.numKb * 64;
-  cudaError_t e = cudaMemsetAsync(dwt_workspace, 0, static_cast<size_t>(Kpad) * d->Co * sizeof(float), stream);
+  cudaError_t e = rsp::zero_async(dwt_workspace, static_cast<size_t>(Kpad) * d->Co * sizeof(float), stream);
   if (e != cudaSuccess) {
     set_error("wgrad memset: %s", cudaGetErrorString(e));
     return RSP_ERR_CUDA;

@@ -531,7 +531,7 @@ int launch_stem_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, 
   p.numRows = p.N * p.To * p.Ho;
   const size_t nw = static_cast<size_t>(Co_logical) * Ci_logical * d->kt * d->kh * d->kw;
   if (!accumulate) {
-    cudaError_t e = cudaMemsetAsync(dw, 0, nw * sizeof(float), stream);
+    cudaError_t e = rsp::zero_async(dw, nw * sizeof(float), stream);
     if (e != cudaSuccess) {
       set_error("stem wgrad memset: %s", cudaGetErrorString(e));
       return RSP_ERR_CUDA;

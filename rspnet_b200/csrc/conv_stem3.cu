@@ -434,7 +434,7 @@ int launch_stem3_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical,
   Stem3WgradParams p{};
   p.x = static_cast<const __nv_bfloat16*>(x);
   // rows outside the clip are copied from 1 KB of zeros at the head of the caller's workspace
-  if (cudaMemsetAsync(zero_row_1k, 0, 1024, stream) != cudaSuccess) {
+  if (rsp::zero_async(zero_row_1k, 1024, stream) != cudaSuccess) {
     set_error("stem3 wgrad: workspace memset failed");
     return RSP_ERR_CUDA;
   }
@@ -445,7 +445,7 @@ int launch_stem3_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical,
   p.numRows = p.N * p.Ti * p.Hi;
   const size_t nw = static_cast<size_t>(Co_logical) * Ci_logical * 27;
   if (!accumulate) {
-    cudaError_t e = cudaMemsetAsync(dw, 0, nw * sizeof(float), stream);
+    cudaError_t e = rsp::zero_async(dw, nw * sizeof(float), stream);
     if (e != cudaSuccess) {
       set_error("stem3 wgrad memset: %s", cudaGetErrorString(e));
       return RSP_ERR_CUDA;

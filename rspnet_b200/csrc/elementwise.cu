@@ -739,19 +739,19 @@ __device__ __forceinline__ void hue_shift(float (&v)[3], float shift) {
   const float hi = floorf(h6);
   const float f = h6 - hi;
   const float val = maxc;
-  const float vt[4] = {val, val * (1.f - (1.f - f) * sat), val * (1.f - sat), val * (1.f - f * sat)};
+  const float tt = val * (1.f - (1.f - f) * sat), pp = val * (1.f - sat), qq = val * (1.f - f * sat);
   int idx = static_cast<int>(hi) % 6;
   if (idx < 0) idx += 6;
-  const int map[3][6] = {{0, 3, 2, 2, 1, 0}, {1, 0, 0, 3, 2, 2}, {2, 2, 1, 0, 0, 3}};
-  v[0] = vt[map[0][idx]];
-  v[1] = vt[map[1][idx]];
-  v[2] = vt[map[2][idx]];
+  // channel_map of functional_tensor.py:293-297 as selects (a table indexed per pixel would live in local memory)
+  v[0] = (idx == 0 || idx == 5) ? val : idx == 1 ? qq : idx == 4 ? tt : pp;
+  v[1] = (idx == 1 || idx == 2) ? val : idx == 0 ? tt : idx == 3 ? qq : pp;
+  v[2] = (idx == 3 || idx == 4) ? val : idx == 2 ? tt : idx == 5 ? qq : pp;
 }
 
 // Resized (bilinear, align_corners=False), optionally gray-scaled pixel of the cropped frame, in [0, 1].
 __device__ __forceinline__ void clip_pixel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ frame_idx,
                                            const int32_t* __restrict__ box, uint8_t fl, const ClipGeom& g, int clip, int t,
-                                           int y, int xs, float (&v)[3]) {
+                                           int y, int xs, const float* __restrict__ lut, float (&v)[3]) {
   const int bi = box[clip * 4 + 0], bj = box[clip * 4 + 1], bh = box[clip * 4 + 2], bw = box[clip * 4 + 3];
   // torch upsample_bilinear2d, align_corners=False: src = scale*(dst+0.5)-0.5 clamped at 0
   const float sh = static_cast<float>(bh) / g.S, sw = static_cast<float>(bw) / g.S;
@@ -768,7 +768,8 @@ __device__ __forceinline__ void clip_pixel(const uint8_t* __restrict__ frames, c
   const uint8_t* p11 = f + (static_cast<size_t>(bi + y1) * g.Ws + bj + x1) * 3;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float a = p00[c] / 255.0f, b = p01[c] / 255.0f, cc = p10[c] / 255.0f, d = p11[c] / 255.0f;
+    // ToTensorVideo's x / 255 from a 256-entry table of the exact quotients (twelve IEEE divisions per pixel otherwise)
+    const float a = lut[p00[c]], b = lut[p01[c]], cc = lut[p10[c]], d = lut[p11[c]];
     v[c] = hy * (hx * a + lx * b) + ly * (hx * cc + lx * d);
   }
   if (fl & 2) {  // RandomGrayScale: ITU-R 601-2 luma, replicated on the three channels
@@ -779,9 +780,14 @@ __device__ __forceinline__ void clip_pixel(const uint8_t* __restrict__ frames, c
 
 // Applies the jitter ops order[first .. last) to one pixel; `mean` is the clip-wide gray mean the contrast op blends with.
 __device__ __forceinline__ void jitter_ops(float (&v)[3], const ClipJitter& jt, int first, int last, float mean) {
-  for (int k = first; k < last; ++k) {
-    const int op = jt.order[k];
-    const float fac = op < 4 ? jt.factor[op] : 0.f;
+  uint32_t order4;
+  memcpy(&order4, jt.order, 4);
+  const float f0 = jt.factor[0], f1 = jt.factor[1], f2 = jt.factor[2], f3 = jt.factor[3];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k < first || k >= last) continue;
+    const int op = (order4 >> (8 * k)) & 0xff;
+    const float fac = op == 0 ? f0 : op == 1 ? f1 : op == 2 ? f2 : f3;
     if (op == 0) {                     // adjust_brightness: blend with black
 #pragma unroll
       for (int c = 0; c < 3; ++c) v[c] = clamp01(fac * v[c] + (1.f - fac) * 0.f);
@@ -805,9 +811,13 @@ __global__ void __launch_bounds__(256) clip_gray_sum_kernel(const uint8_t* __res
                                                             const uint8_t* __restrict__ flags,
                                                             const ClipJitter* __restrict__ jitter, ClipGeom g,
                                                             float* __restrict__ sums, int per_clip_blocks) {
+  __shared__ float lut[256];
+  lut[threadIdx.x] = static_cast<float>(threadIdx.x) / 255.0f;
+  __syncthreads();
   const int clip = blockIdx.x / per_clip_blocks, blk = blockIdx.x - clip * per_clip_blocks;
   const ClipJitter jt = jitter[clip];
   int cpos = -1;
+#pragma unroll
   for (int k = 0; k < 4; ++k)
     if (jt.order[k] == 1) cpos = k;
   float acc = 0.f;
@@ -817,7 +827,7 @@ __global__ void __launch_bounds__(256) clip_gray_sum_kernel(const uint8_t* __res
     for (int i = blk * 256 + threadIdx.x; i < per; i += per_clip_blocks * 256) {
       const int x = i % g.S, y = (i / g.S) % g.S, t = i / (g.S * g.S);
       float v[3];
-      clip_pixel(frames, frame_idx, box, fl, g, clip, t, y, x, v);   // the mean does not depend on the flip
+      clip_pixel(frames, frame_idx, box, fl, g, clip, t, y, x, lut, v);   // the mean does not depend on the flip
       jitter_ops(v, jt, 0, cpos, 0.f);
       acc += luma(v);
     }
@@ -842,18 +852,22 @@ __global__ void __launch_bounds__(256) clip_sample_kernel(const uint8_t* __restr
                                                           const ClipJitter* __restrict__ jitter,
                                                           const float* __restrict__ gray_sums, ClipGeom g,
                                                           void* __restrict__ outv, size_t total) {
+  __shared__ float lut[256];
+  lut[threadIdx.x] = static_cast<float>(threadIdx.x) / 255.0f;
+  __syncthreads();
   for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * 256) {
-    const int x = static_cast<int>(i % g.S);
-    size_t q = i / g.S;
-    const int y = static_cast<int>(q % g.S);
-    q /= g.S;
-    const int t = static_cast<int>(q % g.T);
-    const int clip = static_cast<int>(q / g.T);
+    // 32-bit index arithmetic (64-bit divisions cost ~100 instructions each)
+    const uint32_t plane = static_cast<uint32_t>(g.S) * g.S;
+    const uint32_t i32 = static_cast<uint32_t>(i);                // total < 2^32 is checked by the host
+    const uint32_t ct = i32 / plane;                               // clip * T + t
+    const uint32_t rem = i32 - ct * plane;
+    const int y = static_cast<int>(rem / g.S), x = static_cast<int>(rem - (rem / g.S) * g.S);
+    const int clip = static_cast<int>(ct / g.T), t = static_cast<int>(ct - (ct / g.T) * g.T);
     const uint8_t fl = flags[clip];
     const int xs = (fl & 1) ? (g.S - 1 - x) : x;                 // horizontal flip acts on the resized clip
     float v[3];
-    clip_pixel(frames, frame_idx, box, fl, g, clip, t, y, xs, v);
+    clip_pixel(frames, frame_idx, box, fl, g, clip, t, y, xs, lut, v);
     if (jitter) {
       const float mean = gray_sums[clip] / (static_cast<float>(g.T) * g.S * g.S);
       jitter_ops(v, jitter[clip], 0, 4, mean);
@@ -886,6 +900,7 @@ static int clip_sample_impl(const uint8_t* frames, const int32_t* frame_idx, con
   RSP_REQUIRE((jitter == nullptr) == (gray_sums == nullptr), "clip_sample: jitter and gray_sums go together");
   size_t total = static_cast<size_t>(n_clips) * T * S * S;
   if (total == 0) return rsp::RSP_OK;
+  RSP_REQUIRE(total < (1ull << 32), "clip_sample: more than 2^32 output pixels in one call");
   rsp::ClipGeom g{};
   g.T = T; g.Hs = Hs; g.Ws = Ws; g.S = S;
   for (int c = 0; c < 3; ++c) {
@@ -895,7 +910,7 @@ static int clip_sample_impl(const uint8_t* frames, const int32_t* frame_idx, con
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const rsp::ClipJitter* jt = static_cast<const rsp::ClipJitter*>(jitter);
   if (jt) {
-    if (cudaMemsetAsync(gray_sums, 0, sizeof(float) * n_clips, st) != cudaSuccess) {
+    if (rsp::zero_async(gray_sums, sizeof(float) * n_clips, st) != cudaSuccess) {
       rsp::set_error("clip_sample: memset failed");
       return rsp::RSP_ERR_CUDA;
     }
@@ -1069,7 +1084,7 @@ int rsp_gate_fwd(const void* x, int32_t N, int32_t S, int32_t C, int32_t C_logic
   if (rc != RSP_OK) return rc;
   RSP_REQUIRE(N > 0 && S > 0 && C_logical <= C && C_logical * sizeof(float) <= 48 * 1024, "gate_fwd: bad sizes");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  cudaError_t e = cudaMemsetAsync(sums_ws, 0, static_cast<size_t>(N) * C * sizeof(float), stream);
+  cudaError_t e = rsp::zero_async(sums_ws, static_cast<size_t>(N) * C * sizeof(float), stream);
   if (e != cudaSuccess) {
     set_error("gate_fwd memset: %s", cudaGetErrorString(e));
     return RSP_ERR_CUDA;
@@ -1095,7 +1110,7 @@ int rsp_gate_bwd(const void* dy, const void* x, int32_t N, int32_t S, int32_t C,
   if (rc != RSP_OK) return rc;
   RSP_REQUIRE(N > 0 && S > 0 && C_logical <= C && 2 * C_logical * sizeof(float) <= 48 * 1024, "gate_bwd: bad sizes");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  cudaError_t e = cudaMemsetAsync(dgate_ws, 0, static_cast<size_t>(N) * C * sizeof(float), stream);
+  cudaError_t e = rsp::zero_async(dgate_ws, static_cast<size_t>(N) * C * sizeof(float), stream);
   if (e != cudaSuccess) {
     set_error("gate_bwd memset: %s", cudaGetErrorString(e));
     return RSP_ERR_CUDA;

@@ -594,7 +594,7 @@ static int moco_logits_fwd_impl(const float* q_a, const float* q_m, const float*
                                 float* pos1, float* pos2, float* workspace, int32_t* ranks, void* stream) {
   RSP_REQUIRE(N > 0 && D > 0 && K > 0 && D <= 512, "moco_logits: bad sizes N=%d D=%d K=%d", N, D, K);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (ranks && cudaMemsetAsync(ranks, 0, sizeof(int32_t) * 2 * N, s) != cudaSuccess) {
+  if (ranks && rsp::zero_async(ranks, sizeof(int32_t) * 2 * N, s) != cudaSuccess) {
     set_error("moco_logits: memset failed");
     return RSP_ERR_CUDA;
   }

@@ -172,9 +172,9 @@ def clip_sample(frames: torch.Tensor, frame_idx: torch.Tensor, boxes: torch.Tens
 def jitter_table(records) -> torch.Tensor:
     """[(factor[4], order[4]), ...] -> host uint8 [n, 20] tensor laid out as ``struct ClipJitter``."""
     tab = np.zeros(len(records), dtype=JITTER_DTYPE)
-    for i, (factor, order) in enumerate(records):
-        tab[i]["factor"] = factor
-        tab[i]["order"] = order
+    if records:
+        tab["factor"] = np.asarray([r[0] for r in records], dtype=np.float32)
+        tab["order"] = np.asarray([r[1] for r in records], dtype=np.uint8)
     return torch.from_numpy(tab.view(np.uint8).reshape(len(records), JITTER_DTYPE.itemsize))
 
 
@@ -207,8 +207,11 @@ class GPUClipSampler:
         idx = np.zeros((2, b, t), dtype=np.int32)
         box = np.zeros((2, b, 4), dtype=np.int32)
         flags = np.zeros((2, b), dtype=np.uint8)
+        bases = {}
         for v, n_frames in enumerate(video_lengths):          # worker side: per video
-            base = np.arange(n_frames)
+            base = bases.get(n_frames)
+            if base is None:
+                base = bases[n_frames] = np.arange(n_frames)
             for c in range(2):
                 idx[c, v] = self.temporal(base)
             for c in range(2):
@@ -230,9 +233,22 @@ class GPUClipSampler:
         b = len(video_lengths)
         idx = idx + np.asarray(video_offsets, dtype=np.int32)[None, :, None]
         dev = frames.device
-        t_idx = torch.from_numpy(idx.reshape(2 * b, -1)).to(dev, non_blocking=True)
-        t_box = torch.from_numpy(box.reshape(2 * b, 4)).to(dev, non_blocking=True)
-        t_flags = torch.from_numpy(flags.reshape(2 * b)).to(dev, non_blocking=True)
-        t_jit = jit.to(dev, non_blocking=True) if jit is not None else None
+        # all per-clip tables travel in ONE pinned staging buffer and one async copy: a pageable source would make the
+        # host wait for the stream to reach the copy, i.e. for the previous training step, on every batch
+        n, t = 2 * b, idx.shape[-1]
+        o_box, o_jit = n * t * 4, n * t * 4 + n * 16
+        o_flags = o_jit + n * JITTER_DTYPE.itemsize
+        stage = torch.empty(o_flags + n, dtype=torch.uint8, pin_memory=dev.type == "cuda")
+        hv = stage.numpy()
+        hv[:o_box].view(np.int32)[:] = idx.reshape(-1)
+        hv[o_box:o_jit].view(np.int32)[:] = box.reshape(-1)
+        if jit is not None:
+            hv[o_jit:o_flags] = jit.numpy().reshape(-1)
+        hv[o_flags:] = flags.reshape(-1)
+        dbuf = stage.to(dev, non_blocking=True)
+        t_idx = dbuf[:o_box].view(torch.int32).view(n, t)
+        t_box = dbuf[o_box:o_jit].view(torch.int32).view(n, 4)
+        t_jit = dbuf[o_jit:o_flags].view(n, JITTER_DTYPE.itemsize) if jit is not None else None
+        t_flags = dbuf[o_flags:]
         out = clip_sample(frames, t_idx, t_box, t_flags, self.mean, self.std, self.size, layout, jitter=t_jit)
         return (out[:b], out[b:]), None
