@@ -167,9 +167,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; the only stdout line of this script is the JSON
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL prints its version banner on STDOUT; the only stdout line of this script is the JSON
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
@@ -238,7 +237,9 @@ def run_b200(args):
         q, k = ring[i % len(ring)]
         last["loss"] = engine.step(q, k)
 
-    for i in range(args.warmup):
+    # W warm-up steps as asked, and never fewer than 10: the caching allocator's per-stream pools (main, key-encoder and
+    # filter-gradient streams) and NCCL's channels settle during the first steps
+    for i in range(max(args.warmup, 10)):
         resident_step(i)
     sampler = ClockSampler(local)
     if rank == 0:

@@ -297,16 +297,16 @@ class MoCoDiffLossTwoFc(_MoCoBase):
             with torch.no_grad():
                 self._momentum_update_key_encoder()
                 im_q, im_k, k_neg = self._speed_views(im_q, im_k)
+            # No Tensor.record_stream here: im_k / k_neg stay referenced until this function returns, i.e. until after the
+            # join below, and what the side stream allocates is only reused by the side stream after its next
+            # wait_stream(main).  (record_stream defers block reuse to event polling; the caching allocator then grows
+            # with cudaMalloc in the middle of training steps — seen as sporadic 80-270 ms stalls.)
             side.wait_stream(main)
             with torch.cuda.stream(side), torch.no_grad():
-                im_k.record_stream(side)
-                k_neg.record_stream(side)
                 k_neg_A, k_neg_M, self._enqueue_payload = self._forward_encoder_k(k_neg, return_all=True)
                 k_A, k_M = self._forward_encoder_k(im_k)
             q_A, q_M = self.encoder_q(im_q)
             main.wait_stream(side)
-            for t in (k_neg_A, k_neg_M, self._enqueue_payload, k_A, k_M):
-                t.record_stream(main)
         logits_A, logits_M = self._logits(q_A, q_M, k_A, k_M, k_neg_A, k_neg_M)
         labels_A = torch.zeros(q_A.shape[0], dtype=torch.long, device=q_A.device)
         labels_M = torch.ones_like(labels_A)

@@ -66,10 +66,14 @@ def wgrad_stream():
     return _wgrad_stream
 
 
+_wgrad_keepalive = []     # (x, dy) of every wgrad in flight: released after the join instead of Tensor.record_stream
+
+
 def _join_wgrad():
     global _wgrad_task
     _wgrad_task = -1
     torch.cuda.current_stream().wait_stream(_wgrad_stream)
+    _wgrad_keepalive.clear()   # later main-stream work is ordered after the side stream's reads
 
 
 def _wgrad(desc, x, dy, weight):
@@ -88,8 +92,7 @@ def _wgrad(desc, x, dy, weight):
         _wgrad_task = task
     side = _wgrad_stream
     side.wait_stream(torch.cuda.current_stream())
-    x.record_stream(side)
-    dy.record_stream(side)
+    _wgrad_keepalive.append((x, dy))
     with torch.cuda.stream(side):
         out = ops.conv3d_wgrad(desc, x, dy, weight.shape, out=slot)
     return out if slot is None else slot.view(slot.shape)
