@@ -388,6 +388,7 @@ def run_b200(args):
                                    f"2x{args.frames // 2}x{args.size}x{args.size} clips, K={HYPER['K']}, dim 128",
                        "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "inputs alternate between two 617 MB device batches (> 126 MB L2)"},
+            "encoder_clip_passes_per_s": 3 * value,   # q, k and k_neg forwards of 16-frame clips per video
             "loss": loss_val, "remeasured": remeasured, "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms_step, "clocks": clocks, "e2e": e2e, "e2e_feeds": e2e_feeds, "roofline": roofline,
             "cpu_baseline": cpu,
         }))
