@@ -1,8 +1,10 @@
-"""TEST INFRASTRUCTURE ONLY — loads the *unmodified* reference modules from /root/reference by file path.
+"""TEST / BASELINE INFRASTRUCTURE ONLY — loads the *unmodified* reference modules by file path, from /root/reference
+in the build container or from the git-ignored byte-for-byte copy ``baseline/_ref`` (oracle/install_ref.py) on the
+GPU box.
 
-Used in the build container to (a) pin oracle/rspnet_oracle.py against the real reference and (b) generate the
-golden vectors under tests/golden/ (oracle/make_golden.py).  /root/reference does not exist on the GPU box, so
-nothing that runs there may import this module; tests that use it skip when the directory is absent.
+Used (a) to pin oracle/rspnet_oracle.py against the real reference, (b) to generate the golden vectors under
+tests/golden/ (oracle/make_golden*.py), (c) by ``bench.py --impl reference`` / ``cpu_baseline`` and
+tools/stock_torch_bar.py to time the reference itself.  The product package never imports this module.
 
 Shims applied, none of which changes the reference's arithmetic:
   * modules are loaded with importlib from their file paths because ``import moco`` / ``import models`` need
@@ -19,7 +21,9 @@ from pathlib import Path
 import torch
 import torch.nn.functional as F
 
-REFERENCE_ROOT = Path("/root/reference")
+_LIVE = Path("/root/reference")
+_VENDORED = Path(__file__).resolve().parent.parent / "baseline" / "_ref"   # oracle/install_ref.py (git-ignored copy)
+REFERENCE_ROOT = _LIVE if (_LIVE / "moco" / "builder_diffspeed_diffloss.py").exists() else _VENDORED
 
 
 def available() -> bool:
@@ -41,7 +45,7 @@ def modules():
     """Returns dict(resnet, c3d, s3dg, r2plus1d, wrapper, builder) of reference modules."""
     if not _cache:
         if not available():
-            raise RuntimeError("/root/reference is not present")
+            raise RuntimeError("neither /root/reference nor baseline/_ref is present")
         _cache["resnet"] = _load("_ref_resnet", "models/resnet.py")
         _cache["c3d"] = _load("_ref_c3d", "models/c3d.py")
         _cache["s3dg"] = _load("_ref_s3dg", "models/s3dg.py")
@@ -53,6 +57,7 @@ def modules():
 
 _orig_mrl = F.margin_ranking_loss
 _shimmed = False
+FORCE_CPU = False   # set before install_shims() to run the reference on the host cores of a box that has a GPU
 
 
 def install_shims():
@@ -69,7 +74,7 @@ def install_shims():
 
     F.margin_ranking_loss = margin_ranking_loss
     torch.nn.functional.margin_ranking_loss = margin_ranking_loss
-    if not torch.cuda.is_available():
+    if not torch.cuda.is_available() or FORCE_CPU:
         torch.Tensor.cuda = lambda self, *a, **k: self
 
 

@@ -103,43 +103,61 @@ def r2plus1d_feature(x, sd: State, p: str, train=True):
 
 _S3DG_INC = ["sepInc_3b", "sepInc_3c", "sepInc_4b", "sepInc_4c", "sepInc_4d", "sepInc_4e", "sepInc_4f", "sepInc_5b",
              "sepInc_5c"]
+# models/s3dg.py:105-121, in order: (name, kind, arguments)
+S3DG_STAGES = [("sepConv1", "sep", (7, 2, 3)), ("maxPool1", "pool", ((1, 3, 3), (1, 2, 2), (0, 1, 1))),
+               ("basicConv3d", "basic", ()), ("sep_conv2", "sep", (3, 1, 1)),
+               ("maxPool2", "pool", ((1, 3, 3), (1, 2, 2), (0, 1, 1))), ("sepInc_3b", "inc", ()), ("sepInc_3c", "inc", ()),
+               ("maxPool3", "pool", (3, 2, 1)), ("sepInc_4b", "inc", ()), ("sepInc_4c", "inc", ()), ("sepInc_4d", "inc", ()),
+               ("sepInc_4e", "inc", ()), ("sepInc_4f", "inc", ()), ("maxpool4", "pool", (2, 2, 0)), ("sepInc_5b", "inc", ()),
+               ("sepInc_5c", "inc", ())]
 
 
-def s3dg_feature(x, sd: State, p: str, train=True, upto: Optional[str] = None):
-    """models/s3dg.py:151-153 (get_feature): BasicConv3d (:6-33, BN eps 1e-3 momentum 0.001), sep_conv with
-    self-gating (:36-72), sep_inc (:74-99), feature stack (:105-121)."""
-    def basic(x, name, stride=(1, 1, 1), pad=(0, 0, 0)):
-        y = _conv(x, sd, name + ".conv3d", stride, pad)
-        return _r(F.relu(_bn(y, sd, name + ".bn", train, eps=1e-3, momentum=0.001)))
+def _s3dg_basic(x, sd, name, train, stride=(1, 1, 1), pad=(0, 0, 0)):
+    """BasicConv3d (models/s3dg.py:6-33): conv (no bias) -> BN(eps 1e-3, momentum 0.001) -> ReLU."""
+    y = _conv(x, sd, name + ".conv3d", stride, pad)
+    return _r(F.relu(_bn(y, sd, name + ".bn", train, eps=1e-3, momentum=0.001)))
 
-    def sep(x, name, k, stride, pad):
-        x = basic(x, name + ".sep_conv.0", (stride, stride, stride), (0, pad, pad))
-        x = basic(x, name + ".sep_conv.1", (1, 1, 1), (pad, 0, 0))
-        w = x.mean(dim=(2, 3, 4), keepdim=True)
-        w = torch.sigmoid(F.conv3d(w, sd[name + ".excitation.weight"], sd[name + ".excitation.bias"]))
-        return _r(w * x)
 
-    def inc(x, name):
-        o0 = basic(x, name + ".branch0")
-        o1 = sep(basic(x, name + ".branch1.0"), name + ".branch1.1", 3, 1, 1)
-        o2 = sep(basic(x, name + ".branch2.0"), name + ".branch2.1", 3, 1, 1)
-        o3 = basic(F.max_pool3d(x, 3, 1, 1), name + ".branch3.1")
-        return torch.cat((o0, o1, o2, o3), 1)
+def _s3dg_sep(x, sd, name, train, k, stride, pad):
+    """sep_conv with self-gating (models/s3dg.py:36-72)."""
+    x = _s3dg_basic(x, sd, name + ".sep_conv.0", train, (stride, stride, stride), (0, pad, pad))
+    x = _s3dg_basic(x, sd, name + ".sep_conv.1", train, (1, 1, 1), (pad, 0, 0))
+    w = x.mean(dim=(2, 3, 4), keepdim=True)
+    w = torch.sigmoid(F.conv3d(w, sd[name + ".excitation.weight"], sd[name + ".excitation.bias"]))
+    return _r(w * x)
 
-    f = p + "feature."
-    x = sep(x, f + "sepConv1", 7, 2, 3)
-    x = F.max_pool3d(x, (1, 3, 3), (1, 2, 2), (0, 1, 1))
-    x = basic(x, f + "basicConv3d")
-    x = sep(x, f + "sep_conv2", 3, 1, 1)
-    x = F.max_pool3d(x, (1, 3, 3), (1, 2, 2), (0, 1, 1))
-    x = inc(inc(x, f + "sepInc_3b"), f + "sepInc_3c")
-    if upto == "sepInc_3c":
-        return x
-    x = F.max_pool3d(x, 3, 2, 1)
-    for n in _S3DG_INC[2:7]:
-        x = inc(x, f + n)
-    x = F.max_pool3d(x, 2, 2, 0)
-    return inc(inc(x, f + "sepInc_5b"), f + "sepInc_5c")
+
+def _s3dg_inc(x, sd, name, train):
+    """sep_inc (models/s3dg.py:74-99)."""
+    o0 = _s3dg_basic(x, sd, name + ".branch0", train)
+    o1 = _s3dg_sep(_s3dg_basic(x, sd, name + ".branch1.0", train), sd, name + ".branch1.1", train, 3, 1, 1)
+    o2 = _s3dg_sep(_s3dg_basic(x, sd, name + ".branch2.0", train), sd, name + ".branch2.1", train, 3, 1, 1)
+    o3 = _s3dg_basic(F.max_pool3d(x, 3, 1, 1), sd, name + ".branch3.1", train)
+    return torch.cat((o0, o1, o2, o3), 1)
+
+
+def s3dg_stage(x, sd: State, p: str, stage: str, train=True):
+    """One entry of S3D_G.feature (models/s3dg.py:105-121) on its own; ``p`` is the prefix of the backbone's keys."""
+    kind, args = next((k, a) for n, k, a in S3DG_STAGES if n == stage)
+    name = p + "feature." + stage
+    if kind == "pool":
+        return F.max_pool3d(x, *args)
+    if kind == "basic":
+        return _s3dg_basic(x, sd, name, train)
+    if kind == "sep":
+        return _s3dg_sep(x, sd, name, train, *args)
+    return _s3dg_inc(x, sd, name, train)
+
+
+def s3dg_feature(x, sd: State, p: str, train=True, upto: Optional[str] = None, taps: Optional[list] = None):
+    """models/s3dg.py:151-153 (get_feature): the 16 stages in order.  ``taps`` (a list) receives every stage input."""
+    for stage, _, _ in S3DG_STAGES:
+        if taps is not None:
+            taps.append((stage, x))
+        x = s3dg_stage(x, sd, p, stage, train)
+        if upto == stage:
+            break
+    return x
 
 
 FEATURES = {"resnet18": resnet18_feature, "c3d": c3d_feature, "r2plus1d-vcop": r2plus1d_feature,

@@ -317,16 +317,17 @@ __global__ void rowdots_bwd_kernel(const float* __restrict__ k_a, const float* _
 constexpr int kBwdK = 64;       // queue columns per chunk
 constexpr int kBwdChunks = 4;   // chunks per block
 // queue part of dq_a: dq_a[n] += (1/T) sum_k w[n,k] queue[:,k] with
-// w = g_lse1*softmax1 + g_lse2*softmax2 (+ dense logits grads). D must be 128.
+// w = g_lse1*softmax1 + g_lse2*softmax2 (+ dense logits grads). D is 64, 128 or 256 (moco.dim).
+template <int D>
 __global__ void __launch_bounds__(256) neg_logits_bwd_kernel(
     const float* __restrict__ q_a, const float* __restrict__ queue, int N, int K, float T,
     const float* __restrict__ lse1, const float* __restrict__ lse2, const float* __restrict__ g_lse1,
     const float* __restrict__ g_lse2, const float* __restrict__ g_logits1, const float* __restrict__ g_logits2,
     float* __restrict__ dq_a) {
-  constexpr int D = 128;
+  constexpr int DJ = D / 16;          // feature columns per thread
   extern __shared__ float sm[];
-  float* qs = sm;                     // [16][128]
-  float* Qs = qs + 16 * D;            // [128][kBwdK + 1]
+  float* qs = sm;                     // [16][D]
+  float* Qs = qs + 16 * D;            // [D][kBwdK + 1]
   float* wsm = Qs + D * (kBwdK + 1);  // [16][kBwdK + 1]
   const int n0 = blockIdx.y * 16;
   const int t = threadIdx.x;
@@ -339,9 +340,9 @@ __global__ void __launch_bounds__(256) neg_logits_bwd_kernel(
   const bool nok = n < N;
   const float l1 = nok ? lse1[n] : 0.f, l2 = nok ? lse2[n] : 0.f;
   const float g1 = nok ? g_lse1[n] : 0.f, g2 = nok ? g_lse2[n] : 0.f;
-  float acc[8];
+  float acc[DJ];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int j = 0; j < DJ; ++j) acc[j] = 0.f;
   for (int ch = 0; ch < kBwdChunks; ++ch) {
     const int k0 = (blockIdx.x * kBwdChunks + ch) * kBwdK;
     __syncthreads();
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(256) neg_logits_bwd_kernel(
     }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < DJ; ++j) {
       int dd = c + 16 * j;
       float a = 0.f;
       for (int kk = 0; kk < kBwdK; ++kk) a = fmaf(wsm[r * (kBwdK + 1) + kk], Qs[dd * (kBwdK + 1) + kk], a);
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(256) neg_logits_bwd_kernel(
   }
   if (nok) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(dq_a + static_cast<size_t>(n) * D + c + 16 * j, acc[j] / T);
+    for (int j = 0; j < DJ; ++j) atomicAdd(dq_a + static_cast<size_t>(n) * D + c + 16 * j, acc[j] / T);
   }
 }
 
@@ -645,7 +646,7 @@ int rsp_moco_logits_bwd(const float* q_a, const float* q_m, const float* k_a, co
                         const float* g_lpos_m, const float* g_lneg_m, const float* g_logits1, const float* g_logits2,
                         float* dq_a, float* dq_m, void* stream) {
   (void)q_m;
-  RSP_REQUIRE(D == 128, "moco_logits_bwd: feature dimension must be 128 (got %d)", D);
+  RSP_REQUIRE(D == 64 || D == 128 || D == 256, "moco_logits_bwd: feature dimension must be 64, 128 or 256 (got %d)", D);
   RSP_REQUIRE(N > 0 && K > 0, "moco_logits_bwd: bad sizes N=%d K=%d", N, K);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // positive keys first (overwrites dq), then the queue part accumulates with atomics
@@ -654,9 +655,21 @@ int rsp_moco_logits_bwd(const float* q_a, const float* q_m, const float* k_a, co
                                                  g_logits2, dq_a, dq_m);
   const int per_block = kBwdK * kBwdChunks;
   dim3 grid((K + per_block - 1) / per_block, (N + 15) / 16);
-  size_t smem = (16 * 128 + 128 * (kBwdK + 1) + 16 * (kBwdK + 1)) * sizeof(float);
-  neg_logits_bwd_kernel<<<grid, 256, smem, s>>>(q_a, queue, N, K, temperature, lse1, lse2, g_lse1, g_lse2, g_logits1,
-                                                g_logits2, dq_a);
+  size_t smem = (16 * D + D * (kBwdK + 1) + 16 * (kBwdK + 1)) * sizeof(float);
+#define RSP_LAUNCH_NEG_BWD(DD)                                                                                          \
+  do {                                                                                                                  \
+    static bool attr_set = false;                                                                                       \
+    if (!attr_set) {                                                                                                    \
+      cudaFuncSetAttribute(neg_logits_bwd_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+      attr_set = true;                                                                                                  \
+    }                                                                                                                   \
+    neg_logits_bwd_kernel<DD><<<grid, 256, smem, s>>>(q_a, queue, N, K, temperature, lse1, lse2, g_lse1, g_lse2,       \
+                                                      g_logits1, g_logits2, dq_a);                                      \
+  } while (0)
+  if (D == 64) RSP_LAUNCH_NEG_BWD(64);
+  else if (D == 128) RSP_LAUNCH_NEG_BWD(128);
+  else RSP_LAUNCH_NEG_BWD(256);
+#undef RSP_LAUNCH_NEG_BWD
   return check_launch("moco_logits_bwd");
 }
 

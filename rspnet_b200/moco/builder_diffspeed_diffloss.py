@@ -150,7 +150,11 @@ def flatten_parameters(module: nn.Module) -> Tensor:
 class _MoCoBase(nn.Module):
     """State and kernels shared by the two builder variants."""
 
-    def _init_common(self, base_encoder, dim, K, m, T, diff_speed):
+    def _init_common(self, base_encoder, dim, K, m, T, diff_speed, mlp=False):
+        if dim not in (64, 128, 256):
+            # the logits backward kernel is instantiated for these feature dimensions (csrc/moco.cu); fail at
+            # construction, not inside loss.backward()
+            raise ValueError(f"rspnet_b200: moco.dim must be 64, 128 or 256 (got {dim})")
         self.K = K
         self.m = m
         self.T = T
@@ -158,6 +162,10 @@ class _MoCoBase(nn.Module):
         logger.warning('Using diffspeed: %s', self.diff_speed)
         self.encoder_q = base_encoder(num_classes=dim)
         self.encoder_k = base_encoder(num_classes=dim)
+        if mlp:  # ref :45-48 / :318-321 — the reference's brute-force replacement of the backbone's ``fc``
+            dim_mlp = self.encoder_q.fc.weight.shape[1]
+            self.encoder_q.fc = nn.Sequential(nn.Linear(dim_mlp, dim_mlp), nn.ReLU(), self.encoder_q.fc)
+            self.encoder_k.fc = nn.Sequential(nn.Linear(dim_mlp, dim_mlp), nn.ReLU(), self.encoder_k.fc)
         for param_q, param_k in zip(self.encoder_q.parameters(), self.encoder_k.parameters()):
             param_k.data.copy_(param_q.data)
             param_k.requires_grad = False
@@ -263,9 +271,9 @@ class MoCoDiffLossTwoFc(_MoCoBase):
         dim: feature dimension (default: 128); K: queue size; m: momentum of the key encoder; T: softmax temperature
         """
         super().__init__()
-        if mlp:
-            raise NotImplementedError("mlp=True rewires encoder.fc, which the two-head wrapper does not have")
-        self._init_common(base_encoder, dim, K, m, T, diff_speed)
+        # mlp=True rewires ``encoder.fc``; with the two-head MultiTaskWrapper (no ``fc``) it raises AttributeError in
+        # the reference (:318-321) and does the same here
+        self._init_common(base_encoder, dim, K, m, T, diff_speed, mlp)
         self.gap = nn.AdaptiveAvgPool3d((1, 1, 1))
 
     @torch.no_grad()
@@ -342,9 +350,7 @@ class MoCoDiffLoss(_MoCoBase):
     def __init__(self, base_encoder, dim=128, K=65536, m=0.999, T=0.07, mlp=False,
                  diff_speed: Optional[List[int]] = None):
         super().__init__()
-        if mlp:
-            raise NotImplementedError("mlp=True is not part of any shipped pretrain config")
-        self._init_common(base_encoder, dim, K, m, T, diff_speed)
+        self._init_common(base_encoder, dim, K, m, T, diff_speed, mlp)
 
     @torch.no_grad()
     def _forward_encoder_k(self, im_k, return_all: bool = False):

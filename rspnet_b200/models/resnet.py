@@ -112,7 +112,8 @@ class ResNet(nn.Module):
         x = self.layer3(x)
         return self.layer4(x)
 
-    feature_channels = property(lambda self: self.fc.in_features)
+    # ``fc`` may have been wrapped into Sequential(Linear, ReLU, fc) by the builder's mlp option (builder:45-48)
+    feature_channels = property(lambda self: (self.fc[0] if isinstance(self.fc, nn.Sequential) else self.fc).in_features)
 
     # ---- reference-facing API (NCDHW fp32 in / out) ----------------------------------------------------------
     def get_feature(self, x):

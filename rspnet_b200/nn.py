@@ -28,9 +28,11 @@ def bump_weight_epoch():
 
 # Gradient slots: when a data-parallel wrapper owns one flat gradient buffer it registers the slot of every parameter
 # here; the wgrad kernels then write straight into the slot and autograd adopts that tensor as ``param.grad``
-# (no temporary, no accumulate kernel).  Valid once per backward and parameter: a second use falls back to a temporary.
+# (no temporary, no accumulate kernel).  Valid once per backward and parameter: a second use in the same backward, or
+# a parameter that already carries a gradient (zero_grad(set_to_none=False), gradient accumulation), falls back to a
+# temporary that autograd accumulates.  "Same backward" is the autograd graph-task id, so nothing depends on the
+# caller announcing a new step.
 _grad_slots = {}
-_grad_epoch = 0
 _grad_written = {}
 
 
@@ -40,17 +42,15 @@ def register_grad_slots(params, views):
 
 
 def begin_grad_epoch():
-    """Called once per backward by the engine (after setting the parameters' ``.grad`` to None)."""
-    global _grad_epoch
-    _grad_epoch += 1
+    """Kept for callers of the round-1 API; slot bookkeeping is keyed by the autograd graph task now."""
 
 
-def _grad_slot(weight):
+def _grad_slot(weight, task):
     key = weight.data_ptr()
     v = _grad_slots.get(key)
-    if v is None or weight.grad is not None or _grad_written.get(key) == _grad_epoch or v.shape != weight.shape:
+    if v is None or weight.grad is not None or task == -1 or _grad_written.get(key) == task or v.shape != weight.shape:
         return None
-    _grad_written[key] = _grad_epoch
+    _grad_written[key] = task
     return v
 
 
@@ -78,13 +78,17 @@ def _join_wgrad():
 
 def _wgrad(desc, x, dy, weight):
     global _wgrad_stream, _wgrad_task
-    slot = _grad_slot(weight)
     task = torch._C._current_graph_task_id()
-    if not (wgrad_overlap and x.is_cuda and task != -1):
-        if slot is None:
-            return ops.conv3d_wgrad(desc, x, dy, weight.shape)
+    slot = _grad_slot(weight, task)
+    if slot is None:
+        # No slot: the result is a temporary that autograd's AccumulateGrad (and any post-accumulate hook) reads on the
+        # CURRENT stream right after this function returns, so it must be produced on the current stream.
+        return ops.conv3d_wgrad(desc, x, dy, weight.shape)
+    if not (wgrad_overlap and x.is_cuda):
         ops.conv3d_wgrad(desc, x, dy, weight.shape, out=slot)
         return slot.view(slot.shape)   # a fresh alias: autograd takes it over as param.grad without copying
+    # Slot path: nobody reads the slot before the end of backward except FlatDDP's bucket reduce, which waits on the
+    # side stream; the callback queued on the graph task joins the streams before backward() returns.
     if _wgrad_stream is None:
         _wgrad_stream = torch.cuda.Stream()
     if task != _wgrad_task:
@@ -94,8 +98,8 @@ def _wgrad(desc, x, dy, weight):
     side.wait_stream(torch.cuda.current_stream())
     _wgrad_keepalive.append((x, dy))
     with torch.cuda.stream(side):
-        out = ops.conv3d_wgrad(desc, x, dy, weight.shape, out=slot)
-    return out if slot is None else slot.view(slot.shape)
+        ops.conv3d_wgrad(desc, x, dy, weight.shape, out=slot)
+    return slot.view(slot.shape)
 
 
 def refresh_packed_weights():
@@ -275,11 +279,13 @@ def conv_bn_relu_pool(x, conv: torch.nn.Conv3d, bn: torch.nn.BatchNorm3d, pool: 
 
 
 def conv_bn_act(x, conv: torch.nn.Conv3d, bn: torch.nn.BatchNorm3d, relu: bool = True, residual=None):
-    """Fused Conv3d -> BatchNorm3d(train) -> (+residual) -> (ReLU) on NDHWC bf16 activations."""
-    if not bn.training:
-        raise NotImplementedError("rspnet_b200: only train-mode BatchNorm (the pretraining path) is implemented")
+    """Fused Conv3d -> BatchNorm3d -> (+residual) -> (ReLU) on NDHWC bf16 activations.  Train-mode BN is the pretraining
+    path; eval-mode BN (``model.eval()``: validation, retrieval, feature extraction after the checkpoint hand-off) is an
+    inference-only forward with scale / shift taken from the running statistics."""
     if conv.groups != 1 or tuple(conv.dilation) != (1, 1, 1):
         raise NotImplementedError("rspnet_b200: grouped / dilated Conv3d is not on the pretraining path")
+    if not bn.training:
+        return _conv_bn_act_eval(x, conv, bn, relu, residual)
     momentum = bn.momentum if bn.momentum is not None else 0.0
     if not torch.is_grad_enabled():
         # key-encoder passes: same kernels without the autograd.Function round trip
@@ -291,6 +297,27 @@ def conv_bn_act(x, conv: torch.nn.Conv3d, bn: torch.nn.BatchNorm3d, relu: bool =
     if bn.track_running_stats and bn.num_batches_tracked is not None and not getattr(bn, "_rsp_counter_batched", False):
         bn.num_batches_tracked += 1
     return out
+
+
+def _conv_bn_act_eval(x, conv, bn, relu, residual):
+    """Eval-mode BatchNorm (F.batch_norm(training=False)): y = (conv(x) - running_mean) / sqrt(running_var + eps) * gamma
+    + beta.  Inference only — the backward of frozen-statistics BN is not on the pretraining path."""
+    if torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad):
+        raise NotImplementedError("rspnet_b200: eval-mode BatchNorm is forward-only; wrap the call in torch.no_grad()")
+    co = ops.pad_channels(conv.weight.shape[0])
+    desc = ops.conv_desc(x.shape, co, conv.kernel_size, conv.stride, conv.padding)
+    y = ops.conv3d_fprop(desc, x, _pack_cache.get(conv.weight, desc, 0), _pad_vec(conv.bias, co))
+    with torch.no_grad():   # [C]-sized parameter preparation; padded channels get scale = shift = 0
+        if bn.track_running_stats and bn.running_mean is not None:
+            invstd = torch.rsqrt(bn.running_var.float() + bn.eps)
+            mean = bn.running_mean.float()
+        else:
+            raise NotImplementedError("rspnet_b200: eval-mode BatchNorm needs running statistics")
+        gamma = bn.weight.float() if bn.weight is not None else torch.ones_like(mean)
+        beta = bn.bias.float() if bn.bias is not None else torch.zeros_like(mean)
+        scale = _pad_vec(gamma * invstd, co)
+        shift = _pad_vec(beta - mean * gamma * invstd, co)
+    return ops.bn_act_fwd(y, scale.contiguous(), shift.contiguous(), residual, relu)
 
 
 class ConvBiasAct(torch.autograd.Function):

@@ -10,7 +10,7 @@ from helpers import (build_product_moco, build_product_single_head, check_packed
                      summarize)
 from oracle import rspnet_oracle as oracle
 
-CASES = ["r3d18_w1", "r3d18_w2", "c3d_w1", "r2plus1d_w1", "s3dg_w1"]
+CASES = ["r3d18_w1", "r3d18_w2", "r3d18_w4", "r3d18_w8", "c3d_w1", "r2plus1d_w1", "s3dg_w1"]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -18,6 +18,8 @@ def test_product_init_matches_reference_state_dict(name):
     g = load_golden(name)
     cfg, hyper = g["config"], g["hyper"]
     for rank_rec in g["ranks"]:
+        if not rank_rec["init"]:
+            continue  # slim fixtures keep the initial-state checksums of rank 0 only
         model = build_product_moco(cfg, hyper, rank=rank_rec["rank"])
         sd = model.state_dict()
         assert list(sd.keys()) == list(rank_rec["init"].keys()), "state_dict names / order differ from the reference"
@@ -59,14 +61,19 @@ def test_oracle_matches_reference_goldens(name):
     cfg = g["config"]
     W, B = cfg["world"], cfg["batch"]
     for step, (out, sds) in enumerate(outs):
-        # fp32 on the same CPU kernels: step 0 is tight.  After an SGD update the 2-rank fixture (2 clips per rank,
-        # 1x1x1 feature maps => BatchNorm over two values) amplifies thread-count-dependent rounding of the
-        # reference run (two 4-thread processes) to ~1e-3 on logits of magnitude ~10; the tolerance says so.
+        # fp32 on the same CPU kernels: step 0 is tight.  After an SGD update thread-count-dependent rounding of the
+        # reference run (W processes with 8/W threads each) has been amplified by one optimisation step; the
+        # tolerance says so.
         loose = step > 0 and W > 1
         la, ll = (1e-2, 1e-2) if loose else (2e-4, 1e-5)
         for r in range(W):
             rec = g["ranks"][r]["steps"][step]
             assert rec["n_randperm"] == 3
+            if "shuffled_heads" in rec:
+                # BIT-EXACT routing of shuffle-BN: what the reference's encoder_k received on rank r in the k_neg pass and
+                # in the k pass (forward pre-hook on the unmodified module) against the oracle's `shuffled`
+                for p_i in range(2):
+                    assert torch.equal(out["shuffled"][p_i][r][:, :, 0, 0, :4], rec["shuffled_heads"][p_i]), (r, p_i)
             torch.testing.assert_close(out["logits_a"][r][0], rec["logits1"], rtol=1e-4, atol=la)
             torch.testing.assert_close(out["logits_a"][r][1], rec["logits2"], rtol=1e-4, atol=la)
             torch.testing.assert_close(out["logits_m"][r][0], rec["l_pos_m"], rtol=1e-4, atol=la)
