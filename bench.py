@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Benchmark of the RSPNet pretraining step (BASELINE.json: "pretrain clips/sec (R3D-18, 16x112x112)").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--arch resnet18|c3d|r2plus1d-vcop] [--batch B]
-    python bench.py --impl reference ...      # the reference algorithm on the host CPU cores (oracle port)
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--arch resnet18|c3d|r2plus1d-vcop|s3dg] [--batch B]
+                    [--frames F --size S]    # e.g. BASELINE config 4: --arch s3dg --frames 128 --size 224 --batch 8
+    python bench.py --impl reference ...      # the UNMODIFIED reference (baseline/_ref) on the host CPU cores
 
 One "step" = one full training iteration on a batch of B synthetic videos per GPU: EMA of the key encoder,
 speed re-sampling, two key-encoder forwards (shuffle-BN), query forward, logits + 3-term loss, backward,
@@ -13,7 +14,7 @@ gradient all-reduce, SGD, queue update.  One "clip"  = one video = 
            region, loss read back device->host every step).  Two feeds are measured and both kept in `e2e_feeds`:
            "uint8_frames" — the reference loader's hand-off: uint8 frames cross PCIe, GPUClipSampler (the
            SequentialGPUCollateFn replacement) builds the clips on the device; "fp32_clips" — ready-made fp32 clips, the
-           bare model(clip_q, clip_k) contract.  `e2e` repeats the faster of the two and names it in "feed".
+           bare model(clip_q, clip_k) contract.  `e2e` is the uint8 loader hand-off at every N.
 Prints one JSON line on rank 0.
 """
 import argparse
@@ -31,8 +32,19 @@ sys.path.insert(0, str(ROOT))
 
 HYPER = dict(dim=128, K=16384, m=0.999, T=0.07, diff_speed=[2], margin=2.0, A=1.0, M=1.0, lr=0.1, momentum=0.9,
              weight_decay=1e-4)
-# forward conv GFLOP per 16-frame clip and first-conv share
-CONV_GF = {"resnet18": (16.62, 6.61), "c3d": (76.99, 2.08), "r2plus1d-vcop": (42.72, 1.22)}
+# forward conv GFLOP per 16-frame clip, first-conv share and the clip size they were probed at;
+# other clip sizes scale with frames x height x width (S3D-G 64 x 224^2 = 4.0 x the 16-frame figure)
+CONV_GF = {"resnet18": (16.62, 6.61, 112), "c3d": (76.99, 2.08, 112), "r2plus1d-vcop": (42.72, 1.22, 112),
+           "s3dg": (34.07, 1.89, 224)}
+
+
+def conv_gflop(arch, frames, size):
+    """(forward GFLOP per clip, first-conv GFLOP) at `frames` loaded frames (clip = frames / 2) and size x size."""
+    if arch not in CONV_GF:
+        return None, None
+    fwd, first, base = CONV_GF[arch]
+    scale = (frames / 2 / 16.0) * (size / float(base)) ** 2
+    return fwd * scale, first * scale
 
 
 def parse():
@@ -96,54 +108,100 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
-def cpu_reference_clips_per_s(arch, steps, warmup, batch=4, frames=32, size=112, K=16384):
-    """The reference algorithm (oracle/rspnet_oracle.py, a torch-CPU restatement pinned to the reference by
-    tests/test_oracle_cpu.py) on the host cores: BASELINE config 1 (R3D-18, B=4, K=16384, single process)."""
+def cpu_reference_clips_per_s(arch, steps, warmup, batch=4, frames=32, size=112, K=16384, budget_s=150.0):
+    """The reference's own CPU implementation of the step on the host cores: the UNMODIFIED reference modules from the
+    git-ignored copy baseline/_ref (oracle/install_ref.py; loaded by oracle/ref_loader.py with the three shims of
+    SURVEY.md 8c) — MoCoDiffLossTwoFc + MultiTaskWrapper + backbone under DistributedDataParallel (gloo, world 1),
+    Loss(margin 2), torch.optim.SGD — on BASELINE config 1 (batch 4, 2x16x112x112, K=16384), all host threads.
+    Falls back to the oracle port (oracle/rspnet_oracle.py) only when baseline/_ref is absent.  Returns
+    (clips/s, ms per step, threads, batch, kind, steps actually timed)."""
     import torch
-    from oracle import rspnet_oracle as oracle
-    from rspnet_b200.models import get_model_class
-    from rspnet_b200.moco import MoCoDiffLossTwoFc, MultiTaskWrapper
+    from oracle import ref_loader
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    torch.manual_seed(0)
-    base = get_model_class(arch=arch)
-    # module construction only (random-init weights with the reference's names); the oracle does the arithmetic
-    init = MoCoDiffLossTwoFc(lambda num_classes=128: MultiTaskWrapper(base, num_classes=num_classes), dim=HYPER["dim"],
-                             K=K, m=HYPER["m"], T=HYPER["T"], diff_speed=HYPER["diff_speed"])
-    sd = {k: v.clone() for k, v in init.state_dict().items()}
-    del init
     g = torch.Generator().manual_seed(1234)
     im_q = torch.randn(batch, 3, frames, size, size, generator=g)
     im_k = torch.randn(batch, 3, frames, size, size, generator=g)
-    mom, times = {}, []
+    lr = HYPER["lr"] * batch / 64
+    if ref_loader.available():
+        import torch.distributed as dist
+        kind = "reference"
+        ref_loader.FORCE_CPU = True            # Tensor.cuda() becomes a no-op while the reference runs on the host
+        orig_cuda = torch.Tensor.cuda
+        own_group = not dist.is_initialized()
+        if own_group:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29611")
+            dist.init_process_group("gloo", rank=0, world_size=1)
+        torch.manual_seed(0)
+        model = ref_loader.build_reference_moco(arch, dim=HYPER["dim"], K=K, m=HYPER["m"], T=HYPER["T"],
+                                                diff_speed=HYPER["diff_speed"])
+        ddp = torch.nn.parallel.DistributedDataParallel(model, find_unused_parameters=True)
+        crit = ref_loader.build_reference_loss(HYPER["margin"], HYPER["A"], HYPER["M"])
+        opt = torch.optim.SGD(ddp.parameters(), lr=lr, momentum=HYPER["momentum"], dampening=0,
+                              weight_decay=HYPER["weight_decay"], nesterov=False)
+
+        def step():
+            output, target, rl, rt = ddp(im_q, im_k)
+            loss, _, _ = crit(output, target, rl, rt)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+    else:
+        from oracle import rspnet_oracle as oracle
+        from rspnet_b200.models import get_model_class
+        from rspnet_b200.moco import MoCoDiffLossTwoFc, MultiTaskWrapper
+        kind, own_group = "port", False
+        torch.manual_seed(0)
+        base = get_model_class(arch=arch)
+        init = MoCoDiffLossTwoFc(lambda num_classes=128: MultiTaskWrapper(base, num_classes=num_classes),
+                                 dim=HYPER["dim"], K=K, m=HYPER["m"], T=HYPER["T"], diff_speed=HYPER["diff_speed"])
+        sd = {k: v.clone() for k, v in init.state_dict().items()}
+        del init
+        mom = {}
+
+        def step():
+            oracle.train_step(arch, [sd], [im_q], [im_k], [torch.randperm(batch)],
+                              (torch.randperm(batch), torch.randperm(batch)), d=2, m=HYPER["m"], T=HYPER["T"],
+                              margin=HYPER["margin"], lr=lr, momentum=HYPER["momentum"],
+                              weight_decay=HYPER["weight_decay"], mom_bufs=mom)
+    times, t_start = [], time.perf_counter()
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        oracle.train_step(arch, [sd], [im_q], [im_k], [torch.randperm(batch)],
-                          (torch.randperm(batch), torch.randperm(batch)), d=2, m=HYPER["m"], T=HYPER["T"],
-                          margin=HYPER["margin"], lr=HYPER["lr"] * batch / 64, momentum=HYPER["momentum"],
-                          weight_decay=HYPER["weight_decay"], mom_bufs=mom)
+        step()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s and len(times) >= 3:
+            break    # bounded sample: the whole arm must end within a few minutes whatever --steps asks for
+    if kind == "reference":
+        torch.Tensor.cuda = orig_cuda
+    if own_group:
+        import torch.distributed as dist
+        dist.destroy_process_group()
     ms = statistics.median(times) * 1e3
-    return batch / (ms / 1e3), ms, cores, batch
+    return batch / (ms / 1e3), ms, cores, batch, kind, len(times)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 8))
-    warmup = max(1, min(args.warmup, 2))
-    v, ms, cores, batch = cpu_reference_clips_per_s(args.arch, steps, warmup)
-    sample = f"{steps} steps of {batch} videos ({args.arch}, 2x16x112x112 frames, K=16384) on {cores} host threads"
+    arch = args.arch if args.arch in ("resnet18", "c3d", "r2plus1d-vcop", "s3dg") else "resnet18"
+    v, ms, cores, batch, kind, timed = cpu_reference_clips_per_s(arch, max(1, args.steps), max(1, args.warmup),
+                                                                 frames=args.frames, size=args.size)
+    src = ("the unmodified reference modules (baseline/_ref) under stock torch CPU kernels" if kind == "reference"
+           else "oracle/rspnet_oracle.py (torch CPU restatement; baseline/_ref absent)")
+    sample = (f"{timed} steps of {batch} videos ({arch}, 2x{args.frames // 2}x{args.size}x{args.size} frames, "
+              f"K=16384) on {cores} host threads, {src}")
     print(json.dumps({
         "impl": "reference", "metric": "pretrain clips/sec", "value": v, "unit": "clips/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "steps": timed, "warmup": max(1, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": f"RSPNet {args.arch} pretraining step (MoCoDiffLossTwoFc), per-GPU batch {args.batch} videos, "
+        "config": {"workload": f"RSPNet {arch} pretraining step (MoCoDiffLossTwoFc), per-GPU batch {args.batch} videos, "
                                f"2x{args.frames // 2}x{args.size}x{args.size} clips, K={HYPER['K']}, dim 128",
-                   "sample": f"each CPU step is a batch of {batch} videos of that workload (same clip size, K and loss)"},
-        "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+                   "sample": f"each CPU step is a batch of {batch} videos of that workload (same clip size, K and loss: "
+                             "BASELINE config 1)"},
+        "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -334,7 +392,8 @@ def run_b200(args):
 
         # (1) uint8 frames -> sampler -> step.  Per video the 64 frames its two 32-frame clips are cut from, 128x171
         # (SURVEY.md 8d "pipeline benchmark" frame size); frame indices / boxes / gray / jitter / flip drawn per step.
-        FV, HS, WS = 2 * args.frames, 128, 171
+        FV = 2 * args.frames
+        HS, WS = (128, 171) if args.size <= 112 else (256, 342)
         pyrandom.seed(1234 + rank)
         sampler_k = GPUClipSampler(size=args.size, temporal_size=args.frames, strides=[{"stride": 1, "weight": 1}],
                                    crop_scale=(0.4, 1.0),
@@ -363,22 +422,24 @@ def run_b200(args):
         ms_f = run_feed(host_f, stage_f, lambda st: (st[0], st[1]), False)
         e2e_fp32 = {"value": B * world / (ms_f / 1e3), "unit": "clips/s", "ms_per_step": ms_f, "feed": "fp32_clips",
                     "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 12,
-                    "note": "pinned host fp32 clips [B,3,32,H,W] x 2 straight into PretrainEngine.step (PCIe-bound: "
-                            "617 MB per step)"}
+                    "note": "pinned host fp32 clips [B,3,T,H,W] x 2 straight into PretrainEngine.step (PCIe-bound: "
+                            f"{in_bytes / 1e6:.0f} MB per step)"}
         del host_f, stage_f
-        # both feeds are the public API with host buffers; `e2e` is the one a user would run on this node (the faster):
-        # one GPU is not PCIe-bound and skips the sampler's ~1.5 ms, eight GPUs share the host's memory bandwidth and
-        # win by moving uint8.  Both measurements stay in the line.
-        e2e = dict(e2e_u8 if e2e_u8["value"] >= e2e_fp32["value"] else e2e_fp32)
+        # ONE declared e2e experiment at every N: the reference loader's hand-off (uint8 frames -> device clip sampler ->
+        # step), i.e. the contract of datasets/classification/__init__.py:22-50.  The fp32-clip feed (bare
+        # model(clip_q, clip_k) contract) stays in `e2e_feeds` for comparison.
+        e2e = dict(e2e_u8)
         e2e_feeds = {"uint8_frames": e2e_u8, "fp32_clips": e2e_fp32}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, ms, cores, cb = cpu_reference_clips_per_s("resnet18" if args.arch not in ("resnet18", "c3d") else args.arch,
-                                                     steps=5, warmup=1)
-        cpu = {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "ms_per_step": ms,
-               "sample": f"5 steps of {cb} videos (BASELINE config 1 shape: batch 4, K=16384) on {cores} host threads, "
-                         "oracle/rspnet_oracle.py (torch CPU fp32 restatement of the reference step)"}
+        v, ms, cores, cb, kind, timed = cpu_reference_clips_per_s(
+            "resnet18" if args.arch not in ("resnet18", "c3d") else args.arch, steps=8, warmup=2, budget_s=40.0)
+        cpu = {"value": v, "unit": "clips/s", "cores": cores, "kind": kind, "ms_per_step": ms,
+               "sample": f"{timed} steps of {cb} videos (BASELINE config 1: batch 4, 2x16x112x112, K=16384) on {cores} "
+                         "host threads, " + ("the unmodified reference modules (baseline/_ref) under stock torch CPU "
+                                             "kernels" if kind == "reference" else "oracle/rspnet_oracle.py")}
+    parity = multi_gpu_parity(model, engine, last["loss"], dev) if world > 1 else None
     if rank == 0:
         print(json.dumps({
             "metric": "pretrain clips/sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
@@ -387,13 +448,54 @@ def run_b200(args):
             "config": {"workload": f"RSPNet {args.arch} pretraining step (MoCoDiffLossTwoFc), per-GPU batch {B} videos, "
                                    f"2x{args.frames // 2}x{args.size}x{args.size} clips, K={HYPER['K']}, dim 128",
                        "global_batch": B * world, "parallelism": f"dp{world}",
-                       "l2": "inputs alternate between two 617 MB device batches (> 126 MB L2)"},
+                       "l2": f"inputs alternate between two {in_bytes / 1e6:.0f} MB device batches (> 126 MB L2)"},
             "encoder_clip_passes_per_s": 3 * value,   # q, k and k_neg forwards of 16-frame clips per video
             "loss": loss_val, "remeasured": remeasured, "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms_step, "clocks": clocks, "e2e": e2e, "e2e_feeds": e2e_feeds, "roofline": roofline,
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "multi_gpu_parity": parity,
         }))
     if world > 1:
         dist.destroy_process_group()
+
+
+def multi_gpu_parity(model, engine, loss3, dev):
+    """Evidence carried by every N > 1 line (raises when a check fails, so a broken exchange cannot produce a number):
+    after the timed steps the queue, its pointer and the query-encoder parameters must be BIT-IDENTICAL on all ranks
+    (keys gathered in rank order, gradients averaged, same SGD everywhere), every rank's loss finite, and the shuffle-BN
+    transport must return exactly ``concat_all_gather(x)[idx_shuffle.view(W, -1)[rank]]`` (builder:361-387) on a
+    bench-sized batch — the reference formula evaluated with a plain NCCL all_gather."""
+    import torch
+    import torch.distributed as dist
+    from rspnet_b200 import ops
+    rank, world = dist.get_rank(), dist.get_world_size()
+    res = {}
+
+    def same_everywhere(t):
+        ref = t.clone()
+        dist.broadcast(ref, src=0)
+        return bool(torch.equal(ref, t))
+
+    res["queue_bit_identical"] = same_everywhere(model.queue)
+    res["queue_ptr_identical"] = same_everywhere(model.queue_ptr)
+    res["encoder_q_parameters_bit_identical"] = same_everywhere(engine.flat_q)
+    res["loss_finite"] = bool(torch.isfinite(torch.stack(loss3)).all())
+    k_buf = next(iter(model._exchanges.values()))._bufs[0][0]
+    x = (torch.randn(k_buf.shape, device=dev) + rank).to(k_buf.dtype)
+    got, idx_unshuffle = model._batch_shuffle_ddp(x)
+    idx_shuffle = ops.invert_permutation(idx_unshuffle)
+    parts = [torch.empty_like(x) for _ in range(world)]
+    dist.all_gather(parts, x)
+    want = torch.cat(parts, 0)[idx_shuffle.view(world, -1)[rank]]
+    res["shuffle_equals_reference_formula"] = bool(torch.equal(got, want))
+    res["shuffle_transport"] = next(iter(model._exchanges.values())).mode
+    res["shuffle_bytes_per_rank"] = got.numel() * got.element_size()
+    flags = torch.tensor([1 if v else 0 for k, v in res.items() if isinstance(v, bool)], device=dev)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    names = [k for k, v in res.items() if isinstance(v, bool)]
+    res.update({k: bool(f) for k, f in zip(names, flags.tolist())})
+    if not all(res[k] for k in names):
+        raise RuntimeError(f"multi-GPU parity check failed: {res}")
+    res["ranks"] = world
+    return res
 
 
 def conv_roofline(args, B, ms_step):
@@ -404,11 +506,13 @@ def conv_roofline(args, B, ms_step):
     import torch
     from rspnet_b200 import ops
     peaks_file = ROOT / "MEASURED_PEAKS.json"
-    peak, src = 1590.0, "fallback"
+    # every conv launch below is timed alone (a synchronize on both sides): the BURST figure is the denominator
+    peak, sustained, src = 1590.0, None, "fallback"
     if peaks_file.exists():
         pk = json.loads(peaks_file.read_text())
-        peak, src = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1590.0))), "measured (sustained)"
-    fwd, first = CONV_GF.get(args.arch, (None, None))
+        peak, src = float(pk.get("bf16_tflops", 1590.0)), "measured (burst: each launch is timed in isolation)"
+        sustained = pk.get("bf16_tflops_sustained")
+    fwd, first = conv_gflop(args.arch, args.frames, args.size)
     if fwd is None:
         return None
     from rspnet_b200.models import get_model_class
@@ -464,12 +568,17 @@ def conv_roofline(args, B, ms_step):
     top = [{"pass": n, "conv_layer": li, "gflop_per_launch": round(gf, 1), "ms_per_launch": round(ms, 4),
             "tflops": round(gf / ms, 1), "frac": round(gf / ms / peak, 3), "launches_per_step": weight[n]}
            for _, n, li, gf, ms in per_launch[:4]]
-    # DRAM traffic of the most expensive single launch (R3D-18 stem fprop, batch 64) from the committed ncu --set full capture
-    traffic = 4.61e8 if (args.arch == "resnet18" and B == 64 and args.size == 112) else None
+    # DRAM traffic of the dominant launch: only when a capture of THIS round is committed (profiles/r02_traffic.json,
+    # written from an `ncu --set full` report by tools/ncu_traffic.py); never a constant carried over
+    traffic, traffic_note = None, None
+    tfile = ROOT / "profiles" / "r02_traffic.json"
+    if tfile.exists():
+        t = json.loads(tfile.read_text()).get(f"{args.arch}_b{B}_{args.size}")
+        if t:
+            traffic, traffic_note = t["dram_bytes"], t["note"]
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": traffic,
-            "traffic_note": "dram__bytes_read+write of one conv_stem_kernel launch (algorithmic 5.14e8: 1.03e8 in, 4.11e8 out), "
-                            "profiles/r01_ncu_full_conv_r18.txt" if traffic else None,
+            "frac_of_sustained_peak": (achieved / float(sustained)) if sustained else None,
+            "traffic": traffic, "traffic_note": traffic_note,
             "peak_source": src, "kernel": "tcgen05 conv kernels (conv_direct / conv_igemm / conv_stem / conv_stem3 / conv_wgrad)",
             "top_launches": top,
             "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / ms_step,

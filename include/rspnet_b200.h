@@ -6,7 +6,7 @@
  *
  * Conventions
  *  - every pointer is a DEVICE pointer owned by the caller (PyTorch caching allocator); nothing is
- *    allocated, freed or retained by the library;
+ *    allocated, freed or retained by the library (sole exception: the rsp_peer_* IPC buffers);
  *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
  *  - return value 0 = ok, negative = error (see rsp_last_error(), thread-local);
  *  - activations on the conv path are bf16, channels-last NDHWC ([N][T][H][W][C]); "C" is the STORED
@@ -203,6 +203,24 @@ int rsp_speed_gather(const float* im_q, const float* im_k, const int64_t* perm, 
 /* Batched row gather: dst[i] = src[index[i]] for rows of `row_bytes` (multiple of 16) — the local half of
  * _batch_shuffle_ddp / _batch_unshuffle_ddp (:361-406) and the pack step of the permutation exchange. */
 int rsp_gather_rows(const void* src, const int64_t* index, void* dst, int64_t n_rows, int64_t row_bytes, void* stream);
+/* Shuffle-BN over NVLink peer memory (_batch_shuffle_ddp, :361-387: all_gather + x_gather[idx_this]).  Each rank keeps
+ * its key clips in a buffer its peers have mapped; one kernel per rank pulls the B rows the permutation assigns to it
+ * out of the owners' memory.  These five calls are the only ones that allocate: a peer buffer must be its own
+ * cudaMalloc allocation for the IPC handle, so the library owns it (rsp_peer_alloc / rsp_peer_free).
+ *   rsp_peer_export : 64-byte cudaIpcMemHandle_t of a buffer from rsp_peer_alloc (exchanged between ranks by the caller)
+ *   rsp_peer_open   : maps a peer's buffer into this process (cudaIpcMemLazyEnablePeerAccess); rsp_peer_close unmaps
+ *   rsp_gather_rows_peer : dst[i] = peer_bases[index[i] / rows_per_peer] row (index[i] % rows_per_peer);
+ *                          peer_bases is a DEVICE array of W base pointers (own buffer at [rank]), index int64 on
+ *                          the device (the permutation slice idx_shuffle.view(W,-1)[rank]), rows of row_bytes (% 16).
+ *   rsp_invert_permutation : inv[perm[i]] = i — idx_unshuffle = argsort(idx_shuffle) (:381) without a sort. */
+int rsp_peer_alloc(int64_t bytes, void** dev_ptr);
+int rsp_peer_free(void* dev_ptr);
+int rsp_peer_export(void* dev_ptr, uint8_t* handle64);
+int rsp_peer_open(const uint8_t* handle64, void** mapped);
+int rsp_peer_close(void* mapped);
+int rsp_gather_rows_peer(const void* const* peer_bases, const int64_t* index, void* dst, int64_t n_rows,
+                         int32_t rows_per_peer, int64_t row_bytes, void* stream);
+int rsp_invert_permutation(const int64_t* perm, int64_t* inv, int32_t n, void* stream);
 /* _dequeue_and_enqueue (:345-359): queue[:, ptr:ptr+n] = keys.T; ptr = (ptr+n) % K, ptr read/written on device.
  * queue fp32 [D][K]; keys fp32 [n][D]; queue_ptr int64[1]. K % n must be 0. */
 int rsp_queue_enqueue(float* queue, const float* keys, int64_t* queue_ptr, int32_t D, int32_t K, int32_t n,

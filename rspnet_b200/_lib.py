@@ -77,6 +77,13 @@ SIGNATURES = {
     "rsp_sgd_step": (c_i32, [_P, _P, _P, c_i64, c_f32, c_f32, c_f32, c_f32, c_i32, _P]),
     "rsp_speed_gather": (c_i32, [_P, _P, _P, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P, _P, _P, _P]),
     "rsp_gather_rows": (c_i32, [_P, _P, _P, c_i64, c_i64, _P]),
+    "rsp_peer_alloc": (c_i32, [c_i64, C.POINTER(C.c_void_p)]),
+    "rsp_peer_free": (c_i32, [_P]),
+    "rsp_peer_export": (c_i32, [_P, C.c_char_p]),
+    "rsp_peer_open": (c_i32, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "rsp_peer_close": (c_i32, [_P]),
+    "rsp_gather_rows_peer": (c_i32, [_P, _P, _P, c_i64, c_i32, c_i64, _P]),
+    "rsp_invert_permutation": (c_i32, [_P, _P, c_i32, _P]),
     "rsp_queue_enqueue": (c_i32, [_P, _P, _P, c_i32, c_i32, c_i32, _P]),
     "rsp_moco_logits_workspace": (c_i64, [c_i32, c_i32]),
     "rsp_moco_logits_fwd": (c_i32, [_P] * 7 + [c_i32, c_i32, c_i32, c_f32] + [_P] * 9 + [_P]),

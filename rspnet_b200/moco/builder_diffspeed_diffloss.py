@@ -176,6 +176,8 @@ class _MoCoBase(nn.Module):
         self.materialize_logits = True   # forward() returns [N, 1+K] logits like the reference
         self.overlap_key_passes = True   # key-encoder passes on a side stream next to the query pass (forward())
         self._side_stream = None
+        self._pull_stream = None
+        self._exchanges = {}             # (rows, row shape, dtype) -> exchange.ShuffleExchange (key-clip buffers + transport)
         self._flat_q: Optional[Tensor] = None
         self._flat_k: Optional[Tensor] = None
         assert self.diff_speed is not None, "This branch is for diff speed"
@@ -211,17 +213,32 @@ class _MoCoBase(nn.Module):
         assert self.K % keys.shape[0] == 0  # for simplicity
         ops.queue_enqueue_(self.queue, keys.float(), self.queue_ptr)
 
-    @torch.no_grad()
-    def _draw_shuffle(self, batch_size_all: int) -> Tensor:
-        """The reference's ``torch.randperm(batch_size_all).cuda()`` + broadcast(src=0) (ref :375-378), kept on the host."""
-        return exchange.broadcast_permutation(torch.randperm(batch_size_all))
+    # -- shuffle-BN --------------------------------------------------------------------------------------------
+    def _exchange_for(self, shape, dtype, device) -> "exchange.ShuffleExchange":
+        """The exchange (key-clip buffers + transport) for per-rank batches of this shape ([B, ...])."""
+        key = (tuple(shape), dtype, device)
+        ex = self._exchanges.get(key)
+        if ex is None:
+            ex = self._exchanges[key] = exchange.ShuffleExchange(shape[0], shape[1:], dtype, device)
+        return ex
 
     @torch.no_grad()
-    def _batch_shuffle_ddp(self, x):
-        _, world = exchange.world_info()
-        idx_shuffle = self._draw_shuffle(x.shape[0] * world)
-        idx_unshuffle = torch.argsort(idx_shuffle)
-        return exchange.exchange_rows(x, idx_shuffle, ops.gather_rows), idx_unshuffle
+    def _batch_shuffle_ddp(self, x, idx_shuffle=None, idx_host=None, slot=exchange.ShuffleExchange.SLOT_KNEG):
+        """ref :361-387.  ``x``: this rank's batch; returns (rows ``concat_all_gather(x)[idx_shuffle.view(W,-1)[rank]]``,
+        idx_unshuffle).  forward() pre-draws both permutations of the step (same generator, same order as the reference)
+        and passes ``idx_shuffle`` (int64 [B*W], on the device, already published); called without it this draws and
+        publishes its own permutation like the reference method does."""
+        ex = self._exchange_for(x.shape, x.dtype, x.device)
+        if idx_shuffle is None:
+            if not ex.holds(x, slot):
+                ex.begin_step()[slot].copy_(x)
+            idx_all, idx_hosts = ex.draw(x.shape[0] * ex.world, count=1)
+            ex.publish(idx_all)
+            idx_shuffle, idx_host = idx_all[0], (idx_hosts[0] if idx_hosts is not None else None)
+        elif not ex.holds(x, slot):
+            raise RuntimeError("rspnet_b200: pre-published permutations need the clips in the exchange buffers")
+        idx_unshuffle = ops.invert_permutation(idx_shuffle) if idx_shuffle.is_cuda else torch.argsort(idx_shuffle)
+        return ex.pull(slot, idx_shuffle, idx_host, ops.gather_rows), idx_unshuffle
 
     @torch.no_grad()
     def _batch_unshuffle_ddp(self, x, idx_unshuffle, return_all: bool = False):
@@ -233,8 +250,12 @@ class _MoCoBase(nn.Module):
         return (mine, restored) if return_all else mine
 
     @torch.no_grad()
-    def _forward_encoder_k(self, im_k, return_all: bool = False):
-        im_k, idx_unshuffle = self._batch_shuffle_ddp(rnn.as_ndhwc(im_k))
+    def _forward_encoder_k(self, im_k, return_all: bool = False, idx_shuffle=None, idx_host=None,
+                           slot=exchange.ShuffleExchange.SLOT_KNEG, shuffled=None):
+        if shuffled is None:
+            im_k, idx_unshuffle = self._batch_shuffle_ddp(rnn.as_ndhwc(im_k), idx_shuffle, idx_host, slot)
+        else:
+            im_k, idx_unshuffle = shuffled
         k_a, k_m = self.encoder_k(im_k)
         both = torch.cat([k_a, k_m], dim=1)  # one gather for both heads
         res = self._batch_unshuffle_ddp(both, idx_unshuffle, return_all)
@@ -245,12 +266,18 @@ class _MoCoBase(nn.Module):
         return res[:, :d].contiguous(), res[:, d:].contiguous()
 
     @torch.no_grad()
-    def _speed_views(self, im_q: Tensor, im_k: Tensor):
-        """ref :421-443: draws randperm(B) on the input's device and random.choice(diff_speed), then re-samples."""
+    def _speed_views(self, im_q: Tensor, im_k: Tensor, into_exchange: bool = False):
+        """ref :421-443: draws randperm(B) on the input's device and random.choice(diff_speed), then re-samples.
+        into_exchange: the k / k_neg clips are written straight into this step's exchange buffers (returned as such)."""
         B = im_q.shape[0]
         random_indices = torch.randperm(B, device=im_q.device)
-        diff_speed = random.choice(self.diff_speed)
-        return ops.speed_gather(im_q.float(), im_k.float(), random_indices, int(B * self.alpha), int(diff_speed), 1)
+        diff_speed = int(random.choice(self.diff_speed))
+        outs = None
+        if into_exchange:
+            shape = (B, im_q.shape[2] // diff_speed, im_q.shape[3], im_q.shape[4], 4)   # conv-ready bf16 NDHWC(4)
+            kneg_buf, k_buf = self._exchange_for(shape, torch.bfloat16, im_q.device).begin_step()
+            outs = (None, k_buf, kneg_buf)
+        return ops.speed_gather(im_q.float(), im_k.float(), random_indices, int(B * self.alpha), diff_speed, 1, outs)
 
     def _logits(self, q_a, q_m, k_a, k_m, kn_a, kn_m):
         l1, l2, lpm, lnm, rows, ranks = _LogitsFn.apply(q_a, q_m, k_a, k_m, kn_a, kn_m, self.queue, self.T,
@@ -279,7 +306,7 @@ class MoCoDiffLossTwoFc(_MoCoBase):
     @torch.no_grad()
     def _diff_speed(self, im_q: Tensor, im_k: Tensor):
         q, k, k_neg = self._speed_views(im_q, im_k)
-        kn_a, kn_m, kn_a_all = self._forward_encoder_k(k_neg, return_all=True)
+        kn_a, kn_m, kn_a_all = self._forward_encoder_k(k_neg, return_all=True, slot=exchange.ShuffleExchange.SLOT_KNEG)
         self._enqueue_payload = kn_a_all
         return q, k, kn_a, kn_m
 
@@ -292,27 +319,40 @@ class MoCoDiffLossTwoFc(_MoCoBase):
             with torch.no_grad():
                 self._momentum_update_key_encoder()
                 im_q, im_k, k_neg_A, k_neg_M = self._diff_speed(im_q, im_k)
-                k_A, k_M = self._forward_encoder_k(im_k)
+                k_A, k_M = self._forward_encoder_k(im_k, slot=exchange.ShuffleExchange.SLOT_K)
             q_A, q_M = self.encoder_q(im_q)
         else:
             # The two key-encoder passes (no grad) and the query pass are independent: the key passes go to a side
-            # stream so that the small layer3 / layer4 kernels of one pass fill the SMs the other leaves idle.  Order
-            # of the random draws is the reference's (speed perm, shuffle of k_neg, shuffle of k).
+            # stream so that the small layer3 / layer4 kernels of one pass fill the SMs the other leaves idle.  The
+            # random draws are made up front in the reference's order (speed perm, diff_speed choice, shuffle of k_neg,
+            # shuffle of k — nothing else touches those generators in between in the reference either), so that both
+            # permutations travel in ONE small all-reduce that also orders every peer's pull after every rank's clips.
             main = torch.cuda.current_stream()
             if self._side_stream is None:
                 self._side_stream = torch.cuda.Stream()
-            side = self._side_stream
+                self._pull_stream = torch.cuda.Stream()
+            side, pull = self._side_stream, self._pull_stream
+            SL = exchange.ShuffleExchange
             with torch.no_grad():
                 self._momentum_update_key_encoder()
-                im_q, im_k, k_neg = self._speed_views(im_q, im_k)
-            # No Tensor.record_stream here: im_k / k_neg stay referenced until this function returns, i.e. until after the
-            # join below, and what the side stream allocates is only reused by the side stream after its next
-            # wait_stream(main).  (record_stream defers block reuse to event polling; the caching allocator then grows
-            # with cudaMalloc in the middle of training steps — seen as sporadic 80-270 ms stalls.)
+                im_q, im_k, k_neg = self._speed_views(im_q, im_k, into_exchange=True)
+                ex = self._exchange_for(k_neg.shape, k_neg.dtype, k_neg.device)
+                idx_all, idx_host = ex.draw(k_neg.shape[0] * ex.world, count=2)
+            # No Tensor.record_stream here: the exchange buffers are persistent, and what the side streams allocate is
+            # only reused by them after their next wait_stream(main).  (record_stream defers block reuse to event
+            # polling; the caching allocator then grows with cudaMalloc in the middle of training steps.)
             side.wait_stream(main)
             with torch.cuda.stream(side), torch.no_grad():
-                k_neg_A, k_neg_M, self._enqueue_payload = self._forward_encoder_k(k_neg, return_all=True)
-                k_A, k_M = self._forward_encoder_k(im_k)
+                ex.publish(idx_all)
+                pull.wait_stream(side)
+                with torch.cuda.stream(pull):   # the k rows cross NVLink while the k_neg pass runs
+                    k_shuffled = self._batch_shuffle_ddp(im_k, idx_all[1], None if idx_host is None else idx_host[1],
+                                                         SL.SLOT_K)
+                k_neg_A, k_neg_M, self._enqueue_payload = self._forward_encoder_k(
+                    k_neg, return_all=True, idx_shuffle=idx_all[0], idx_host=None if idx_host is None else idx_host[0],
+                    slot=SL.SLOT_KNEG)
+                side.wait_stream(pull)
+                k_A, k_M = self._forward_encoder_k(None, shuffled=k_shuffled)
             q_A, q_M = self.encoder_q(im_q)
             main.wait_stream(side)
         logits_A, logits_M = self._logits(q_A, q_M, k_A, k_M, k_neg_A, k_neg_M)

@@ -267,15 +267,18 @@ def sgd_step_(p, grad, mom, lr, momentum, weight_decay, grad_scale=1.0, first_st
          float(grad_scale), int(first_step), stream_ptr())
 
 
-def speed_gather(im_q, im_k, perm, n_s1: int, d: int, layout: int):
-    """_diff_speed re-sampling. layout 0 -> fp32 NCDHW, 1 -> bf16 NDHWC(4)."""
+def speed_gather(im_q, im_k, perm, n_s1: int, d: int, layout: int, outs=None):
+    """_diff_speed re-sampling. layout 0 -> fp32 NCDHW, 1 -> bf16 NDHWC(4).  ``outs`` = (q, k, k_neg) destination
+    tensors (entries may be None): the key clips are written straight into the peer-visible exchange buffers."""
     b, c, t, h, w = im_q.shape
     tr = t // d
     dev = im_q.device
-    if layout == 0:
-        outs = [torch.empty((b, c, tr, h, w), dtype=torch.float32, device=dev) for _ in range(3)]
-    else:
-        outs = [torch.empty((b, tr, h, w, 4), dtype=torch.bfloat16, device=dev) for _ in range(3)]
+    shape, dtype = (((b, c, tr, h, w), torch.float32) if layout == 0 else ((b, tr, h, w, 4), torch.bfloat16))
+    outs = list(outs) if outs is not None else [None, None, None]
+    for i in range(3):
+        if outs[i] is None:
+            outs[i] = torch.empty(shape, dtype=dtype, device=dev)
+        assert tuple(outs[i].shape) == shape and outs[i].dtype == dtype and outs[i].is_contiguous()
     call("rsp_speed_gather", ptr(im_q.contiguous()), ptr(im_k.contiguous()), ptr(perm), b, c, t, h, w, n_s1, d, layout,
          ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), stream_ptr())
     return outs
@@ -289,6 +292,23 @@ def gather_rows(src: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
     if index.numel():
         call("rsp_gather_rows", ptr(src), ptr(index), ptr(out), index.numel(), row_bytes, stream_ptr())
     return out
+
+
+def gather_rows_peer(peer_table: torch.Tensor, index: torch.Tensor, rows_per_peer: int, row_shape, dtype) -> torch.Tensor:
+    """dst[i] = peer[index[i] // rows_per_peer][index[i] % rows_per_peer]; ``peer_table`` int64 [W] of device base
+    pointers (NVLink-mapped peer buffers, own buffer at [rank]), ``index`` int64 on the device."""
+    n = index.numel()
+    out = torch.empty((n,) + tuple(row_shape), dtype=dtype, device=index.device)
+    row_bytes = out[0].numel() * out.element_size()
+    call("rsp_gather_rows_peer", ptr(peer_table), ptr(index), ptr(out), n, int(rows_per_peer), row_bytes, stream_ptr())
+    return out
+
+
+def invert_permutation(perm: torch.Tensor) -> torch.Tensor:
+    """argsort of a permutation (int64, device): inv[perm[i]] = i."""
+    inv = torch.empty_like(perm)
+    call("rsp_invert_permutation", ptr(perm), ptr(inv), perm.numel(), stream_ptr())
+    return inv
 
 
 def queue_enqueue_(queue, keys, queue_ptr):

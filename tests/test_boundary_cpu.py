@@ -223,7 +223,18 @@ def _gloo_worker(rank, world, port, tmp):
     idx = exchange.broadcast_permutation(torch.randperm(batch * world))
     mine = exchange.exchange_rows(x, idx, lambda s, i: s[i])
     gathered = exchange.all_gather_rows(x)
-    torch.save(dict(x=x, idx=idx, mine=mine, gathered=gathered), Path(tmp) / f"r{rank}.pt")
+    # the builder-facing transport object (all_to_all mode under gloo): two steps, two key batches per step
+    ex = exchange.ShuffleExchange(batch, (4, 3), torch.float32, torch.device("cpu"))
+    steps = []
+    for step in range(2):
+        kneg_buf, k_buf = ex.begin_step()
+        kneg_buf.copy_(x + step)
+        k_buf.copy_(-x - step)
+        idx2, host2 = ex.draw(batch * world, count=2)
+        ex.publish(idx2)
+        steps.append(dict(idx=idx2.clone(), kneg=ex.pull(ex.SLOT_KNEG, idx2[0], host2[0], lambda s, i: s[i]),
+                          k=ex.pull(ex.SLOT_K, idx2[1], host2[1], lambda s, i: s[i])))
+    torch.save(dict(x=x, idx=idx, mine=mine, gathered=gathered, steps=steps, mode=ex.mode), Path(tmp) / f"r{rank}.pt")
     dist.barrier()
     dist.destroy_process_group()
 
@@ -237,3 +248,8 @@ def test_exchange_two_ranks_gloo(tmp_path):
     for r in range(world):
         assert torch.equal(recs[r]["gathered"], torch.cat(xs, 0))
         assert torch.equal(recs[r]["mine"], _exchange_reference(xs, recs[0]["idx"], r, world))
+        assert recs[r]["mode"] == "a2a"
+        for step, st in enumerate(recs[r]["steps"]):
+            assert torch.equal(st["idx"], recs[0]["steps"][step]["idx"])       # rank 0's two permutations everywhere
+            assert torch.equal(st["kneg"], _exchange_reference([x + step for x in xs], st["idx"][0], r, world))
+            assert torch.equal(st["k"], _exchange_reference([-x - step for x in xs], st["idx"][1], r, world))

@@ -57,8 +57,8 @@ def main():
     taps = {"shuffle_in": [], "shuffle_out": [], "unshuffle_in": [], "unshuffle_out": []}
     orig_shuffle, orig_unshuffle = model._batch_shuffle_ddp, model._batch_unshuffle_ddp
 
-    def tap_shuffle(x):
-        out, idx_unshuffle = orig_shuffle(x)
+    def tap_shuffle(x, *a, **k):
+        out, idx_unshuffle = orig_shuffle(x, *a, **k)
         taps["shuffle_in"].append(x)
         taps["shuffle_out"].append((out, idx_unshuffle))
         return out, idx_unshuffle
@@ -70,6 +70,15 @@ def main():
         return res if return_all else res[0]
 
     model._batch_shuffle_ddp, model._batch_unshuffle_ddp = tap_shuffle, tap_unshuffle
+    kneg_ptr = []
+    orig_views = model._speed_views
+
+    def tap_views(*a, **k):
+        q, kk, kn = orig_views(*a, **k)
+        kneg_ptr.append(kn.data_ptr())
+        return q, kk, kn
+
+    model._speed_views = tap_views
     im_q, im_k = make_inputs(cfg, rank, 0)
     try:
         output, target, rl, rt = ddp(im_q.cuda(), im_k.cuda())
@@ -87,9 +96,11 @@ def main():
 
     # ---- bit-exact: shuffle-BN routing -----------------------------------------------------------------------
     idx_dev = [rec0["idx_shuffle_neg"].cuda(), rec0["idx_shuffle_pos"].cuda()]
+    # forward() issues the k pull (on its own stream) before the k_neg pass: order the taps by pass
+    order = sorted(range(2), key=lambda i: 0 if taps["shuffle_in"][i].data_ptr() == kneg_ptr[0] else 1)
     for p_i, pname in enumerate(("k_neg", "k")):
-        x_local = taps["shuffle_in"][p_i]                       # bf16 NDHWC [B, T, H, W, 4]
-        got, idx_unshuffle = taps["shuffle_out"][p_i]
+        x_local = taps["shuffle_in"][order[p_i]]                # bf16 NDHWC [B, T, H, W, 4]
+        got, idx_unshuffle = taps["shuffle_out"][order[p_i]]
         want = ref_all_gather(x_local)[idx_dev[p_i].view(world, -1)[rank]]          # builder:383-387
         check(f"shuffled batch of the {pname} pass == concat_all_gather(x)[idx_shuffle.view(W,-1)[rank]] (bit-exact, "
               f"{got.numel() * 2 / 1e6:.1f} MB)", torch.equal(got, want))
