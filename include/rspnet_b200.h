@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RSP_ABI_VERSION 1
+#define RSP_ABI_VERSION 2
 
 int rsp_abi_version(void);
 /* Checks that the current device is compute capability 10.x; caches the SM count. */
@@ -116,18 +116,25 @@ int rsp_maxpool3d_bwd(const rsp_pool3d_desc* d, const void* dy, const uint8_t* i
 
 /* Fused BatchNorm(train) -> ReLU -> MaxPool3d (reference: models/resnet.py:203-206 bn1/relu/maxpool after conv1,
  * models/c3d.py:111-139 bn/relu/pool1..4).  x is the conv output (bf16 NDHWC, the pool's input geometry); scale/shift/
- * mean/invstd come from rsp_bn_finalize.  The post-activation tensor is never materialised.
- *   fwd        : y bf16 [N][To][Ho][Wo][C], idx uint8 argmax inside the window (first maximum in (kt,kh,kw) order)
- *   bwd_dz     : dz = [bn(x) > 0] * (pool gradient routed by idx), written as bf16 in x's layout, and
- *                sum_dz[c] += sum dz, sum_dz_xhat[c] += sum dz*xhat (both must be zero on entry);
- *                rsp_bn_act_bwd_apply(dout = dz, relu = 0) then yields the gradient w.r.t. the conv output.
+ * mean/invstd come from rsp_bn_finalize.  The post-activation tensor is never materialised, and neither is the pool
+ * gradient at input resolution.
+ *   fwd      : y bf16 [N][To][Ho][Wo][C]; idx uint8 argmax inside the window (first maximum in (kt,kh,kw) order) and
+ *              xmax bf16 = x at that argmax, both [N][To][Ho][Wo][C] — pass both or, for no-grad passes, NULL for both
+ *   bwd_sums : sum_dz[c] += sum_o dy*[bn(xmax) > 0], sum_dz_xhat[c] += sum_o dy*[..]*(xmax-mean)*invstd (zero on entry):
+ *              the two BatchNorm-backward reductions from the POOLED tensors only
+ *   bwd_dx   : dx = gamma*invstd*(dz - sum_dz/M - xhat*sum_dz_xhat/M), M = N*Ti*Hi*Wi, with dz scattered from (dy, idx)
+ *              into a shared-memory tile of input rows and x streamed once; gamma has C_logical entries.
  * rsp_bn_relu_maxpool_supported: 1 when the geometry fits the kernels' shared-memory tiles (else use the unfused calls). */
 int rsp_bn_relu_maxpool_supported(const rsp_pool3d_desc* d);
 int rsp_bn_relu_maxpool_fwd(const rsp_pool3d_desc* d, const void* x, const float* scale, const float* shift, void* y,
-                            uint8_t* idx, void* stream);
-int rsp_bn_relu_maxpool_bwd_dz(const rsp_pool3d_desc* d, const void* dy, const uint8_t* idx, const void* x,
-                               const float* scale, const float* shift, const float* mean, const float* invstd,
-                               float* sum_dz, float* sum_dz_xhat, void* dz, void* stream);
+                            uint8_t* idx, void* xmax, void* stream);
+int rsp_bn_relu_maxpool_bwd_sums(const rsp_pool3d_desc* d, const void* dy, const void* xmax, const float* scale,
+                                 const float* shift, const float* mean, const float* invstd, float* sum_dz,
+                                 float* sum_dz_xhat, void* stream);
+int rsp_bn_relu_maxpool_bwd_dx(const rsp_pool3d_desc* d, const void* dy, const uint8_t* idx, const void* xmax,
+                               const void* x, const float* scale, const float* shift, const float* mean,
+                               const float* invstd, const float* gamma, int32_t C_logical, const float* sum_dz,
+                               const float* sum_dz_xhat, void* dx, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Projection heads (reference: moco/split_wrapper.py:128-152,164-169): global average pool over the

@@ -60,8 +60,10 @@ SIGNATURES = {
     "rsp_maxpool3d_fwd": (c_i32, [C.POINTER(PoolDesc), _P, _P, _P, _P]),
     "rsp_maxpool3d_bwd": (c_i32, [C.POINTER(PoolDesc), _P, _P, _P, _P]),
     "rsp_bn_relu_maxpool_supported": (c_i32, [C.POINTER(PoolDesc)]),
-    "rsp_bn_relu_maxpool_fwd": (c_i32, [C.POINTER(PoolDesc), _P, _P, _P, _P, _P, _P]),
-    "rsp_bn_relu_maxpool_bwd_dz": (c_i32, [C.POINTER(PoolDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "rsp_bn_relu_maxpool_fwd": (c_i32, [C.POINTER(PoolDesc), _P, _P, _P, _P, _P, _P, _P]),
+    "rsp_bn_relu_maxpool_bwd_sums": (c_i32, [C.POINTER(PoolDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "rsp_bn_relu_maxpool_bwd_dx": (c_i32, [C.POINTER(PoolDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, c_i32, _P, _P, _P,
+                                           _P]),
     "rsp_head_fwd": (c_i32, [_P, c_i32, c_i32, c_i32, c_i32, c_i32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "rsp_head_bwd": (c_i32, [_P, _P, _P, _P, _P, c_i32, c_i32, c_i32, c_i32, c_i32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "rsp_gate_fwd": (c_i32, [_P, c_i32, c_i32, c_i32, c_i32, _P, _P, _P, _P, _P, _P, _P]),
@@ -117,7 +119,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError here = header/library mismatch
             fn.restype = res
             fn.argtypes = args
-        if lib.rsp_abi_version() != 1:
+        if lib.rsp_abi_version() != 2:
             raise RuntimeError("rspnet_b200: ABI version mismatch between python binding and library")
         _lib = lib
     return _lib

@@ -1,4 +1,4 @@
-// Fused train-mode BatchNorm + ReLU + MaxPool3d on bf16 NDHWC tensors, forward and backward.
+// Fused train-mode BatchNorm + ReLU + MaxPool3d on bf16 NDHWC tensors, forward.
 //
 // Reference call sites: models/resnet.py:203-206 (conv1 -> bn1 -> relu -> maxpool k3 s2 p1) and models/c3d.py:111-139
 // (conv -> bn -> relu -> pool1..4).  Unfused, the post-activation tensor is written and read back once in the forward
@@ -6,16 +6,16 @@
 // bn reduce -> bn apply).  Here:
 //   forward : raw conv-output rows (bf16) --bulk copy--> smem; window scan on sign(scale)*x; affine + ReLU once per output
 //             --> pooled y + uint8 argmax
-//   backward: dz(input position) = [bn(x) > 0] * sum of dy over the windows whose argmax is this position, rebuilt from
-//             (dy, argmax) staged in smem, written once as bf16 and reduced to (sum dz, sum dz*xhat); the plain BN-apply
-//             kernel then turns dz into dx.
-// HBM traffic per input element: forward 2 B read (+ pooled output); backward 2 B read + 2 B write, then 4 B read + 2 B write.
+//             --> pooled y (+ uint8 argmax and the raw value at the argmax in grad-enabled passes)
+//   backward: bn_pool_bwd.cu (reductions from the pooled tensors, then one scatter + stream pass).
+// HBM traffic per input element: forward 2 B read (+ pooled outputs).
 #include "common.cuh"
 #include "rspnet_b200.h"
 
 namespace rsp {
 
 int device_sm_count();
+int bn_pool_bwd_row_bytes_ok(const rsp_pool3d_desc* d);
 
 namespace {
 
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_fwd_kernel(const uint4* _
                                                                   const float* __restrict__ scale,
                                                                   const float* __restrict__ shift,
                                                                   uint4* __restrict__ y, uint2* __restrict__ idx,
-                                                                  const FPGeom p) {
+                                                                  uint4* __restrict__ xmax, const FPGeom p) {
   extern __shared__ __align__(128) uint4 tile[];  // [kt][rowsIn][Wi][G] raw bf16
   __shared__ __align__(8) uint64_t bar;
   const int kt = KT ? KT : p.kt, kh = KH ? KH : p.kh, kw = KW ? KW : p.kw;
@@ -168,153 +168,16 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_fwd_kernel(const uint4* _
       for (int e = 0; e < 8; ++e) f[e] = fmaxf(fmaf(f[e], fabsf(sc[e]), sf[e]), 0.f);  // |s| * (sign*x) = s*x
       const size_t o = (((static_cast<size_t>(n) * p.To + to) * p.Ho + ho0 + hb) * p.Wo + wo) * G + g;
       y[o] = pack8(f);
-      uint2 iv;
-      iv.x = __byte_perm(bi[0], bi[1], 0x6420);
-      iv.y = __byte_perm(bi[2], bi[3], 0x6420);
-      idx[o] = iv;
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// backward, pass 1: one tile = HB input rows of one (n, ti); bulk copies stage dy / argmax of every window that can select
-// them plus the x rows themselves.  dz = [bn(x) > 0] * (sum of dy over the windows whose argmax is this position) is written
-// as bf16 and reduced to per-channel (sum dz, sum dz*xhat); pass 2 is the plain BN-backward apply kernel on dz.
-// Input pixels are visited class by class (wi mod sw) so that the lanes of a warp share the same candidate windows.
-// ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2) bn_relu_maxpool_bwd_kernel(
-    const uint4* __restrict__ dy, const uint2* __restrict__ idx, const uint4* __restrict__ x,
-    const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
-    const float* __restrict__ invstd, float* __restrict__ sum_dz, float* __restrict__ sum_dz_xhat,
-    uint4* __restrict__ dz_out, const FPGeom p, int maxWin) {
-  extern __shared__ __align__(128) uint4 stage[];        // dy vectors | x rows | argmax vectors | tables
-  const int G = p.C >> 3;
-  const int rowVecs = p.Wi * G, orowVecs = p.Wo * G;
-  uint4* xs = stage + maxWin;
-  uint2* sidx = reinterpret_cast<uint2*>(xs + p.HB * rowVecs);
-  int* wtab = reinterpret_cast<int*>(sidx + maxWin);     // [Wi]  w_lo | w_hi << 16
-  int* htab = wtab + p.Wi;                               // [HB]  h_lo | h_hi << 16
-  __shared__ __align__(8) uint64_t bar;
-  __shared__ float red[2 * 256 * 8];
-  const int g = threadIdx.x % G;
-  float sc[8], sf[8], mu[8], a0[8], a1[8];   // a0 = sum dz, a1 = sum dz*(x - mean)  (invstd applied at the end)
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int c = g * 8 + e;
-    sc[e] = scale[c];
-    sf[e] = shift[c];
-    mu[e] = mean[c];
-    a0[e] = a1[e] = 0.f;
-  }
-  for (int wi = threadIdx.x; wi < p.Wi; wi += 256) {
-    const int lo = max(0, ceil_div(wi + p.pw - p.kw + 1, p.sw)), hi = min(p.Wo - 1, floor_div(wi + p.pw, p.sw));
-    wtab[wi] = lo | (hi << 16);
-  }
-  if (threadIdx.x == 0) {
-    mbar_init(&bar, 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-  const int perClass = (p.Wi + p.sw - 1) / p.sw;   // pixels of one w-class per row
-  uint32_t phase = 0;
-  for (int tIdx = blockIdx.x; tIdx < p.numTiles; tIdx += gridDim.x, phase ^= 1) {
-    const int band = tIdx % p.bands;
-    const int q = tIdx / p.bands;
-    const int ti = q % p.Ti, n = q / p.Ti;
-    const int hi0 = band * p.HB;
-    const int hbEff = min(p.HB, p.Hi - hi0);
-    const int to_lo = max(0, ceil_div(ti + p.pt - p.kt + 1, p.st)), to_hi = min(p.To - 1, floor_div(ti + p.pt, p.st));
-    const int ho_lo = max(0, ceil_div(hi0 + p.ph - p.kh + 1, p.sh));
-    const int ho_hi = min(p.Ho - 1, floor_div(hi0 + hbEff - 1 + p.ph, p.sh));
-    const int nto = max(0, to_hi - to_lo + 1), nho = max(0, ho_hi - ho_lo + 1);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      fence_proxy_async_smem();
-      const uint32_t rows = static_cast<uint32_t>(nho) * orowVecs;       // vectors per candidate frame
-      const uint32_t xbytes = static_cast<uint32_t>(hbEff) * rowVecs * 16u;
-      mbar_arrive_expect_tx(&bar, xbytes + static_cast<uint32_t>(nto) * rows * 24u);
-      bulk_g2s(xs, x + ((static_cast<size_t>(n) * p.Ti + ti) * p.Hi + hi0) * rowVecs, xbytes, &bar);
-      if (rows)
-        for (int tt = 0; tt < nto; ++tt) {
-          const size_t o = ((static_cast<size_t>(n) * p.To + to_lo + tt) * p.Ho + ho_lo) * orowVecs;
-          bulk_g2s(stage + tt * rows, dy + o, rows * 16u, &bar);
-          bulk_g2s(sidx + tt * rows, idx + o, rows * 8u, &bar);
-        }
-    }
-    if (threadIdx.x < hbEff) {
-      const int hi = hi0 + threadIdx.x;
-      const int lo = max(ho_lo, ceil_div(hi + p.ph - p.kh + 1, p.sh)), hh = min(ho_hi, floor_div(hi + p.ph, p.sh));
-      htab[threadIdx.x] = lo | (hh << 16);
-    }
-    __syncthreads();
-    mbar_wait(&bar, phase);
-    const int items = hbEff * p.sw * perClass * G;
-    for (int it = threadIdx.x; it < items; it += 256) {
-      const int r = it / G;
-      const int r2 = r / perClass;
-      const int kk = r - r2 * perClass;
-      const int hb = r2 / p.sw, cls = r2 - hb * p.sw;
-      const int wi = kk * p.sw + cls;
-      if (wi >= p.Wi) continue;
-      const int hi = hi0 + hb;
-      float acc[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-      const int ht = htab[hb], wt = wtab[wi];
-      const int h_lo = ht & 0xffff, h_hi = ht >> 16, w_lo = wt & 0xffff, w_hi = wt >> 16;
-      for (int to = to_lo; to <= to_hi; ++to) {
-        const int a = ti + p.pt - to * p.st;
-        for (int ho = h_lo; ho <= h_hi; ++ho) {
-          const int b = hi + p.ph - ho * p.sh;
-          const int base = ((to - to_lo) * nho + (ho - ho_lo)) * orowVecs + g;
-          for (int wo = w_lo; wo <= w_hi; ++wo) {
-            const int c = wi + p.pw - wo * p.sw;
-            const uint32_t lin4 = static_cast<uint32_t>((a * p.kh + b) * p.kw + c) * 0x01010101u;
-            const uint2 iv = sidx[base + wo * G];
-            uint4 d = stage[base + wo * G];
-            const uint32_t m0 = __vcmpeq4(iv.x, lin4), m1 = __vcmpeq4(iv.y, lin4);
-            if ((m0 | m1) == 0) continue;
-            d.x &= __byte_perm(m0, 0, 0x1100);
-            d.y &= __byte_perm(m0, 0, 0x3322);
-            d.z &= __byte_perm(m1, 0, 0x1100);
-            d.w &= __byte_perm(m1, 0, 0x3322);
-            float f[8];
-            unpack8(d, f);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[e] += f[e];
-          }
-        }
+      if (idx) {          // grad-enabled pass: the backward needs the argmax and the raw value it selected
+        uint2 iv;
+        iv.x = __byte_perm(bi[0], bi[1], 0x6420);
+        iv.y = __byte_perm(bi[2], bi[3], 0x6420);
+        idx[o] = iv;
+        uint4 xm;
+        xm.x = best[0] ^ flip[0]; xm.y = best[1] ^ flip[1]; xm.z = best[2] ^ flip[2]; xm.w = best[3] ^ flip[3];
+        xmax[o] = xm;
       }
-      const int xi = (hb * p.Wi + wi) * G + g;
-      float xv[8];
-      unpack8(xs[xi], xv);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float dz = fmaf(xv[e], sc[e], sf[e]) > 0.f ? acc[e] : 0.f;
-        acc[e] = dz;
-        a0[e] += dz;
-        a1[e] = fmaf(dz, xv[e] - mu[e], a1[e]);
-      }
-      dz_out[((static_cast<size_t>(n) * p.Ti + ti) * p.Hi + hi0) * rowVecs + xi] = pack8(acc);
     }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    red[threadIdx.x * 8 + e] = a0[e];
-    red[2048 + threadIdx.x * 8 + e] = a1[e];
-  }
-  __syncthreads();
-  const int reps = 256 / G;
-  for (int c = threadIdx.x; c < p.C; c += 256) {
-    const int gg = c >> 3, e = c & 7;
-    float t0 = 0.f, t1 = 0.f;
-    for (int r = 0; r < reps; ++r) {
-      t0 += red[(r * G + gg) * 8 + e];
-      t1 += red[2048 + (r * G + gg) * 8 + e];
-    }
-    atomicAdd(sum_dz + c, t0);
-    atomicAdd(sum_dz_xhat + c, t1 * invstd[c]);
   }
 }
 
@@ -342,12 +205,6 @@ using namespace rsp;
 
 extern "C" {
 
-static int bwd_smem_bytes(const FPGeom& g, int& maxWin) {
-  const int nto = (g.kt + g.st - 1) / g.st, nho = (g.HB + g.kh - 2) / g.sh + 1;
-  maxWin = nto * nho * g.Wo * (g.C / 8);
-  return maxWin * 24 + g.HB * g.Wi * (g.C / 8) * 16 + (g.Wi + g.HB) * 4 + 16;
-}
-
 int rsp_bn_relu_maxpool_supported(const rsp_pool3d_desc* d) {
   // C % 16: the argmax rows move with 16-byte-granular bulk copies
   if (d->C % 16 != 0 || 256 % (d->C / 8) != 0 || d->kt > 8 || d->kh > 8 || d->kw > 8) return 0;
@@ -355,17 +212,16 @@ int rsp_bn_relu_maxpool_supported(const rsp_pool3d_desc* d) {
   if (static_cast<size_t>(d->kt) * d->kh * row > static_cast<size_t>(kFusedSmemBudget)) return 0;
   FPGeom g;
   if (fill_fp(g, d) != RSP_OK) return 0;
-  g.HB = g.Hi < 4 ? g.Hi : 4;
-  int maxWin;
-  return bwd_smem_bytes(g, maxWin) <= 200 * 1024 ? 1 : 0;
+  return bn_pool_bwd_row_bytes_ok(d);   // the backward keeps one fp32 row tile in shared memory (bn_pool_bwd.cu)
 }
 
 int rsp_bn_relu_maxpool_fwd(const rsp_pool3d_desc* d, const void* x, const float* scale, const float* shift, void* y,
-                            uint8_t* idx, void* stream) {
+                            uint8_t* idx, void* xmax, void* stream) {
   FPGeom g;
   int rc = fill_fp(g, d);
   if (rc != RSP_OK) return rc;
   RSP_REQUIRE(rsp_bn_relu_maxpool_supported(d), "bn_relu_maxpool_fwd: one window row set does not fit in shared memory");
+  RSP_REQUIRE((idx == nullptr) == (xmax == nullptr), "bn_relu_maxpool_fwd: idx and xmax are written together or not at all");
   const size_t row = static_cast<size_t>(g.Wi) * g.C * 2;
   // as many output rows per tile as the smem budget allows (fewer re-reads of rows shared by neighbouring windows)
   int hb = 1;
@@ -391,7 +247,8 @@ int rsp_bn_relu_maxpool_fwd(const rsp_pool3d_desc* d, const void* x, const float
                              smem);                                                                                    \
     if (e == cudaSuccess)                                                                                              \
       bn_relu_maxpool_fwd_kernel<KT, KH, KW><<<static_cast<unsigned>(grid), 256, smem, s>>>(                           \
-          static_cast<const uint4*>(x), scale, shift, static_cast<uint4*>(y), reinterpret_cast<uint2*>(idx), g);      \
+          static_cast<const uint4*>(x), scale, shift, static_cast<uint4*>(y), reinterpret_cast<uint2*>(idx),          \
+          static_cast<uint4*>(xmax), g);                                                                               \
   } while (0)
   if (g.kt == 3 && g.kh == 3 && g.kw == 3) RSP_LAUNCH_POOL_FWD(3, 3, 3);
   else if (g.kt == 2 && g.kh == 2 && g.kw == 2) RSP_LAUNCH_POOL_FWD(2, 2, 2);
@@ -406,38 +263,6 @@ int rsp_bn_relu_maxpool_fwd(const rsp_pool3d_desc* d, const void* x, const float
     return RSP_ERR_CUDA;
   }
   return check_launch("bn_relu_maxpool_fwd");
-}
-
-int rsp_bn_relu_maxpool_bwd_dz(const rsp_pool3d_desc* d, const void* dy, const uint8_t* idx, const void* x,
-                               const float* scale, const float* shift, const float* mean, const float* invstd,
-                               float* sum_dz, float* sum_dz_xhat, void* dz, void* stream) {
-  FPGeom g;
-  int rc = fill_fp(g, d);
-  if (rc != RSP_OK) return rc;
-  g.HB = g.Hi < 4 ? g.Hi : 4;
-  g.rowsIn = 0;
-  g.bands = (g.Hi + g.HB - 1) / g.HB;
-  const long long tiles = static_cast<long long>(g.N) * g.Ti * g.bands;
-  if (tiles == 0) return RSP_OK;
-  RSP_REQUIRE(tiles < (1ll << 31), "bn_relu_maxpool_bwd: too many tiles");
-  g.numTiles = static_cast<int>(tiles);
-  int maxWin;
-  const int smem = bwd_smem_bytes(g, maxWin);
-  RSP_REQUIRE(d->C % 16 == 0 && smem <= 200 * 1024,
-              "bn_relu_maxpool_bwd: window staging (%d bytes) does not fit in shared memory", smem);
-  const int fit = (210 * 1024) / (smem + 17 * 1024);
-  const int per_sm = fit < 1 ? 1 : (fit > 2 ? 2 : fit);
-  long long grid = static_cast<long long>(device_sm_count()) * per_sm;
-  if (grid > tiles) grid = tiles;
-  cudaError_t e = cudaFuncSetAttribute(bn_relu_maxpool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) {
-    set_error("cudaFuncSetAttribute(bn_relu_maxpool_bwd): %s", cudaGetErrorString(e));
-    return RSP_ERR_CUDA;
-  }
-  bn_relu_maxpool_bwd_kernel<<<static_cast<unsigned>(grid), 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint4*>(dy), reinterpret_cast<const uint2*>(idx), static_cast<const uint4*>(x), scale, shift, mean,
-      invstd, sum_dz, sum_dz_xhat, static_cast<uint4*>(dz), g, maxWin);
-  return check_launch("bn_relu_maxpool_bwd");
 }
 
 }  // extern "C"

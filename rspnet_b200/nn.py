@@ -230,18 +230,18 @@ class ConvBNReLUPool(torch.autograd.Function):
         desc, y, (scale, shift, mean, invstd) = _conv_bn_stats(x, weight, bias, gamma, beta, running_mean, running_var,
                                                                kernel, stride, padding, eps, momentum)
         pdesc = ops.pool_desc(y.shape, pool_k, pool_s, pool_p)
-        out, idx = ops.bn_relu_maxpool_fwd(pdesc, y, scale, shift)
+        out, idx, xmax = ops.bn_relu_maxpool_fwd(pdesc, y, scale, shift)
         ctx.desc, ctx.pdesc = desc, pdesc
         ctx.has_bias = bias is not None
-        ctx.save_for_backward(x, weight, y, idx, scale, shift, mean, invstd, gamma)
+        ctx.save_for_backward(x, weight, y, idx, xmax, scale, shift, mean, invstd, gamma)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, weight, y, idx, scale, shift, mean, invstd, gamma = ctx.saved_tensors
+        x, weight, y, idx, xmax, scale, shift, mean, invstd, gamma = ctx.saved_tensors
         desc = ctx.desc
-        dy, dgamma, dbeta = ops.bn_relu_maxpool_bwd(ctx.pdesc, dout.contiguous(), idx, y, scale, shift, mean, invstd,
-                                                    gamma)
+        dy, dgamma, dbeta = ops.bn_relu_maxpool_bwd(ctx.pdesc, dout.contiguous(), idx, xmax, y, scale, shift, mean,
+                                                    invstd, gamma)
         dw = _wgrad(desc, x, dy, weight)
         dx = None
         if ctx.needs_input_grad[0]:
@@ -269,7 +269,7 @@ def conv_bn_relu_pool(x, conv: torch.nn.Conv3d, bn: torch.nn.BatchNorm3d, pool: 
     if not torch.is_grad_enabled():
         _, y, (scale, shift, _, _) = _conv_bn_stats(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean,
                                                     bn.running_var, k, s, p, bn.eps, momentum)
-        out = ops.bn_relu_maxpool_fwd(ops.pool_desc(y.shape, pk, ps, pp), y, scale, shift)[0]
+        out = ops.bn_relu_maxpool_fwd(ops.pool_desc(y.shape, pk, ps, pp), y, scale, shift, aux=False)[0]
     else:
         out = ConvBNReLUPool.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, k, s,
                                    p, bn.eps, momentum, pk, ps, pp)

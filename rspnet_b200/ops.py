@@ -181,26 +181,28 @@ def bn_relu_maxpool_supported(desc: PoolDesc) -> bool:
     return bool(_lib.load().rsp_bn_relu_maxpool_supported(C.byref(desc)))
 
 
-def bn_relu_maxpool_fwd(desc: PoolDesc, x, scale, shift):
-    """maxpool(relu(x*scale + shift)) without materialising the activation; returns (y, argmax)."""
+def bn_relu_maxpool_fwd(desc: PoolDesc, x, scale, shift, aux: bool = True):
+    """maxpool(relu(x*scale + shift)) without materialising the activation.  Returns (y, argmax, x_max); with
+    ``aux=False`` (no-grad passes) the argmax and the raw value it selected are neither tracked nor written."""
     to, ho, wo = desc.out_dims()
     y = torch.empty((desc.N, to, ho, wo, desc.C), dtype=torch.bfloat16, device=x.device)
-    idx = torch.empty((desc.N, to, ho, wo, desc.C), dtype=torch.uint8, device=x.device)
-    call("rsp_bn_relu_maxpool_fwd", C.byref(desc), ptr(x), ptr(scale), ptr(shift), ptr(y), ptr(idx), stream_ptr())
-    return y, idx
+    idx = torch.empty((desc.N, to, ho, wo, desc.C), dtype=torch.uint8, device=x.device) if aux else None
+    xmax = torch.empty_like(y) if aux else None
+    call("rsp_bn_relu_maxpool_fwd", C.byref(desc), ptr(x), ptr(scale), ptr(shift), ptr(y), ptr(idx), ptr(xmax),
+         stream_ptr())
+    return y, idx, xmax
 
 
-def bn_relu_maxpool_bwd(desc: PoolDesc, dy, idx, x, scale, shift, mean, invstd, gamma):
-    """Gradient w.r.t. the conv output x plus (dgamma, dbeta) of the fused BN -> ReLU -> MaxPool block."""
+def bn_relu_maxpool_bwd(desc: PoolDesc, dy, idx, xmax, x, scale, shift, mean, invstd, gamma):
+    """Gradient w.r.t. the conv output x plus (dgamma, dbeta) of the fused BN -> ReLU -> MaxPool block: the two BN
+    reductions from the pooled tensors (dy, x_max), then one pass that scatters dy and streams x (csrc/bn_pool_bwd.cu)."""
     c = x.shape[-1]
-    m = x.numel() // c
     sums = torch.zeros((2, c), dtype=torch.float32, device=x.device)
-    dz = torch.empty_like(x)
-    call("rsp_bn_relu_maxpool_bwd_dz", C.byref(desc), ptr(dy), ptr(idx), ptr(x), ptr(scale), ptr(shift), ptr(mean),
-         ptr(invstd), ptr(sums[0]), ptr(sums[1]), ptr(dz), stream_ptr())
+    call("rsp_bn_relu_maxpool_bwd_sums", C.byref(desc), ptr(dy), ptr(xmax), ptr(scale), ptr(shift), ptr(mean),
+         ptr(invstd), ptr(sums[0]), ptr(sums[1]), stream_ptr())
     dx = torch.empty_like(x)
-    call("rsp_bn_act_bwd_apply", ptr(dz), None, ptr(x), ptr(mean), ptr(invstd), ptr(gamma), ptr(sums[0]), ptr(sums[1]),
-         0, ptr(dx), None, m, c, gamma.numel(), stream_ptr())
+    call("rsp_bn_relu_maxpool_bwd_dx", C.byref(desc), ptr(dy), ptr(idx), ptr(xmax), ptr(x), ptr(scale), ptr(shift),
+         ptr(mean), ptr(invstd), ptr(gamma), gamma.numel(), ptr(sums[0]), ptr(sums[1]), ptr(dx), stream_ptr())
     cl = gamma.numel()
     return dx, sums[1][:cl], sums[0][:cl]
 

@@ -31,7 +31,7 @@ def test_header_symbols_all_exported(lib):
 def test_binding_table_matches_header(lib):
     from rspnet_b200 import _lib
     assert sorted(_lib.SIGNATURES) == _declared_symbols()
-    assert lib.rsp_abi_version() == 1
+    assert lib.rsp_abi_version() == 2
 
 
 def test_no_cpu_path():

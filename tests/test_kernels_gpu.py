@@ -306,14 +306,19 @@ def test_bn_relu_maxpool_fused(k, s, p, shape):
     assert ops.bn_relu_maxpool_supported(desc)
     act = ops.bn_act_fwd(xn, scale, shift, None, True)
     y2, idx2 = ops.maxpool3d_fwd(desc, act)
-    y1, idx1 = ops.bn_relu_maxpool_fwd(desc, xn, scale, shift)
+    y1, idx1, xmax1 = ops.bn_relu_maxpool_fwd(desc, xn, scale, shift)
+    y0 = ops.bn_relu_maxpool_fwd(desc, xn, scale, shift, aux=False)[0]       # the no-grad (key encoder) variant
+    assert torch.equal(y0, y1)
+    # x_max is the raw conv output at the argmax: the activation of it is the pooled value wherever that is positive
+    act_max = torch.relu(xmax1.float() * scale + shift).bfloat16()
+    assert torch.equal(act_max[y1.float() > 0], y1[y1.float() > 0])
     # same values bit for bit; the argmax may differ only where the winner is not unique after the activation (ReLU-clamped
     # windows, two inputs rounding to the same bf16) — positions whose gradient is masked or equivalent
     assert torch.equal(y1, y2)
     live = y2.float() > 0
     assert (idx1[live] == idx2[live]).float().mean().item() > 0.99
     dy = ops.to_ndhwc_bf16(rand(n, c, *y1.shape[1:4], seed=4), c)
-    dx1, dgamma1, dbeta1 = ops.bn_relu_maxpool_bwd(desc, dy, idx1, xn, scale, shift, mean, invstd, gamma)
+    dx1, dgamma1, dbeta1 = ops.bn_relu_maxpool_bwd(desc, dy, idx1, xmax1, xn, scale, shift, mean, invstd, gamma)
     dpool = ops.maxpool3d_bwd(desc, dy, idx2)               # rounds the routed gradient to bf16 (the fused path does not)
     dx2, _, dgamma2, dbeta2 = ops.bn_act_bwd(dpool, act, xn, mean, invstd, gamma, True, False)
     # windows whose winner differs (activation-rounding ties, see above) route their gradient elsewhere: robust statistic

@@ -101,18 +101,19 @@ pool = {}
 
 
 def pool_fwd():
-    pool["out"], pool["idx"] = ops.bn_relu_maxpool_fwd(pd, ys, scale, shift)
+    pool["out"], pool["idx"], pool["xmax"] = ops.bn_relu_maxpool_fwd(pd, ys, scale, shift)
 
 
 def pool_bwd():
-    ops.bn_relu_maxpool_bwd(pd, pool["dout"], pool["idx"], ys, scale, shift, mean0, inv0, gamma)
+    ops.bn_relu_maxpool_bwd(pd, pool["dout"], pool["idx"], pool["xmax"], ys, scale, shift, mean0, inv0, gamma)
 
 
 pool_fwd()
 pool["dout"] = torch.randn_like(pool["out"])
 no = pool["out"].numel()
-jobs.append(("bn_relu_maxpool_fwd", 2 * ns + 3 * no, pool_fwd))
-jobs.append(("bn_relu_maxpool_bwd_dz + bn_act_bwd_apply", (2 * ns + 3 * no + 2 * ns) + (4 * ns + 2 * ns), pool_bwd))
+jobs.append(("bn_relu_maxpool_fwd (+ argmax, x_max)", 2 * ns + 5 * no, pool_fwd))
+jobs.append(("bn_relu_maxpool_fwd, no-grad variant", 2 * ns + 2 * no, lambda: ops.bn_relu_maxpool_fwd(pd, ys, scale, shift, aux=False)))
+jobs.append(("bn_relu_maxpool_bwd_sums + bn_relu_maxpool_bwd_dx", 4 * no + (5 * no + 2 * ns + 2 * ns), pool_bwd))
 
 torch.cuda.synchronize()
 if mode == "time":

@@ -53,7 +53,7 @@ if arch == "resnet18":
     pd = ops.pool_desc(y.shape, (3, 3, 3), (2, 2, 2), (1, 1, 1))
     scale, shift = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda") * 0.1
     mean, invstd, gamma = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda"), torch.ones(c, device="cuda")
-    out, idx = ops.bn_relu_maxpool_fwd(pd, y, scale, shift)
-    ops.bn_relu_maxpool_bwd(pd, torch.randn_like(out), idx, y, scale, shift, mean, invstd, gamma)
+    out, idx, xmax = ops.bn_relu_maxpool_fwd(pd, y, scale, shift)
+    ops.bn_relu_maxpool_bwd(pd, torch.randn_like(out), idx, xmax, y, scale, shift, mean, invstd, gamma)
     torch.cuda.synchronize()
 torch.cuda.profiler.stop()
