@@ -222,6 +222,10 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # the ONLY stdout line of this script is the JSON: libraries that print banners on stdout (NCCL's version line) go to
+    # stderr for the duration of the run
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -324,6 +328,18 @@ def run_b200(args):
         resident_step(i)
         host_ms_step = min(host_ms_step, (time.perf_counter() - t0) * 1e3)
     barrier()
+    # device time of the phases of a step (CUDA events on the main stream; median of 10 steps, max over ranks)
+    engine.phase_log = []
+    for i in range(10):
+        resident_step(i)
+    barrier()
+    ph = torch.tensor([[m[j].elapsed_time(m[j + 1]) for j in range(3)] for m in engine.phase_log], device=dev)
+    engine.phase_log = None
+    ph = ph.median(dim=0).values
+    if world > 1:
+        dist.all_reduce(ph, op=dist.ReduceOp.MAX)
+    phases = dict(zip(("forward_3_encoder_passes_and_logits", "loss_and_backward_with_gradient_allreduce", "sgd"),
+                      [round(v, 3) for v in ph.tolist()]))
     clocks = sampler.stop() if rank == 0 else None
     loss_val = float(last["loss"][0])
     ms_step = ms_total / args.steps
@@ -441,7 +457,8 @@ def run_b200(args):
                                              "kernels" if kind == "reference" else "oracle/rspnet_oracle.py")}
     parity = multi_gpu_parity(model, engine, last["loss"], dev) if world > 1 else None
     if rank == 0:
-        print(json.dumps({
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps({
             "metric": "pretrain clips/sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -451,8 +468,8 @@ def run_b200(args):
                        "l2": f"inputs alternate between two {in_bytes / 1e6:.0f} MB device batches (> 126 MB L2)"},
             "encoder_clip_passes_per_s": 3 * value,   # q, k and k_neg forwards of 16-frame clips per video
             "loss": loss_val, "remeasured": remeasured, "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms_step, "clocks": clocks, "e2e": e2e, "e2e_feeds": e2e_feeds, "roofline": roofline,
-            "cpu_baseline": cpu, "multi_gpu_parity": parity,
-        }))
+            "cpu_baseline": cpu, "multi_gpu_parity": parity, "phases_ms": phases,
+        }) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -38,6 +38,7 @@ class PretrainEngine:
         self.flat_q, _ = self.model.flat_parameters()
         self.momentum_buf = torch.zeros_like(self.flat_q)
         self._first = True
+        self.phase_log = None     # set to a list to collect CUDA events at the phase boundaries of every step (bench.py)
         # the eight AverageMeters of pretrain.py:97-106, kept on the device (meters.py); off by default like any logging
         self.meters = None
         if track_metrics:
@@ -58,15 +59,28 @@ class PretrainEngine:
         """One optimisation step; returns (loss, loss_A, loss_M) as device scalars (no host sync)."""
         # gradients are produced straight into their slots of the flat buffer (rnn.register_grad_slots); slots of
         # parameters that receive nothing are zeroed by FlatDDP._finalize
+        marks = [] if self.phase_log is not None else None
+
+        def mark():
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append(ev)
+
         for p in self.ddp._params:
             p.grad = None
-        rnn.begin_grad_epoch()
+        mark()
         output, target, ranking_logits, ranking_target = self.ddp(clip_q, clip_k)
+        mark()
         loss, loss_a, loss_m = self.criterion(output, target, ranking_logits, ranking_target)
         loss.backward()
+        mark()
         for lo, hi in self.ddp.used_segments():
             ops.sgd_step_(self.flat_q[lo:hi], self.ddp.flat_grad[lo:hi], self.momentum_buf[lo:hi], self.lr,
                           self.momentum, self.weight_decay, 1.0, self._first)
+        mark()
+        if marks is not None:
+            self.phase_log.append(marks)
         self._first = False
         rnn.bump_weight_epoch()
         if self.meters is not None:

@@ -12,6 +12,7 @@ Random draws are made with the same generators in the same order as the referenc
 permutations, queue pointers and gathered keys are bit-identical.
 """
 import logging
+import os
 import random
 from typing import List, Optional, Tuple
 
@@ -174,7 +175,8 @@ class _MoCoBase(nn.Module):
         self.register_buffer("queue_ptr", torch.zeros(1, dtype=torch.long))
         self.alpha = 0.5
         self.materialize_logits = True   # forward() returns [N, 1+K] logits like the reference
-        self.overlap_key_passes = True   # key-encoder passes on a side stream next to the query pass (forward())
+        # key-encoder passes on a side stream next to the query pass (forward())
+        self.overlap_key_passes = os.environ.get("RSP_KEY_OVERLAP", "1") != "0"
         self._side_stream = None
         self._pull_stream = None
         self._exchanges = {}             # (rows, row shape, dtype) -> exchange.ShuffleExchange (key-clip buffers + transport)

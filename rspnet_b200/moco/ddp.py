@@ -11,6 +11,7 @@ Differences by design:
 * parameters that receive no gradient (``encoder.fc``; hence find_unused_parameters=True upstream) keep
   ``grad = None`` so that torch.optim.SGD skips them exactly as it does in the reference.
 """
+import os
 from typing import List
 
 import torch
@@ -23,6 +24,7 @@ from . import exchange
 class FlatDDP(nn.Module):
     def __init__(self, module: nn.Module, bucket_bytes: int = 32 << 20):
         super().__init__()
+        bucket_bytes = int(float(os.environ.get("RSP_DDP_BUCKET_MB", bucket_bytes / (1 << 20))) * (1 << 20))
         self.module = module
         self.rank, self.world = exchange.world_info()
         flat_q, flat_k = module.flat_parameters()

@@ -11,6 +11,7 @@ The conv path works on bf16 NDHWC tensors ``[N, T, H, W, C]``.  Each fused block
 Packed bf16 filter operands are cached per parameter and invalidated by ``bump_weight_epoch()`` (called by the
 EMA / SGD kernels, which update parameters through raw pointers) or by torch's own version counter.
 """
+import os
 from typing import Optional
 
 import torch
@@ -57,7 +58,7 @@ def _grad_slot(weight, task):
 # Filter gradients are off the critical path of backward (only the optimizer / the all-reduce read them), so they run
 # on a side stream while the main stream carries on with dgrad and the next layer; a callback queued on the autograd
 # graph task joins the streams when backward ends (FlatDDP waits on the same stream before it reduces a bucket).
-wgrad_overlap = True
+wgrad_overlap = os.environ.get("RSP_WGRAD_OVERLAP", "1") != "0"
 _wgrad_stream = None
 _wgrad_task = -1          # autograd graph task that already has the join callback queued
 

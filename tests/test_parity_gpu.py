@@ -290,7 +290,7 @@ def _verbatim_loop(overlap: bool, set_to_none: bool, steps: int = 3):
     path = ROOT / "baseline" / "_ref" / "config" / "pretrain" / "resnet18.jsonnet"
     if not path.exists():
         pytest.skip("baseline/_ref/config is not installed (python oracle/install_ref.py in the build container)")
-    cfg = get_config(path, ["{batch_size: 4, moco+: {k: 64}}"])
+    cfg = get_config(path, ["{batch_size: 8, moco+: {k: 64}}"])
     initialize_seed(0)
     rnn.wgrad_overlap = overlap
     try:
@@ -306,9 +306,9 @@ def _verbatim_loop(overlap: bool, set_to_none: bool, steps: int = 3):
         gen = torch.Generator().manual_seed(11)
         log = []
         for step in range(steps):
-            clip_q = torch.randn(4, 3, 8, 64, 64, generator=gen)
-            clip_k = torch.randn(4, 3, 8, 64, 64, generator=gen)
-            draws = [torch.randperm(4, generator=gen) for _ in range(3)]
+            clip_q = torch.randn(8, 3, 8, 64, 64, generator=gen)
+            clip_k = torch.randn(8, 3, 8, 64, 64, generator=gen)
+            draws = [torch.randperm(8, generator=gen) for _ in range(3)]
             replay, _ = _replay_randperm(draws)
             orig = torch.randperm
             torch.randperm = replay
@@ -357,7 +357,7 @@ def test_verbatim_reference_loop_tracks_oracle_and_is_stream_safe():
             assert d_loss < (0.03 if step == 0 else 0.6) and d_logit < (0.14 if step == 0 else 3.2), (step, d_loss, d_logit)
     finally:
         oracle.EMULATE_BF16 = False
-    assert int(sd1["queue_ptr"]) == int(sd["queue_ptr"]) == 12
+    assert int(sd1["queue_ptr"]) == int(sd["queue_ptr"]) == 24
     for k in ("encoder_q.encoder.bn1.weight", "encoder_q.fc1.2.bias", "encoder_k.encoder.bn1.weight",
               "encoder_q.encoder.layer4.1.bn2.bias"):
         # three chaotic steps at lr 0.00625: parameters have moved by ~1e-2, the two trajectories by up to that much apart
@@ -366,22 +366,42 @@ def test_verbatim_reference_loop_tracks_oracle_and_is_stream_safe():
         if ".encoder.fc." in k and k.startswith("encoder_q."):
             assert torch.equal(sd1[k], sd0[k]), k
     # ---- (2) stream safety ------------------------------------------------------------------------------------
+    # At random init this small network is chaotic (fp32 atomics reorder the BN statistics by an ulp and the first-layer
+    # gradient moves by percents, tools/oracle_sensitivity.py), so the yardstick is a REPEAT of the same configuration:
+    # a variant must agree with the base run as well as the base run agrees with itself.  A filter gradient read before
+    # its side-stream kernel finished would be stale (previous step) or partial: direction and norm far off.
+    def agreement(log_b, step):
+        worst_c, worst_r = 1.0, 1.0
+        for k, ga in log[step]["grads"].items():
+            gb = log_b[step]["grads"][k]
+            if ga.abs().max() < 1e-7 or ga.numel() < 64:
+                continue
+            worst_c = min(worst_c, _cos(ga, gb))
+            r = gb.norm().item() / ga.norm().item()
+            worst_r = max(worst_r, r, 1.0 / max(r, 1e-12))
+        return worst_c, worst_r
+
+    pkeys = [k for k in sd1 if k.startswith("encoder_q.") and not k.endswith(
+        ("running_mean", "running_var", "num_batches_tracked"))]
+
+    def param_gap(sd_b):
+        return max(((sd1[k].float() - sd_b[k].float()).abs().max().item(), k) for k in pkeys)
+
+    _, _, _, log_rep, sd1_rep = _verbatim_loop(overlap=True, set_to_none=True)
+    base_c, base_r = agreement(log_rep, 0)
+    base_gap = param_gap(sd1_rep)
+    print(f"[verbatim loop] repeat of the base run, step 0: worst gradient cosine {base_c:.4f}, worst norm ratio {base_r:.3f}; "
+          f"max query-encoder parameter difference after 3 steps {base_gap[0]:.2e} ({base_gap[1]})")
     for overlap, set_to_none in ((False, True), (True, False)):
         _, _, sd0_b, log_b, sd1_b = _verbatim_loop(overlap=overlap, set_to_none=set_to_none)
         assert all(torch.equal(sd0[k], sd0_b[k]) for k in sd0)
-        for step, (a, b) in enumerate(zip(log, log_b)):
-            assert set(a["grads"]) == set(b["grads"])
-            for k in a["grads"]:
-                ga, gb = a["grads"][k], b["grads"][k]
-                scale = max(ga.abs().max().item(), 1e-12)
-                # identical kernels, identical inputs at step 0; later steps inherit the ulp-level differences of the
-                # atomically accumulated filter gradients through one / two parameter updates
-                tol = 2e-3 if step == 0 else 5e-2
-                assert (ga - gb).abs().max().item() <= tol * scale, (overlap, set_to_none, step, k,
-                                                                     (ga - gb).abs().max().item() / scale)
-        worst = max((sd1[k].float() - sd1_b[k].float()).abs().max().item() for k in sd1 if k != "queue")
-        print(f"[verbatim loop] overlap={overlap} set_to_none={set_to_none}: max parameter difference after 3 steps {worst:.2e}")
-        assert worst < 1e-2
+        assert [set(a["grads"]) for a in log] == [set(b["grads"]) for b in log_b]
+        c, r = agreement(log_b, 0)
+        worst, worst_k = param_gap(sd1_b)
+        print(f"[verbatim loop] overlap={overlap} set_to_none={set_to_none}: step-0 worst gradient cosine {c:.4f}, worst norm "
+              f"ratio {r:.3f}; max query-encoder parameter difference after 3 steps {worst:.2e} ({worst_k})")
+        assert c > min(0.9, base_c - 0.05) and r < max(1.15, base_r + 0.1), (overlap, set_to_none, c, r, base_c, base_r)
+        assert worst < max(3e-2, 3 * base_gap[0]), (worst, worst_k, base_gap)
 
 
 def test_single_head_builder_matches_reference_golden():
