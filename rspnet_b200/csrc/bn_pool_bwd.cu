@@ -11,10 +11,11 @@
 //     dx[p] = gamma*invstd*dz[p]  +  A*x[p] + B,   A = -gamma*invstd^2*c2,  B = -gamma*invstd*(c1 - mean*invstd*c2),
 //     c1 = sum_dz / M,  c2 = sum_dz_xhat / M.
 // Pass 1 (bn_pool_bwd_sums_kernel) streams dy and x_max once (1/8 of the input size for the R3D-18 stem pool);
-// pass 2 (bn_pool_bwd_dx_kernel) takes one tile of input rows, scatters gamma*invstd*dy of every window that can select
-// a position of the tile into an fp32 shared-memory tile (shared-memory atomics: two overlapping windows may pick the
-// same position), then streams x once and writes dx once.  dz is never materialised at input resolution.
-// HBM traffic per input element: 2 B read + 2 B written (+ the pooled dy / argmax / x_max reads, L2-resident re-reads).
+// pass 2a (bn_pool_bwd_dense_kernel) streams x once and writes dx = A*x + B once; pass 2b (bn_pool_bwd_scatter_kernel)
+// streams the pooled tensors once more and adds gamma*invstd*dy at each argmax with native bf16x2 atomics (the value is
+// rounded to bf16 twice: once as A*x + B, once by the add — within the stated bf16 tolerance of the conv path).
+// dz is never materialised at input resolution and nothing is tiled: no shared-memory staging, no window scan.
+// HBM traffic per input element: 2 B read + 2 B written, plus twice the pooled tensors (5 B per OUTPUT element).
 #include "common.cuh"
 #include "rspnet_b200.h"
 
@@ -109,89 +110,102 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_sums_kernel(const uint4* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// pass 2: dx for one tile of HB input rows of one (n, ti)
-//   acc (shared, fp32) [HB][Wi][8][G]  <- scatter of gamma*invstd*dy*[bn(x_max) > 0] from every window whose argmax falls
-//                                          into the tile (element order [e][g]: conflict-free for the dense phase)
-//   dx = acc + A*x + B
+// pass 2a: dense part, dx = A*x + B (pure streaming; A, B per channel from the two sums)
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bn_pool_bwd_dx_kernel(
+__global__ void __launch_bounds__(256) bn_pool_bwd_dense_kernel(const uint4* __restrict__ x,
+                                                                const float* __restrict__ mean,
+                                                                const float* __restrict__ invstd,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ sum_dz,
+                                                                const float* __restrict__ sum_dz_xhat,
+                                                                uint4* __restrict__ dx, int C, int C_logical, float invM,
+                                                                long long nvec) {
+  const int G = C >> 3;
+  const int g = threadIdx.x % G;        // fixed per thread: 256 % G == 0 and the stride is a multiple of 256
+  float A[8], Bc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = g * 8 + e;
+    const float is = invstd[c];
+    const float gm = c < C_logical ? gamma[c] : 0.f;     // padded channels: zero gradient
+    const float c1 = sum_dz[c] * invM, c2 = sum_dz_xhat[c] * invM;
+    A[e] = -gm * is * is * c2;
+    Bc[e] = -gm * is * (c1 - mean[c] * is * c2);
+  }
+  const long long stride = static_cast<long long>(gridDim.x) * 256;
+  long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  for (; i + 3 * stride < nvec; i += 4 * stride) {      // four independent 16-byte loads in flight per thread
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = __ldg(x + i + k * stride);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float f[8];
+      unpack8b(v[k], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = fmaf(A[e], f[e], Bc[e]);
+      dx[i + k * stride] = pack8b(f);
+    }
+  }
+  for (; i < nvec; i += stride) {
+    float f[8];
+    unpack8b(__ldg(x + i), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = fmaf(A[e], f[e], Bc[e]);
+    dx[i] = pack8b(f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// pass 2b: sparse part, dx[argmax] += gamma*invstd*dy wherever bn(x_max) > 0 — one (output pixel, 8 channels) per thread,
+// one native bf16x2 atomic add (ATOM.ADD.BF16x2, the other half adds zero) per live channel; two overlapping windows
+// that selected the same input position simply add twice.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bn_pool_bwd_scatter_kernel(
     const uint4* __restrict__ dy, const uint2* __restrict__ idx, const uint4* __restrict__ xmax,
-    const uint4* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
-    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-    const float* __restrict__ sum_dz, const float* __restrict__ sum_dz_xhat, uint4* __restrict__ dx, const BPGeom p,
-    int C_logical) {
-  extern __shared__ __align__(16) float acc[];          // [HB * Wi][8][G]
+    const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ invstd,
+    const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx, const BPGeom p, int C_logical) {
   __shared__ int taps[256];                             // window-local index -> a | b << 8 | c << 16
   const int G = p.C >> 3;
   const int g = threadIdx.x % G;
-  const int nTaps = p.kt * p.kh * p.kw;
-  for (int i = threadIdx.x; i < nTaps; i += 256) {
+  for (int i = threadIdx.x; i < p.kt * p.kh * p.kw; i += 256) {
     const int c = i % p.kw, b = (i / p.kw) % p.kh, a = i / (p.kw * p.kh);
     taps[i] = a | (b << 8) | (c << 16);
   }
-  float sc[8], sf[8], gi[8], A[8], Bc[8];
+  float sc[8], sf[8], gi[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int c = g * 8 + e;
     sc[e] = scale[c];
     sf[e] = shift[c];
-    const float is = invstd[c];
-    const float gm = c < C_logical ? gamma[c] : 0.f;     // padded channels: zero gradient
-    const float c1 = sum_dz[c] * p.invM, c2 = sum_dz_xhat[c] * p.invM;
-    gi[e] = gm * is;
-    A[e] = -gm * is * is * c2;
-    Bc[e] = -gm * is * (c1 - mean[c] * is * c2);
+    gi[e] = (c < C_logical ? gamma[c] : 0.f) * invstd[c];
   }
-  const int rowVecs = p.Wi * G, orowVecs = p.Wo * G;
-  for (int tIdx = blockIdx.x; tIdx < p.numTiles; tIdx += gridDim.x) {
-    const int band = tIdx % p.bands;
-    const int q = tIdx / p.bands;
-    const int ti = q % p.Ti, n = q / p.Ti;
-    const int hi0 = band * p.HB;
-    const int hbEff = min(p.HB, p.Hi - hi0);
-    const int to_lo = max(0, cdiv(ti + p.pt - p.kt + 1, p.st)), to_hi = min(p.To - 1, fdiv(ti + p.pt, p.st));
-    const int ho_lo = max(0, cdiv(hi0 + p.ph - p.kh + 1, p.sh));
-    const int ho_hi = min(p.Ho - 1, fdiv(hi0 + hbEff - 1 + p.ph, p.sh));
-    const int nto = max(0, to_hi - to_lo + 1), nho = max(0, ho_hi - ho_lo + 1);
-    __syncthreads();                                     // previous tile's dense phase is done with acc
-    const int tileVecs4 = hbEff * rowVecs * 2;           // float4 count of the accumulator tile
-    for (int i = threadIdx.x; i < tileVecs4; i += 256) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    // ---- scatter phase: one (output pixel, channel group) per thread and iteration --------------------------------
-    const int items = nto * nho * orowVecs;
-    for (int it = threadIdx.x; it < items; it += 256) {
-      const int r = it / orowVecs;
-      const int v = it - r * orowVecs;                   // wo * G + g  (g == this thread's group: orowVecs % G == 0)
-      const int to = to_lo + r / nho, ho = ho_lo + r % nho;
-      const int wo = v / G;
-      const size_t o = ((static_cast<size_t>(n) * p.To + to) * p.Ho + ho) * orowVecs + v;
-      const uint2 iv = __ldg(idx + o);
-      float d[8], xv[8];
-      unpack8b(__ldg(dy + o), d);
-      unpack8b(__ldg(xmax + o), xv);
-      const int t0 = to * p.st - p.pt - ti, h0 = ho * p.sh - p.ph - hi0, w0 = wo * p.sw - p.pw;
+  __syncthreads();
+  const long long stride = static_cast<long long>(gridDim.x) * 256;
+  for (long long o = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; o < p.outVecs; o += stride) {
+    const uint2 iv = __ldg(idx + o);
+    float d[8], xv[8];
+    unpack8b(__ldg(dy + o), d);
+    unpack8b(__ldg(xmax + o), xv);
+    long long pix = o / G;                               // ((n*To + to)*Ho + ho)*Wo + wo
+    const int wo = static_cast<int>(pix % p.Wo);
+    pix /= p.Wo;
+    const int ho = static_cast<int>(pix % p.Ho);
+    pix /= p.Ho;
+    const int to = static_cast<int>(pix % p.To);
+    const long long n = pix / p.To;
+    const int t0 = to * p.st - p.pt, h0 = ho * p.sh - p.ph, w0 = wo * p.sw - p.pw;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const uint32_t word = e < 4 ? iv.x : iv.y;
-        const int tp = taps[(word >> (8 * (e & 3))) & 0xffu];
-        const int hh = h0 + ((tp >> 8) & 0xff);
-        if (t0 + (tp & 0xff) != 0 || hh < 0 || hh >= hbEff) continue;
-        if (!(fmaf(xv[e], sc[e], sf[e]) > 0.f)) continue;
-        const int ww = w0 + (tp >> 16);
-        atomicAdd(acc + (static_cast<size_t>(hh) * p.Wi + ww) * p.C + e * G + g, gi[e] * d[e]);
-      }
-    }
-    __syncthreads();
-    // ---- dense phase -------------------------------------------------------------------------------------------------
-    const size_t base = ((static_cast<size_t>(n) * p.Ti + ti) * p.Hi + hi0) * rowVecs;
-    const int tileVecs = hbEff * rowVecs;
-    for (int i = threadIdx.x; i < tileVecs; i += 256) {  // i = pixel * G + g
-      float xv[8], o[8];
-      unpack8b(__ldg(x + base + i), xv);
-      const float* a = acc + static_cast<size_t>(i / G) * p.C + g;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = a[e * G] + fmaf(A[e], xv[e], Bc[e]);
-      dx[base + i] = pack8b(o);
+    for (int e = 0; e < 8; ++e) {
+      if (!(fmaf(xv[e], sc[e], sf[e]) > 0.f)) continue;
+      const uint32_t word = e < 4 ? iv.x : iv.y;
+      const int tp = taps[(word >> (8 * (e & 3))) & 0xffu];
+      const long long pos = ((n * p.Ti + t0 + (tp & 0xff)) * p.Hi + h0 + ((tp >> 8) & 0xff)) * p.Wi + w0 + (tp >> 16);
+      __nv_bfloat16* target = dx + pos * p.C + g * 8 + e;
+      const float v = gi[e] * d[e];
+      // the bf16x2 word that holds the target; the partner half adds +0
+      const uint32_t add = (e & 1) ? pack_bf16x2(0.f, v) : pack_bf16x2(v, 0.f);
+      asm volatile("red.global.add.noftz.bf16x2 [%0], %1;" ::"l"(target - (e & 1)), "r"(add) : "memory");
     }
   }
 }
@@ -212,12 +226,11 @@ int fill_bp(BPGeom& g, const rsp_pool3d_desc* d) {
   return RSP_OK;
 }
 
-constexpr int kAccBudget = 64 * 1024;   // fp32 accumulator tile per CTA: three CTAs per SM
-
 }  // namespace
 
 int bn_pool_bwd_row_bytes_ok(const rsp_pool3d_desc* d) {
-  return static_cast<size_t>(d->Wi) * d->C * 4 <= static_cast<size_t>(kAccBudget) ? 1 : 0;
+  (void)d;
+  return 1;   // the backward has no shared-memory tile: any geometry the forward takes
 }
 
 }  // namespace rsp
@@ -250,37 +263,23 @@ int rsp_bn_relu_maxpool_bwd_dx(const rsp_pool3d_desc* d, const void* dy, const u
   BPGeom g;
   int rc = fill_bp(g, d);
   if (rc != RSP_OK) return rc;
-  const size_t rowBytes = static_cast<size_t>(g.Wi) * g.C * 4;
-  RSP_REQUIRE(rowBytes <= static_cast<size_t>(kAccBudget),
-              "bn_relu_maxpool_bwd_dx: one input row (%zu bytes of fp32) does not fit the accumulator tile", rowBytes);
-  int hb = static_cast<int>(kAccBudget / rowBytes);
-  if (hb > g.Hi) hb = g.Hi;
-  if (hb > 8) hb = 8;
-  g.HB = hb;
-  g.bands = (g.Hi + hb - 1) / hb;
-  const long long tiles = static_cast<long long>(g.N) * g.Ti * g.bands;
-  if (tiles == 0) return RSP_OK;
-  RSP_REQUIRE(tiles < (1ll << 31), "bn_relu_maxpool_bwd_dx: too many tiles");
-  g.numTiles = static_cast<int>(tiles);
-  const int smem = static_cast<int>(hb * rowBytes);
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(bn_pool_bwd_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(bn_pool_bwd_dx): %s", cudaGetErrorString(e));
-      return RSP_ERR_CUDA;
-    }
-    attr_smem = smem;
-  }
-  int per_sm = (220 * 1024) / (smem + 2048);
-  per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
-  long long grid = static_cast<long long>(device_sm_count()) * per_sm;
-  if (grid > tiles) grid = tiles;
-  bn_pool_bwd_dx_kernel<<<static_cast<unsigned>(grid), 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint4*>(dy), reinterpret_cast<const uint2*>(idx), static_cast<const uint4*>(xmax),
-      static_cast<const uint4*>(x), scale, shift, mean, invstd, gamma, sum_dz, sum_dz_xhat, static_cast<uint4*>(dx), g,
-      C_logical);
-  return check_launch("bn_relu_maxpool_bwd_dx");
+  const long long inVecs = static_cast<long long>(g.N) * g.Ti * g.Hi * g.Wi * (g.C / 8);
+  if (inVecs == 0) return RSP_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long cap = static_cast<long long>(device_sm_count()) * 8;
+  long long blocks = (inVecs + 256 * 8 - 1) / (256 * 8);
+  if (blocks > cap) blocks = cap;
+  bn_pool_bwd_dense_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(
+      static_cast<const uint4*>(x), mean, invstd, gamma, sum_dz, sum_dz_xhat, static_cast<uint4*>(dx), g.C, C_logical,
+      g.invM, inVecs);
+  rc = check_launch("bn_relu_maxpool_bwd_dx (dense)");
+  if (rc != RSP_OK || g.outVecs == 0) return rc;
+  blocks = (g.outVecs + 256 * 2 - 1) / (256 * 2);
+  if (blocks > cap) blocks = cap;
+  bn_pool_bwd_scatter_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(
+      static_cast<const uint4*>(dy), reinterpret_cast<const uint2*>(idx), static_cast<const uint4*>(xmax), scale, shift,
+      invstd, gamma, static_cast<__nv_bfloat16*>(dx), g, C_logical);
+  return check_launch("bn_relu_maxpool_bwd_dx (scatter)");
 }
 
 }  // extern "C"

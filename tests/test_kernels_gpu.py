@@ -291,6 +291,8 @@ def test_maxpool_fwd_bwd(k, s, p, shape):
                                           ((1, 2, 2), (1, 2, 2), (0, 0, 0), (2, 64, 3, 8, 8)),
                                           ((2, 2, 2), (2, 2, 2), (0, 0, 0), (1, 128, 4, 6, 6)),
                                           ((2, 2, 2), (2, 2, 2), (0, 0, 0), (2, 512, 4, 7, 7)),
+                                          ((3, 3, 3), (2, 2, 2), (1, 1, 1), (3, 64, 7, 16, 56)),
+                                          ((3, 2, 2), (2, 2, 2), (1, 0, 0), (2, 128, 5, 9, 12)),
                                           ((3, 3, 3), (1, 1, 1), (1, 1, 1), (1, 256, 3, 5, 5))])
 def test_bn_relu_maxpool_fused(k, s, p, shape):
     """The fused BN -> ReLU -> MaxPool kernels against (a) the two-step kernels (bit-identical pooled values) and (b) torch
@@ -310,8 +312,9 @@ def test_bn_relu_maxpool_fused(k, s, p, shape):
     y0 = ops.bn_relu_maxpool_fwd(desc, xn, scale, shift, aux=False)[0]       # the no-grad (key encoder) variant
     assert torch.equal(y0, y1)
     # x_max is the raw conv output at the argmax: the activation of it is the pooled value wherever that is positive
-    act_max = torch.relu(xmax1.float() * scale + shift).bfloat16()
-    assert torch.equal(act_max[y1.float() > 0], y1[y1.float() > 0])
+    # (the kernel uses one fused multiply-add: a bf16 ulp of slack)
+    act_max = torch.relu(xmax1.float() * scale + shift)
+    torch.testing.assert_close(act_max[y1.float() > 0], y1.float()[y1.float() > 0], rtol=1e-2, atol=1e-3)
     # same values bit for bit; the argmax may differ only where the winner is not unique after the activation (ReLU-clamped
     # windows, two inputs rounding to the same bf16) — positions whose gradient is masked or equivalent
     assert torch.equal(y1, y2)
