@@ -338,8 +338,8 @@ def run_b200(args):
     ph = ph.median(dim=0).values
     if world > 1:
         dist.all_reduce(ph, op=dist.ReduceOp.MAX)
-    phases = dict(zip(("forward_3_encoder_passes_and_logits", "loss_and_backward_with_gradient_allreduce", "sgd"),
-                      [round(v, 3) for v in ph.tolist()]))
+    phases = dict(zip(("forward_3_encoder_passes_and_logits", "loss_backward_gradient_allreduce_and_per_bucket_sgd",
+                       "after_backward"), [round(v, 3) for v in ph.tolist()]))
     clocks = sampler.stop() if rank == 0 else None
     loss_val = float(last["loss"][0])
     ms_step = ms_total / args.steps

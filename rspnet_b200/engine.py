@@ -44,11 +44,21 @@ class PretrainEngine:
         if track_metrics:
             from .meters import ContrastiveMeters
             self.meters = ContrastiveMeters(self.flat_q.device)
+        # SGD runs bucket by bucket inside backward, on the stream where each bucket's all-reduced gradient becomes final
+        # (FlatDDP.bucket_hook): only the last small bucket's reduce + update is left after the final wgrad kernel.  The
+        # 1/world of DDP's mean is folded into the update (grad_scale), not spent on a pass over the gradient.
+        self.ddp.bucket_hook = self._sgd_segments
+        self.ddp.defer_average = True
         self._bind_grads()
 
     def _bind_grads(self):
         for p, v in zip(self.ddp._params, self.ddp._views):
             p.grad = v
+
+    def _sgd_segments(self, segments):
+        for lo, hi in segments:
+            ops.sgd_step_(self.flat_q[lo:hi], self.ddp.flat_grad[lo:hi], self.momentum_buf[lo:hi], self.lr,
+                          self.momentum, self.weight_decay, 1.0 / self.ddp.world, self._first)
 
     def set_epoch(self, epoch: int):
         """CosineAnnealingLR(T_max=num_epochs, eta_min=lr/1000) evaluated per epoch (pretrain.py:74-79)."""
@@ -73,11 +83,8 @@ class PretrainEngine:
         output, target, ranking_logits, ranking_target = self.ddp(clip_q, clip_k)
         mark()
         loss, loss_a, loss_m = self.criterion(output, target, ranking_logits, ranking_target)
-        loss.backward()
+        loss.backward()          # includes the gradient all-reduce and the SGD update of every bucket (_sgd_segments)
         mark()
-        for lo, hi in self.ddp.used_segments():
-            ops.sgd_step_(self.flat_q[lo:hi], self.ddp.flat_grad[lo:hi], self.momentum_buf[lo:hi], self.lr,
-                          self.momentum, self.weight_decay, 1.0, self._first)
         mark()
         if marks is not None:
             self.phase_log.append(marks)

@@ -59,6 +59,13 @@ class FlatDDP(nn.Module):
         self._armed = False
         self._comm_stream = torch.cuda.Stream() if (self.world > 1 and flat_q.is_cuda) else None
         self.used_parameter_ids = None  # indices that received gradients in the last backward
+        # Optimizer-in-backward: ``bucket_hook(segments)`` is called once per bucket, on the stream on which that
+        # bucket's gradient becomes final (after its all-reduce), with the [lo, hi) ranges of the flat buffers whose
+        # parameters received gradients.  ``defer_average`` leaves the SUM in the flat gradient (the hook's optimizer
+        # multiplies by 1/world itself) instead of spending one elementwise pass per bucket on the mean.
+        self.bucket_hook = None
+        self.defer_average = False
+        self._hook_stream = None
         for i, p in enumerate(self._params):
             p.register_post_accumulate_grad_hook(self._make_hook(i))
         from .. import nn as rnn
@@ -89,24 +96,51 @@ class FlatDDP(nn.Module):
                 self._reduce_bucket(b)
         return hook
 
+    def _bucket_segments(self, b):
+        """Contiguous [lo, hi) ranges of bucket ``b`` whose parameters have received their gradient."""
+        segs = []
+        for i in sorted(self._buckets[b]):
+            if i not in self._fired:
+                continue
+            lo, hi = self._bounds[i]
+            if segs and segs[-1][1] == lo:
+                segs[-1][1] = hi
+            else:
+                segs.append([lo, hi])
+        return [tuple(s) for s in segs]
+
     def _reduce_bucket(self, b):
-        if self.world == 1:
-            return
+        from .. import nn as rnn
         idxs = self._buckets[b]
         lo = min(self._bounds[i][0] for i in idxs)
         hi = max(self._bounds[i][1] for i in idxs)
         seg = self.flat_grad[lo:hi]
-        if self._comm_stream is not None:
-            self._comm_stream.wait_stream(torch.cuda.current_stream())
-            from .. import nn as rnn
-            if rnn.wgrad_stream() is not None:      # filter gradients are produced on their own stream
-                self._comm_stream.wait_stream(rnn.wgrad_stream())
-            with torch.cuda.stream(self._comm_stream):
-                dist.all_reduce(seg)
-                seg.mul_(1.0 / self.world)
+        if self.world > 1 and self._comm_stream is not None:
+            stream = self._comm_stream
+        elif self.bucket_hook is not None and seg.is_cuda:
+            if self._hook_stream is None:
+                self._hook_stream = torch.cuda.Stream()
+            stream = self._hook_stream
         else:
-            dist.all_reduce(seg)
-            seg.mul_(1.0 / self.world)
+            stream = None
+        if stream is None:
+            if self.world > 1:
+                dist.all_reduce(seg)
+                if not self.defer_average:
+                    seg.mul_(1.0 / self.world)
+            if self.bucket_hook is not None:
+                self.bucket_hook(self._bucket_segments(b))
+            return
+        stream.wait_stream(torch.cuda.current_stream())
+        if rnn.wgrad_stream() is not None:      # filter gradients are produced on their own stream
+            stream.wait_stream(rnn.wgrad_stream())
+        with torch.cuda.stream(stream):
+            if self.world > 1:
+                dist.all_reduce(seg)
+                if not self.defer_average:
+                    seg.mul_(1.0 / self.world)
+            if self.bucket_hook is not None:
+                self.bucket_hook(self._bucket_segments(b))
 
     def _finalize(self):
         # buckets holding parameters that never fired (unused parameters): zero their slots, reduce anyway so that
@@ -117,8 +151,9 @@ class FlatDDP(nn.Module):
                     if i not in self._fired:
                         self._views[i].zero_()
                 self._reduce_bucket(b)
-        if self._comm_stream is not None:
-            torch.cuda.current_stream().wait_stream(self._comm_stream)
+        for st in (self._comm_stream, self._hook_stream):
+            if st is not None:
+                torch.cuda.current_stream().wait_stream(st)
         for i, p in enumerate(self._params):
             if i not in self._fired:
                 p.grad = None
