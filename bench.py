@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every step from Python instead of replaying CUDA graphs")
     return ap.parse_args()
 
 
@@ -254,7 +255,7 @@ def run_b200(args):
         dim=HYPER["dim"], K=HYPER["K"], m=HYPER["m"], T=HYPER["T"], diff_speed=HYPER["diff_speed"]).to(dev)
     lr = scale_learning_rate(HYPER["lr"], world, args.batch)
     engine = PretrainEngine(model, Loss(HYPER["margin"], HYPER["A"], HYPER["M"]), lr, HYPER["momentum"],
-                            HYPER["weight_decay"])
+                            HYPER["weight_decay"], cuda_graph=not args.no_graph)
 
     B = args.batch
     shape = (B, 3, args.frames, args.size, args.size)
@@ -301,7 +302,14 @@ def run_b200(args):
 
     # W warm-up steps as asked, and never fewer than 10: the caching allocator's per-stream pools (main, key-encoder and
     # filter-gradient streams) and NCCL's channels settle during the first steps
-    for i in range(max(args.warmup, 10)):
+    # kernels one step launches: counted on the first (eager) warm-up steps through the C-ABI call counter; CUDA-graph
+    # replays launch exactly the recorded kernels without passing through Python
+    counter["on"], counter["n"] = True, 0
+    resident_step(0)
+    resident_step(1)
+    launches_per_step = counter["n"] // 2
+    counter["on"] = False
+    for i in range(2, max(args.warmup, 10)):
         resident_step(i)
     sampler = ClockSampler(local)
     if rank == 0:
@@ -318,7 +326,10 @@ def run_b200(args):
         counter["n"] = 0
         ms_total = timed(resident_step, args.steps, detail)
     counter["on"] = False
-    launches = counter["n"]          # C-ABI kernel launches inside the timed region (K steps)
+    graphs_on = engine.cuda_graph and any(g is not None for g in engine._graphs)
+    # kernels of the repo's library launched inside the timed region (K steps): counted call by call when the steps
+    # are enqueued from Python, K x the kernels recorded per step when they are replayed from CUDA graphs
+    launches = launches_per_step * args.steps if graphs_on else counter["n"]
     # host cost of enqueueing one step, measured on an empty launch queue (in the timed loop the CPU runs ahead until the
     # driver's launch queue fills and then advances at the GPU's pace)
     host_ms_step = float("inf")
@@ -328,7 +339,9 @@ def run_b200(args):
         resident_step(i)
         host_ms_step = min(host_ms_step, (time.perf_counter() - t0) * 1e3)
     barrier()
-    # device time of the phases of a step (CUDA events on the main stream; median of 10 steps, max over ranks)
+    graphs_state = graphs_on
+    # device time of the phases of a step (CUDA events on the main stream; median of 10 steps, max over ranks); these
+    # steps are enqueued eagerly (events cannot be recorded inside a replayed graph)
     engine.phase_log = []
     for i in range(10):
         resident_step(i)
@@ -469,9 +482,25 @@ def run_b200(args):
             "encoder_clip_passes_per_s": 3 * value,   # q, k and k_neg forwards of 16-frame clips per video
             "loss": loss_val, "remeasured": remeasured, "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms_step, "clocks": clocks, "e2e": e2e, "e2e_feeds": e2e_feeds, "roofline": roofline,
             "cpu_baseline": cpu, "multi_gpu_parity": parity, "phases_ms": phases,
+            "cuda_graph": {"replayed": graphs_state, "error": engine.graph_error,
+                           "kernels_recorded_per_step": launches_per_step},
         }) + "\n").encode())
+    # Teardown: captured graphs hold NCCL kernels, and destroying the communicator underneath them can block for
+    # minutes (seen once: the NCCL watchdog aborted the process 8 minutes after the JSON line).  The line is out; release
+    # the graphs, let every rank pass a last barrier, and leave without the communicator teardown — with a hard stop
+    # in case anything still hangs.
+    sys.stdout.flush()
+    sys.stderr.flush()
+    hard_stop = threading.Timer(60.0, os._exit, args=(0,))
+    hard_stop.daemon = True
+    hard_stop.start()
+    engine._graphs = [None, None]
+    engine._graph_pool = None
+    torch.cuda.synchronize()
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 def multi_gpu_parity(model, engine, loss3, dev):

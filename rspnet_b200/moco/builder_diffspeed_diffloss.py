@@ -268,12 +268,32 @@ class _MoCoBase(nn.Module):
         return res[:, :d].contiguous(), res[:, d:].contiguous()
 
     @torch.no_grad()
-    def _speed_views(self, im_q: Tensor, im_k: Tensor, into_exchange: bool = False):
-        """ref :421-443: draws randperm(B) on the input's device and random.choice(diff_speed), then re-samples.
-        into_exchange: the k / k_neg clips are written straight into this step's exchange buffers (returned as such)."""
+    def draw_step(self, im_q: Tensor, static: Optional[dict] = None):
+        """Every random draw of one forward(), in the reference's order and from the same generators: randperm(B) on the
+        input's device (ref :424), random.choice(diff_speed) (:426), then the two CPU randperm(B*W) of the k_neg and k
+        shuffles (:375; nothing else touches those generators in between in the reference either).  Returns
+        (random_indices, diff_speed, idx_all [2, B*W] on the device, host copy or None).  ``static``: persistent device
+        tensors {"random_indices", "idx_all"} to fill (what a captured CUDA graph of the step reads)."""
         B = im_q.shape[0]
         random_indices = torch.randperm(B, device=im_q.device)
         diff_speed = int(random.choice(self.diff_speed))
+        shape = (B, im_q.shape[2] // diff_speed, im_q.shape[3], im_q.shape[4], 4)
+        ex = self._exchange_for(shape, torch.bfloat16, im_q.device)
+        if static is not None:
+            static["random_indices"].copy_(random_indices)
+            random_indices = static["random_indices"]
+        idx_all, idx_host = ex.draw(B * ex.world, count=2, out=None if static is None else static["idx_all"])
+        return random_indices, diff_speed, idx_all, idx_host
+
+    @torch.no_grad()
+    def _speed_views(self, im_q: Tensor, im_k: Tensor, into_exchange: bool = False, random_indices=None,
+                     diff_speed=None):
+        """ref :421-443: draws randperm(B) on the input's device and random.choice(diff_speed), then re-samples.
+        into_exchange: the k / k_neg clips are written straight into this step's exchange buffers (returned as such)."""
+        B = im_q.shape[0]
+        if random_indices is None:
+            random_indices = torch.randperm(B, device=im_q.device)
+            diff_speed = int(random.choice(self.diff_speed))
         outs = None
         if into_exchange:
             shape = (B, im_q.shape[2] // diff_speed, im_q.shape[3], im_q.shape[4], 4)   # conv-ready bf16 NDHWC(4)
@@ -312,10 +332,11 @@ class MoCoDiffLossTwoFc(_MoCoBase):
         self._enqueue_payload = kn_a_all
         return q, k, kn_a, kn_m
 
-    def forward(self, im_q, im_k):
+    def forward(self, im_q, im_k, draws=None):
         """
         Input: im_q, im_k: [B, 3, T, H, W] clips (T = diff_speed * clip length).
         Output: (logits1, logits2), labels_A (zeros), (l_pos_M, l_neg_M), labels_M (ones) — as the reference.
+        ``draws``: the result of ``draw_step`` when the caller made the step's random draws itself (CUDA-graph replays).
         """
         if not (self.overlap_key_passes and im_q.is_cuda):
             with torch.no_grad():
@@ -337,9 +358,10 @@ class MoCoDiffLossTwoFc(_MoCoBase):
             SL = exchange.ShuffleExchange
             with torch.no_grad():
                 self._momentum_update_key_encoder()
-                im_q, im_k, k_neg = self._speed_views(im_q, im_k, into_exchange=True)
+                random_indices, diff_speed, idx_all, idx_host = draws if draws is not None else self.draw_step(im_q)
+                im_q, im_k, k_neg = self._speed_views(im_q, im_k, into_exchange=True, random_indices=random_indices,
+                                                      diff_speed=diff_speed)
                 ex = self._exchange_for(k_neg.shape, k_neg.dtype, k_neg.device)
-                idx_all, idx_host = ex.draw(k_neg.shape[0] * ex.world, count=2)
             # No Tensor.record_stream here: the exchange buffers are persistent, and what the side streams allocate is
             # only reused by them after their next wait_stream(main).  (record_stream defers block reuse to event
             # polling; the caching allocator then grows with cudaMalloc in the middle of training steps.)

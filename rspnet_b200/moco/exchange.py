@@ -256,10 +256,11 @@ class ShuffleExchange:
         return x.data_ptr() == b.data_ptr() and tuple(x.shape) == tuple(b.shape) and x.dtype == b.dtype
 
     # ---- permutations -------------------------------------------------------------------------------------------
-    def draw(self, n_all: int, count: int = 2):
+    def draw(self, n_all: int, count: int = 2, out: Optional[torch.Tensor] = None):
         """``count`` x the reference's ``torch.randperm(batch_size_all)`` (builder:375) on this rank's CPU generator, in
         order.  Returns (device int64 [count, n_all], host copy or None).  Every rank consumes its generator like the
-        reference; ranks other than 0 contribute zeros so that the sum all-reduce in publish() yields rank 0's draw."""
+        reference; ranks other than 0 contribute zeros so that the sum all-reduce in publish() yields rank 0's draw.
+        ``out``: a persistent device tensor to fill instead of a fresh one (CUDA-graph replays read it)."""
         perms = [torch.randperm(n_all) for _ in range(count)]
         if self.mode == "a2a":
             host = torch.stack(perms)
@@ -275,7 +276,7 @@ class ShuffleExchange:
                 host[j].copy_(p)
         else:
             host.zero_()
-        dev = torch.empty((count, n_all), dtype=torch.int64, device=self.device)
+        dev = out if out is not None else torch.empty((count, n_all), dtype=torch.int64, device=self.device)
         dev.copy_(host, non_blocking=True)
         self._ring.mark(i)
         return dev, None

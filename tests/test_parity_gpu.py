@@ -404,6 +404,52 @@ def test_verbatim_reference_loop_tracks_oracle_and_is_stream_safe():
         assert worst < max(3e-2, 3 * base_gap[0]), (worst, worst_k, base_gap)
 
 
+def test_cuda_graph_engine_matches_eager_engine():
+    """PretrainEngine(cuda_graph=True): after three eager steps the whole step is replayed from two alternating CUDA
+    graphs.  Against an eager engine from the same seed, inputs and generator states: the random draws must be consumed
+    identically (CPU / CUDA / python generator states equal afterwards — the draws stay on the host, in the reference's
+    order), integer state must agree exactly, and the loss trajectory must stay as close as two eager runs stay to each
+    other (fp32 atomics make every run chaotic at random init)."""
+    import random as pyrandom
+    from rspnet_b200.engine import PretrainEngine
+    from rspnet_b200.moco import Loss
+    cfg = dict(arch="resnet18", seed=0, K=64)
+    hyper = dict(dim=128, m=0.999, T=0.07, diff_speed=[2])
+    gen = torch.Generator().manual_seed(21)
+    ring = [(torch.randn(8, 3, 8, 64, 64, generator=gen).cuda(), torch.randn(8, 3, 8, 64, 64, generator=gen).cuda())
+            for _ in range(2)]
+
+    def run(graph: bool, steps: int = 9):
+        model = build_product_moco(cfg, hyper, rank=0).cuda()
+        eng = PretrainEngine(model, Loss(2.0, 1.0, 1.0), lr=0.00625, cuda_graph=graph)
+        torch.manual_seed(77)
+        torch.cuda.manual_seed(78)
+        pyrandom.seed(79)
+        losses = []
+        for i in range(steps):
+            losses.append(torch.stack(eng.step(*ring[i % 2])).cpu())
+        torch.cuda.synchronize()
+        state = (torch.get_rng_state(), torch.cuda.get_rng_state(), pyrandom.getstate())
+        return eng, model, torch.stack(losses), state
+
+    eng_e, model_e, loss_e, st_e = run(False)
+    eng_e2, _, loss_e2, _ = run(False)
+    eng_g, model_g, loss_g, st_g = run(True)
+    assert eng_g.graph_error is None, eng_g.graph_error
+    assert eng_g.cuda_graph and all(g is not None for g in eng_g._graphs), "the step was not captured"
+    assert eng_g._graph_steps == 6 and eng_g._eager_steps == 3
+    assert torch.equal(st_e[0], st_g[0]) and torch.equal(st_e[1], st_g[1]) and st_e[2] == st_g[2], \
+        "graph replays consumed the random generators differently from the eager path"
+    assert int(model_g.queue_ptr) == int(model_e.queue_ptr) == (9 * 8) % 64
+    assert torch.isfinite(loss_g).all()
+    d_rep = (loss_e - loss_e2).abs().max(dim=1).values
+    d_g = (loss_e - loss_g).abs().max(dim=1).values
+    print(f"[cuda graph] |dloss| per step, eager vs eager repeat: {[round(v, 4) for v in d_rep.tolist()]}")
+    print(f"[cuda graph] |dloss| per step, eager vs graph replay: {[round(v, 4) for v in d_g.tolist()]}")
+    assert d_g[:3].max() <= max(2 * d_rep[:3].max().item(), 0.02)       # identical eager code path
+    assert d_g.max() <= max(3 * d_rep.max().item(), 0.5), (d_g, d_rep)   # chaotic trajectory: yardstick = the repeat
+
+
 def test_single_head_builder_matches_reference_golden():
     """MoCoDiffLoss.forward (builder:184-245, one projection head = the backbone's fc) on the B200 against the fixture of
     the unmodified reference: integer state bit-exact, logits / loss within the stated bf16 tolerance of the conv path."""
