@@ -131,9 +131,8 @@ def cpu_reference_clips_per_s(arch, steps, warmup, batch=4, frames=32, size=112,
         orig_cuda = torch.Tensor.cuda
         own_group = not dist.is_initialized()
         if own_group:
-            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-            os.environ.setdefault("MASTER_PORT", "29611")
-            dist.init_process_group("gloo", rank=0, world_size=1)
+            # an in-process store: no rendezvous port (under torchrun MASTER_PORT belongs to the launcher's store)
+            dist.init_process_group("gloo", store=dist.HashStore(), rank=0, world_size=1)
         torch.manual_seed(0)
         model = ref_loader.build_reference_moco(arch, dim=HYPER["dim"], K=K, m=HYPER["m"], T=HYPER["T"],
                                                 diff_speed=HYPER["diff_speed"])
