@@ -13,9 +13,19 @@
 // warp, the filter slab of one frame tap (kh*4 KB) with another; rows outside the image are zeroed in place.
 //
 // CTA (persistent, 1/SM): 4 epilogue warps, 1 producer warp, 1 MMA warp.  One iteration = 8 output rows of one
-// (n, to) = four 128x64 accumulators in TMEM, double buffered (512 columns) so the epilogue of iteration i overlaps the
+// (n, to) = two 128x128 accumulators in TMEM, double buffered (512 columns) so the epilogue of iteration i overlaps the
 // MMAs of i+1.  Pipeline stage = one frame tap a: {21 input rows, kh*4 KB filter slab}, 4 stages.  (All 148 SMs stream
 // the same 196 KB filter from L2 over and over: eight rows per slab fetch instead of four halves that traffic.)
+//
+// Row pairing (N = 128).  An SS-form M128 N64 K16 MMA holds the pipe for 48 clocks (operand fetch: 6 KB at 128 B/clk) for
+// 32 clocks of math; N = 128 costs 64 for 64.  Input row r feeds output row h with filter row b = r - 2h AND output row
+// h + 1 with filter row b - 2, so ONE MMA with B = [W[b]; W[b-2]] (128 filter columns) serves both from a single A fetch.
+// A tile covers 4 output rows: M halves = input rows (r, r + 4) (rows are stored in four h-phases, 1 KB apart within a
+// phase), N halves = output rows (+0, +1):  D[i][k] = output row 4m + 2i + k.  Per tile and frame tap the input rows
+// rho = r - 2*h0 = 0..8 are visited: rho 2..6 as N = 128, rho 0,1 (only W[rho] -> k = 0) and rho 7,8 (only W[rho-2] ->
+// k = 1) as N = 64 MMAs on one half of the accumulator: (5*64 + 4*48) * 2 clocks per 4 rows instead of 7*2*2*48 (-24 %).
+// The filter slab keeps W[b-2] exactly 1 KB (= 8 co-groups * SBO) behind W[b]: [kchunk 4][b: 6,4,2,0,5,3,1][8][8][8].
+// Frame taps that fall outside the clip (pt = 3: 12 of 112 (to, a) pairs) are skipped instead of multiplied by zeros.
 #include "common.cuh"
 #include "rspnet_b200.h"
 
@@ -23,7 +33,7 @@ namespace rsp {
 
 struct StemParams {
   const __nv_bfloat16* x;    // [N][Ti][Hi][Wi][4]
-  const __nv_bfloat16* wst;  // [kt][kh][4 kchunk][8 co-group][8 co][8 k] bf16
+  const __nv_bfloat16* wst;  // [kt][4 kchunk][7 slots: b = 6,4,2,0,5,3,1][8 co-group][8 co][8 k] bf16
   __nv_bfloat16* y;          // [N][To][Ho][Wo][64]
   const float* bias;
   float* stats;              // optional [2][64]: += per-channel sum / sum of squares of the stored output
@@ -36,8 +46,10 @@ struct StemParams {
 constexpr int kStemThreads = 192;
 constexpr int kStemStages = 4;
 constexpr int kStemRowBytes = 1024;   // 128 pixel slots of 8 B; slot s holds input pixel s - 4
-constexpr int kStemOutRows = 8;       // output rows per iteration: four M=128 tiles (two rows each) share one filter slab
-constexpr int kStemMaxRows = 22;      // rows per A slab (two h-phases x 11)
+constexpr int kStemOutRows = 8;       // output rows per iteration: two 128x128 tiles (four rows each) share one filter slab
+constexpr int kStemPerPhase = 6;      // rows of one h-phase (input row mod 4), stored 1024 B apart
+constexpr int kStemMaxRows = 4 * kStemPerPhase;  // row slots per A slab (21 used)
+constexpr int kStemKChunk = 7 * 1024; // bytes of one 8-element K chunk of a filter slab (7 filter rows x 64 co x 16 B)
 constexpr int kStemASlab = kStemMaxRows * kStemRowBytes;
 constexpr int kStemBSlabMax = 7 * 4096;
 constexpr int kStemStageBytes = kStemASlab + kStemBSlabMax;
@@ -57,6 +69,18 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
                : "memory");
 }
 
+// frame taps a in [a_lo, a_hi) read a frame inside the clip; the others contribute nothing and are skipped by the
+// producer and the MMA lane alike (an empty range cannot happen for pt < kt, but is mapped to "all taps, zero rows")
+__device__ __forceinline__ void stem_tap_range(const StemParams& p, int to, int& a_lo, int& a_hi) {
+  const int t0 = to * p.st - p.pt;
+  a_lo = t0 < 0 ? -t0 : 0;
+  a_hi = p.Ti - t0 < p.kt ? p.Ti - t0 : p.kt;
+  if (a_lo >= a_hi) {
+    a_lo = 0;
+    a_hi = p.kt;
+  }
+}
+
 __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -68,8 +92,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
 
   const int t = threadIdx.x;
   const int warp = t >> 5;
-  const int rowsA = (kStemOutRows - 1) * p.sh + p.kh;   // input rows feeding the output rows of one iteration
-  const int perPhase = (rowsA + p.sh - 1) / p.sh; // rows of one h-phase, stored 1024 B apart
+  constexpr int rowsA = (kStemOutRows - 1) * 2 + 7;     // input rows feeding the output rows of one iteration (sh 2, kh 7)
   const uint32_t bslab_bytes = static_cast<uint32_t>(p.kh) * 4096u;
 
   // zero the A slabs once: halo pixel slots are never written afterwards
@@ -99,13 +122,15 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
     uint32_t ph = 0;
     const int lane = t & 31;
     const uint32_t rowBytes = static_cast<uint32_t>(p.Wi) * 8u;
-    const int rowSlot = ((lane % p.sh) * perPhase + lane / p.sh) * kStemRowBytes + 32;
+    const int rowSlot = ((lane & 3) * kStemPerPhase + (lane >> 2)) * kStemRowBytes + 32;
     for (int it = blockIdx.x; it < p.numIters; it += gridDim.x) {
       const int hq = it % p.hq;
       const int q = it / p.hq;
       const int to = q % p.To, n = q / p.To;
       const int hi0 = hq * kStemOutRows * p.sh - p.ph;
-      for (int a = 0; a < p.kt; ++a) {
+      int a_lo, a_hi;
+      stem_tap_range(p, to, a_lo, a_hi);
+      for (int a = a_lo; a < a_hi; ++a) {
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* aslab = smem + s * kStemStageBytes;
         const int ti = to * p.st - p.pt + a;
@@ -118,7 +143,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
         // rows outside the image: plain zero stores (the slot may hold a previous row), made visible to the async proxy
         for (unsigned m = zmask; m; m &= m - 1) {
           const int j = __ffs(m) - 1;
-          uint4* dst = reinterpret_cast<uint4*>(aslab + ((j % p.sh) * perPhase + j / p.sh) * kStemRowBytes + 32);
+          uint4* dst = reinterpret_cast<uint4*>(aslab + ((j & 3) * kStemPerPhase + (j >> 2)) * kStemRowBytes + 32);
           for (int c = lane; c < (p.Wi >> 1); c += 32) dst[c] = make_uint4(0, 0, 0, 0);
         }
         if (zmask) fence_proxy_async_smem();
@@ -161,8 +186,8 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
 #pragma unroll
         for (int jx = 0; jx < 32; ++jx) ra[jx] = qa[jx] = 0.f;
 #pragma unroll 1
-        for (int m = 0; m < kStemOutRows / 2; ++m) {
-          const int ho = hq * kStemOutRows + 2 * m + (ew >> 1);
+        for (int m = 0; m < kStemOutRows / 2; ++m) {   // 64-column block m: tile m / 2, N half m % 2
+          const int ho = hq * kStemOutRows + 4 * (m >> 1) + 2 * (ew >> 1) + (m & 1);
           const int ow = (ew & 1) * 32 + lane;
           const bool ok = ho < p.Ho && ow < p.Wo;
           __nv_bfloat16* orow =
@@ -217,7 +242,8 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
   } else {
     // ------------------------------------------------------------------ MMA issuer
     // one elected lane waits, issues and commits (no warp-level re-convergence between stages)
-    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+    constexpr uint32_t idesc128 = make_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t idesc64 = make_idesc_bf16(128, 64, 0, 0);
     uint32_t iter_ctr = 0;
     int s = 0;
     uint32_t ph = 0;
@@ -225,9 +251,12 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
     for (int it = blockIdx.x; leader && it < p.numIters; it += gridDim.x, ++iter_ctr) {
       const int buf = iter_ctr & 1;
       const uint32_t aph = (iter_ctr >> 1) & 1;
+      const int to = (it / p.hq) % p.To;
+      int a_lo, a_hi;
+      stem_tap_range(p, to, a_lo, a_hi);
       mbar_wait(&acc_empty[buf], aph ^ 1);
       tc_fence_after_sync();
-      for (int a = 0; a < p.kt; ++a) {
+      for (int a = a_lo; a < a_hi; ++a) {
         mbar_wait(&full_bar[s], ph);
         fence_proxy_async_smem();
         tc_fence_after_sync();
@@ -235,24 +264,33 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
         // issuing thread spends ~2 instructions per MMA instead of rebuilding 64-bit descriptors
         const uint32_t aslab = smem_u32(smem + s * kStemStageBytes);
         const uint64_t abase = make_smem_desc_nosw(aslab, 16, 128);
-        const uint64_t bbase = make_smem_desc_nosw(aslab + kStemASlab, 1024, 128);
+        const uint64_t bbase = make_smem_desc_nosw(aslab + kStemASlab, kStemKChunk, 128);
         const uint32_t dcol = tmem_base + buf * 256;
+        const uint32_t fresh = (a == a_lo) ? 0u : 1u;
+        // input rows rho = 2..6 first: the N = 128 MMA of rho = 2 is the one that may overwrite both halves of a tile
 #pragma unroll
-        for (int b = 0; b < 7; ++b) {
+        for (int o = 0; o < 9; ++o) {
+          constexpr int kOrder[9] = {2, 3, 4, 5, 6, 0, 1, 7, 8};
+          const int rho = kOrder[o];
+          // filter row whose 1 KB block the descriptor starts at, and the accumulator half an N = 64 MMA writes
+          const int b0 = rho <= 6 ? rho : rho - 2;
+          const int bslot = (b0 & 1) ? 4 + (5 - b0) / 2 : (6 - b0) / 2;
+          const bool wide = rho >= 2 && rho <= 6;
+          const int khalf = rho >= 7 ? 64 : 0;
 #pragma unroll
-          for (int m = 0; m < kStemOutRows / 2; ++m) {
-            constexpr int kPerPhase = 11;                      // ((kStemOutRows - 1) * 2 + 7 + 1) / 2
-            const int j = 4 * m + b;                           // 2*m*sh + b
-            const int arow = ((j & 1) * kPerPhase + (j >> 1)) * kStemRowBytes;
+          for (int m = 0; m < kStemOutRows / 4; ++m) {
+            const int j = 8 * m + rho;                         // input row of the tile's first M half
+            const int arow = ((j & 3) * kStemPerPhase + (j >> 2)) * kStemRowBytes;
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
-              umma_bf16(dcol + m * 64, abase + static_cast<uint64_t>((arow + ks * 32) >> 4),
-                        bbase + static_cast<uint64_t>((b * 4096 + ks * 2048) >> 4), idesc, (a | b | ks) != 0);
+              umma_bf16(dcol + m * 128 + khalf, abase + static_cast<uint64_t>((arow + ks * 32) >> 4),
+                        bbase + static_cast<uint64_t>((ks * 2 * kStemKChunk + bslot * 1024) >> 4),
+                        wide ? idesc128 : idesc64, (o | ks) != 0 ? 1u : fresh);
             }
           }
         }
         umma_commit(&empty_bar[s]);
-        if (a == p.kt - 1) umma_commit(&acc_full[buf]);
+        if (a == a_hi - 1) umma_commit(&acc_full[buf]);
         if (++s == kStemStages) {
           s = 0;
           ph ^= 1;
@@ -266,19 +304,23 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
   if (warp == 5) tmem_dealloc(tmem_base, 512);
 }
 
-// w fp32 [64][Ci<=4][kt][kh][7] -> wst bf16 [kt][kh][4][8][8][8]; K slot q = kchunk*8 + e: pixel slot q/4 (kw = slot-1), ch q%4
+// w fp32 [64][Ci<=4][kt][7][7] -> wst bf16 [kt][4 kchunk][7 slots][8 co-group][8 co][8 k]; slot order b = 6,4,2,0,5,3,1 so
+// that W[b-2] lies 1 KB behind W[b]; K slot q = kchunk*8 + e: pixel slot q/4 (kw = slot-1), ch q%4
 __global__ void pack_weight_stem_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wst, int Co, int Ci,
                                         int kt, int kh, int kw) {
   size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   size_t total = static_cast<size_t>(kt) * kh * 2048;
   if (idx >= total) return;
-  int e = idx & 7, r = (idx >> 3) & 7, g = (idx >> 6) & 7, j = (idx >> 9) & 3;
-  int ab = static_cast<int>(idx >> 11);
-  int a = ab / kh, b = ab - a * kh;
+  int e = idx & 7, r = (idx >> 3) & 7, g = (idx >> 6) & 7;
+  int rest = static_cast<int>(idx >> 9);        // (a * 4 + kchunk) * 7 + slot
+  int slot = rest % 7;
+  int j = (rest / 7) & 3;
+  int a = rest / 28;
+  int b = slot < 4 ? 6 - 2 * slot : 5 - 2 * (slot - 4);
   int co = g * 8 + r;
   int qk = j * 8 + e;
-  int slot = qk >> 2, ch = qk & 3;
-  int c = slot - 1;
+  int pslot = qk >> 2, ch = qk & 3;
+  int c = pslot - 1;
   float v = 0.f;
   if (co < Co && ch < Ci && c >= 0 && c < kw)
     v = w[(((static_cast<size_t>(co) * Ci + ch) * kt + a) * kh + b) * kw + c];

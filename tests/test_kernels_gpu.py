@@ -377,6 +377,9 @@ CONV_CASES = [
     (2, 64, 128, (4, 8, 8), (1, 1, 1), (2, 2, 2), (0, 0, 0)),
     (2, 128, 256, (2, 6, 6), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
     (1, 3, 64, (6, 20, 20), (7, 7, 7), (1, 2, 2), (3, 3, 3)),
+    # row-paired RGB stem: several 8-row iterations per frame, ragged last iteration, clipped frame taps at both ends
+    (2, 3, 64, (9, 44, 36), (7, 7, 7), (1, 2, 2), (3, 3, 3)),
+    (2, 3, 45, (3, 32, 28), (1, 7, 7), (1, 2, 2), (0, 3, 3)),
     (2, 3, 64, (4, 12, 12), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
     (3, 256, 512, (2, 7, 7), (3, 3, 3), (2, 2, 2), (1, 1, 1)),
     # 3x3x3 unit-stride RGB stem (C3D conv1): the even/odd raw-row kernel, ragged H and odd T
