@@ -14,7 +14,7 @@ REPO = ROOT.parent
 CSRC = ROOT / "csrc"
 LIB_DIR = ROOT / "lib"
 LIB_PATH = LIB_DIR / "librspnet_b200.so"
-SOURCES = ["common.cu", "conv_igemm.cu", "conv_stem.cu", "conv_stem3.cu", "conv_direct.cu", "elementwise.cu", "bn_pool.cu", "bn_pool_bwd.cu", "moco.cu", "peer.cu"]
+SOURCES = ["common.cu", "conv_igemm.cu", "conv_stem.cu", "conv_stem3.cu", "conv_direct.cu", "conv_wgrad_direct.cu", "elementwise.cu", "bn_pool.cu", "bn_pool_bwd.cu", "moco.cu", "peer.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

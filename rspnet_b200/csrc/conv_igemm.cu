@@ -1072,6 +1072,8 @@ int launch_stem3(const rsp_conv3d_desc* d, const void* x, const void* wst, const
                  int sm_count, cudaStream_t stream);
 int launch_stem3_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const void* x, const void* dy,
                        void* zero_row_1k, float* dw, int accumulate, int sm_count, cudaStream_t stream);
+bool wgrad_direct_supported(const rsp_conv3d_desc* d);
+int launch_wgrad_direct(const rsp_conv3d_desc* d, const void* x, const void* dy, float* dwt, cudaStream_t stream);
 bool direct_supported(const rsp_conv3d_desc* d, int transposed);
 int launch_direct(const rsp_conv3d_desc* d, int transposed, const void* x, const void* wgt, const float* bias, void* y,
                   float* stats, cudaStream_t stream);
@@ -1342,6 +1344,24 @@ int rsp_conv3d_dgrad(const rsp_conv3d_desc* d, const void* dy, const void* wd, v
   return dispatch_igemm<MODE_GENERIC>(p, stream);
 }
 
+// Timing / A-B switch (tools only, not in the public header): bit 0 = never take the direct wgrad kernel,
+// bit 1 = take it whenever the geometry allows.
+static int g_wgrad_debug = 0;
+int rsp_debug_wgrad(int flags) {
+  g_wgrad_debug = flags;
+  return 0;
+}
+
+// The plane-run kernel pays a fixed 9 x 64 x 64 fp32 atomic epilogue per CTA and stages halo rows with every chunk:
+// measured on R3D-18 at batch 64 it wins on layer1 (0.200 -> 0.094 ms), layer2 (0.077 -> 0.061) and layer3 (0.058 ->
+// 0.053); tiny problems stay on the generic kernel.
+static bool wgrad_direct_wanted(const rsp_conv3d_desc* d) {
+  if (!wgrad_direct_supported(d)) return false;
+  if (g_wgrad_debug & 2) return true;
+  const long long pixels = static_cast<long long>(d->N) * d->Ti * d->Hi * d->Wi;
+  return pixels >= 4096;
+}
+
 int rsp_conv3d_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const void* x, const void* dy,
                      float* dwt_workspace, float* dw, int accumulate, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -1365,7 +1385,10 @@ int rsp_conv3d_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, c
     return RSP_ERR_CUDA;
   }
   const int sms = device_sm_count();
-  rc = mode == MODE_GENERIC ? dispatch_wgrad<MODE_GENERIC>(p, sms, stream) : dispatch_wgrad<MODE_SMALLC>(p, sms, stream);
+  if (mode == MODE_GENERIC && !(g_wgrad_debug & 1) && wgrad_direct_wanted(d))
+    rc = launch_wgrad_direct(d, x, dy, dwt_workspace, stream);
+  else
+    rc = mode == MODE_GENERIC ? dispatch_wgrad<MODE_GENERIC>(p, sms, stream) : dispatch_wgrad<MODE_SMALLC>(p, sms, stream);
   if (rc != RSP_OK) return rc;
   const int taps = d->kt * d->kh * d->kw;
   if (mode == MODE_GENERIC && taps <= 343) {

@@ -430,6 +430,45 @@ def test_conv3d_fprop_dgrad_wgrad(n, ci, co, dims, k, s, p):
         close(ops.to_ncdhw_f32(dx, ci), xr.grad, 1e-2)
 
 
+WGRAD_DIRECT_CASES = [
+    # (n, ci, co, dims): 3x3x3 / 1x3x3 unit-stride filters through the plane-run wgrad (forced with rsp_debug_wgrad(2))
+    (3, 64, 64, (4, 28, 28), (3, 3, 3), (1, 1, 1)),     # R3D-18 layer1 plane, several chunks per plane
+    (2, 64, 64, (3, 9, 7), (3, 3, 3), (1, 1, 1)),       # one short chunk, Wp = 9 < 16
+    (2, 128, 64, (2, 14, 14), (3, 3, 3), (1, 1, 1)),    # two ci chunks
+    (1, 64, 128, (5, 12, 20), (3, 3, 3), (1, 1, 1)),    # two co chunks, odd frame count
+    (2, 64, 64, (2, 16, 16), (1, 3, 3), (0, 1, 1)),     # separable spatial filter (kt = 1)
+]
+
+
+@pytest.mark.parametrize("n,ci,co,dims,k,p", WGRAD_DIRECT_CASES)
+def test_conv3d_wgrad_direct(n, ci, co, dims, k, p):
+    """Plane-run filter gradient (conv_wgrad_direct.cu) vs torch fp32 on bf16-rounded inputs, 1e-2 of the tensor max, and
+    vs the generic kernel."""
+    ops = _ops()
+    from rspnet_b200 import _lib
+    x = rand(n, ci, *dims, seed=1)
+    w = rand(co, ci, *k, seed=2)
+    xr = x.bfloat16().float()
+    wr = w.clone().requires_grad_(True)
+    yref = F.conv3d(xr, wr, None, (1, 1, 1), p)
+    dy = rand(*yref.shape, seed=4)
+    yref.backward(dy.bfloat16().float())
+    xn = ops.to_ndhwc_bf16(x, ci)
+    dyn = ops.to_ndhwc_bf16(dy, co)
+    desc = ops.conv_desc(xn.shape, co, k, (1, 1, 1), p)
+    lib = _lib.load()
+    try:
+        lib.rsp_debug_wgrad(2)
+        dw = ops.conv3d_wgrad(desc, xn, dyn, w.shape)
+        lib.rsp_debug_wgrad(1)
+        dw_generic = ops.conv3d_wgrad(desc, xn, dyn, w.shape)
+    finally:
+        lib.rsp_debug_wgrad(0)
+    scale = wr.grad.abs().max().item()
+    assert (dw - wr.grad).abs().max().item() <= 1e-2 * scale
+    assert (dw - dw_generic).abs().max().item() <= 2e-3 * scale   # same bf16 operands, different summation order
+
+
 # ------------------------------------------------------------------------------------------------ S3D-G pieces
 @pytest.mark.parametrize("c_l", [64, 208, 24])
 def test_gate_fwd_bwd(c_l):

@@ -9,6 +9,11 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from rspnet_b200 import ops  # noqa: E402
 from rspnet_b200.models import get_model_class  # noqa: E402
 
+import os  # noqa: E402
+from rspnet_b200 import _lib  # noqa: E402
+if os.environ.get("RSP_WGRAD_DEBUG"):   # 1: never the plane-run wgrad, 2: wherever the geometry allows
+    _lib.load().rsp_debug_wgrad(int(os.environ["RSP_WGRAD_DEBUG"]))
+
 arch = sys.argv[1] if len(sys.argv) > 1 else "resnet18"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 shapes = []
