@@ -114,6 +114,13 @@ int make_tmap_u64_rows(CUtensorMap* out, const void* base, int rank, const unsig
   return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_UINT64, CU_TENSOR_MAP_SWIZZLE_NONE, base, rank, dims, strides_bytes, box);
 }
 
+// Same with a traversal stride per dimension (box[i] is the traversed extent: box[i] / estr[i] elements are copied).
+int make_tmap_u64_rows_strided(CUtensorMap* out, const void* base, int rank, const unsigned long long* dims,
+                               const unsigned long long* strides_bytes, const unsigned* box, const unsigned* estr) {
+  return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_UINT64, CU_TENSOR_MAP_SWIZZLE_NONE, base, rank, dims, strides_bytes, box,
+                     estr);
+}
+
 int device_sm_count() {
   if (g_sm_count == 0) {
     int dev = 0;

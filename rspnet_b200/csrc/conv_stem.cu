@@ -31,7 +31,13 @@
 
 namespace rsp {
 
+int make_tmap_u64_rows(CUtensorMap* out, const void* base, int rank, const unsigned long long* dims,
+                       const unsigned long long* strides_bytes, const unsigned* box);
+int make_tmap_u64_rows_strided(CUtensorMap* out, const void* base, int rank, const unsigned long long* dims,
+                               const unsigned long long* strides_bytes, const unsigned* box, const unsigned* estr);
+
 struct StemParams {
+  CUtensorMap tmapX;         // x as 8-byte pixels {Wi, Hi, Ti, N}, box {128, 24 at row stride 4 = 6 rows, 1, 1}, no swizzle
   const __nv_bfloat16* x;    // [N][Ti][Hi][Wi][4]
   const __nv_bfloat16* wst;  // [kt][4 kchunk][7 slots: b = 6,4,2,0,5,3,1][8 co-group][8 co][8 k] bf16
   __nv_bfloat16* y;          // [N][To][Ho][Wo][64]
@@ -81,7 +87,7 @@ __device__ __forceinline__ void stem_tap_range(const StemParams& p, int to, int&
   }
 }
 
-__global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemParams p) {
+__global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const __grid_constant__ StemParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStemStages * kStemStageBytes);
@@ -92,7 +98,6 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
 
   const int t = threadIdx.x;
   const int warp = t >> 5;
-  constexpr int rowsA = (kStemOutRows - 1) * 2 + 7;     // input rows feeding the output rows of one iteration (sh 2, kh 7)
   const uint32_t bslab_bytes = static_cast<uint32_t>(p.kh) * 4096u;
 
   // zero the A slabs once: halo pixel slots are never written afterwards
@@ -117,50 +122,40 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const StemPa
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 4) {
-    // ------------------------------------------------------------------ producer (bulk copies, one lane per input row)
-    int s = 0;
-    uint32_t ph = 0;
-    const int lane = t & 31;
-    const uint32_t rowBytes = static_cast<uint32_t>(p.Wi) * 8u;
-    const int rowSlot = ((lane & 3) * kStemPerPhase + (lane >> 2)) * kStemRowBytes + 32;
-    for (int it = blockIdx.x; it < p.numIters; it += gridDim.x) {
-      const int hq = it % p.hq;
-      const int q = it / p.hq;
-      const int to = q % p.To, n = q / p.To;
-      const int hi0 = hq * kStemOutRows * p.sh - p.ph;
-      int a_lo, a_hi;
-      stem_tap_range(p, to, a_lo, a_hi);
-      for (int a = a_lo; a < a_hi; ++a) {
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* aslab = smem + s * kStemStageBytes;
-        const int ti = to * p.st - p.pt + a;
-        const bool tok = ti >= 0 && ti < p.Ti;
-        const int hi = hi0 + lane;                         // lane j owns input row j of the slab
-        const bool mine = lane < rowsA;
-        const bool ok = mine && tok && hi >= 0 && hi < p.Hi;
-        const unsigned okmask = __ballot_sync(0xffffffffu, ok);
-        const unsigned zmask = __ballot_sync(0xffffffffu, mine && !ok);
-        // rows outside the image: plain zero stores (the slot may hold a previous row), made visible to the async proxy
-        for (unsigned m = zmask; m; m &= m - 1) {
-          const int j = __ffs(m) - 1;
-          uint4* dst = reinterpret_cast<uint4*>(aslab + ((j & 3) * kStemPerPhase + (j >> 2)) * kStemRowBytes + 32);
-          for (int c = lane; c < (p.Wi >> 1); c += 32) dst[c] = make_uint4(0, 0, 0, 0);
-        }
-        if (zmask) fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive_expect_tx(&full_bar[s], bslab_bytes + static_cast<uint32_t>(__popc(okmask)) * rowBytes);
-          bulk_copy_g2s(smem_u32(aslab + kStemASlab), p.wst + static_cast<size_t>(a) * p.kh * 2048, bslab_bytes,
-                        &full_bar[s]);
-        }
-        if (ok) {
-          const __nv_bfloat16* src = p.x + ((static_cast<size_t>(n) * p.Ti + ti) * p.Hi + hi) * p.Wi * 4;
-          bulk_copy_g2s(smem_u32(aslab) + rowSlot, src, rowBytes, &full_bar[s]);
-        }
-        __syncwarp();
-        if (++s == kStemStages) {
-          s = 0;
-          ph ^= 1;
+    // ------------------------------------------------------------------ producer (one lane)
+    // per stage: one bulk copy of the filter slab and one TMA box per h-phase: {128 pixel slots from pixel -4, every 4th
+    // input row, 6 rows} lands as the 6 rows of that phase 1 KB apart; halo pixels and rows outside the image are zero-filled
+    // by the TMA unit (the 21 per-row cp.async.bulk requests this replaces cost ~100 clocks each in the copy unit)
+    if (elect_one()) {
+      tma_prefetch_desc(&p.tmapX);
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t tx = bslab_bytes + 4u * kStemPerPhase * kStemRowBytes;
+      for (int it = blockIdx.x; it < p.numIters; it += gridDim.x) {
+        const int hq = it % p.hq;
+        const int q = it / p.hq;
+        const int to = q % p.To, n = q / p.To;
+        const int hi0 = hq * kStemOutRows * p.sh - p.ph;
+        int a_lo, a_hi;
+        stem_tap_range(p, to, a_lo, a_hi);
+        for (int a = a_lo; a < a_hi; ++a) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          const uint32_t aslab = smem_u32(smem + s * kStemStageBytes);
+          const int ti = to * p.st - p.pt + a;
+          mbar_arrive_expect_tx(&full_bar[s], tx);
+          bulk_copy_g2s(aslab + kStemASlab, p.wst + static_cast<size_t>(a) * p.kh * 2048, bslab_bytes, &full_bar[s]);
+#pragma unroll
+          for (int phase = 0; phase < 4; ++phase) {
+            asm volatile(
+                "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                ::"r"(aslab + phase * kStemPerPhase * kStemRowBytes), "l"(&p.tmapX), "r"(smem_u32(&full_bar[s])),
+                  "r"(-4), "r"(hi0 + phase), "r"(ti), "r"(n)
+                : "memory");
+          }
+          if (++s == kStemStages) {
+            s = 0;
+            ph ^= 1;
+          }
         }
       }
     }
@@ -347,6 +342,15 @@ int launch_stem(const rsp_conv3d_desc* d, const void* x, const void* wst, const 
   p.kt = d->kt; p.kh = d->kh; p.st = d->st; p.sh = d->sh; p.pt = d->pt; p.ph = d->ph;
   p.hq = (p.Ho + kStemOutRows - 1) / kStemOutRows;
   p.numIters = p.N * p.To * p.hq;
+  {
+    const unsigned long long W = p.Wi, H = p.Hi, T = p.Ti;
+    const unsigned long long xdims[4] = {W, H, T, static_cast<unsigned long long>(p.N)};
+    const unsigned long long xstrides[3] = {W * 8, H * W * 8, T * H * W * 8};
+    const unsigned xbox[4] = {128, 4 * kStemPerPhase, 1, 1};
+    const unsigned xestr[4] = {1, 4, 1, 1};
+    int rc = make_tmap_u64_rows_strided(&p.tmapX, x, 4, xdims, xstrides, xbox, xestr);
+    if (rc != RSP_OK) return rc;
+  }
   constexpr int smem = kStemStages * kStemStageBytes + 1024 + 256;
   cudaError_t e = cudaFuncSetAttribute(conv_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) {
@@ -376,12 +380,17 @@ int pack_stem(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const fl
 //       >= Wo zero-filled)
 //   D[set][j] = [16 rows x 8 slots] x [64 co]: window chunk j (slots 2j, 2j+1) of filter-row set `set`; a CTA keeps
 //       2 sets x 4 chunks = 512 TMEM columns while it streams output rows, then adds them into dW with fp32 atomics.
+//   N = 128 by shifting dY: sum_k X[window(k) chunk j] dY[k-1] = sum_k X[window(k+1) chunk j] dY[k] and window(k+1) chunk j
+//       is window(k) chunk j+1 (one output pixel = two input pixels = one chunk).  So the B operand {dY[k-1] | dY[k]} —
+//       the same panel, second half one 128-byte row further — makes ONE M128 x N128 MMA (64 clocks, full rate) produce
+//       chunks j+1 and j where two N = 64 MMAs took 2 x 48.  The dY box starts at pixel -1 (zero-filled) for that.
 // The 49 filter rows are split over two groups of CTAs (25 + 24 rows), so dY is read twice (an M = 64 formulation with
 // the roles swapped needs four groups and runs the tensor core at half rate).
 // grid: x = workers over output rows within a group, y = group.
 // =====================================================================================================================
 struct StemWgradParams {
-  CUtensorMap tmapDy;       // dy as {64, Wo, N*To*Ho}, box {64, 64, 1}: one output row per copy, pixels >= Wo zero-filled
+  CUtensorMap tmapDy;       // dy as {64, Wo, N*To*Ho}, box {64, 72, 1} from pixel -1: one output row per copy, zero-filled outside
+  CUtensorMap tmapX;        // x as 8-byte pixels {Wi, Hi, Ti, N}, box {128, kh, 1, 1}, no swizzle
   const __nv_bfloat16* x;   // [N][Ti][Hi][Wi][4]
   float* dw;                // [Co][Ci][kt][kh][kw] fp32, accumulated atomically
   int N, Ti, Hi, Wi, To, Ho, Wo;
@@ -392,7 +401,8 @@ struct StemWgradParams {
 };
 
 constexpr int kSWStages = 5;
-constexpr int kSWDyBytes = 64 * 128;
+constexpr int kSWDyRows = 72;              // pixel -1 .. 70 of one output row (64 K rows + the shifted panel's extra row)
+constexpr int kSWDyBytes = kSWDyRows * 128;
 constexpr int kSWRowSlots = 32;
 constexpr int kSWStageBytes = kSWDyBytes + kSWRowSlots * kStemRowBytes;
 
@@ -435,62 +445,54 @@ __global__ void __launch_bounds__(192, 1) conv_stem_wgrad_kernel(const __grid_co
 
   if (iters > 0 && nr > 0) {
     if (warp == 4) {
-      // ---------------- producer: one TMA box for the dY row, one bulk copy per raw input row (lane fr owns filter row fr)
-      const int lane = t & 31;
-      const uint32_t rowBytes = static_cast<uint32_t>(p.Wi) * 8u;
-      const int fr = f0 + lane;
-      const int al = fr / p.kh, b = fr - al * p.kh;
-      if (lane == 0) tma_prefetch_desc(&p.tmapDy);
-      int s = 0;
-      uint32_t ph = 0;
-      int ho = blockIdx.x % p.Ho, to = (blockIdx.x / p.Ho) % p.To, n = blockIdx.x / (p.Ho * p.To);
-      const int dho = gridDim.x % p.Ho, dto = (gridDim.x / p.Ho) % p.To, dn = gridDim.x / (p.Ho * p.To);
-      for (int r = blockIdx.x; r < p.numRows; r += gridDim.x) {
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        const uint32_t stage = smem_u32(smem + s * kSWStageBytes);
-        const int ti = to * p.st - p.pt + al;
-        const int hi = ho * p.sh - p.ph + b;
-        const bool mine = lane < nr;
-        const bool ok = mine && ti >= 0 && ti < p.Ti && hi >= 0 && hi < p.Hi;
-        const unsigned okmask = __ballot_sync(0xffffffffu, ok);
-        const unsigned zmask = __ballot_sync(0xffffffffu, mine && !ok);
-        for (unsigned m = zmask; m; m &= m - 1) {
-          const int j = __ffs(m) - 1;
-          uint4* dst = reinterpret_cast<uint4*>(smem + s * kSWStageBytes + kSWDyBytes + j * kStemRowBytes + 32);
-          for (int c = lane; c < (p.Wi >> 1); c += 32) dst[c] = make_uint4(0, 0, 0, 0);
-        }
-        if (zmask) fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive_expect_tx(&full_bar[s], kSWDyBytes + static_cast<uint32_t>(__popc(okmask)) * rowBytes);
+      // ---------------- producer (one lane): one TMA box for the dY row, one per frame tap for its kh raw input rows
+      // ({128 pixel slots from pixel -4, kh rows}: rows land 1 KB apart in filter-row order, everything outside the clip —
+      // halo pixels, rows above / below the image, frames before / after the clip — is zero-filled by the TMA unit).
+      // (25 per-row cp.async.bulk requests per stage bounded this kernel at ~100 clocks per request.)
+      if (elect_one()) {
+        tma_prefetch_desc(&p.tmapDy);
+        tma_prefetch_desc(&p.tmapX);
+        const int a0 = f0 / p.kh, na = nr / p.kh;
+        const uint32_t tx = kSWDyBytes + static_cast<uint32_t>(na * p.kh) * kStemRowBytes;
+        int s = 0;
+        uint32_t ph = 0;
+        int ho = blockIdx.x % p.Ho, to = (blockIdx.x / p.Ho) % p.To, n = blockIdx.x / (p.Ho * p.To);
+        const int dho = gridDim.x % p.Ho, dto = (gridDim.x / p.Ho) % p.To, dn = gridDim.x / (p.Ho * p.To);
+        for (int r = blockIdx.x; r < p.numRows; r += gridDim.x) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          const uint32_t stage = smem_u32(smem + s * kSWStageBytes);
+          mbar_arrive_expect_tx(&full_bar[s], tx);
           asm volatile(
               "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-              ::"r"(stage), "l"(&p.tmapDy), "r"(smem_u32(&full_bar[s])), "r"(0), "r"(0), "r"(r)
+              ::"r"(stage), "l"(&p.tmapDy), "r"(smem_u32(&full_bar[s])), "r"(0), "r"(-1), "r"(r)
               : "memory");
-        }
-        if (ok) {
-          const __nv_bfloat16* src = p.x + ((static_cast<size_t>(n) * p.Ti + ti) * p.Hi + hi) * p.Wi * 4;
-          bulk_copy_g2s(stage + kSWDyBytes + lane * kStemRowBytes + 32, src, rowBytes, &full_bar[s]);
-        }
-        __syncwarp();
-        if (++s == kSWStages) {
-          s = 0;
-          ph ^= 1;
-        }
-        ho += dho;
-        to += dto;
-        n += dn;
-        if (ho >= p.Ho) {
-          ho -= p.Ho;
-          ++to;
-        }
-        if (to >= p.To) {
-          to -= p.To;
-          ++n;
+          for (int al = 0; al < na; ++al) {
+            asm volatile(
+                "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                ::"r"(stage + kSWDyBytes + al * p.kh * kStemRowBytes), "l"(&p.tmapX), "r"(smem_u32(&full_bar[s])),
+                  "r"(-4), "r"(ho * p.sh - p.ph), "r"(to * p.st - p.pt + a0 + al), "r"(n)
+                : "memory");
+          }
+          if (++s == kSWStages) {
+            s = 0;
+            ph ^= 1;
+          }
+          ho += dho;
+          to += dto;
+          n += dn;
+          if (ho >= p.Ho) {
+            ho -= p.Ho;
+            ++to;
+          }
+          if (to >= p.To) {
+            to -= p.To;
+            ++n;
+          }
         }
       }
     } else if (warp < 4) {
-      // ---------------- epilogue: D lane = (filter row within the set) * 8 + k-slot element, columns = co
+      // ---------------- epilogue: D lane = (filter row within the set) * 8 + k-slot element, columns = co; the 64-column
+      // block `blk` of a set holds window chunk blk ^ 1 (the shifted dY panel comes first)
       mbar_wait(accum_bar, 0);
       tc_fence_after_sync();
       const int lane = t & 31;
@@ -501,7 +503,8 @@ __global__ void __launch_bounds__(192, 1) conv_stem_wgrad_kernel(const __grid_co
         const int fr = f0 + set * 16 + frl;
         const bool row_ok = (set * 16 + frl) < nr;
         const int a = fr / p.kh, b = fr - a * p.kh;
-        for (int j = 0; j < 4; ++j) {
+        for (int blk = 0; blk < 4; ++blk) {
+          const int j = blk ^ 1;
           const int c = 2 * j + (e >> 2) - 1;           // window slot 2j + e/4 holds tap c = slot - 1
           const bool ok = row_ok && ch < p.Ci && c >= 0 && c < p.kw;
           float* dst = p.dw + ((static_cast<size_t>(ok ? ch : 0) * p.kt + (ok ? a : 0)) * p.kh + (ok ? b : 0)) * p.kw + (ok ? c : 0);
@@ -509,7 +512,7 @@ __global__ void __launch_bounds__(192, 1) conv_stem_wgrad_kernel(const __grid_co
 #pragma unroll 1
           for (int c0 = 0; c0 < 64; c0 += 32) {
             uint32_t v[32];
-            tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + (set * 4 + j) * 64 + c0, v);
+            tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + (set * 4 + blk) * 64 + c0, v);
             tmem_ld_wait();
             if (ok) {
 #pragma unroll
@@ -521,7 +524,7 @@ __global__ void __launch_bounds__(192, 1) conv_stem_wgrad_kernel(const __grid_co
       }
     } else {
       // ---------------- MMA lane
-      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+      constexpr uint32_t idesc = make_idesc_bf16(128, 128, 1, 1);
       const bool leader = elect_one();
       int s = 0;
       uint32_t ph = 0;
@@ -531,16 +534,17 @@ __global__ void __launch_bounds__(192, 1) conv_stem_wgrad_kernel(const __grid_co
         tc_fence_after_sync();
         const uint32_t stage = smem_u32(smem + s * kSWStageBytes);
         // A: raw rows; M chunk = the same 2-pixel window (16 B) of 16 consecutive filter rows (rows are 1 KB apart -> SBO),
-        //    K: pixels 16 B apart, 8-pixel groups 128 B apart (LBO).  B: 16 pixels = two 8-row groups of the dY panel.
+        //    K: pixels 16 B apart, 8-pixel groups 128 B apart (LBO).  B: 16 pixels = two 8-row groups of the dY panel;
+        //    N panel 0 = rows k (pixel k - 1), N panel 1 = rows k + 1 (pixel k): LBO = one 128-byte row.
         const uint64_t abase = make_smem_desc_nosw(stage + kSWDyBytes, 128, kStemRowBytes);
-        const uint64_t bbase = make_smem_desc_sw128(stage, 8192, 1024);
+        const uint64_t bbase = make_smem_desc_sw128(stage, 128, 1024);
         for (int set = 0; set < nsets; ++set) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int jj = 0; jj < 2; ++jj) {   // chunks 2jj + 1 (shifted panel) and 2jj
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-              umma_bf16(tmem_base + (set * 4 + j) * 64,
-                        abase + static_cast<uint64_t>((set * 16 * kStemRowBytes + j * 16 + ks * 256) >> 4),
+              umma_bf16(tmem_base + (set * 2 + jj) * 128,
+                        abase + static_cast<uint64_t>((set * 16 * kStemRowBytes + jj * 32 + ks * 256) >> 4),
                         bbase + static_cast<uint64_t>((ks * 2048) >> 4), idesc, (it | ks) != 0);
             }
           }
@@ -585,17 +589,24 @@ int launch_stem_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, 
     set_error("cudaFuncSetAttribute(conv_stem_wgrad): %s", cudaGetErrorString(e));
     return RSP_ERR_CUDA;
   }
-  const int frTotal = d->kt * d->kh;
-  const int groups = (frTotal + kSWRowSlots - 1) / kSWRowSlots;
-  p.rowsPerGroup = (frTotal + groups - 1) / groups;
+  // whole frame taps per CTA group (a raw-row box holds the kh rows of one frame tap): 4 + 3 taps for kt = 7
+  const int tapsPerGroup = kSWRowSlots / d->kh < d->kt ? kSWRowSlots / d->kh : d->kt;
+  const int groups = (d->kt + tapsPerGroup - 1) / tapsPerGroup;
+  p.rowsPerGroup = tapsPerGroup * d->kh;
   int workers = sm_count / groups;
   if (workers < 1) workers = 1;
   if (workers > p.numRows) workers = p.numRows;
   {
     const unsigned long long dims[3] = {64, static_cast<unsigned long long>(p.Wo), static_cast<unsigned long long>(p.numRows)};
     const unsigned long long strides[2] = {128, static_cast<unsigned long long>(p.Wo) * 128};
-    const unsigned box[3] = {64, 64, 1};
+    const unsigned box[3] = {64, kSWDyRows, 1};
     int rc = make_tmap_bf16(&p.tmapDy, dy, 3, dims, strides, box);
+    if (rc != RSP_OK) return rc;
+    const unsigned long long W = p.Wi, H = p.Hi, T = p.Ti;
+    const unsigned long long xdims[4] = {W, H, T, static_cast<unsigned long long>(p.N)};
+    const unsigned long long xstrides[3] = {W * 8, H * W * 8, T * H * W * 8};
+    const unsigned xbox[4] = {128, static_cast<unsigned>(d->kh), 1, 1};
+    rc = make_tmap_u64_rows(&p.tmapX, x, 4, xdims, xstrides, xbox);
     if (rc != RSP_OK) return rc;
   }
   dim3 grid(workers, groups);
