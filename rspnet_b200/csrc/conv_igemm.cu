@@ -35,7 +35,9 @@ struct GatherGeom {
   int pt, ph, pw;
   int transposed;            // 0: src = d*s - p + k ; 1: src = (d + p - k)/s when divisible
   int pxs;                   // SMALLC: w-pixels per (kt,kh) segment (4 or 8)
-  int numKb;                 // number of 64-wide K blocks
+  int numKb;                 // number of 64-wide K blocks that are walked
+  int kbSkip;                // K blocks in front of them that are skipped: frame taps that read padding for EVERY pixel
+                             // (a 3x3x3 filter on a one-frame tensor — R3D-18 layer4 — only ever sees its middle frame tap)
   long long M;               // N*Td*Hd*Wd
   int fast;                  // 1: source offset is linear in the tap (fprop, or dgrad with unit strides) and k <= 8
   unsigned long long mulW, mulH, mulT;  // ceil(2^sh / d) for row decoding without integer division
@@ -309,8 +311,8 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
       const uint32_t dst0 = swz(t >> 3, chunk * 16);  // rows (t>>3)+16i share the swizzle phase: + i*2048
       const int dirCs = g.transposed ? -g.Cs : g.Cs;
       const int cchunks = g.Cs >> 6;
-      int cc = kbBegin % cchunks;
-      int tap = kbBegin / cchunks;
+      int cc = (kbBegin + g.kbSkip) % cchunks;
+      int tap = (kbBegin + g.kbSkip) / cchunks;
       int c = tap % g.kw;
       tap /= g.kw;
       int b = tap % g.kh;
@@ -330,7 +332,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
         }
         const int kbw = g.cls ? (((g.wa0 + g.was * a) * g.wkh + (g.wb0 + g.wbs * b)) * g.wkw + (g.wc0 + g.wcs * c)) *
                                         cchunks + cc
-                              : kbBegin + kb;
+                              : kbBegin + kb + g.kbSkip;
         cp_async_mbar_arrive(&full_bar[s]);
         if (t == 0) {   // the filter tile of this K block: one bulk tensor copy, counted in bytes on the same barrier
           mbar_arrive_expect_tx(&full_bar[s], B_BYTES);
@@ -362,11 +364,11 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
         mbar_wait(&empty_bar[s], ph ^ 1);
         const uint32_t a_panel = smem_u32(smem + s * STAGE_BYTES);
         const uint32_t b_panel = a_panel + A_BYTES;
-        gather_panel<MODE, 128>(g, a_panel, kbBegin + kb, t, rows);
+        gather_panel<MODE, 128>(g, a_panel, kbBegin + kb + g.kbSkip, t, rows);
         cp_async_mbar_arrive(&full_bar[s]);
         if (t == 0) {
           mbar_arrive_expect_tx(&full_bar[s], B_BYTES);
-          tma_load_2d(b_panel, &p.tmapW, &full_bar[s], (kbBegin + kb) * 64, n0);
+          tma_load_2d(b_panel, &p.tmapW, &full_bar[s], (kbBegin + kb + g.kbSkip) * 64, n0);
         } else {
           mbar_arrive(&full_bar[s]);
         }
@@ -539,8 +541,8 @@ __global__ void __launch_bounds__(kWgradThreads) conv_wgrad_kernel(const __grid_
         bool kbok[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          const int kb = kb0 + j;
-          kbok[j] = kb < g.numKb;
+          const int kb = kb0 + j + g.kbSkip;
+          kbok[j] = kb0 + j < g.numKb;
           const int tap = kb / cchunks, cc = kb - tap * cchunks;
           ta[j] = tap / (g.kh * g.kw);
           const int rem = tap - ta[j] * g.kh * g.kw;
@@ -608,8 +610,8 @@ __global__ void __launch_bounds__(kWgradThreads) conv_wgrad_kernel(const __grid_
           for (int j = 0; j < NB; ++j)
             tma_load_2d(stage + (2 + j) * PANEL, &p.tmapDy, &full_bar[s], n0 + j * 64, static_cast<int>(prow0));
         }
-        gather_panel<MODE, 64>(g, stage, kb0, t, rows);
-        gather_panel<MODE, 64>(g, stage + PANEL, kb0 + 1, t, rows);
+        gather_panel<MODE, 64>(g, stage, kb0 + g.kbSkip, t, rows);
+        gather_panel<MODE, 64>(g, stage + PANEL, kb0 + 1 + g.kbSkip, t, rows);
         cp_async_mbar_arrive(&full_bar[s]);
         if (t != 0) mbar_arrive(&full_bar[s]);
       }
@@ -619,7 +621,7 @@ __global__ void __launch_bounds__(kWgradThreads) conv_wgrad_kernel(const __grid_
       tc_fence_after_sync();
       const int krow = kb0 * 64 + warp * 32 + (t & 31);
       const bool row_ok = krow < g.numKb * 64;
-      float* drow = p.dwt + static_cast<size_t>(row_ok ? krow : 0) * p.Nout + n0;
+      float* drow = p.dwt + static_cast<size_t>(row_ok ? krow + g.kbSkip * 64 : 0) * p.Nout + n0;
 #pragma unroll 1
       for (int c0 = 0; c0 < NT; c0 += 32) {
         uint32_t v[32];
@@ -869,6 +871,7 @@ static int fill_geom(GatherGeom& g, const rsp_conv3d_desc* d, int mode, int tran
   g.pt = d->pt; g.ph = d->ph; g.pw = d->pw;
   g.transposed = transposed;
   g.pxs = 0;
+  g.kbSkip = 0;
   if (!transposed) {
     g.Ts = d->Ti; g.Hs = d->Hi; g.Ws = d->Wi; g.Cs = d->Ci;
     g.Td = To; g.Hd = Ho; g.Wd = Wo;
@@ -906,6 +909,30 @@ static int fill_geom(GatherGeom& g, const rsp_conv3d_desc* d, int mode, int tran
 }
 
 static int conv_mode(const rsp_conv3d_desc* d) { return d->Ci == 4 ? MODE_SMALLC : MODE_GENERIC; }
+
+// Frame taps that read temporal padding for every pixel of the problem contribute exact zeros: drop their K blocks
+// (they form a prefix and a suffix of the tap order).  Returns the K blocks of the full filter row.
+static int skip_dead_frame_taps(GatherGeom& g) {
+  const int full = g.numKb;
+  if (g.cls || (g.transposed && (g.st != 1 || g.sh != 1 || g.sw != 1))) return full;
+  int aLo = g.kt, aHi = 0;
+  for (int a = 0; a < g.kt; ++a) {
+    bool live = false;
+    for (int td = 0; td < g.Td && !live; ++td) {
+      const int ts = g.transposed ? td + g.pt - a : td * g.st - g.pt + a;
+      live = ts >= 0 && ts < g.Ts;
+    }
+    if (live) {
+      if (a < aLo) aLo = a;
+      aHi = a + 1;
+    }
+  }
+  if (aLo >= aHi || (aLo == 0 && aHi == g.kt)) return full;
+  const int perTap = g.kh * g.kw * (g.Cs / 64);
+  g.kbSkip = aLo * perTap;
+  g.numKb = (aHi - aLo) * perTap;
+  return full;
+}
 
 // split-K finalize: out = bf16(acc + bias)
 __global__ void __launch_bounds__(256) splitk_finalize_kernel(const float4* __restrict__ acc,
@@ -1233,7 +1260,9 @@ int rsp_conv3d_fprop(const rsp_conv3d_desc* d, const void* x, const void* wp, co
   p.Nout = d->Co;
   p.acc = mode == MODE_GENERIC ? static_cast<float*>(workspace) : nullptr;
   p.stats = stats;
-  return mode == MODE_GENERIC ? dispatch_igemm<MODE_GENERIC>(p, stream) : dispatch_igemm<MODE_SMALLC>(p, stream);
+  if (mode != MODE_GENERIC) return dispatch_igemm<MODE_SMALLC>(p, stream);
+  const int fullKb = skip_dead_frame_taps(p.g);
+  return dispatch_igemm<MODE_GENERIC>(p, stream, fullKb);
 }
 
 // One parity class of a strided dgrad: destination pixels (st*t'+par_t, ...) only see the taps a = a0 + st*i with
@@ -1341,7 +1370,8 @@ int rsp_conv3d_dgrad(const rsp_conv3d_desc* d, const void* dy, const void* wd, v
   p.bias = nullptr;
   p.Nout = d->Ci;
   p.acc = static_cast<float*>(workspace);
-  return dispatch_igemm<MODE_GENERIC>(p, stream);
+  const int fullKb = skip_dead_frame_taps(p.g);
+  return dispatch_igemm<MODE_GENERIC>(p, stream, fullKb);
 }
 
 // Timing / A-B switch (tools only, not in the public header): bit 0 = never take the direct wgrad kernel,
@@ -1379,6 +1409,7 @@ int rsp_conv3d_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, c
   p.dwt = dwt_workspace;
   p.Nout = d->Co;
   const int Kpad = p.g.numKb * 64;
+  if (mode == MODE_GENERIC) skip_dead_frame_taps(p.g);   // their rows of dwt stay zero
   cudaError_t e = rsp::zero_async(dwt_workspace, static_cast<size_t>(Kpad) * d->Co * sizeof(float), stream);
   if (e != cudaSuccess) {
     set_error("wgrad memset: %s", cudaGetErrorString(e));

@@ -382,6 +382,9 @@ CONV_CASES = [
     (2, 3, 45, (3, 32, 28), (1, 7, 7), (1, 2, 2), (0, 3, 3)),
     (2, 3, 64, (4, 12, 12), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
     (3, 256, 512, (2, 7, 7), (3, 3, 3), (2, 2, 2), (1, 1, 1)),
+    # one-frame tensors (R3D-18 layer4): the outer frame taps only read padding and are skipped as whole K blocks
+    (5, 128, 128, (1, 4, 4), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (9, 64, 128, (1, 5, 4), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
     # 3x3x3 unit-stride RGB stem (C3D conv1): the even/odd raw-row kernel, ragged H and odd T
     (1, 3, 64, (3, 10, 14), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
     (2, 3, 64, (5, 33, 112), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
