@@ -464,13 +464,13 @@ int rsp_bn_relu_maxpool_fwd(const rsp_pool3d_desc* d, const void* x, const float
       cudaStream_t s = static_cast<cudaStream_t>(stream);
       cudaError_t e;
       if (idx) {
-        e = cudaFuncSetAttribute(bn_relu_maxpool_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        e = cudaFuncSetAttribute(bn_relu_maxpool_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
         if (e == cudaSuccess)
           bn_relu_maxpool_sweep_kernel<true><<<static_cast<unsigned>(grid), kSweepThreads, smem, s>>>(
               static_cast<const uint4*>(x), scale, shift, static_cast<uint4*>(y), reinterpret_cast<uint2*>(idx),
               static_cast<uint4*>(xmax), sg);
       } else {
-        e = cudaFuncSetAttribute(bn_relu_maxpool_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        e = cudaFuncSetAttribute(bn_relu_maxpool_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
         if (e == cudaSuccess)
           bn_relu_maxpool_sweep_kernel<false><<<static_cast<unsigned>(grid), kSweepThreads, smem, s>>>(
               static_cast<const uint4*>(x), scale, shift, static_cast<uint4*>(y), nullptr, nullptr, sg);

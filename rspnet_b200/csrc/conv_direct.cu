@@ -441,10 +441,10 @@ int launch_direct(const rsp_conv3d_desc* d, int transposed, const void* x, const
   const int grid = p.numItems < sms ? p.numItems : sms;
   cudaError_t e;
   if (NT == 64) {
-    e = cudaFuncSetAttribute(conv_direct_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    e = cudaFuncSetAttribute(conv_direct_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) conv_direct_kernel<64><<<grid, kDirThreads, smem, stream>>>(p);
   } else {
-    e = cudaFuncSetAttribute(conv_direct_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    e = cudaFuncSetAttribute(conv_direct_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) conv_direct_kernel<128><<<grid, kDirThreads, smem, stream>>>(p);
   }
   if (e != cudaSuccess) {

@@ -322,8 +322,9 @@ int launch_wgrad_direct(const rsp_conv3d_desc* d, const void* x, const void* dy,
     rc = make_tmap_bf16(&p.tmapDy, dy, 5, ddims, dstrides, dbox);
     if (rc != RSP_OK) return rc;
   }
-  cudaError_t e = cudaFuncSetAttribute(conv_wgrad_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem));
+  // always the device maximum: the attribute is per function, not per launch, and a tool that re-launches a captured
+  // graph node on its own (ncu --graph-profiling node) would otherwise see the value of the LAST eager launch
+  cudaError_t e = cudaFuncSetAttribute(conv_wgrad_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(conv_wgrad_direct): %s", cudaGetErrorString(e));
     return RSP_ERR_CUDA;
