@@ -748,6 +748,17 @@ __device__ __forceinline__ void hue_shift(float (&v)[3], float shift) {
   v[2] = (idx == 3 || idx == 4) ? val : idx == 2 ? tt : idx == 5 ? qq : pp;
 }
 
+// ToTensorVideo's x / 255 for a byte, correctly rounded (== the IEEE quotient float(b) / 255.0f for all 256 values, checked
+// exhaustively): one multiply by fl(1/255) and one FMA refinement step.  A 256-entry shared-memory table costs a 3-4-way
+// bank-conflicted LDS per tap instead (the sampler was bound by its LSU wavefronts).
+__device__ __forceinline__ float unit255(uint8_t b) {
+  const float f = __uint_as_float(0x4B000000u | b) - 8388608.0f;   // exact u8 -> float without the conversion pipe
+  const float k = __uint_as_float(0x3B808081u);                     // fl(1 / 255)
+  const float q = f * k;
+  const float r = fmaf(-q, 255.0f, f);
+  return fmaf(r, k, q);
+}
+
 // Resized (bilinear, align_corners=False), optionally gray-scaled pixel of the cropped frame, in [0, 1].
 __device__ __forceinline__ void clip_pixel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ frame_idx,
                                            const int32_t* __restrict__ box, uint8_t fl, const ClipGeom& g, int clip, int t,
@@ -768,13 +779,62 @@ __device__ __forceinline__ void clip_pixel(const uint8_t* __restrict__ frames, c
   const uint8_t* p11 = f + (static_cast<size_t>(bi + y1) * g.Ws + bj + x1) * 3;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    // ToTensorVideo's x / 255 from a 256-entry table of the exact quotients (twelve IEEE divisions per pixel otherwise)
-    const float a = lut[p00[c]], b = lut[p01[c]], cc = lut[p10[c]], d = lut[p11[c]];
+    const float a = unit255(p00[c]), b = unit255(p01[c]), cc = unit255(p10[c]), d = unit255(p11[c]);
     v[c] = hy * (hx * a + lx * b) + ly * (hx * cc + lx * d);
   }
   if (fl & 2) {  // RandomGrayScale: ITU-R 601-2 luma, replicated on the three channels
     const float gray = luma(v);
     v[0] = v[1] = v[2] = gray;
+  }
+}
+
+// Four horizontally adjacent output pixels x .. x+3 of row y (x % 4 == 0): the row terms (source rows, vertical weights,
+// frame pointer) are computed once and the 48 byte loads of the quad are independent of each other — the one-pixel-per-
+// thread form is bound by the latency of its dependent chain (index -> pointer -> bytes -> table), not by bandwidth.
+// Per pixel the arithmetic is exactly clip_pixel's.
+__device__ __forceinline__ void clip_pixels4(const uint8_t* __restrict__ frames, const int32_t* __restrict__ frame_idx,
+                                             const int32_t* __restrict__ box, uint8_t fl, const ClipGeom& g, int clip, int t,
+                                             int y, int x, const float* __restrict__ lut, float (&v)[4][3]) {
+  const int bi = box[clip * 4 + 0], bj = box[clip * 4 + 1], bh = box[clip * 4 + 2], bw = box[clip * 4 + 3];
+  const float sh = static_cast<float>(bh) / g.S, sw = static_cast<float>(bw) / g.S;
+  float fy = sh * (y + 0.5f) - 0.5f;
+  fy = fy < 0.f ? 0.f : fy;
+  const int y0 = static_cast<int>(fy);
+  const int y1 = y0 + (y0 < bh - 1 ? 1 : 0);
+  const float ly = fy - y0, hy = 1.f - ly;
+  const uint8_t* f = frames + static_cast<size_t>(frame_idx[clip * g.T + t]) * g.Hs * g.Ws * 3;
+  const uint8_t* r0 = f + (static_cast<size_t>(bi + y0) * g.Ws + bj) * 3;
+  const uint8_t* r1 = f + (static_cast<size_t>(bi + y1) * g.Ws + bj) * 3;
+  uint8_t b00[4][3], b01[4][3], b10[4][3], b11[4][3];
+  float lx[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int xs = (fl & 1) ? (g.S - 1 - (x + j)) : (x + j);   // horizontal flip acts on the resized clip
+    float fx = sw * (xs + 0.5f) - 0.5f;
+    fx = fx < 0.f ? 0.f : fx;
+    const int x0 = static_cast<int>(fx);
+    const int x1 = x0 + (x0 < bw - 1 ? 1 : 0);
+    lx[j] = fx - x0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      b00[j][c] = r0[x0 * 3 + c];
+      b01[j][c] = r0[x1 * 3 + c];
+      b10[j][c] = r1[x0 * 3 + c];
+      b11[j][c] = r1[x1 * 3 + c];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float hx = 1.f - lx[j];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float a = unit255(b00[j][c]), b = unit255(b01[j][c]), cc = unit255(b10[j][c]), d = unit255(b11[j][c]);
+      v[j][c] = hy * (hx * a + lx[j] * b) + ly * (hx * cc + lx[j] * d);
+    }
+    if (fl & 2) {
+      const float gray = luma(v[j]);
+      v[j][0] = v[j][1] = v[j][2] = gray;
+    }
   }
 }
 
@@ -811,9 +871,7 @@ __global__ void __launch_bounds__(256) clip_gray_sum_kernel(const uint8_t* __res
                                                             const uint8_t* __restrict__ flags,
                                                             const ClipJitter* __restrict__ jitter, ClipGeom g,
                                                             float* __restrict__ sums, int per_clip_blocks) {
-  __shared__ float lut[256];
-  lut[threadIdx.x] = static_cast<float>(threadIdx.x) / 255.0f;
-  __syncthreads();
+  const float* lut = nullptr;   // (the x / 255 table is gone: unit255)
   const int clip = blockIdx.x / per_clip_blocks, blk = blockIdx.x - clip * per_clip_blocks;
   const ClipJitter jt = jitter[clip];
   int cpos = -1;
@@ -844,6 +902,140 @@ __global__ void __launch_bounds__(256) clip_gray_sum_kernel(const uint8_t* __res
   }
 }
 
+// fp32 NCDHW output with colour jitter, two passes IN PLACE (the gray-sum pass above re-gathers every pixel — 12 byte loads,
+// 12 table look-ups, bilinear blend — only to throw it away):
+//   pass A: gather + the jitter ops in front of the contrast op, store the pixel into the output tensor, sum its gray level;
+//   pass B: stream over the output tensor: remaining ops (they need the clip-wide gray mean) + normalise, in place.
+// Same arithmetic on the same fp32 values as the single-pass kernel, so the pixels are bit-identical to it.
+__global__ void __launch_bounds__(256) clip_sample_pre_kernel(const uint8_t* __restrict__ frames,
+                                                              const int32_t* __restrict__ frame_idx,
+                                                              const int32_t* __restrict__ box,
+                                                              const uint8_t* __restrict__ flags,
+                                                              const ClipJitter* __restrict__ jitter, ClipGeom g,
+                                                              float* __restrict__ sums, float* __restrict__ out,
+                                                              int per_clip_blocks) {
+  const float* lut = nullptr;   // (the x / 255 table is gone: unit255)
+  const int clip = blockIdx.x / per_clip_blocks, blk = blockIdx.x - clip * per_clip_blocks;
+  const ClipJitter jt = jitter[clip];
+  int split = 4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (jt.order[k] == 1) split = k;
+  const int per = g.T * g.S * g.S;
+  const uint32_t plane2 = static_cast<uint32_t>(g.S) * g.S;
+  const uint8_t fl = flags[clip];
+  float* oc = out + static_cast<size_t>(clip) * 3 * per;
+  float acc = 0.f;
+  if ((g.S & 3) == 0) {
+    for (int q = blk * 256 + threadIdx.x; q < (per >> 2); q += per_clip_blocks * 256) {
+      const uint32_t i = static_cast<uint32_t>(q) * 4u;
+      const uint32_t t = i / plane2, rem = i - t * plane2;
+      const int y = static_cast<int>(rem / g.S), x = static_cast<int>(rem - (rem / g.S) * g.S);
+      float v[4][3];
+      clip_pixels4(frames, frame_idx, box, fl, g, clip, static_cast<int>(t), y, x, lut, v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        jitter_ops(v[j], jt, 0, split, 0.f);
+        acc += luma(v[j]);
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        *reinterpret_cast<float4*>(oc + i + static_cast<size_t>(c) * per) = make_float4(v[0][c], v[1][c], v[2][c], v[3][c]);
+    }
+  } else {
+    for (int i = blk * 256 + threadIdx.x; i < per; i += per_clip_blocks * 256) {
+      const uint32_t t = static_cast<uint32_t>(i) / plane2, rem = static_cast<uint32_t>(i) - t * plane2;
+      const int y = static_cast<int>(rem / g.S), x = static_cast<int>(rem - (rem / g.S) * g.S);
+      const int xs = (fl & 1) ? (g.S - 1 - x) : x;                 // horizontal flip acts on the resized clip
+      float v[3];
+      clip_pixel(frames, frame_idx, box, fl, g, clip, static_cast<int>(t), y, xs, lut, v);
+      jitter_ops(v, jt, 0, split, 0.f);
+      acc += luma(v);
+      oc[i] = v[0];
+      oc[i + per] = v[1];
+      oc[i + 2 * per] = v[2];
+    }
+  }
+  __shared__ float red[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0 && split < 4) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    atomicAdd(sums + clip, s);
+  }
+}
+
+__global__ void __launch_bounds__(256) clip_sample_post_kernel(const ClipJitter* __restrict__ jitter,
+                                                               const float* __restrict__ gray_sums, ClipGeom g,
+                                                               float* __restrict__ out, int per_clip_blocks) {
+  const int clip = blockIdx.x / per_clip_blocks, blk = blockIdx.x - clip * per_clip_blocks;
+  const ClipJitter jt = jitter[clip];
+  int split = 4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (jt.order[k] == 1) split = k;
+  const int per = g.T * g.S * g.S;
+  const float mean = gray_sums[clip] / (static_cast<float>(g.T) * g.S * g.S);
+  float* oc = out + static_cast<size_t>(clip) * 3 * per;
+  if ((per & 3) == 0) {
+    for (int q = blk * 256 + threadIdx.x; q < (per >> 2); q += per_clip_blocks * 256) {
+      float4* p0 = reinterpret_cast<float4*>(oc) + q;
+      float4* p1 = reinterpret_cast<float4*>(oc + per) + q;
+      float4* p2 = reinterpret_cast<float4*>(oc + 2 * static_cast<size_t>(per)) + q;
+      const float4 a = *p0, b = *p1, c4 = *p2;
+      float v[4][3] = {{a.x, b.x, c4.x}, {a.y, b.y, c4.y}, {a.z, b.z, c4.z}, {a.w, b.w, c4.w}};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        jitter_ops(v[j], jt, split, 4, mean);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[j][c] = (v[j][c] - g.mean[c]) / g.stdv[c];
+      }
+      *p0 = make_float4(v[0][0], v[1][0], v[2][0], v[3][0]);
+      *p1 = make_float4(v[0][1], v[1][1], v[2][1], v[3][1]);
+      *p2 = make_float4(v[0][2], v[1][2], v[2][2], v[3][2]);
+    }
+    return;
+  }
+  for (int i = blk * 256 + threadIdx.x; i < per; i += per_clip_blocks * 256) {
+    float v[3] = {oc[i], oc[i + per], oc[i + 2 * per]};
+    jitter_ops(v, jt, split, 4, mean);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = (v[c] - g.mean[c]) / g.stdv[c];
+    oc[i] = v[0];
+    oc[i + per] = v[1];
+    oc[i + 2 * per] = v[2];
+  }
+}
+
+// fp32 NCDHW output without colour jitter, four pixels per thread (S % 4 == 0).
+__global__ void __launch_bounds__(256) clip_sample4_kernel(const uint8_t* __restrict__ frames,
+                                                           const int32_t* __restrict__ frame_idx,
+                                                           const int32_t* __restrict__ box,
+                                                           const uint8_t* __restrict__ flags, ClipGeom g,
+                                                           float* __restrict__ out, size_t total4) {
+  const float* lut = nullptr;   // (the x / 255 table is gone: unit255)
+  const uint32_t plane2 = static_cast<uint32_t>(g.S) * g.S;
+  const size_t per = static_cast<size_t>(g.T) * plane2;
+  for (size_t q = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; q < total4; q += static_cast<size_t>(gridDim.x) * 256) {
+    const uint32_t i32 = static_cast<uint32_t>(q) * 4u;            // total < 2^32 is checked by the host
+    const uint32_t ct = i32 / plane2;                              // clip * T + t
+    const uint32_t rem = i32 - ct * plane2;
+    const int y = static_cast<int>(rem / g.S), x = static_cast<int>(rem - (rem / g.S) * g.S);
+    const int clip = static_cast<int>(ct / g.T), t = static_cast<int>(ct - (ct / g.T) * g.T);
+    float v[4][3];
+    clip_pixels4(frames, frame_idx, box, flags[clip], g, clip, t, y, x, lut, v);
+    const size_t o = (static_cast<size_t>(clip) * 3 * g.T + t) * plane2 + rem;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      *reinterpret_cast<float4*>(out + o + c * per) =
+          make_float4((v[0][c] - g.mean[c]) / g.stdv[c], (v[1][c] - g.mean[c]) / g.stdv[c],
+                      (v[2][c] - g.mean[c]) / g.stdv[c], (v[3][c] - g.mean[c]) / g.stdv[c]);
+  }
+}
+
 template <int LAYOUT>
 __global__ void __launch_bounds__(256) clip_sample_kernel(const uint8_t* __restrict__ frames,
                                                           const int32_t* __restrict__ frame_idx,
@@ -852,9 +1044,7 @@ __global__ void __launch_bounds__(256) clip_sample_kernel(const uint8_t* __restr
                                                           const ClipJitter* __restrict__ jitter,
                                                           const float* __restrict__ gray_sums, ClipGeom g,
                                                           void* __restrict__ outv, size_t total) {
-  __shared__ float lut[256];
-  lut[threadIdx.x] = static_cast<float>(threadIdx.x) / 255.0f;
-  __syncthreads();
+  const float* lut = nullptr;   // (the x / 255 table is gone: unit255)
   for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * 256) {
     // 32-bit index arithmetic (64-bit divisions cost ~100 instructions each)
@@ -914,6 +1104,17 @@ static int clip_sample_impl(const uint8_t* frames, const int32_t* frame_idx, con
       rsp::set_error("clip_sample: memset failed");
       return rsp::RSP_ERR_CUDA;
     }
+    if (layout == 0) {   // fp32 output: two passes in place (see clip_sample_pre_kernel)
+      int pcb = (T * S * S + 256 * 4 - 1) / (256 * 4);
+      if (pcb < 1) pcb = 1;
+      if (pcb > 512) pcb = 512;
+      rsp::clip_sample_pre_kernel<<<n_clips * pcb, 256, 0, st>>>(frames, frame_idx, box, flags, jt, g, gray_sums,
+                                                                 static_cast<float*>(out), pcb);
+      int rc = rsp::check_launch("clip_sample_pre");
+      if (rc != rsp::RSP_OK) return rc;
+      rsp::clip_sample_post_kernel<<<n_clips * pcb, 256, 0, st>>>(jt, gray_sums, g, static_cast<float*>(out), pcb);
+      return rsp::check_launch("clip_sample_post");
+    }
     int per_clip_blocks = (T * S * S + 256 * 8 - 1) / (256 * 8);
     if (per_clip_blocks < 1) per_clip_blocks = 1;
     if (per_clip_blocks > 64) per_clip_blocks = 64;
@@ -923,7 +1124,10 @@ static int clip_sample_impl(const uint8_t* frames, const int32_t* frame_idx, con
     if (rc != rsp::RSP_OK) return rc;
   }
   unsigned grid = rsp::ew_grid(total, 256);
-  if (layout == 0)
+  if (layout == 0 && !jt && (S & 3) == 0)
+    rsp::clip_sample4_kernel<<<rsp::ew_grid(total / 4, 256), 256, 0, st>>>(frames, frame_idx, box, flags, g,
+                                                                          static_cast<float*>(out), total / 4);
+  else if (layout == 0)
     rsp::clip_sample_kernel<0><<<grid, 256, 0, st>>>(frames, frame_idx, box, flags, jt, gray_sums, g, out, total);
   else
     rsp::clip_sample_kernel<1><<<grid, 256, 0, st>>>(frames, frame_idx, box, flags, jt, gray_sums, g, out, total);
