@@ -1010,120 +1010,6 @@ __global__ void __launch_bounds__(256) clip_sample_post_kernel(const ClipJitter*
   }
 }
 
-// fp32 NCDHW output, source rows staged in shared memory.  One CTA = kBand output rows of one (clip, frame): the source rows
-// its bilinear taps touch (<= kBand * Hs / S + 3 rows of the crop box, 3 bytes per pixel) are copied once with coalesced
-// 4-byte loads, then every output pixel reads its 12 tap bytes from shared memory.  (Gathering the bytes straight from
-// global memory costs ~50 L1 sector look-ups per warp and pixel; the kernel was bound by that, not by HBM.)
-//   PRE = false: resize / gray / flip / normalise (no colour jitter);
-//   PRE = true : pass A of the jitter path (ops in front of the contrast op, un-normalised pixel stored, gray level summed).
-// Per pixel the arithmetic is exactly clip_pixel's.
-constexpr int kBand = 16;
-
-template <bool PRE>
-__global__ void __launch_bounds__(256) clip_band_kernel(const uint8_t* __restrict__ frames,
-                                                        const int32_t* __restrict__ frame_idx,
-                                                        const int32_t* __restrict__ box, const uint8_t* __restrict__ flags,
-                                                        const ClipJitter* __restrict__ jitter, ClipGeom g,
-                                                        float* __restrict__ sums, float* __restrict__ out, int maxRows,
-                                                        int pitch) {
-  extern __shared__ __align__(16) uint8_t rowbuf[];   // [maxRows][pitch]
-  const int band = blockIdx.x, t = blockIdx.y, clip = blockIdx.z;
-  const int bi = box[clip * 4 + 0], bj = box[clip * 4 + 1], bh = box[clip * 4 + 2], bw = box[clip * 4 + 3];
-  const uint8_t fl = flags[clip];
-  const float sh = static_cast<float>(bh) / g.S, sw = static_cast<float>(bw) / g.S;
-  const int yA = band * kBand, yB = min(yA + kBand, g.S) - 1;          // output rows of this CTA
-  auto src_row = [&](int y, int& y0, int& y1, float& ly) {
-    float fy = sh * (y + 0.5f) - 0.5f;
-    fy = fy < 0.f ? 0.f : fy;
-    y0 = static_cast<int>(fy);
-    y1 = y0 + (y0 < bh - 1 ? 1 : 0);
-    ly = fy - y0;
-  };
-  int ys0, ys1, tmp;
-  float tl;
-  src_row(yA, ys0, tmp, tl);
-  src_row(yB, tmp, ys1, tl);
-  const int rows = ys1 - ys0 + 1;
-  if (rows > maxRows) __trap();
-  const uint8_t* f = frames + static_cast<size_t>(frame_idx[clip * g.T + t]) * g.Hs * g.Ws * 3;
-  const uint32_t nb = static_cast<uint32_t>(bw) * 3u;
-  for (int k = threadIdx.x >> 5; k < rows; k += 8) {                     // one warp per source row
-    const uint8_t* gr = f + (static_cast<size_t>(bi + ys0 + k) * g.Ws + bj) * 3;
-    const uint32_t mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(gr) & 3u);
-    const uint32_t* gw = reinterpret_cast<const uint32_t*>(gr - mis);
-    uint32_t* sw32 = reinterpret_cast<uint32_t*>(rowbuf + k * pitch);
-    const uint32_t words = (mis + nb + 3u) >> 2;
-    for (uint32_t w = threadIdx.x & 31; w < words; w += 32) sw32[w] = __ldg(gw + w);
-  }
-  __syncthreads();
-
-  ClipJitter jt{};
-  int split = 4;
-  if (PRE) {
-    jt = jitter[clip];
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (jt.order[k] == 1) split = k;
-  }
-  const int per = g.T * g.S * g.S;
-  float* oc = out + static_cast<size_t>(clip) * 3 * per + static_cast<size_t>(t) * g.S * g.S;
-  float acc = 0.f;
-  const int npix = (yB - yA + 1) * g.S;
-  for (int i = threadIdx.x; i < npix; i += 256) {
-    const int yl = i / g.S, x = i - yl * g.S, y = yA + yl;
-    int y0, y1;
-    float ly;
-    src_row(y, y0, y1, ly);
-    const float hy = 1.f - ly;
-    const int xs = (fl & 1) ? (g.S - 1 - x) : x;                 // horizontal flip acts on the resized clip
-    float fx = sw * (xs + 0.5f) - 0.5f;
-    fx = fx < 0.f ? 0.f : fx;
-    const int x0 = static_cast<int>(fx);
-    const int x1 = x0 + (x0 < bw - 1 ? 1 : 0);
-    const float lx = fx - x0, hx = 1.f - lx;
-    const uint32_t base = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(f)) + static_cast<uint32_t>(bj) * 3u;
-    const uint32_t m0 = (base + static_cast<uint32_t>(bi + y0) * static_cast<uint32_t>(g.Ws) * 3u) & 3u;
-    const uint32_t m1 = (base + static_cast<uint32_t>(bi + y1) * static_cast<uint32_t>(g.Ws) * 3u) & 3u;
-    const uint8_t* r0 = rowbuf + (y0 - ys0) * pitch + m0;
-    const uint8_t* r1 = rowbuf + (y1 - ys0) * pitch + m1;
-    float v[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float a = unit255(r0[x0 * 3 + c]), b = unit255(r0[x1 * 3 + c]), cc = unit255(r1[x0 * 3 + c]),
-                  d = unit255(r1[x1 * 3 + c]);
-      v[c] = hy * (hx * a + lx * b) + ly * (hx * cc + lx * d);
-    }
-    if (fl & 2) {  // RandomGrayScale: ITU-R 601-2 luma, replicated on the three channels
-      const float gray = luma(v);
-      v[0] = v[1] = v[2] = gray;
-    }
-    const int o = y * g.S + x;
-    if (PRE) {
-      jitter_ops(v, jt, 0, split, 0.f);
-      acc += luma(v);
-      oc[o] = v[0];
-      oc[o + per] = v[1];
-      oc[o + 2 * per] = v[2];
-    } else {
-      oc[o] = (v[0] - g.mean[0]) / g.stdv[0];
-      oc[o + per] = (v[1] - g.mean[1]) / g.stdv[1];
-      oc[o + 2 * per] = (v[2] - g.mean[2]) / g.stdv[2];
-    }
-  }
-  if (PRE) {
-    __shared__ float red[8];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0 && split < 4) {
-      float s2 = 0.f;
-      for (int w = 0; w < 8; ++w) s2 += red[w];
-      atomicAdd(sums + clip, s2);
-    }
-  }
-}
-
 // fp32 NCDHW output without colour jitter, four pixels per thread (S % 4 == 0).
 __global__ void __launch_bounds__(256) clip_sample4_kernel(const uint8_t* __restrict__ frames,
                                                            const int32_t* __restrict__ frame_idx,
@@ -1196,12 +1082,6 @@ __global__ void __launch_bounds__(256) clip_sample_kernel(const uint8_t* __restr
 
 }  // namespace rsp
 
-static int g_sampler_debug = 0;   // bit 0: never take the shared-memory-staged gather (A/B timing, tests)
-extern "C" int rsp_debug_sampler(int flags) {
-  g_sampler_debug = flags;
-  return 0;
-}
-
 static int clip_sample_impl(const uint8_t* frames, const int32_t* frame_idx, const int32_t* box, const uint8_t* flags,
                             const void* jitter, float* gray_sums, const float* mean3, const float* std3, int32_t n_clips,
                             int32_t T, int32_t Hs, int32_t Ws, int32_t S, int32_t layout, void* out, void* stream) {
@@ -1219,32 +1099,6 @@ static int clip_sample_impl(const uint8_t* frames, const int32_t* frame_idx, con
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const rsp::ClipJitter* jt = static_cast<const rsp::ClipJitter*>(jitter);
-  // shared-memory-staged gather for the fp32 layout when one band's source rows fit in 48 KB
-  const int bandRows = static_cast<int>(static_cast<long long>(Hs) * (rsp::kBand - 1) / S) + 4;
-  const int bandPitch = (Ws * 3 + 3 + 3) / 4 * 4 + 4;
-  const bool banded = layout == 0 && static_cast<long long>(bandRows) * bandPitch <= 48 * 1024 && n_clips <= 65535 &&
-                      T <= 65535 && !(g_sampler_debug & 1);
-  if (banded) {
-    const dim3 grid((S + rsp::kBand - 1) / rsp::kBand, T, n_clips);
-    const size_t smem = static_cast<size_t>(bandRows) * bandPitch;
-    if (!jt) {
-      rsp::clip_band_kernel<false><<<grid, 256, smem, st>>>(frames, frame_idx, box, flags, nullptr, g, nullptr,
-                                                            static_cast<float*>(out), bandRows, bandPitch);
-      return rsp::check_launch("clip_band");
-    }
-    if (rsp::zero_async(gray_sums, sizeof(float) * n_clips, st) != cudaSuccess) {
-      rsp::set_error("clip_sample: memset failed");
-      return rsp::RSP_ERR_CUDA;
-    }
-    rsp::clip_band_kernel<true><<<grid, 256, smem, st>>>(frames, frame_idx, box, flags, jt, g, gray_sums,
-                                                         static_cast<float*>(out), bandRows, bandPitch);
-    int rc = rsp::check_launch("clip_band (pre)");
-    if (rc != rsp::RSP_OK) return rc;
-    int pcb = (T * S * S + 256 * 4 - 1) / (256 * 4);
-    pcb = pcb < 1 ? 1 : (pcb > 512 ? 512 : pcb);
-    rsp::clip_sample_post_kernel<<<n_clips * pcb, 256, 0, st>>>(jt, gray_sums, g, static_cast<float*>(out), pcb);
-    return rsp::check_launch("clip_sample_post");
-  }
   if (jt) {
     if (rsp::zero_async(gray_sums, sizeof(float) * n_clips, st) != cudaSuccess) {
       rsp::set_error("clip_sample: memset failed");

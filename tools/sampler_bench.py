@@ -8,11 +8,6 @@ import torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from rspnet_b200.sampler import GPUClipSampler  # noqa: E402
 
-import os  # noqa: E402
-from rspnet_b200 import _lib  # noqa: E402
-if os.environ.get("RSP_SAMPLER_DEBUG"):   # 1: global-memory gather kernels instead of the shared-memory-staged ones
-    _lib.load().rsp_debug_sampler(int(os.environ["RSP_SAMPLER_DEBUG"]))
-
 B, FV, HS, WS = 64, 64, 128, 171
 frames = torch.randint(0, 256, (B * FV, HS, WS, 3), dtype=torch.uint8, device="cuda")
 offsets, lengths = [v * FV for v in range(B)], [FV] * B
