@@ -48,7 +48,10 @@ def main():
             loss = (y[0] * w1).sum() + (y[1] * w2).sum()
             outs = [y[0].detach().clone(), y[1].detach().clone()]
         loss.backward()
-        grads = {k: pack(p.grad) for k, p in model.named_parameters()
+        # the stem filter gradient (the end of the longest backward chain) is kept in full so that its direction is
+        # gated over all 65,856 values, not over a 32-value prefix; the 7 M-value layer4 filter stays a summary
+        grads = {k: (p.grad.detach().clone() if k == "encoder.conv1.weight" else pack(p.grad))
+                 for k, p in model.named_parameters()
                  if p.grad is not None and (not k.startswith("encoder.") or k in ("encoder.conv1.weight",
                                                                                   "encoder.layer4.1.conv2.weight"))}
         out["cases"].append(dict(case=case, keys=list(model.state_dict().keys()), init=init, outs=outs,

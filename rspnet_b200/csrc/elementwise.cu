@@ -60,8 +60,45 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const uint4* __rest
       is[i] = invstd[g * 8 + i];
     }
   }
-  for (size_t row = static_cast<size_t>(blockIdx.x) * rows_per_iter + rsub; active && row < M;
-       row += static_cast<size_t>(gridDim.x) * rows_per_iter) {
+  const size_t rstride = static_cast<size_t>(gridDim.x) * rows_per_iter;
+  size_t row = static_cast<size_t>(blockIdx.x) * rows_per_iter + rsub;
+  // two rows per trip with all loads issued up front (the sums still run in row order: results are unchanged)
+  for (; active && row + rstride < M; row += 2 * rstride) {
+    const size_t o0 = row * G + g, o1 = (row + rstride) * G + g;
+    const uint4 xa = __ldg(x + o0), xb = __ldg(x + o1);
+    uint4 da = make_uint4(0, 0, 0, 0), db = da, oa = da, ob = da;
+    if (MODE == 1) {
+      da = __ldg(dout + o0);
+      db = __ldg(dout + o1);
+      if (relu) {
+        oa = __ldg(out + o0);
+        ob = __ldg(out + o1);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      float xv[8];
+      unpack8(u ? xb : xa, xv);
+      if (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          a[i] += xv[i];
+          b[i] = fmaf(xv[i], xv[i], b[i]);
+        }
+      } else {
+        float dv[8], ov[8];
+        unpack8(u ? db : da, dv);
+        if (relu) unpack8(u ? ob : oa, ov);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float dz = (relu && !(ov[i] > 0.f)) ? 0.f : dv[i];
+          a[i] += dz;
+          b[i] = fmaf(dz, (xv[i] - mu[i]) * is[i], b[i]);
+        }
+      }
+    }
+  }
+  for (; active && row < M; row += rstride) {
     size_t o = row * G + g;
     float xv[8];
     unpack8(__ldg(x + o), xv);
@@ -210,6 +247,55 @@ __global__ void __launch_bounds__(256) bn_finalize_act_fwd_kernel(
   }
   __syncthreads();
   const int G = C >> 3;
+  if (256 % G == 0) {
+    // the block start and the grid stride are multiples of G: a thread keeps its channel group, so scale / shift live in
+    // registers and the loop is four independent 16-byte loads (+ residuals) in flight per thread — no 64-bit modulo and
+    // no shared-memory reads per element
+    const int g = threadIdx.x % G;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      sc[e] = ssc[g * 8 + e];
+      sh[e] = ssh[g * 8 + e];
+    }
+    const size_t stride = static_cast<size_t>(gridDim.x) * 256;
+    size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+      uint4 xr[4], rr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) xr[u] = __ldg(x + i + u * stride);
+      if (res) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) rr[u] = __ldg(res + i + u * stride);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float xv[8], rv[8];
+        unpack8(xr[u], xv);
+        if (res) unpack8(rr[u], rv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float y = fmaf(xv[e], sc[e], sh[e]);
+          if (res) y += rv[e];
+          xv[e] = relu ? fmaxf(y, 0.f) : y;
+        }
+        out[i + u * stride] = pack8(xv);
+      }
+    }
+    for (; i < nvec; i += stride) {
+      float xv[8], rv[8];
+      unpack8(__ldg(x + i), xv);
+      if (res) unpack8(__ldg(res + i), rv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float y = fmaf(xv[e], sc[e], sh[e]);
+        if (res) y += rv[e];
+        xv[e] = relu ? fmaxf(y, 0.f) : y;
+      }
+      out[i] = pack8(xv);
+    }
+    return;
+  }
   for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < nvec;
        i += static_cast<size_t>(gridDim.x) * 256) {
     int g = static_cast<int>(i % G);
@@ -247,6 +333,52 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
   }
   __syncthreads();
   const int G = C >> 3;
+  if (256 % G == 0) {   // see bn_finalize_act_fwd_kernel: per-thread channel group, parameters in registers, two rows in flight
+    const int g = threadIdx.x % G;
+    float mu[8], is[8], kk[8], m1[8], m2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      mu[e] = smu[g * 8 + e];
+      is[e] = sis[g * 8 + e];
+      kk[e] = sk[g * 8 + e];
+      m1[e] = s1[g * 8 + e];
+      m2[e] = s2[g * 8 + e];
+    }
+    const size_t stride = static_cast<size_t>(gridDim.x) * 256;
+    size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
+    auto one = [&](size_t at, const uint4& dr, const uint4& xr, const uint4& orr) {
+      float dv[8], ov[8], xv[8], o[8];
+      unpack8(dr, dv);
+      unpack8(xr, xv);
+      if (relu) unpack8(orr, ov);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float dz = (relu && !(ov[e] > 0.f)) ? 0.f : dv[e];
+        dv[e] = dz;
+        float xh = (xv[e] - mu[e]) * is[e];
+        o[e] = kk[e] * (dz - m1[e] - xh * m2[e]);
+      }
+      dx[at] = pack8(o);
+      if (dres) dres[at] = pack8(dv);
+    };
+    for (; i + stride < nvec; i += 2 * stride) {
+      const uint4 d0 = __ldg(dout + i), d1 = __ldg(dout + i + stride);
+      const uint4 x0 = __ldg(x + i), x1 = __ldg(x + i + stride);
+      uint4 o0 = make_uint4(0, 0, 0, 0), o1 = o0;
+      if (relu) {
+        o0 = __ldg(out + i);
+        o1 = __ldg(out + i + stride);
+      }
+      one(i, d0, x0, o0);
+      one(i + stride, d1, x1, o1);
+    }
+    for (; i < nvec; i += stride) {
+      const uint4 d0 = __ldg(dout + i), x0 = __ldg(x + i);
+      const uint4 o0 = relu ? __ldg(out + i) : make_uint4(0, 0, 0, 0);
+      one(i, d0, x0, o0);
+    }
+    return;
+  }
   for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < nvec;
        i += static_cast<size_t>(gridDim.x) * 256) {
     int g = static_cast<int>(i % G);

@@ -777,6 +777,14 @@ def test_head_variants_match_reference_golden(idx):
             assert 0.8 < ratio < 1.25, (k, ratio)
             assert _cos(gk[:32], gref["head"]) > 0.8, (k, _cos(gk[:32], gref["head"]))
             continue
+        if k == "encoder.conv1.weight":
+            # stem filter gradient, all 65,856 values (the end of the longest backward chain; 4 clips of 8x64x64 leave
+            # layer4's BatchNorm 16 values per channel).  Calibration: stock torch bf16 autocast of the UNMODIFIED
+            # reference against its own fp32 run on this fixture gives 0.893-0.913 here (and 0.80-0.92 over the first 32
+            # values, which is why the prefix is no longer gated); the gate is 2x that deviation.
+            c = _cos(named[k].grad.detach().float().cpu().flatten(), gref.flatten())
+            assert c > 0.79, (k, c)
+            continue
         gots.append(named[k].grad.detach().float().cpu().flatten())
         refs.append(gref.flatten())
         if gref.abs().max() > 1e-6 and not k.endswith("conv1.bias"):
