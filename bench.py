@@ -376,9 +376,17 @@ def run_b200(args):
         loss_done = [torch.cuda.Event() for _ in range(2)]
         seen = {"loss": None}
 
-        def run_feed(host, stage, make_inputs, stage_free_after_inputs):
-            ready = [torch.cuda.Event() for _ in range(2)]
-            consumed = [torch.cuda.Event() for _ in range(2)]
+        def run_feed(host, stage, make_inputs, sampled):
+            """`sampled`: the inputs of a step are BUILT on the device from the staged bytes (clip sampler).  Then three
+            stages are in flight, each on its own stream: H2D of step i+2 | sampler of step i+1, writing straight into
+            the input pair the captured step reads (PretrainEngine.next_input_pair) | step i.  Otherwise the staged
+            tensors are the inputs themselves and only the copy of step i+1 overlaps step i."""
+            ready = [torch.cuda.Event() for _ in range(2)]      # H2D of the slot has landed
+            consumed = [torch.cuda.Event() for _ in range(2)]   # the staged bytes of the slot have been read
+            built = [torch.cuda.Event() for _ in range(2)]      # the sampler has written the slot's clips
+            stepped = [torch.cuda.Event() for _ in range(2)]    # the step that read the slot's clips has finished
+            clips = [None, None]
+            build_stream = torch.cuda.Stream() if sampled else None
 
             def prefetch(i):
                 s = i % 2
@@ -388,22 +396,41 @@ def run_b200(args):
                         dst.copy_(src, non_blocking=True)
                     ready[s].record(copy_stream)
 
+            def build(i, ahead):
+                s = i % 2
+                with torch.cuda.stream(build_stream):
+                    build_stream.wait_event(ready[s])
+                    build_stream.wait_event(stepped[s])      # step i-2 read the buffers this fills
+                    clips[s] = make_inputs(stage[s], engine.next_input_pair(ahead))
+                    consumed[s].record(build_stream)
+                    built[s].record(build_stream)
+
             tick = {"i": 0}
 
             def e2e_step(_):
                 i = tick["i"]
                 tick["i"] += 1
                 s = i % 2
-                if i == 0:
-                    prefetch(0)
-                prefetch(i + 1)  # next step's inputs move while this step computes
-                torch.cuda.current_stream().wait_event(ready[s])
-                clip_q, clip_k = make_inputs(stage[s])
-                if stage_free_after_inputs:     # the sampler has read the frames: the next copy may overwrite them
-                    consumed[s].record()
-                loss = engine.step(clip_q, clip_k)
-                if not stage_free_after_inputs:
-                    consumed[s].record()
+                main = torch.cuda.current_stream()
+                if sampled:
+                    if i == 0:
+                        prefetch(0)
+                        prefetch(1)
+                        build(0, 0)
+                    build(i + 1, 1)      # next step's clips are sampled while this step computes
+                    prefetch(i + 2)      # and the frames of the step after that cross PCIe
+                    main.wait_event(built[s])
+                    clip_q, clip_k = clips[s]
+                    loss = engine.step(clip_q, clip_k)
+                    stepped[s].record(main)
+                else:
+                    if i == 0:
+                        prefetch(0)
+                    prefetch(i + 1)      # next step's inputs move while this step computes
+                    main.wait_event(ready[s])
+                    clip_q, clip_k = make_inputs(stage[s], None)
+                    loss = engine.step(clip_q, clip_k)
+                    consumed[s].record(main)
                 loss_host[s].copy_(torch.stack(loss), non_blocking=True)
                 loss_done[s].record()
                 # the caller reads every step's loss on the host, one step behind the device (as a logging loop does):
@@ -416,7 +443,9 @@ def run_b200(args):
                 consumed[s].record()
             for i in range(max(2, args.warmup)):
                 e2e_step(i)
-            return timed(e2e_step, args.steps) / args.steps
+            ms = timed(e2e_step, args.steps) / args.steps
+            torch.cuda.synchronize()
+            return ms
 
         # (1) uint8 frames -> sampler -> step.  Per video the 64 frames its two 32-frame clips are cut from, 128x171
         # (SURVEY.md 8d "pipeline benchmark" frame size); frame indices / boxes / gray / jitter / flip drawn per step.
@@ -430,8 +459,8 @@ def run_b200(args):
         stage_u8 = [(torch.empty((B * FV, HS, WS, 3), dtype=torch.uint8, device=dev),) for _ in range(2)]
         offsets, lengths = [v * FV for v in range(B)], [FV] * B
 
-        def from_frames(st):
-            (clip_q, clip_k), _ = sampler_k(st[0], offsets, lengths)
+        def from_frames(st, out):
+            (clip_q, clip_k), _ = sampler_k(st[0], offsets, lengths, out=out)
             return clip_q, clip_k
 
         ms_u8 = run_feed(host_u8, stage_u8, from_frames, True)
@@ -439,15 +468,17 @@ def run_b200(args):
         e2e_u8 = {"value": B * world / (ms_u8 / 1e3), "unit": "clips/s", "ms_per_step": ms_u8, "feed": "uint8_frames",
                "h2d_bytes_per_step": u8_bytes + 2 * B * (args.frames * 4 + 16 + 1 + 20), "d2h_bytes_per_step": 12,
                "note": f"loader hand-off as in the reference: pinned host uint8 frames ({FV} frames of {HS}x{WS} per video) "
-                       "-> double-buffered H2D on a copy stream -> clip sampler kernel (crop, bilinear resize, gray, "
-                       "colour jitter, flip, normalise; decisions drawn on the host per step) -> PretrainEngine.step; "
+                       "-> double-buffered H2D on a copy stream -> clip sampler kernels on a second stream (crop, bilinear "
+                       "resize, gray, colour jitter, flip, normalise; decisions drawn on the host per step), written "
+                       "into the input pair of the captured step -> PretrainEngine.step; three stages in flight (copy "
+                       "of step i+2, sampling of step i+1, step i); "
                        "every step's loss is copied to pinned host memory and read there one step later (the timed "
                        "region ends with a full synchronize)"}
         del host_u8, stage_u8
         # (2) ready-made fp32 clips
         host_f = [(torch.randn(shape).pin_memory(), torch.randn(shape).pin_memory()) for _ in range(2)]
         stage_f = [(torch.empty(shape, device=dev), torch.empty(shape, device=dev)) for _ in range(2)]
-        ms_f = run_feed(host_f, stage_f, lambda st: (st[0], st[1]), False)
+        ms_f = run_feed(host_f, stage_f, lambda st, out: (st[0], st[1]), False)
         e2e_fp32 = {"value": B * world / (ms_f / 1e3), "unit": "clips/s", "ms_per_step": ms_f, "feed": "fp32_clips",
                     "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 12,
                     "note": "pinned host fp32 clips [B,3,T,H,W] x 2 straight into PretrainEngine.step (PCIe-bound: "

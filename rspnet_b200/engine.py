@@ -145,6 +145,17 @@ class PretrainEngine:
         self._graphs = [None, None]
         self._graph_pool = None
 
+    def next_input_pair(self, ahead: int = 0) -> Optional[Tuple[torch.Tensor, torch.Tensor]]:
+        """The ``(clip_q, clip_k)`` buffers that the next graph-mode step (``ahead=0``; ``ahead=1``: the one after it)
+        reads in place, or None while that step would still run eagerly / be captured.  A loader that fills them
+        (``GPUClipSampler(..., out=pair)``) and passes them to ``step`` saves the device copy of both clips into the
+        captured graph's inputs.  Two graphs alternate, so the pair also belongs to the step two steps earlier: fill it
+        only after that step has finished (stream-order the fill behind it)."""
+        if not (self.cuda_graph and self._graph_capable and self._eager_steps >= 3):
+            return None
+        G = self._graphs[(self._graph_steps + ahead) & 1]
+        return None if G is None else (G["q"], G["k"])
+
     def _graph_step(self, clip_q, clip_k):
         slot = self._graph_steps & 1
         key = (tuple(clip_q.shape), tuple(clip_k.shape), clip_q.dtype, self.lr, self.momentum, self.weight_decay)

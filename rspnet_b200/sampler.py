@@ -145,17 +145,19 @@ class ColorJitter:
 
 def clip_sample(frames: torch.Tensor, frame_idx: torch.Tensor, boxes: torch.Tensor, flags: torch.Tensor,
                 mean: Sequence[float], std: Sequence[float], size: int, layout: int = 0,
-                jitter: Optional[torch.Tensor] = None) -> torch.Tensor:
+                jitter: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """frames uint8 [F,H,W,3] (device); frame_idx int32 [n,T]; boxes int32 [n,4]; flags uint8 [n]; jitter: uint8
-    [n, 20] device view of a ``JITTER_DTYPE`` table, or None."""
+    [n, 20] device view of a ``JITTER_DTYPE`` table, or None.  ``out``: an existing contiguous clip tensor of the
+    layout's shape and dtype to fill in place (e.g. the input buffers of a captured training step)."""
     assert frames.dtype == torch.uint8 and frames.is_contiguous() and frames.shape[-1] == 3
     n, t = frame_idx.shape
     _, hs, ws, _ = frames.shape
     dev = frames.device
-    if layout == 0:
-        out = torch.empty((n, 3, t, size, size), dtype=torch.float32, device=dev)
-    else:
-        out = torch.empty((n, t, size, size, 4), dtype=torch.bfloat16, device=dev)
+    shape, dtype = ((n, 3, t, size, size), torch.float32) if layout == 0 else ((n, t, size, size, 4), torch.bfloat16)
+    if out is None:
+        out = torch.empty(shape, dtype=dtype, device=dev)
+    elif tuple(out.shape) != shape or out.dtype != dtype or out.device != dev or not out.is_contiguous():
+        raise ValueError(f"clip_sample: out must be a contiguous {dtype} tensor of shape {shape} on {dev}")
     m3 = (C.c_float * 3)(*[float(v) for v in mean])
     s3 = (C.c_float * 3)(*[float(v) for v in std])
     if jitter is None:
@@ -227,7 +229,9 @@ class GPUClipSampler:
         return idx, box, flags, (jitter_table(jit[0] + jit[1]) if jit is not None else None)
 
     def __call__(self, frames: torch.Tensor, video_offsets: Sequence[int], video_lengths: Sequence[int],
-                 layout: int = 0):
+                 layout: int = 0, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+        """``out``: optional ``(clip_q, clip_k)`` buffers to fill in place — ``PretrainEngine.next_input_pair()`` hands
+        out the pair the next captured step reads, which saves the copy of both clips into the graph's inputs."""
         _, h, w, _ = frames.shape
         idx, box, flags, jit = self.draw(video_lengths, h, w)
         b = len(video_lengths)
@@ -250,5 +254,11 @@ class GPUClipSampler:
         t_box = dbuf[o_box:o_jit].view(torch.int32).view(n, 4)
         t_jit = dbuf[o_jit:o_flags].view(n, JITTER_DTYPE.itemsize) if jit is not None else None
         t_flags = dbuf[o_flags:]
-        out = clip_sample(frames, t_idx, t_box, t_flags, self.mean, self.std, self.size, layout, jitter=t_jit)
-        return (out[:b], out[b:]), None
+        if out is None:
+            out = clip_sample(frames, t_idx, t_box, t_flags, self.mean, self.std, self.size, layout, jitter=t_jit)
+            return (out[:b], out[b:]), None
+        for c, dst in enumerate(out):   # caller-owned buffers need not be adjacent: one launch per clip set
+            rows = slice(c * b, (c + 1) * b)
+            clip_sample(frames, t_idx[rows], t_box[rows], t_flags[rows], self.mean, self.std, self.size, layout,
+                        jitter=None if t_jit is None else t_jit[rows], out=dst)
+        return (out[0], out[1]), None

@@ -157,3 +157,17 @@ def test_gpu_clip_sampler_contract():
         (clip_q, clip_k), label = s(frames, [0, 96, 192], [96, 96, 96])
         assert label is None and clip_q.shape == clip_k.shape == (3, 3, 8, 32, 32) and clip_q.dtype == torch.float32
         assert torch.isfinite(clip_q).all() and torch.isfinite(clip_k).all()
+        # caller-owned, non-adjacent output buffers (the input pair of a captured step): same draws -> same pixels
+        state = random.getstate()
+        (ref_q, ref_k), _ = s(frames, [0, 96, 192], [96, 96, 96])
+        random.setstate(state)
+        bufs = (torch.full_like(ref_q, float("nan")), torch.full_like(ref_k, float("nan")))
+        (out_q, out_k), _ = s(frames, [0, 96, 192], [96, 96, 96], out=bufs)
+        assert out_q.data_ptr() == bufs[0].data_ptr() and out_k.data_ptr() == bufs[1].data_ptr()
+        if jitter is None:
+            assert torch.equal(out_q, ref_q) and torch.equal(out_k, ref_k)
+        else:   # the clip-wide gray mean is an atomic float sum: last-bit run-to-run differences, amplified by hue
+            assert (out_q - ref_q).abs().max() < 2e-3 and (out_k - ref_k).abs().max() < 2e-3
+            assert (out_q - ref_q).abs().mean() < 1e-6
+    with pytest.raises(ValueError):
+        s(frames, [0, 96, 192], [96, 96, 96], out=(torch.empty(3, 3, 8, 32, 16, device="cuda"),) * 2)
