@@ -655,7 +655,7 @@ def conv_roofline(args, B, ms_step):
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "frac_of_sustained_peak": (achieved / float(sustained)) if sustained else None,
             "traffic": traffic, "traffic_note": traffic_note,
-            "peak_source": src, "kernel": "tcgen05 conv kernels (conv_direct / conv_igemm / conv_stem / conv_stem3 / conv_wgrad)",
+            "peak_source": src, "kernel": "tcgen05 conv kernels (conv_direct / conv_igemm / conv_stem / conv_stem3 / conv_wgrad / conv_wgrad_direct)",
             "top_launches": top,
             "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / ms_step,
             "per_pass_ms": tot_ms, "algorithmic_gflop_per_step": flops / 1e9}
