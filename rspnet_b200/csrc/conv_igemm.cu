@@ -1087,6 +1087,7 @@ static int dispatch_wgrad(WgradParams& p, int sm_count, cudaStream_t stream) {
 
 int device_sm_count();
 bool stem_supported(const rsp_conv3d_desc* d);
+bool stem_fprop_supported(const rsp_conv3d_desc* d);
 int launch_stem(const rsp_conv3d_desc* d, const void* x, const void* wst, const float* bias, void* y, float* stats,
                 int sm_count, cudaStream_t stream);
 int pack_stem(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const float* w, void* wst,
@@ -1126,7 +1127,7 @@ int64_t rsp_conv3d_packed_elems(const rsp_conv3d_desc* d, int which) {
   if (kpad < 0) return kpad;
   if (which == 1) return static_cast<int64_t>(d->Ci) * kpad;
   int64_t n = static_cast<int64_t>(d->Co) * kpad;
-  if (stem_supported(d)) n += static_cast<int64_t>(d->kt) * d->kh * 2048;  // direct-conv filter slabs appended
+  if (stem_fprop_supported(d)) n += static_cast<int64_t>(d->Co / 64) * d->kt * d->kh * 2048;  // direct-conv filter slabs appended
   if (stem3_supported(d)) n += 2 * 9 * 1024 + 512;   // two filter sets + a zero row
   return n;
 }
@@ -1152,7 +1153,7 @@ int rsp_conv3d_pack_weight(const rsp_conv3d_desc* d, int Ci_logical, int Co_logi
                                                           Ci_logical, d->Ci, d->kt, d->kh, d->kw, g.pxs, Kpad);
     rc = check_launch("pack_weight_fprop");
     if (rc != RSP_OK) return rc;
-    if (stem_supported(d))
+    if (stem_fprop_supported(d))
       return pack_stem(d, Ci_logical, Co_logical, w, static_cast<__nv_bfloat16*>(wp) + total, stream);
     if (stem3_supported(d)) return pack_stem3(Ci_logical, Co_logical, w, static_cast<__nv_bfloat16*>(wp) + total, stream);
     return RSP_OK;
@@ -1207,7 +1208,7 @@ int rsp_conv3d_pack_weights(int32_t n, const rsp_conv3d_desc* descs, const int32
     if (rc != RSP_OK) return rc;
     for (int i = 0; i < b.n; ++i) {
       const rsp_conv3d_desc* d = descs + base + i;
-      if (stem_supported(d)) {
+      if (stem_fprop_supported(d)) {
         rc = pack_stem(d, b.j[i].Ci, b.j[i].Co, b.j[i].w, b.j[i].wp + static_cast<size_t>(d->Co) * b.j[i].Kpad, stream);
         if (rc != RSP_OK) return rc;
       }
@@ -1244,7 +1245,7 @@ int rsp_conv3d_fprop(const rsp_conv3d_desc* d, const void* x, const void* wp, co
   int rc = fill_geom(p.g, d, mode, 0);
   if (rc != RSP_OK) return rc;
   RSP_REQUIRE(d->Co % 64 == 0, "conv3d fprop: Co=%d must be a multiple of 64", d->Co);
-  if (stem_supported(d)) {
+  if (stem_fprop_supported(d)) {
     const __nv_bfloat16* wst = static_cast<const __nv_bfloat16*>(wp) + static_cast<size_t>(d->Co) * p.g.numKb * 64;
     return launch_stem(d, x, wst, bias, y, stats, device_sm_count(), stream);
   }

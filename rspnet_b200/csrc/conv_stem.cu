@@ -40,9 +40,10 @@ struct StemParams {
   CUtensorMap tmapX;         // x as 8-byte pixels {Wi, Hi, Ti, N}, box {128, 24 at row stride 4 = 6 rows, 1, 1}, no swizzle
   const __nv_bfloat16* x;    // [N][Ti][Hi][Wi][4]
   const __nv_bfloat16* wst;  // [kt][4 kchunk][7 slots: b = 6,4,2,0,5,3,1][8 co-group][8 co][8 k] bf16
-  __nv_bfloat16* y;          // [N][To][Ho][Wo][64]
-  const float* bias;
-  float* stats;              // optional [2][64]: += per-channel sum / sum of squares of the stored output
+  __nv_bfloat16* y;          // [N][To][Ho][Wo][ldc], already offset to this launch's 64-channel group
+  const float* bias;         // offset likewise
+  float* stats;              // optional [2][ldc] (offset likewise): += per-channel sum / sum of squares of the stored output
+  int ldc;                   // stored output channels (a multiple of 64; one launch per 64-channel group)
   int N, Ti, Hi, Wi, To, Ho, Wo;
   int kt, kh, st, sh, pt, ph;
   int hq;        // ceil(Ho / kStemOutRows)
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const __grid
           const int ow = (ew & 1) * 32 + lane;
           const bool ok = ho < p.Ho && ow < p.Wo;
           __nv_bfloat16* orow =
-              p.y + ((((static_cast<size_t>(n) * p.To + to) * p.Ho + (ok ? ho : 0)) * p.Wo) + (ok ? ow : 0)) * 64;
+              p.y + ((((static_cast<size_t>(n) * p.To + to) * p.Ho + (ok ? ho : 0)) * p.Wo) + (ok ? ow : 0)) * p.ldc;
           uint32_t v[32];
           tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * 256 + m * 64 + c0, v);
           tmem_ld_wait();
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const __grid
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         atomicAdd(p.stats + h * 32 + lane, ssum[h]);
-        atomicAdd(p.stats + 64 + h * 32 + lane, ssq[h]);
+        atomicAdd(p.stats + p.ldc + h * 32 + lane, ssq[h]);
       }
     }
   } else {
@@ -322,6 +323,16 @@ __global__ void pack_weight_stem_kernel(const float* __restrict__ w, __nv_bfloat
   wst[idx] = __float2bfloat16(v);
 }
 
+bool stem_supported(const rsp_conv3d_desc* d);
+
+// fprop: any number of 64-channel output groups (one launch each: R(2+1)D's 1x7x7 stem has 83 -> 128 stored channels);
+// the wgrad kernel below holds one group.
+bool stem_fprop_supported(const rsp_conv3d_desc* d) {
+  rsp_conv3d_desc one = *d;
+  one.Co = 64;
+  return d->Co % 64 == 0 && d->Co >= 64 && d->Co <= 256 && stem_supported(&one);
+}
+
 bool stem_supported(const rsp_conv3d_desc* d) {
   const int Wo = (d->Wi + 2 * d->pw - d->kw) / d->sw + 1;
   return d->Ci == 4 && d->Co == 64 && d->kw == 7 && d->sw == 2 && d->pw == 3 && d->kh == 7 && d->sh == 2 && (d->Wi % 2) == 0 && d->Wi + 4 <= 124 && Wo <= 64 && ((kStemOutRows - 1) * d->sh + d->kh) <= kStemMaxRows;
@@ -358,16 +369,32 @@ int launch_stem(const rsp_conv3d_desc* d, const void* x, const void* wst, const 
     return RSP_ERR_CUDA;
   }
   int grid = p.numIters < sm_count ? p.numIters : sm_count;
-  conv_stem_kernel<<<grid, kStemThreads, smem, stream>>>(p);
-  return check_launch("conv_stem");
+  p.ldc = d->Co;
+  for (int g = 0; g < d->Co / 64; ++g) {   // one launch per 64-channel group (filter slabs are packed group by group)
+    p.wst = static_cast<const __nv_bfloat16*>(wst) + static_cast<size_t>(g) * d->kt * d->kh * 2048;
+    p.y = static_cast<__nv_bfloat16*>(y) + g * 64;
+    p.bias = bias ? bias + g * 64 : nullptr;
+    p.stats = stats ? stats + g * 64 : nullptr;
+    conv_stem_kernel<<<grid, kStemThreads, smem, stream>>>(p);
+    int rc = check_launch("conv_stem");
+    if (rc != RSP_OK) return rc;
+  }
+  return RSP_OK;
 }
 
 int pack_stem(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const float* w, void* wst,
               cudaStream_t stream) {
   size_t total = static_cast<size_t>(d->kt) * d->kh * 2048;
-  pack_weight_stem_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
-      w, static_cast<__nv_bfloat16*>(wst), Co_logical, Ci_logical, d->kt, d->kh, d->kw);
-  return check_launch("pack_weight_stem");
+  for (int g = 0; g < d->Co / 64; ++g) {   // one slab set per 64-channel output group
+    const int co_left = Co_logical - g * 64;
+    pack_weight_stem_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+        w + static_cast<size_t>(g) * 64 * Ci_logical * d->kt * d->kh * d->kw,
+        static_cast<__nv_bfloat16*>(wst) + g * total, co_left < 0 ? 0 : (co_left > 64 ? 64 : co_left), Ci_logical, d->kt,
+        d->kh, d->kw);
+    int rc = check_launch("pack_weight_stem");
+    if (rc != RSP_OK) return rc;
+  }
+  return RSP_OK;
 }
 
 

@@ -380,6 +380,9 @@ CONV_CASES = [
     # row-paired RGB stem: several 8-row iterations per frame, ragged last iteration, clipped frame taps at both ends
     (2, 3, 64, (9, 44, 36), (7, 7, 7), (1, 2, 2), (3, 3, 3)),
     (2, 3, 45, (3, 32, 28), (1, 7, 7), (1, 2, 2), (0, 3, 3)),
+    # R(2+1)D-vcop stem: 83 mid channels = two 64-channel output groups (one stem launch each), ragged second group
+    (2, 3, 83, (3, 32, 28), (1, 7, 7), (1, 2, 2), (0, 3, 3)),
+    (1, 3, 128, (8, 40, 36), (7, 7, 7), (1, 2, 2), (3, 3, 3)),
     (2, 3, 64, (4, 12, 12), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
     (3, 256, 512, (2, 7, 7), (3, 3, 3), (2, 2, 2), (1, 1, 1)),
     # one-frame tensors (R3D-18 layer4): the outer frame taps only read padding and are skipped as whole K blocks
