@@ -416,13 +416,14 @@ int pack_stem(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const fl
 // grid: x = workers over output rows within a group, y = group.
 // =====================================================================================================================
 struct StemWgradParams {
-  CUtensorMap tmapDy;       // dy as {64, Wo, N*To*Ho}, box {64, 72, 1} from pixel -1: one output row per copy, zero-filled outside
+  CUtensorMap tmapDy;       // dy as {Co stored, Wo, N*To*Ho}, box {64, 72, 1} from (co0, pixel -1): one output row per copy, zero-filled outside
   CUtensorMap tmapX;        // x as 8-byte pixels {Wi, Hi, Ti, N}, box {128, kh, 1, 1}, no swizzle
   const __nv_bfloat16* x;   // [N][Ti][Hi][Wi][4]
   float* dw;                // [Co][Ci][kt][kh][kw] fp32, accumulated atomically
   int N, Ti, Hi, Wi, To, Ho, Wo;
   int kt, kh, kw, st, sh, pt, ph;
-  int Co, Ci;               // logical
+  int Co, Ci;               // logical (Co: channels of this launch's 64-channel group, dw points at its first filter)
+  int co0;                  // first stored dY channel of the group
   int numRows;              // N*To*Ho
   int rowsPerGroup;         // filter rows (a, b) per CTA group (<= 32)
 };
@@ -491,7 +492,7 @@ __global__ void __launch_bounds__(192, 1) conv_stem_wgrad_kernel(const __grid_co
           mbar_arrive_expect_tx(&full_bar[s], tx);
           asm volatile(
               "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-              ::"r"(stage), "l"(&p.tmapDy), "r"(smem_u32(&full_bar[s])), "r"(0), "r"(-1), "r"(r)
+              ::"r"(stage), "l"(&p.tmapDy), "r"(smem_u32(&full_bar[s])), "r"(p.co0), "r"(-1), "r"(r)
               : "memory");
           for (int al = 0; al < na; ++al) {
             asm volatile(
@@ -624,8 +625,9 @@ int launch_stem_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, 
   if (workers < 1) workers = 1;
   if (workers > p.numRows) workers = p.numRows;
   {
-    const unsigned long long dims[3] = {64, static_cast<unsigned long long>(p.Wo), static_cast<unsigned long long>(p.numRows)};
-    const unsigned long long strides[2] = {128, static_cast<unsigned long long>(p.Wo) * 128};
+    const unsigned long long Cst = static_cast<unsigned long long>(d->Co);
+    const unsigned long long dims[3] = {Cst, static_cast<unsigned long long>(p.Wo), static_cast<unsigned long long>(p.numRows)};
+    const unsigned long long strides[2] = {Cst * 2, static_cast<unsigned long long>(p.Wo) * Cst * 2};
     const unsigned box[3] = {64, kSWDyRows, 1};
     int rc = make_tmap_bf16(&p.tmapDy, dy, 3, dims, strides, box);
     if (rc != RSP_OK) return rc;
@@ -637,8 +639,16 @@ int launch_stem_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, 
     if (rc != RSP_OK) return rc;
   }
   dim3 grid(workers, groups);
-  conv_stem_wgrad_kernel<<<grid, 192, smem, stream>>>(p);
-  return check_launch("conv_stem_wgrad");
+  const size_t perCo = static_cast<size_t>(Ci_logical) * d->kt * d->kh * d->kw;
+  for (int g = 0; g * 64 < Co_logical; ++g) {   // one launch per 64-channel group of dY (x is re-read per group)
+    p.co0 = g * 64;
+    p.Co = Co_logical - g * 64 < 64 ? Co_logical - g * 64 : 64;
+    p.dw = dw + static_cast<size_t>(g) * 64 * perCo;
+    conv_stem_wgrad_kernel<<<grid, 192, smem, stream>>>(p);
+    int rc = check_launch("conv_stem_wgrad");
+    if (rc != RSP_OK) return rc;
+  }
+  return RSP_OK;
 }
 
 }  // namespace rsp
