@@ -16,6 +16,7 @@
 //
 // CTA (persistent, 1/SM): warps 0-3 epilogue, warp 4 TMA producer (one elected lane), warp 5 MMA issuer.
 // Rings: 2 plane buffers, 3-6 filter tiles, 2 TMEM accumulator sets (G * NT columns each).
+#include <cstdlib>
 #include "common.cuh"
 #include "rspnet_b200.h"
 
@@ -369,7 +370,17 @@ static bool direct_geometry(const rsp_conv3d_desc* d, int transposed, DirectPara
     const long long gatherTiles = ((static_cast<long long>(p.N) * p.To * p.Ho * p.Wo + 127) / 128) * (Nout / NT);
     if (p.P < 128 * p.G && gatherTiles >= 6ll * device_sm_count()) return false;
   }
-  if (p.kh * p.kw < 2) return false;                 // 1x1 filters have nothing to reuse
+  if (p.kh * p.kw < 2) {
+    // kt x 1 x 1 filters reuse nothing inside a plane, but the gather kernel pays for them twice: its im2col producer
+    // issues one cp.async per 16 bytes, and with K = kt * Cs this short every 128-position tile is a CTA of its own with
+    // its set-up cost.  The persistent TMA pipeline here has neither (R(2+1)D @ 16x56x56, batch 32: 3x1x1 fprop 128 -> 64
+    // 0.385 -> 0.176 ms, 192 -> 64 0.43 -> 0.24 ms; dgrad 64 -> 192 1.00 -> 0.38 ms; S3D-G's unit-stride 1x1x1 branches: 26 -> 17 us at 28x28).
+    static const int mode1x1 = [] {
+      const char* e = getenv("RSP_DIRECT_1X1");   // 0: never, 1: temporal filters only, 2 (default): also unit-stride 1x1x1
+      return e ? atoi(e) : 2;
+    }();
+    if (mode1x1 == 0 || (mode1x1 == 1 && p.kt < 2)) return false;
+  }
   p.groups = (p.P + 128 * p.G - 1) / (128 * p.G);
   if (p.Wp > 256) return false;                                          // TMA box extent
   p.rowsBuf = (128 * p.G + p.kh * p.Wp + p.kw - 3) / p.Wp + 1;           // see the header: run + halo, row aligned

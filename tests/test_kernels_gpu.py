@@ -396,6 +396,14 @@ CONV_CASES = [
     (1, 128, 128, (3, 20, 22), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
     (2, 64, 192, (2, 24, 20), (1, 3, 3), (1, 1, 1), (0, 1, 1)),
     (1, 128, 64, (2, 30, 26), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    # temporal 3x1x1 filters of R(2+1)D: the dgrad into 192 / 320 stored channels takes the direct kernel (kh*kw = 1)
+    (2, 144, 64, (5, 24, 20), (3, 1, 1), (1, 1, 1), (1, 0, 0)),
+    (1, 288, 128, (3, 28, 28), (3, 1, 1), (1, 1, 1), (1, 0, 0)),
+    (1, 64, 64, (7, 20, 20), (7, 1, 1), (1, 1, 1), (3, 0, 0)),
+    # unit-stride 1x1x1 (S3D-G inception branches) through the same persistent TMA pipeline
+    (2, 192, 64, (4, 14, 14), (1, 1, 1), (1, 1, 1), (0, 0, 0)),
+    (1, 64, 128, (3, 28, 28), (1, 1, 1), (1, 1, 1), (0, 0, 0)),
+    (1, 256, 192, (2, 20, 12), (1, 1, 1), (1, 1, 1), (0, 0, 0)),
 ]
 
 
