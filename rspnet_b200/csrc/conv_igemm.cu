@@ -1086,8 +1086,8 @@ static int dispatch_wgrad(WgradParams& p, int sm_count, cudaStream_t stream) {
 }
 
 int device_sm_count();
-bool stem_supported(const rsp_conv3d_desc* d);
 bool stem_fprop_supported(const rsp_conv3d_desc* d);
+bool stem_wgrad_supported(const rsp_conv3d_desc* d);
 int launch_stem(const rsp_conv3d_desc* d, const void* x, const void* wst, const float* bias, void* y, float* stats,
                 int sm_count, cudaStream_t stream);
 int pack_stem(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, const float* w, void* wst,
@@ -1401,7 +1401,7 @@ int rsp_conv3d_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, c
   int rc = fill_geom(p.g, d, mode, 0);
   if (rc != RSP_OK) return rc;
   RSP_REQUIRE(d->Co % 64 == 0, "conv3d wgrad: Co=%d must be a multiple of 64", d->Co);
-  if (stem_fprop_supported(d) && d->kh * 2 * 32 <= 448)
+  if (stem_wgrad_supported(d))
     return launch_stem_wgrad(d, Ci_logical, Co_logical, x, dy, dw, accumulate, device_sm_count(), stream);
   if (stem3_supported(d))
     return launch_stem3_wgrad(d, Ci_logical, Co_logical, x, dy, dwt_workspace, dw, accumulate, device_sm_count(), stream);

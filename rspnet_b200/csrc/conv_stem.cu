@@ -44,6 +44,8 @@ struct StemParams {
   const float* bias;         // offset likewise
   float* stats;              // optional [2][ldc] (offset likewise): += per-channel sum / sum of squares of the stored output
   int ldc;                   // stored output channels (a multiple of 64; one launch per 64-channel group)
+  int x0, ow0, wlim;         // column tile of this launch: input pixel held by slot 0 (2*ow0 - 4), first output column,
+                             // number of output columns (<= 60); one launch per tile, a single tile up to Wi = 120
   int N, Ti, Hi, Wi, To, Ho, Wo;
   int kt, kh, st, sh, pt, ph;
   int hq;        // ceil(Ho / kStemOutRows)
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const __grid
             asm volatile(
                 "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                 ::"r"(aslab + phase * kStemPerPhase * kStemRowBytes), "l"(&p.tmapX), "r"(smem_u32(&full_bar[s])),
-                  "r"(-4), "r"(hi0 + phase), "r"(ti), "r"(n)
+                  "r"(p.x0), "r"(hi0 + phase), "r"(ti), "r"(n)
                 : "memory");
           }
           if (++s == kStemStages) {
@@ -185,9 +187,9 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const __grid
         for (int m = 0; m < kStemOutRows / 2; ++m) {   // 64-column block m: tile m / 2, N half m % 2
           const int ho = hq * kStemOutRows + 4 * (m >> 1) + 2 * (ew >> 1) + (m & 1);
           const int ow = (ew & 1) * 32 + lane;
-          const bool ok = ho < p.Ho && ow < p.Wo;
+          const bool ok = ho < p.Ho && ow < p.wlim;
           __nv_bfloat16* orow =
-              p.y + ((((static_cast<size_t>(n) * p.To + to) * p.Ho + (ok ? ho : 0)) * p.Wo) + (ok ? ow : 0)) * p.ldc;
+              p.y + ((((static_cast<size_t>(n) * p.To + to) * p.Ho + (ok ? ho : 0)) * p.Wo) + (ok ? p.ow0 + ow : 0)) * p.ldc;
           uint32_t v[32];
           tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * 256 + m * 64 + c0, v);
           tmem_ld_wait();
@@ -256,7 +258,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const __grid
         mbar_wait(&full_bar[s], ph);
         fence_proxy_async_smem();
         tc_fence_after_sync();
-        // kh == 7 and sh == 2 (stem_supported): every descriptor is a compile-time offset from two bases, so the
+        // kh == 7 and sh == 2 (stem_filter_ok): every descriptor is a compile-time offset from two bases, so the
         // issuing thread spends ~2 instructions per MMA instead of rebuilding 64-bit descriptors
         const uint32_t aslab = smem_u32(smem + s * kStemStageBytes);
         const uint64_t abase = make_smem_desc_nosw(aslab, 16, 128);
@@ -323,19 +325,23 @@ __global__ void pack_weight_stem_kernel(const float* __restrict__ w, __nv_bfloat
   wst[idx] = __float2bfloat16(v);
 }
 
-bool stem_supported(const rsp_conv3d_desc* d);
-
-// fprop: any number of 64-channel output groups (one launch each: R(2+1)D's 1x7x7 stem has 83 -> 128 stored channels);
-// the wgrad kernel below holds one group.
-bool stem_fprop_supported(const rsp_conv3d_desc* d) {
-  rsp_conv3d_desc one = *d;
-  one.Co = 64;
-  return d->Co % 64 == 0 && d->Co >= 64 && d->Co <= 256 && stem_supported(&one);
+static bool stem_filter_ok(const rsp_conv3d_desc* d) {
+  return d->Ci == 4 && d->kw == 7 && d->sw == 2 && d->pw == 3 && d->kh == 7 && d->sh == 2 && (d->Wi % 2) == 0 &&
+         ((kStemOutRows - 1) * d->sh + d->kh) <= kStemMaxRows;
 }
 
-bool stem_supported(const rsp_conv3d_desc* d) {
+// fprop: any number of 64-channel output groups (R(2+1)D's 1x7x7 stem has 83 -> 128 stored channels) and any number of
+// column tiles of up to 60 output pixels (S3D-G at 224 x 224: two tiles of 56) — one launch per (group, tile)
+bool stem_fprop_supported(const rsp_conv3d_desc* d) {
   const int Wo = (d->Wi + 2 * d->pw - d->kw) / d->sw + 1;
-  return d->Ci == 4 && d->Co == 64 && d->kw == 7 && d->sw == 2 && d->pw == 3 && d->kh == 7 && d->sh == 2 && (d->Wi % 2) == 0 && d->Wi + 4 <= 124 && Wo <= 64 && ((kStemOutRows - 1) * d->sh + d->kh) <= kStemMaxRows;
+  return stem_filter_ok(d) && d->Co % 64 == 0 && d->Co >= 64 && d->Co <= 256 && Wo >= 1 && Wo <= 240;
+}
+
+// wgrad (below): one launch per 64-channel group of dY, rows of up to 120 pixels
+bool stem_wgrad_supported(const rsp_conv3d_desc* d) {
+  const int Wo = (d->Wi + 2 * d->pw - d->kw) / d->sw + 1;
+  return stem_filter_ok(d) && d->Co % 64 == 0 && d->Co >= 64 && d->Co <= 256 && d->Wi + 4 <= 124 && Wo <= 64 &&
+         d->kh * 2 * 32 <= 448;
 }
 
 int launch_stem(const rsp_conv3d_desc* d, const void* x, const void* wst, const float* bias, void* y, float* stats,
@@ -370,14 +376,20 @@ int launch_stem(const rsp_conv3d_desc* d, const void* x, const void* wst, const 
   }
   int grid = p.numIters < sm_count ? p.numIters : sm_count;
   p.ldc = d->Co;
+  const int wtiles = (p.Wo + 59) / 60, wt = (p.Wo + wtiles - 1) / wtiles;
   for (int g = 0; g < d->Co / 64; ++g) {   // one launch per 64-channel group (filter slabs are packed group by group)
     p.wst = static_cast<const __nv_bfloat16*>(wst) + static_cast<size_t>(g) * d->kt * d->kh * 2048;
     p.y = static_cast<__nv_bfloat16*>(y) + g * 64;
     p.bias = bias ? bias + g * 64 : nullptr;
     p.stats = stats ? stats + g * 64 : nullptr;
-    conv_stem_kernel<<<grid, kStemThreads, smem, stream>>>(p);
-    int rc = check_launch("conv_stem");
-    if (rc != RSP_OK) return rc;
+    for (int w = 0; w < wtiles; ++w) {     // and per column tile
+      p.ow0 = w * wt;
+      p.x0 = 2 * p.ow0 - 4;
+      p.wlim = p.Wo - p.ow0 < wt ? p.Wo - p.ow0 : wt;
+      conv_stem_kernel<<<grid, kStemThreads, smem, stream>>>(p);
+      int rc = check_launch("conv_stem");
+      if (rc != RSP_OK) return rc;
+    }
   }
   return RSP_OK;
 }

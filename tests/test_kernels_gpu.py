@@ -383,6 +383,10 @@ CONV_CASES = [
     # R(2+1)D-vcop stem: 83 mid channels = two 64-channel output groups (one stem launch each), ragged second group
     (2, 3, 83, (3, 32, 28), (1, 7, 7), (1, 2, 2), (0, 3, 3)),
     (1, 3, 128, (8, 40, 36), (7, 7, 7), (1, 2, 2), (3, 3, 3)),
+    # wide rows (S3D-G at 224 x 224): column tiles of up to 60 output pixels, one stem launch each; ragged last tile
+    (1, 3, 64, (2, 30, 224), (1, 7, 7), (1, 2, 2), (0, 3, 3)),
+    (1, 3, 64, (3, 20, 122), (1, 7, 7), (1, 2, 2), (0, 3, 3)),
+    (1, 3, 83, (2, 18, 136), (1, 7, 7), (1, 2, 2), (0, 3, 3)),
     (2, 3, 64, (4, 12, 12), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
     (3, 256, 512, (2, 7, 7), (3, 3, 3), (2, 2, 2), (1, 1, 1)),
     # one-frame tensors (R3D-18 layer4): the outer frame taps only read padding and are skipped as whole K blocks
