@@ -337,11 +337,9 @@ bool stem_fprop_supported(const rsp_conv3d_desc* d) {
   return stem_filter_ok(d) && d->Co % 64 == 0 && d->Co >= 64 && d->Co <= 256 && Wo >= 1 && Wo <= 240;
 }
 
-// wgrad (below): one launch per 64-channel group of dY, rows of up to 120 pixels
+// wgrad (below): one launch per (64-channel group of dY, column tile of up to 60 output pixels)
 bool stem_wgrad_supported(const rsp_conv3d_desc* d) {
-  const int Wo = (d->Wi + 2 * d->pw - d->kw) / d->sw + 1;
-  return stem_filter_ok(d) && d->Co % 64 == 0 && d->Co >= 64 && d->Co <= 256 && d->Wi + 4 <= 124 && Wo <= 64 &&
-         d->kh * 2 * 32 <= 448;
+  return stem_fprop_supported(d) && d->kh * 2 * 32 <= 448;
 }
 
 int launch_stem(const rsp_conv3d_desc* d, const void* x, const void* wst, const float* bias, void* y, float* stats,
@@ -436,6 +434,7 @@ struct StemWgradParams {
   int kt, kh, kw, st, sh, pt, ph;
   int Co, Ci;               // logical (Co: channels of this launch's 64-channel group, dw points at its first filter)
   int co0;                  // first stored dY channel of the group
+  int x0;                   // input pixel held by slot 0 of a raw row: 2 * (first output column of the tile) - 4
   int numRows;              // N*To*Ho
   int rowsPerGroup;         // filter rows (a, b) per CTA group (<= 32)
 };
@@ -510,7 +509,7 @@ __global__ void __launch_bounds__(192, 1) conv_stem_wgrad_kernel(const __grid_co
             asm volatile(
                 "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                 ::"r"(stage + kSWDyBytes + al * p.kh * kStemRowBytes), "l"(&p.tmapX), "r"(smem_u32(&full_bar[s])),
-                  "r"(-4), "r"(ho * p.sh - p.ph), "r"(to * p.st - p.pt + a0 + al), "r"(n)
+                  "r"(p.x0), "r"(ho * p.sh - p.ph), "r"(to * p.st - p.pt + a0 + al), "r"(n)
                 : "memory");
           }
           if (++s == kSWStages) {
@@ -637,28 +636,36 @@ int launch_stem_wgrad(const rsp_conv3d_desc* d, int Ci_logical, int Co_logical, 
   if (workers < 1) workers = 1;
   if (workers > p.numRows) workers = p.numRows;
   {
-    const unsigned long long Cst = static_cast<unsigned long long>(d->Co);
-    const unsigned long long dims[3] = {Cst, static_cast<unsigned long long>(p.Wo), static_cast<unsigned long long>(p.numRows)};
-    const unsigned long long strides[2] = {Cst * 2, static_cast<unsigned long long>(p.Wo) * Cst * 2};
-    const unsigned box[3] = {64, kSWDyRows, 1};
-    int rc = make_tmap_bf16(&p.tmapDy, dy, 3, dims, strides, box);
-    if (rc != RSP_OK) return rc;
     const unsigned long long W = p.Wi, H = p.Hi, T = p.Ti;
     const unsigned long long xdims[4] = {W, H, T, static_cast<unsigned long long>(p.N)};
     const unsigned long long xstrides[3] = {W * 8, H * W * 8, T * H * W * 8};
     const unsigned xbox[4] = {128, static_cast<unsigned>(d->kh), 1, 1};
-    rc = make_tmap_u64_rows(&p.tmapX, x, 4, xdims, xstrides, xbox);
+    int rc = make_tmap_u64_rows(&p.tmapX, x, 4, xdims, xstrides, xbox);
     if (rc != RSP_OK) return rc;
   }
   dim3 grid(workers, groups);
   const size_t perCo = static_cast<size_t>(Ci_logical) * d->kt * d->kh * d->kw;
-  for (int g = 0; g * 64 < Co_logical; ++g) {   // one launch per 64-channel group of dY (x is re-read per group)
-    p.co0 = g * 64;
-    p.Co = Co_logical - g * 64 < 64 ? Co_logical - g * 64 : 64;
-    p.dw = dw + static_cast<size_t>(g) * 64 * perCo;
-    conv_stem_wgrad_kernel<<<grid, 192, smem, stream>>>(p);
-    int rc = check_launch("conv_stem_wgrad");
+  const unsigned long long Cst = static_cast<unsigned long long>(d->Co);
+  const int wtiles = (p.Wo + 59) / 60, wt = (p.Wo + wtiles - 1) / wtiles;
+  for (int w = 0; w < wtiles; ++w) {
+    // column tile: the dY map is restricted to the tile's pixels (base shifted, W = tile width), so that the box from
+    // pixel -1 zero-fills its first row and everything right of the tile — every output pixel is summed exactly once
+    const int ow0 = w * wt, wlim = p.Wo - ow0 < wt ? p.Wo - ow0 : wt;
+    const unsigned long long dims[3] = {Cst, static_cast<unsigned long long>(wlim), static_cast<unsigned long long>(p.numRows)};
+    const unsigned long long strides[2] = {Cst * 2, static_cast<unsigned long long>(p.Wo) * Cst * 2};
+    const unsigned box[3] = {64, kSWDyRows, 1};
+    int rc = make_tmap_bf16(&p.tmapDy, static_cast<const __nv_bfloat16*>(dy) + static_cast<size_t>(ow0) * Cst, 3, dims,
+                            strides, box);
     if (rc != RSP_OK) return rc;
+    p.x0 = 2 * ow0 - 4;
+    for (int g = 0; g * 64 < Co_logical; ++g) {   // one launch per 64-channel group of dY (x is re-read per group)
+      p.co0 = g * 64;
+      p.Co = Co_logical - g * 64 < 64 ? Co_logical - g * 64 : 64;
+      p.dw = dw + static_cast<size_t>(g) * 64 * perCo;
+      conv_stem_wgrad_kernel<<<grid, 192, smem, stream>>>(p);
+      rc = check_launch("conv_stem_wgrad");
+      if (rc != RSP_OK) return rc;
+    }
   }
   return RSP_OK;
 }
