@@ -408,6 +408,14 @@ CONV_CASES = [
     (2, 192, 64, (4, 14, 14), (1, 1, 1), (1, 1, 1), (0, 0, 0)),
     (1, 64, 128, (3, 28, 28), (1, 1, 1), (1, 1, 1), (0, 0, 0)),
     (1, 256, 192, (2, 20, 12), (1, 1, 1), (1, 1, 1), (0, 0, 0)),
+    # strided pointwise / temporal filters (residual shortcuts of R3D-18 / R(2+1)D, R(2+1)D's 3x1x1 s(2,1,1)) at plane
+    # sizes where the direct kernel takes their unit-stride counterparts
+    (2, 64, 128, (4, 28, 28), (1, 1, 1), (2, 2, 2), (0, 0, 0)),
+    (2, 64, 64, (3, 56, 56), (1, 1, 1), (1, 2, 2), (0, 0, 0)),
+    (2, 64, 128, (6, 14, 14), (1, 1, 1), (2, 1, 1), (0, 0, 0)),
+    (1, 128, 64, (5, 27, 29), (1, 1, 1), (2, 2, 2), (0, 0, 0)),
+    (2, 256, 128, (8, 28, 28), (3, 1, 1), (2, 1, 1), (1, 0, 0)),
+    (1, 64, 64, (7, 20, 20), (3, 1, 1), (2, 1, 1), (1, 0, 0)),
 ]
 
 
